@@ -1,0 +1,514 @@
+// api.cu -- context management and the host-facing C ABI of libzipc_b200 (include/zipc_b200.h).
+//
+// Everything here is plumbing: argument checks, staging host memory to the device, ordering the
+// kernel launches of crc32.cu / adler32.cu / inflate.cu / deflate.cu on the ctx stream, and
+// returning per-member results.  There is no CPU implementation of any codec step in this file.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+
+#include "common.cuh"
+
+namespace zb {
+
+uint32_t gf_mul_host(uint32_t a, uint32_t b) { return gf_mul(a, b); }
+
+int set_cuda_error(zipc_b200_ctx *ctx, cudaError_t e, const char *what) {
+  if (ctx) {
+    ctx->last_error = std::string(what) + ": " + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")";
+  }
+  cudaGetLastError();  // clear the sticky-less error state
+  return e == cudaErrorMemoryAllocation ? ZIPC_ERR_NOMEM
+         : (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) ? ZIPC_ERR_NO_DEVICE
+                                                                        : ZIPC_ERR_CUDA;
+}
+
+int DevBuf::reserve(size_t bytes) {
+  if (bytes <= cap) return ZIPC_OK;
+  if (p) { cudaFree(p); p = nullptr; cap = 0; }
+  size_t want = bytes + bytes / 8 + 4096;
+  if (cudaMalloc(&p, want) != cudaSuccess) {
+    cudaGetLastError();
+    if (cudaMalloc(&p, bytes) != cudaSuccess) { cudaGetLastError(); p = nullptr; return ZIPC_ERR_NOMEM; }
+    want = bytes;
+  }
+  cap = want;
+  return ZIPC_OK;
+}
+void DevBuf::release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+int PinBuf::reserve(size_t bytes) {
+  if (bytes <= cap) return ZIPC_OK;
+  if (p) { cudaFreeHost(p); p = nullptr; cap = 0; }
+  size_t want = bytes + bytes / 8 + 4096;
+  if (cudaHostAlloc(&p, want, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); p = nullptr; return ZIPC_ERR_NOMEM; }
+  cap = want;
+  return ZIPC_OK;
+}
+void PinBuf::release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+
+namespace {
+
+bool is_pinned(const void *p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeHost;
+}
+
+constexpr size_t kStageChunk = 16u << 20;
+
+// host -> device.  Pinned sources are DMA'd directly; pageable ones go through a double-buffered
+// pinned staging ring so that the CPU copy of chunk k+1 overlaps the DMA of chunk k.
+int h2d(zipc_b200_ctx *ctx, void *d, const void *h, size_t bytes) {
+  if (!bytes) return ZIPC_OK;
+  if (is_pinned(h)) {
+    ZB_CUDA(ctx, cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return ZIPC_OK;
+  }
+  if (bytes <= (1u << 16)) {
+    ZB_CUDA(ctx, cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return ZIPC_OK;
+  }
+  if (int st = ctx->h_stage.reserve(2 * kStageChunk)) return st;
+  cudaEvent_t ev[2];
+  ZB_CUDA(ctx, cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming));
+  ZB_CUDA(ctx, cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming));
+  size_t off = 0;
+  int k = 0;
+  bool used[2] = {false, false};
+  int rc = ZIPC_OK;
+  while (off < bytes) {
+    size_t m = std::min(kStageChunk, bytes - off);
+    uint8_t *s = ctx->h_stage.as<uint8_t>() + (size_t)k * kStageChunk;
+    if (used[k]) cudaEventSynchronize(ev[k]);
+    std::memcpy(s, static_cast<const uint8_t *>(h) + off, m);
+    cudaError_t e = cudaMemcpyAsync(static_cast<uint8_t *>(d) + off, s, m, cudaMemcpyHostToDevice, ctx->stream);
+    if (e != cudaSuccess) { rc = set_cuda_error(ctx, e, "h2d staging"); break; }
+    cudaEventRecord(ev[k], ctx->stream);
+    used[k] = true;
+    off += m;
+    k ^= 1;
+  }
+  for (int i = 0; i < 2; i++) { if (used[i]) cudaEventSynchronize(ev[i]); cudaEventDestroy(ev[i]); }
+  return rc;
+}
+
+// device -> host, same idea in the other direction.  Synchronous on return.
+int d2h(zipc_b200_ctx *ctx, void *h, const void *d, size_t bytes) {
+  if (!bytes) return ZIPC_OK;
+  if (is_pinned(h) || bytes <= (1u << 16)) {
+    ZB_CUDA(ctx, cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    ZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ZIPC_OK;
+  }
+  if (int st = ctx->h_stage.reserve(2 * kStageChunk)) return st;
+  cudaEvent_t ev[2];
+  ZB_CUDA(ctx, cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming));
+  ZB_CUDA(ctx, cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming));
+  size_t off = 0, pend_off[2] = {0, 0}, pend_len[2] = {0, 0};
+  int k = 0, rc = ZIPC_OK;
+  while (off < bytes || pend_len[0] || pend_len[1]) {
+    if (pend_len[k]) {  // drain the buffer we are about to reuse
+      cudaEventSynchronize(ev[k]);
+      std::memcpy(static_cast<uint8_t *>(h) + pend_off[k], ctx->h_stage.as<uint8_t>() + (size_t)k * kStageChunk, pend_len[k]);
+      pend_len[k] = 0;
+    }
+    if (off < bytes) {
+      size_t m = std::min(kStageChunk, bytes - off);
+      cudaError_t e = cudaMemcpyAsync(ctx->h_stage.as<uint8_t>() + (size_t)k * kStageChunk,
+                                      static_cast<const uint8_t *>(d) + off, m, cudaMemcpyDeviceToHost, ctx->stream);
+      if (e != cudaSuccess) { rc = set_cuda_error(ctx, e, "d2h staging"); break; }
+      cudaEventRecord(ev[k], ctx->stream);
+      pend_off[k] = off; pend_len[k] = m;
+      off += m;
+    }
+    k ^= 1;
+  }
+  cudaEventDestroy(ev[0]); cudaEventDestroy(ev[1]);
+  return rc;
+}
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) & ~(a - 1); }
+
+// Uploads n host ranges into ctx->d_in and returns their device addresses.  When the ranges are
+// (nearly) one contiguous host span -- members of an in-memory archive -- the span is sent with one
+// copy; otherwise ranges are packed back to back (4-byte aligned).
+int upload_ranges(zipc_b200_ctx *ctx, size_t n, const void *const *src, const size_t *len,
+                  std::vector<const uint8_t *> &d_ptr) {
+  d_ptr.assign(n, nullptr);
+  if (!n) return ZIPC_OK;
+  uintptr_t lo = ~(uintptr_t)0, hi = 0;
+  size_t sum = 0;
+  for (size_t i = 0; i < n; i++) {
+    if (!len[i]) continue;
+    if (!src[i]) return ZIPC_ERR_INVALID_ARG;
+    uintptr_t a = (uintptr_t)src[i];
+    lo = std::min(lo, a); hi = std::max(hi, a + len[i]);
+    sum += len[i];
+  }
+  if (!sum) {
+    if (int st = ctx->d_in.reserve(64)) return st;
+    for (size_t i = 0; i < n; i++) d_ptr[i] = ctx->d_in.as<uint8_t>();
+    return ZIPC_OK;
+  }
+  size_t span = hi - lo;
+  if (span <= sum + sum / 4 + 65536) {
+    size_t pre = lo & 15;  // keep the host alignment so 16-byte paths stay aligned
+    if (int st = ctx->d_in.reserve(pre + span + 64)) return st;
+    uint8_t *base = ctx->d_in.as<uint8_t>() + pre;
+    if (int st = h2d(ctx, base, (const void *)lo, span)) return st;
+    for (size_t i = 0; i < n; i++) d_ptr[i] = len[i] ? base + ((uintptr_t)src[i] - lo) : base;
+    return ZIPC_OK;
+  }
+  size_t total = 0;
+  std::vector<size_t> off(n);
+  for (size_t i = 0; i < n; i++) { off[i] = total; total += align_up(len[i], 16); }
+  if (int st = ctx->d_in.reserve(total + 64)) return st;
+  // pack into pinned memory first, then one DMA
+  if (int st = ctx->h_stage.reserve(std::max(total, 2 * kStageChunk))) return st;
+  uint8_t *hs = ctx->h_stage.as<uint8_t>();
+  for (size_t i = 0; i < n; i++) if (len[i]) std::memcpy(hs + off[i], src[i], len[i]);
+  ZB_CUDA(ctx, cudaMemcpyAsync(ctx->d_in.p, hs, total, cudaMemcpyHostToDevice, ctx->stream));
+  ZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  for (size_t i = 0; i < n; i++) d_ptr[i] = ctx->d_in.as<uint8_t>() + off[i];
+  return ZIPC_OK;
+}
+
+__global__ void make_crc_segs_kernel(const InflateTask *tasks, const InflateResult *res, uint32_t n, CrcSeg *segs) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  CrcSeg s;
+  s.ptr = tasks[i].dst;
+  s.len = res[i].status == ZIPC_OK ? res[i].out_len : 0;
+  s.init = 0xFFFFFFFFu;
+  s._pad = 0;
+  segs[i] = s;
+}
+__global__ void xor_ffffffff_kernel(uint32_t *v, uint32_t n) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) v[i] ^= 0xFFFFFFFFu;
+}
+
+// Core of every inflate entry point.  All pointers in d_src / d_dst are device addresses.
+// cap[i] == ZIPC_SIZE_UNKNOWN is not accepted here (the callers resolve sizes first).
+int inflate_core(zipc_b200_ctx *ctx, int ck, int adler_mode, size_t n, const std::vector<const uint8_t *> &d_src,
+                 const size_t *src_len, const std::vector<uint8_t *> &d_dst, const std::vector<size_t> &cap,
+                 bool count_only, size_t *out_len, uint32_t *checksum, int *status) {
+  if (!n) return ZIPC_OK;
+  if (n > 0xFFFFFFF0ull) return ZIPC_ERR_INVALID_ARG;
+  // longest streams first: the tail of the dynamic queue is made of short ones
+  std::vector<uint32_t> order(n);
+  std::iota(order.begin(), order.end(), 0u);
+  std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return src_len[a] > src_len[b]; });
+  if (int st = ctx->h_desc.reserve(n * sizeof(InflateTask))) return st;
+  if (int st = ctx->d_desc.reserve(n * (sizeof(InflateTask) + sizeof(CrcSeg)))) return st;
+  if (int st = ctx->d_res.reserve(n * (sizeof(InflateResult) + sizeof(uint32_t)))) return st;
+  if (int st = ctx->h_res.reserve(n * (sizeof(InflateResult) + sizeof(uint32_t)))) return st;
+  InflateTask *ht = ctx->h_desc.as<InflateTask>();
+  for (size_t k = 0; k < n; k++) {
+    uint32_t i = order[k];
+    ht[k].src = d_src[i]; ht[k].src_len = src_len[i];
+    ht[k].dst = count_only ? nullptr : d_dst[i];
+    ht[k].dst_cap = cap[i] == ZIPC_SIZE_UNKNOWN ? ~0ull : (uint64_t)cap[i];
+  }
+  InflateTask *dt = ctx->d_desc.as<InflateTask>();
+  CrcSeg *dsegs = reinterpret_cast<CrcSeg *>(dt + n);
+  InflateResult *dr = ctx->d_res.as<InflateResult>();
+  uint32_t *dck = reinterpret_cast<uint32_t *>(dr + n);
+  ZB_CUDA(ctx, cudaMemcpyAsync(dt, ht, n * sizeof(InflateTask), cudaMemcpyHostToDevice, ctx->stream));
+  if (int st = inflate_launch(ctx, dt, (uint32_t)n, dr, count_only)) return st;
+  bool crc = !count_only && ck == ZIPC_CK_CRC32;
+  if (crc) {
+    make_crc_segs_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(dt, dr, (uint32_t)n, dsegs);
+    ctx->launches++;
+    if (int st = crc32_launch_segments(ctx, dsegs, (uint32_t)n, dck)) return st;
+    xor_ffffffff_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(dck, (uint32_t)n);
+    ctx->launches++;
+  }
+  InflateResult *hr = ctx->h_res.as<InflateResult>();
+  uint32_t *hck = reinterpret_cast<uint32_t *>(hr + n);
+  ZB_CUDA(ctx, cudaMemcpyAsync(hr, dr, n * sizeof(InflateResult) + (crc ? n * sizeof(uint32_t) : 0),
+                               cudaMemcpyDeviceToHost, ctx->stream));
+  ZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  for (size_t k = 0; k < n; k++) {
+    uint32_t i = order[k];
+    status[i] = (int)hr[k].status;
+    out_len[i] = (size_t)hr[k].out_len;
+    if (checksum) checksum[i] = crc && hr[k].status == ZIPC_OK ? hck[k] : 0u;
+  }
+  if (!count_only && ck == ZIPC_CK_ADLER32 && checksum) {
+    std::vector<const uint8_t *> p(n);
+    std::vector<uint64_t> l(n);
+    for (size_t i = 0; i < n; i++) { p[i] = d_dst[i]; l[i] = status[i] == ZIPC_OK ? out_len[i] : 0; }
+    std::vector<uint32_t> a(n);
+    if (int st = adler32_ranges(ctx, p.data(), l.data(), n, adler_mode, a.data())) return st;
+    for (size_t i = 0; i < n; i++) checksum[i] = status[i] == ZIPC_OK ? a[i] : 0u;
+  }
+  return ZIPC_OK;
+}
+
+// Shared tail of the host-pointer batch calls: lay out the arena, run, copy back.
+int finish_to_host(zipc_b200_ctx *ctx, size_t n, const std::vector<size_t> &off, const size_t *len, size_t total,
+                   void *dst, size_t dst_cap, size_t *dst_need, size_t *dst_off) {
+  ctx->last_off = off;
+  ctx->last_len.assign(len, len + n);
+  ctx->last_total = total;
+  for (size_t i = 0; i < n; i++) dst_off[i] = off[i];
+  if (dst_need) *dst_need = total;
+  if (!dst || dst_cap < total) return ZIPC_ERR_DST_TOO_SMALL;
+  return d2h(ctx, dst, ctx->d_out.p, total);
+}
+
+}  // namespace
+}  // namespace zb
+
+using namespace zb;
+
+extern "C" {
+
+int zipc_b200_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+int zipc_b200_ctx_create(int device, zipc_b200_ctx **out) {
+  if (!out) return ZIPC_ERR_INVALID_ARG;
+  *out = nullptr;
+  int n = zipc_b200_device_count();
+  if (n <= 0) return ZIPC_ERR_NO_DEVICE;
+  if (device < 0 || device >= n) return ZIPC_ERR_INVALID_ARG;
+  zipc_b200_ctx *ctx = new (std::nothrow) zipc_b200_ctx();
+  if (!ctx) return ZIPC_ERR_NOMEM;
+  ctx->device = device;
+  cudaError_t e = cudaSetDevice(device);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+  cudaDeviceProp prop;
+  if (e == cudaSuccess) e = cudaGetDeviceProperties(&prop, device);
+  if (e != cudaSuccess) { int st = set_cuda_error(ctx, e, "ctx_create"); delete ctx; return st; }
+  ctx->sm_count = prop.multiProcessorCount;
+  if (int st = crc_tables_upload(ctx)) { zipc_b200_ctx_destroy(ctx); return st; }
+  *out = ctx;
+  return ZIPC_OK;
+}
+
+void zipc_b200_ctx_destroy(zipc_b200_ctx *ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  ctx->d_in.release(); ctx->d_out.release(); ctx->d_desc.release(); ctx->d_res.release();
+  ctx->d_scratch.release(); ctx->d_scratch2.release(); ctx->d_small.release();
+  ctx->h_stage.release(); ctx->h_res.release(); ctx->h_desc.release();
+  if (ctx->d_crc_tabs) cudaFree(ctx->d_crc_tabs);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+const char *zipc_b200_last_error(const zipc_b200_ctx *ctx) { return ctx ? ctx->last_error.c_str() : ""; }
+void *zipc_b200_ctx_stream(zipc_b200_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+uint64_t zipc_b200_ctx_launches(const zipc_b200_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int zipc_b200_host_alloc(size_t bytes, void **ptr) {
+  if (!ptr) return ZIPC_ERR_INVALID_ARG;
+  if (cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); *ptr = nullptr; return ZIPC_ERR_NOMEM; }
+  return ZIPC_OK;
+}
+void zipc_b200_host_free(void *ptr) { if (ptr) cudaFreeHost(ptr); }
+
+int zipc_b200_dev_alloc(zipc_b200_ctx *ctx, size_t bytes, void **dptr) {
+  if (!ctx || !dptr) return ZIPC_ERR_INVALID_ARG;
+  DeviceGuard g(ctx->device);
+  ZB_CUDA(ctx, cudaMalloc(dptr, bytes ? bytes : 1));
+  return ZIPC_OK;
+}
+void zipc_b200_dev_free(zipc_b200_ctx *ctx, void *dptr) {
+  if (!ctx || !dptr) return;
+  DeviceGuard g(ctx->device);
+  cudaFree(dptr);
+}
+int zipc_b200_memcpy_h2d(zipc_b200_ctx *ctx, void *dptr, const void *src, size_t bytes) {
+  if (!ctx) return ZIPC_ERR_INVALID_ARG;
+  DeviceGuard g(ctx->device);
+  if (int st = h2d(ctx, dptr, src, bytes)) return st;
+  ZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return ZIPC_OK;
+}
+int zipc_b200_memcpy_d2h(zipc_b200_ctx *ctx, void *dst, const void *dptr, size_t bytes) {
+  if (!ctx) return ZIPC_ERR_INVALID_ARG;
+  DeviceGuard g(ctx->device);
+  return d2h(ctx, dst, dptr, bytes);
+}
+int zipc_b200_sync(zipc_b200_ctx *ctx) {
+  if (!ctx) return ZIPC_ERR_INVALID_ARG;
+  DeviceGuard g(ctx->device);
+  ZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return ZIPC_OK;
+}
+
+// ---- checksums -------------------------------------------------------------------------------------
+int zipc_b200_crc32_dev_async(zipc_b200_ctx *ctx, const void *d_src, size_t len, uint32_t *d_crc) {
+  if (!ctx || !d_crc || (!d_src && len)) return ZIPC_ERR_INVALID_ARG;
+  DeviceGuard g(ctx->device);
+  return crc32_launch_buffer(ctx, static_cast<const uint8_t *>(d_src), len, d_crc);
+}
+
+int zipc_b200_crc32_dev(zipc_b200_ctx *ctx, const void *d_src, size_t len, uint32_t *crc) {
+  if (!ctx || !crc || (!d_src && len)) return ZIPC_ERR_INVALID_ARG;
+  DeviceGuard g(ctx->device);
+  if (int st = ctx->d_small.reserve(256)) return st;
+  uint32_t *d_crc = ctx->d_small.as<uint32_t>() + 32;
+  if (int st = crc32_launch_buffer(ctx, static_cast<const uint8_t *>(d_src), len, d_crc)) return st;
+  ZB_CUDA(ctx, cudaMemcpyAsync(crc, d_crc, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  ZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return ZIPC_OK;
+}
+
+int zipc_b200_crc32(zipc_b200_ctx *ctx, const void *src, size_t len, uint32_t *crc) {
+  if (!ctx || !crc || (!src && len)) return ZIPC_ERR_INVALID_ARG;
+  DeviceGuard g(ctx->device);
+  size_t pre = (uintptr_t)src & 15;
+  if (int st = ctx->d_in.reserve(pre + len + 64)) return st;
+  uint8_t *d = ctx->d_in.as<uint8_t>() + pre;
+  if (int st = h2d(ctx, d, src, len)) return st;
+  return zipc_b200_crc32_dev(ctx, d, len, crc);
+}
+
+int zipc_b200_adler32_dev(zipc_b200_ctx *ctx, const void *d_src, size_t len, int mode, uint32_t *adler) {
+  if (!ctx || !adler || (!d_src && len) || (mode != ZIPC_ADLER_REF_COMPAT && mode != ZIPC_ADLER_RFC1950))
+    return ZIPC_ERR_INVALID_ARG;
+  DeviceGuard g(ctx->device);
+  return adler32_launch_buffer(ctx, static_cast<const uint8_t *>(d_src), len, mode, adler);
+}
+
+int zipc_b200_adler32(zipc_b200_ctx *ctx, const void *src, size_t len, int mode, uint32_t *adler) {
+  if (!ctx || !adler || (!src && len)) return ZIPC_ERR_INVALID_ARG;
+  DeviceGuard g(ctx->device);
+  size_t pre = (uintptr_t)src & 15;
+  if (int st = ctx->d_in.reserve(pre + len + 64)) return st;
+  uint8_t *d = ctx->d_in.as<uint8_t>() + pre;
+  if (int st = h2d(ctx, d, src, len)) return st;
+  return zipc_b200_adler32_dev(ctx, d, len, mode, adler);
+}
+
+int zipc_b200_crc32_batch(zipc_b200_ctx *ctx, size_t n, const void *const *src, const size_t *len, uint32_t *crc) {
+  if (!ctx || (n && (!src || !len || !crc))) return ZIPC_ERR_INVALID_ARG;
+  if (!n) return ZIPC_OK;
+  DeviceGuard g(ctx->device);
+  std::vector<const uint8_t *> dp;
+  if (int st = upload_ranges(ctx, n, src, len, dp)) return st;
+  if (int st = ctx->h_desc.reserve(n * sizeof(CrcSeg))) return st;
+  if (int st = ctx->d_desc.reserve(n * sizeof(CrcSeg))) return st;
+  if (int st = ctx->d_res.reserve(n * sizeof(uint32_t))) return st;
+  CrcSeg *hs = ctx->h_desc.as<CrcSeg>();
+  for (size_t i = 0; i < n; i++) { hs[i].ptr = dp[i]; hs[i].len = len[i]; hs[i].init = 0xFFFFFFFFu; hs[i]._pad = 0; }
+  ZB_CUDA(ctx, cudaMemcpyAsync(ctx->d_desc.p, hs, n * sizeof(CrcSeg), cudaMemcpyHostToDevice, ctx->stream));
+  if (int st = crc32_launch_segments(ctx, ctx->d_desc.as<CrcSeg>(), (uint32_t)n, ctx->d_res.as<uint32_t>())) return st;
+  ZB_CUDA(ctx, cudaMemcpyAsync(crc, ctx->d_res.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  ZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  for (size_t i = 0; i < n; i++) crc[i] ^= 0xFFFFFFFFu;
+  return ZIPC_OK;
+}
+
+// ---- inflate ---------------------------------------------------------------------------------------
+int zipc_b200_inflate_batch(zipc_b200_ctx *ctx, int ck, int adler_mode, size_t n, const void *const *src,
+                            const size_t *src_len, const size_t *max_out, void *dst, size_t dst_cap,
+                            size_t *dst_need, size_t *dst_off, size_t *dst_len, uint32_t *checksum, int *status) {
+  if (!ctx || ck < 0 || ck > 2 || (n && (!src || !src_len || !dst_off || !dst_len || !status)))
+    return ZIPC_ERR_INVALID_ARG;
+  if (dst_need) *dst_need = 0;
+  if (!n) return ZIPC_OK;
+  DeviceGuard g(ctx->device);
+  std::vector<const uint8_t *> d_src;
+  if (int st = upload_ranges(ctx, n, src, src_len, d_src)) return st;
+  // resolve unknown output sizes with a count-only pass (no bytes are written)
+  std::vector<size_t> cap(n);
+  bool any_unknown = false;
+  for (size_t i = 0; i < n; i++) { cap[i] = max_out ? max_out[i] : ZIPC_SIZE_UNKNOWN; any_unknown |= cap[i] == ZIPC_SIZE_UNKNOWN; }
+  std::vector<uint8_t *> d_dst(n, nullptr);
+  if (any_unknown) {
+    std::vector<size_t> cl(n);
+    std::vector<int> cs(n);
+    if (int st = inflate_core(ctx, ZIPC_CK_NONE, adler_mode, n, d_src, src_len, d_dst, cap, true, cl.data(), nullptr, cs.data()))
+      return st;
+    for (size_t i = 0; i < n; i++)
+      if (cap[i] == ZIPC_SIZE_UNKNOWN) cap[i] = cs[i] == ZIPC_OK ? cl[i] : 0;
+  }
+  std::vector<size_t> off(n);
+  size_t total = 0;
+  for (size_t i = 0; i < n; i++) { off[i] = total; total += align_up(cap[i], 16); }
+  if (int st = ctx->d_out.reserve(total + 64)) return st;
+  for (size_t i = 0; i < n; i++) d_dst[i] = ctx->d_out.as<uint8_t>() + off[i];
+  if (int st = inflate_core(ctx, ck, adler_mode, n, d_src, src_len, d_dst, cap, false, dst_len, checksum, status)) return st;
+  return finish_to_host(ctx, n, off, dst_len, total, dst, dst_cap, dst_need, dst_off);
+}
+
+int zipc_b200_fetch(zipc_b200_ctx *ctx, void *dst, size_t dst_cap) {
+  if (!ctx || !dst) return ZIPC_ERR_INVALID_ARG;
+  if (dst_cap < ctx->last_total) return ZIPC_ERR_DST_TOO_SMALL;
+  DeviceGuard g(ctx->device);
+  return d2h(ctx, dst, ctx->d_out.p, ctx->last_total);
+}
+
+int zipc_b200_inflate_batch_dev(zipc_b200_ctx *ctx, int ck, int adler_mode, size_t n, const void *d_src_v,
+                                const size_t *src_off, const size_t *src_len, void *d_dst_v, const size_t *dst_off,
+                                const size_t *max_out, size_t *dst_len, uint32_t *checksum, int *status) {
+  if (!ctx || ck < 0 || ck > 2 || (n && (!d_src_v || !src_off || !src_len || !d_dst_v || !dst_off || !max_out || !dst_len || !status)))
+    return ZIPC_ERR_INVALID_ARG;
+  if (!n) return ZIPC_OK;
+  DeviceGuard g(ctx->device);
+  std::vector<const uint8_t *> d_src(n);
+  std::vector<uint8_t *> d_dst(n);
+  std::vector<size_t> cap(n);
+  for (size_t i = 0; i < n; i++) {
+    if (max_out[i] == ZIPC_SIZE_UNKNOWN) return ZIPC_ERR_INVALID_ARG;
+    d_src[i] = static_cast<const uint8_t *>(d_src_v) + src_off[i];
+    d_dst[i] = static_cast<uint8_t *>(d_dst_v) + dst_off[i];
+    cap[i] = max_out[i];
+  }
+  return inflate_core(ctx, ck, adler_mode, n, d_src, src_len, d_dst, cap, false, dst_len, checksum, status);
+}
+
+int zipc_b200_zlib_decompress_batch(zipc_b200_ctx *ctx, int adler_mode, size_t n, const void *const *src,
+                                    const size_t *src_len, const size_t *max_out, void *dst, size_t dst_cap,
+                                    size_t *dst_need, size_t *dst_off, size_t *dst_len, uint32_t *expect,
+                                    uint32_t *found, int *status) {
+  if (!ctx || (n && (!src || !src_len || !dst_off || !dst_len || !status))) return ZIPC_ERR_INVALID_ARG;
+  if (dst_need) *dst_need = 0;
+  if (!n) return ZIPC_OK;
+  // header checks in the reference's order (zipc_deflate.ml:722-731); bad streams become empty tasks
+  std::vector<const void *> body(n);
+  std::vector<size_t> blen(n);
+  std::vector<int> pre(n, ZIPC_OK);
+  std::vector<uint32_t> exp(n, 0);
+  for (size_t i = 0; i < n; i++) {
+    const uint8_t *s = static_cast<const uint8_t *>(src[i]);
+    size_t len = src_len[i];
+    body[i] = s; blen[i] = 0;
+    if (len < 6) { pre[i] = ZIPC_ERR_CORRUPTED; continue; }
+    unsigned cmf = s[0], flg = s[1];
+    if ((256 * cmf + flg) % 31 != 0) { pre[i] = ZIPC_ERR_CORRUPTED; continue; }
+    if ((cmf & 0x0F) != 8) { pre[i] = ZIPC_ERR_ZLIB_METHOD; if (found) found[i] = cmf & 0x0F; continue; }
+    if ((cmf >> 4) > 7) { pre[i] = ZIPC_ERR_ZLIB_WINDOW; continue; }
+    if (flg & 0x20) { pre[i] = ZIPC_ERR_ZLIB_DICT; continue; }
+    exp[i] = (uint32_t)s[len - 4] << 24 | (uint32_t)s[len - 3] << 16 | (uint32_t)s[len - 2] << 8 | s[len - 1];
+    body[i] = s + 2;
+    blen[i] = len - 4;  // as the reference: two bytes into the trailer (zipc_deflate.ml:732)
+  }
+  std::vector<uint32_t> ad(n);
+  std::vector<size_t> mo(n);
+  for (size_t i = 0; i < n; i++) mo[i] = pre[i] ? 0 : (max_out ? max_out[i] : ZIPC_SIZE_UNKNOWN);
+  int rc = zipc_b200_inflate_batch(ctx, ZIPC_CK_ADLER32, adler_mode, n, body.data(), blen.data(), mo.data(), dst, dst_cap,
+                                   dst_need, dst_off, dst_len, ad.data(), status);
+  if (rc != ZIPC_OK && rc != ZIPC_ERR_DST_TOO_SMALL) return rc;
+  for (size_t i = 0; i < n; i++) {
+    if (pre[i]) { status[i] = pre[i]; dst_len[i] = 0; continue; }
+    if (status[i] == ZIPC_OK) {
+      if (expect) expect[i] = exp[i];
+      if (found) found[i] = ad[i];
+      if (ad[i] != exp[i]) status[i] = ZIPC_ERR_CHECKSUM;
+    }
+  }
+  return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,130 @@
+// common.cuh -- internals shared by the libzipc_b200 translation units (not part of the ABI).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/zipc_b200.h"
+
+#define ZIPC_B200_VERSION "0.1.0"
+
+namespace zb {
+
+// ---- GF(2)[x] / P arithmetic for CRC-32 (reflected, P = 0xedb88320; x^0 is bit 31) -----------
+// Used on both sides: host (table generation, combine) and device (tile / lane alignment).
+constexpr uint32_t kCrcPoly = 0xedb88320u;
+
+__host__ __device__ inline uint32_t gf_mul(uint32_t a, uint32_t b) {
+  uint32_t p = 0;
+#pragma unroll 8
+  for (int i = 0; i < 32; i++) {
+    p ^= b & (0u - (a >> 31));
+    a <<= 1;
+    b = (b >> 1) ^ (kCrcPoly & (0u - (b & 1u)));
+  }
+  return p;
+}
+
+// x^(8*nbytes) mod P, host side (square and multiply over a 64-entry x^(2^k) table).
+uint32_t gf_xpow8(uint64_t nbytes);
+
+// ---- grow-only device / pinned buffers ------------------------------------------------------
+struct DevBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+  int reserve(size_t bytes);  // returns ZIPC_OK / ZIPC_ERR_NOMEM; contents are NOT preserved
+  void release();
+  template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+struct PinBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+  int reserve(size_t bytes);
+  void release();
+  template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+// ---- device descriptors ---------------------------------------------------------------------
+struct CrcSeg {       // one CRC-32 work item: state after running `len` bytes from `init`
+  const uint8_t *ptr;
+  uint64_t len;
+  uint32_t init;
+  uint32_t _pad;
+};
+
+struct AdlerSeg {     // one Adler-32 work item: sums over [ptr, ptr+len)
+  const uint8_t *ptr;
+  uint32_t len;       // <= 5552
+  uint32_t _pad;
+};
+
+struct InflateTask {  // one deflate stream to inflate
+  const uint8_t *src;
+  uint64_t src_len;
+  uint8_t *dst;       // may be null in count-only mode
+  uint64_t dst_cap;   // ?decompressed_size, or ~0ull when unknown (count-only pass)
+};
+struct InflateResult {
+  uint64_t out_len;
+  uint32_t status;
+  uint32_t _pad;
+};
+
+}  // namespace zb
+
+// ---- the context -------------------------------------------------------------------------------
+struct zipc_b200_ctx {
+  int device = 0;
+  int sm_count = 0;
+  cudaStream_t stream = nullptr;
+  std::string last_error;
+  uint64_t launches = 0;
+
+  // constant tables on the device
+  uint32_t *d_crc_tabs = nullptr;   // see crc32.cu: strided[4][256] | std[4][256] | xp16[32]
+  // work buffers (grow-only)
+  zb::DevBuf d_in, d_out, d_desc, d_res, d_scratch, d_scratch2, d_small;
+  zb::PinBuf h_stage, h_res, h_desc;
+
+  // results of the last batch call kept for zipc_b200_fetch()
+  std::vector<size_t> last_off, last_len;
+  size_t last_total = 0;
+};
+
+namespace zb {
+
+int set_cuda_error(zipc_b200_ctx *ctx, cudaError_t e, const char *what);
+#define ZB_CUDA(ctx, call)                                        \
+  do {                                                            \
+    cudaError_t _e = (call);                                      \
+    if (_e != cudaSuccess) return zb::set_cuda_error(ctx, _e, #call); \
+  } while (0)
+
+// RAII device guard
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+// ---- kernels' host launchers (each .cu exports these) -----------------------------------------
+// crc32.cu
+int crc_tables_upload(zipc_b200_ctx *ctx);
+// state-after-init for each segment (device descriptors), results to d_states[nseg]
+int crc32_launch_segments(zipc_b200_ctx *ctx, const CrcSeg *d_segs, uint32_t nseg, uint32_t *d_states);
+// whole-buffer CRC-32 (final value, init/xorout applied) into *d_crc
+int crc32_launch_buffer(zipc_b200_ctx *ctx, const uint8_t *d_src, uint64_t len, uint32_t *d_crc);
+// adler32.cu
+int adler32_launch_buffer(zipc_b200_ctx *ctx, const uint8_t *d_src, uint64_t len, int mode, uint32_t *h_out);
+// per-range Adler-32 for n ranges given as (ptr,len) on the host; results (final values) to h_out
+int adler32_ranges(zipc_b200_ctx *ctx, const uint8_t *const *d_ptrs, const uint64_t *lens, size_t n, int mode,
+                   uint32_t *h_out);
+// inflate.cu
+int inflate_launch(zipc_b200_ctx *ctx, const InflateTask *d_tasks, uint32_t n, InflateResult *d_results,
+                   bool count_only);
+
+}  // namespace zb
