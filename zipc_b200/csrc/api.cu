@@ -425,13 +425,15 @@ int zipc_b200_inflate_batch(zipc_b200_ctx *ctx, int ck, int adler_mode, size_t n
   bool any_unknown = false;
   for (size_t i = 0; i < n; i++) { cap[i] = max_out ? max_out[i] : ZIPC_SIZE_UNKNOWN; any_unknown |= cap[i] == ZIPC_SIZE_UNKNOWN; }
   std::vector<uint8_t *> d_dst(n, nullptr);
+  std::vector<int> cs;
+  std::vector<char> was_unknown(n, 0);
   if (any_unknown) {
     std::vector<size_t> cl(n);
-    std::vector<int> cs(n);
+    cs.assign(n, ZIPC_OK);
     if (int st = inflate_core(ctx, ZIPC_CK_NONE, adler_mode, n, d_src, src_len, d_dst, cap, true, cl.data(), nullptr, cs.data()))
       return st;
     for (size_t i = 0; i < n; i++)
-      if (cap[i] == ZIPC_SIZE_UNKNOWN) cap[i] = cs[i] == ZIPC_OK ? cl[i] : 0;
+      if (cap[i] == ZIPC_SIZE_UNKNOWN) { was_unknown[i] = 1; cap[i] = cs[i] == ZIPC_OK ? cl[i] : 0; }
   }
   std::vector<size_t> off(n);
   size_t total = 0;
@@ -439,6 +441,9 @@ int zipc_b200_inflate_batch(zipc_b200_ctx *ctx, int ck, int adler_mode, size_t n
   if (int st = ctx->d_out.reserve(total + 64)) return st;
   for (size_t i = 0; i < n; i++) d_dst[i] = ctx->d_out.as<uint8_t>() + off[i];
   if (int st = inflate_core(ctx, ck, adler_mode, n, d_src, src_len, d_dst, cap, false, dst_len, checksum, status)) return st;
+  // a stream of unknown size that failed while being sized keeps that (uncapped) verdict
+  for (size_t i = 0; i < n; i++)
+    if (was_unknown[i] && cs[i] != ZIPC_OK) { status[i] = cs[i]; dst_len[i] = 0; if (checksum) checksum[i] = 0; }
   return finish_to_host(ctx, n, off, dst_len, total, dst, dst_cap, dst_need, dst_off);
 }
 

@@ -31,15 +31,21 @@ namespace {
 
 constexpr int LB = 9;        // literal/length table bits
 constexpr int DB = 7;        // distance table bits (>= 6: the area also hosts the 128-entry code-length table)
-constexpr int WARPS = 4;     // warps per CTA (one CTA per SM: tables fill shared memory)
+constexpr int G = 8;         // streams (decoder state machines) per warp: lanes 0..G-1 lead
+constexpr int K = 8;         // tokens a leader decodes per round
+constexpr int WARPS = 16;    // warps per CTA (one CTA per SM: tables fill shared memory)
 constexpr int THREADS = WARPS * 32;
-constexpr uint16_t ENT_LONG = 0xFFFF;  // code longer than the table: canonical walk
+constexpr uint32_t ENT_LONG = 0xFFFFFFFFu;  // code longer than the table: canonical walk (0xFFFF in 16-bit tables)
 constexpr int SYMS_PER_SLOT = 320;     // sorted symbols: 288 litlen + 32 dist
 
 // per-lane shared memory record
+// lit entry  (16 bit): [3:0] code length, [6:4] kind (0..5 = length symbol with that many extra bits,
+//                       6 = end of block, 7 = literal), [15:7] value (literal byte / length base)
+// dist entry (32 bit): [3:0] code length, [7:4] extra bits, [31:8] distance base
+// 0 = invalid code (corrupt stream); all ones = code longer than the table (canonical walk)
 struct __align__(16) LaneTabs {
   uint16_t lit[1 << LB];
-  uint16_t dist[1 << DB];
+  uint32_t dist[1 << DB];
   uint16_t lit_cnt[16];
   uint16_t dist_cnt[16];
 };
@@ -51,7 +57,9 @@ struct __align__(16) WarpScratch {
   int err;
 };
 
-constexpr size_t kSmemBytes = sizeof(LaneTabs) * (THREADS + 1) + sizeof(WarpScratch) * WARPS + 256;
+constexpr int QN = K * G;      // tokens per warp round
+constexpr size_t kSmemBytes = sizeof(LaneTabs) * (WARPS * G + 1) + sizeof(WarpScratch) * WARPS +
+                              sizeof(uint32_t) * WARPS * QN * 2 + sizeof(uint16_t) * WARPS * (QN + 2) * 2 + 64 + 128 + 64;
 
 enum : uint32_t { S_IDLE = 0, S_HDR = 1, S_DATA = 2, S_STORED = 3, S_FINISH = 4, S_EXIT = 5 };
 
@@ -70,29 +78,34 @@ __constant__ uint8_t c_clen_order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4
 
 // ---- bit reader: 64-bit buffer refilled with aligned 32-bit words --------------------------------
 struct BitReader {
-  const uint32_t *wp;    // next word to load
+  const uint32_t *wp;    // next word to load into `ahead`
   const uint32_t *wend;  // first word not to load (words past the stream read as 0)
   uint64_t buf;
   uint32_t n;            // valid bits in buf
-  uint64_t loaded;       // stream bits loaded so far (can exceed 8*len by < 64+32 bits)
+  uint32_t ahead;        // the word after the ones in buf, already fetched (hides the load latency)
+  uint64_t loaded;       // stream bits moved into buf so far (can exceed 8*len by < 64+32 bits)
+  __device__ __forceinline__ uint32_t fetch() {
+    uint32_t w = wp < wend ? *wp : 0u;
+    wp++;
+    return w;
+  }
   __device__ __forceinline__ void seek(const uint8_t *base, uint64_t len, uint64_t byte_pos) {
     const uint8_t *p = base + byte_pos;
     uint32_t a = (uint32_t)((uintptr_t)p & 3);
     wp = reinterpret_cast<const uint32_t *>(p - a);
     wend = reinterpret_cast<const uint32_t *>(((uintptr_t)(base + len) + 3) & ~(uintptr_t)3);
-    uint32_t w = wp < wend ? *wp : 0u;
-    wp++;
+    uint32_t w = fetch();
     buf = (uint64_t)(w >> (8 * a));
     n = 32 - 8 * a;
     loaded = byte_pos * 8 + n;
+    ahead = fetch();
   }
   __device__ __forceinline__ void refill() {  // afterwards n >= 33
     if (n <= 32) {
-      uint32_t w = wp < wend ? *wp : 0u;
-      wp++;
-      buf |= (uint64_t)w << n;
+      buf |= (uint64_t)ahead << n;
       n += 32;
       loaded += 32;
+      ahead = fetch();
     }
   }
   __device__ __forceinline__ uint32_t peek(uint32_t cnt) const { return (uint32_t)buf & ((1u << cnt) - 1u); }
@@ -122,16 +135,21 @@ __device__ __forceinline__ int canon_decode(BitReader &br, const uint16_t *cnt, 
 // sorted symbol list syms (global).  Follows Huffman.init_decoder (reference :355-391) for what is accepted:
 // over-subscribed -> corrupt; incomplete -> corrupt unless empty or a single code of length 1.
 // max_valid_sym: symbols above it decode to "corrupt" (286/287 and 30/31 of the fixed codes).
-__device__ void build_decoder_warp(WarpScratch &ws, int first, int n, int bits, uint16_t *lut, uint16_t *cnt,
-                                   uint16_t *syms, int max_valid_sym, int lane) {
+template <bool IS_DIST>
+__device__ void build_decoder_warp(WarpScratch &ws, int first, int n, int bits, void *lut_v, uint16_t *cnt,
+                                   uint16_t *syms, const uint16_t *s_len_tab, const uint32_t *s_dist_tab, int lane) {
+  uint16_t *lut16 = reinterpret_cast<uint16_t *>(lut_v);
+  uint32_t *lut32 = reinterpret_cast<uint32_t *>(lut_v);
   if (lane < 16) ws.cnt[lane] = 0;
   __syncwarp();
   for (int i = lane; i < n; i += 32) {
     int l = ws.len[first + i];
     if (l) atomicAdd(&ws.cnt[l], 1u);
   }
-  uint32_t *lut32 = reinterpret_cast<uint32_t *>(lut);  // clear the table: 0 = invalid
-  for (int i = lane; i < (1 << bits) / 2; i += 32) lut32[i] = 0;
+  {  // clear the table: 0 = invalid
+    const int words = IS_DIST ? (1 << bits) : (1 << bits) / 2;
+    for (int i = lane; i < words; i += 32) lut32[i] = 0;
+  }
   __syncwarp();
   if (lane == 0) {
     int available = 1, num_codes = 0, code = 0, bad = 0;
@@ -175,31 +193,54 @@ __device__ void build_decoder_warp(WarpScratch &ws, int first, int n, int bits, 
     uint32_t code = (uint32_t)ws.next[l] + (uint32_t)(j - (int)ws.symoff[l]);
     uint32_t rev = __brev(code) >> (32 - l);
     if (l <= bits) {
-      uint16_t e = sym > max_valid_sym ? (uint16_t)0 : (uint16_t)((l << 12) | sym);
-      for (uint32_t k = rev; k < (1u << bits); k += (1u << l)) lut[k] = e;
+      if (IS_DIST) {
+        uint32_t e = 0;                                   // 30, 31 never occur in valid data (:608)
+        if (sym <= 29) { uint32_t dt = s_dist_tab[sym]; e = ((dt & 0xFFFFu) << 8) | ((dt >> 16) << 4) | (uint32_t)l; }
+        for (uint32_t k = rev; k < (1u << bits); k += (1u << l)) lut32[k] = e;
+      } else {
+        uint16_t e = 0;                                   // 286, 287 never occur in valid data (:598)
+        if (sym < 256) e = (uint16_t)((sym << 7) | (7 << 4) | l);
+        else if (sym == 256) e = (uint16_t)((6 << 4) | l);
+        else if (sym <= 285) { uint32_t lt = s_len_tab[sym - 257]; e = (uint16_t)(((lt & 0x1FFu) << 7) | ((lt >> 9) << 4) | (uint32_t)l); }
+        for (uint32_t k = rev; k < (1u << bits); k += (1u << l)) lut16[k] = e;
+      }
     } else {
-      lut[rev & ((1u << bits) - 1u)] = ENT_LONG;
+      if (IS_DIST) lut32[rev & ((1u << bits) - 1u)] = ENT_LONG;
+      else lut16[rev & ((1u << bits) - 1u)] = 0xFFFF;
     }
   }
   __syncwarp();
 }
 
 // ---- the kernel ------------------------------------------------------------------------------------------
+// Each warp serves G streams: lanes 0..G-1 ("leaders") run one decoder state machine each and decode up to
+// K tokens per round into a small queue; then all 32 lanes execute the queued tokens, token index by token
+// index, with the bytes of the G concurrent tokens flattened over the lanes.
 template <bool COUNT_ONLY>
 __global__ void __launch_bounds__(THREADS, 1)
 inflate_kernel(const InflateTask *__restrict__ tasks, uint32_t ntasks, InflateResult *__restrict__ results,
                unsigned int *__restrict__ queue, uint16_t *__restrict__ g_syms) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
-  LaneTabs *tabs = reinterpret_cast<LaneTabs *>(smem_raw);
-  LaneTabs &fixed = tabs[THREADS];
-  WarpScratch *wss = reinterpret_cast<WarpScratch *>(tabs + THREADS + 1);
+  LaneTabs *tabs = reinterpret_cast<LaneTabs *>(smem_raw);                 // [WARPS*G] + fixed
+  LaneTabs &fixed = tabs[WARPS * G];
+  WarpScratch *wss = reinterpret_cast<WarpScratch *>(tabs + WARPS * G + 1);
+  uint32_t *tokq = reinterpret_cast<uint32_t *>(wss + WARPS);              // [WARPS][2][K][G]
+  uint16_t *tbq = reinterpret_cast<uint16_t *>(tokq + WARPS * QN * 2);     // [WARPS][2][QN+2] flattened byte bases
+  uint16_t *s_len_tab = tbq + WARPS * (QN + 2) * 2;
+  uint32_t *s_dist_tab = reinterpret_cast<uint32_t *>(s_len_tab + 32);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   WarpScratch &ws = wss[warp];
-  LaneTabs &mine = tabs[threadIdx.x];
-  const uint32_t slot = blockIdx.x * THREADS + threadIdx.x;
+  const bool leader = lane < G;
+  LaneTabs &mine = tabs[warp * G + (leader ? lane : 0)];
+  uint2 *myq = reinterpret_cast<uint2 *>(tokq + warp * QN * 2);  // [j*G+g]: x = dep << 31 | len << 16 | dist-or-byte, y = output offset inside the round
+  uint16_t *tb = tbq + warp * (QN + 2) * 2;       // exclusive byte offsets of the independent tokens
+  const uint32_t slot = (blockIdx.x * WARPS + warp) * G + (leader ? lane : 0);
   uint16_t *my_syms = g_syms + (size_t)slot * SYMS_PER_SLOT;
-  uint16_t *fixed_syms = g_syms + (size_t)(gridDim.x * THREADS + blockIdx.x) * SYMS_PER_SLOT;
+  uint16_t *fixed_syms = g_syms + (size_t)(gridDim.x * WARPS * G + blockIdx.x) * SYMS_PER_SLOT;
 
+  if (threadIdx.x < 29) s_len_tab[threadIdx.x] = c_len_tab[threadIdx.x];
+  if (threadIdx.x < 30) s_dist_tab[threadIdx.x] = c_dist_tab[threadIdx.x];
+  __syncthreads();
   // fixed-Huffman decoders, once per CTA (reference :334-349)
   if (warp == 0) {
     for (int i = lane; i < 320; i += 32) {
@@ -208,28 +249,33 @@ inflate_kernel(const InflateTask *__restrict__ tasks, uint32_t ntasks, InflateRe
     }
     if (lane == 0) ws.err = 0;
     __syncwarp();
-    build_decoder_warp(ws, 0, 288, LB, fixed.lit, fixed.lit_cnt, fixed_syms, 285, lane);
-    build_decoder_warp(ws, 288, 32, DB, fixed.dist, fixed.dist_cnt, fixed_syms + 288, 29, lane);
+    build_decoder_warp<false>(ws, 0, 288, LB, fixed.lit, fixed.lit_cnt, fixed_syms, s_len_tab, s_dist_tab, lane);
+    build_decoder_warp<true>(ws, 288, 32, DB, fixed.dist, fixed.dist_cnt, fixed_syms + 288, s_len_tab, s_dist_tab, lane);
   }
   __syncthreads();
 
-  // per-lane decoder state
-  uint32_t state = S_IDLE, task = 0, status = ZIPC_OK;
+  // per-leader decoder state (lanes >= G carry dead copies)
+  uint32_t state = leader ? S_IDLE : S_EXIT, task = 0, status = ZIPC_OK;
   BitReader br{};
   const uint8_t *src = nullptr;
   uint64_t src_len = 0;
   uint8_t *dst = nullptr;
   uint64_t out_pos = 0, out_cap = 0;
-  bool final_blk = false, need_build = false;
+  bool final_blk = false, need_build = false, first_task = true;
   uint32_t hlit = 0, hdist = 0;
-  uint32_t stored_left = 0;
-  const uint16_t *lit_lut = nullptr, *dist_lut = nullptr, *lit_cnt = nullptr, *dist_cnt = nullptr;
+  uint32_t stored_len = 0;
+  const uint8_t *stored_src = nullptr;
+  const uint16_t *lit_lut = nullptr, *lit_cnt = nullptr, *dist_cnt = nullptr;
+  const uint32_t *dist_lut = nullptr;
   const uint16_t *lit_syms = nullptr, *dist_syms = nullptr;
 
   for (;;) {
-    // ---- A: idle lanes pull work ---------------------------------------------------------------------
+    // ---- A: idle leaders pull work -------------------------------------------------------------------
     if (state == S_IDLE) {
-      task = atomicAdd(queue, 1u);
+      // first task: interleaved over the CTAs so the longest streams (sorted first) spread over all SMs;
+      // afterwards from the shared queue, which starts behind the statically assigned ones
+      if (first_task) { task = (uint32_t)((lane * WARPS + warp) * gridDim.x + blockIdx.x); first_task = false; }
+      else task = atomicAdd(queue, 1u);
       if (task < ntasks) {
         const InflateTask t = tasks[task];
         src = t.src; src_len = t.src_len; dst = t.dst; out_cap = t.dst_cap;
@@ -262,7 +308,9 @@ inflate_kernel(const InflateTask *__restrict__ tasks, uint32_t ntasks, InflateRe
         } else if (out_pos + length > out_cap) {
           status = ZIPC_ERR_SIZE_EXCEEDED; state = S_FINISH;
         } else {
-          stored_left = length;
+          stored_len = length;
+          stored_src = src + pos;
+          br.seek(src, src_len, pos + length);
           state = S_STORED;
         }
       } else if (type == 1) {
@@ -350,9 +398,9 @@ inflate_kernel(const InflateTask *__restrict__ tasks, uint32_t ntasks, InflateRe
       while (m) {
         int L = __ffs(m) - 1;
         m &= m - 1;
-        LaneTabs &lt = tabs[warp * 32 + L];
+        LaneTabs &lt = tabs[warp * G + L];
         uint32_t nl = __shfl_sync(0xffffffffu, hlit, L), nd = __shfl_sync(0xffffffffu, hdist, L);
-        uint16_t *syms = g_syms + (size_t)(blockIdx.x * THREADS + warp * 32 + L) * SYMS_PER_SLOT;
+        uint16_t *syms = g_syms + (size_t)((blockIdx.x * WARPS + warp) * G + L) * SYMS_PER_SLOT;
         const uint8_t *lens = reinterpret_cast<const uint8_t *>(lt.lit);
         __syncwarp();
         for (uint32_t i = lane; i < 320; i += 32) ws.len[i] = i < nl + nd ? lens[i] : 0;
@@ -360,12 +408,11 @@ inflate_kernel(const InflateTask *__restrict__ tasks, uint32_t ntasks, InflateRe
         __syncwarp();
         if (ws.len[256] == 0) { if (lane == 0) ws.err = 1; }  // no end-of-block code (:662)
         __syncwarp();
-        if (!ws.err) build_decoder_warp(ws, 0, (int)nl, LB, lt.lit, lt.lit_cnt, syms, 285, lane);
+        if (!ws.err) build_decoder_warp<false>(ws, 0, (int)nl, LB, lt.lit, lt.lit_cnt, syms, s_len_tab, s_dist_tab, lane);
         __syncwarp();
-        if (!ws.err) build_decoder_warp(ws, (int)nl, (int)nd, DB, lt.dist, lt.dist_cnt, syms + 288, 29, lane);
+        if (!ws.err) build_decoder_warp<true>(ws, (int)nl, (int)nd, DB, lt.dist, lt.dist_cnt, syms + 288, s_len_tab, s_dist_tab, lane);
         __syncwarp();
         int err = ws.err;
-        __threadfence_block();
         if (lane == L) {
           need_build = false;
           if (err) { status = ZIPC_ERR_CORRUPTED; state = S_FINISH; }
@@ -379,104 +426,189 @@ inflate_kernel(const InflateTask *__restrict__ tasks, uint32_t ntasks, InflateRe
       }
     }
 
-    // ---- D: one token per lane (reference :593-616) ----------------------------------------------------
-    uint32_t tok_len = 0, tok_per = 0;
-    const uint8_t *tok_src = nullptr;
-    uint8_t *tok_dst = nullptr;
+    // ---- D: leaders decode up to K tokens each (reference :593-616) -----------------------------------------
+    uint32_t ntok = 0;
+    const uint64_t batch_pos = out_pos;  // output position of this leader's first queued token
     if (state == S_DATA) {
-      br.refill();
-      uint32_t e = lit_lut[br.peek(LB)];
-      int sym;
-      if (e == ENT_LONG) sym = canon_decode(br, lit_cnt, lit_syms);
-      else if (e == 0) sym = -1;
-      else { sym = (int)(e & 0x1FFu); br.drop(e >> 12); }
-      if (sym < 0 || sym > 285) { status = ZIPC_ERR_CORRUPTED; state = S_FINISH; }
-      else if (sym < 256) {
-        if (br.consumed() > src_len * 8) { status = ZIPC_ERR_CORRUPTED; state = S_FINISH; }
-        else if (out_pos + 1 > out_cap) { status = ZIPC_ERR_SIZE_EXCEEDED; state = S_FINISH; }
+      const uint64_t src_bits = src_len * 8;
+      uint32_t rel = 0;                                                     // bytes produced in this round
+      uint32_t hist = out_pos < 32768 ? (uint32_t)out_pos : 32768u;         // reachable history, capped
+      uint64_t room = out_cap - out_pos;
+      for (int k = 0; k < K; k++) {
+        br.refill();
+        uint32_t e = lit_lut[br.peek(LB)];
+        uint32_t kind, val;
+        if (e != 0 && e != 0xFFFFu) { br.drop(e & 15u); kind = (e >> 4) & 7u; val = e >> 7; }
         else {
-          if (!COUNT_ONLY) dst[out_pos] = (uint8_t)sym;
-          out_pos++;
+          int sym = e ? canon_decode(br, lit_cnt, lit_syms) : -1;
+          if (sym < 0 || sym > 285) { status = ZIPC_ERR_CORRUPTED; state = S_FINISH; break; }
+          if (sym < 256) { kind = 7; val = (uint32_t)sym; }
+          else if (sym == 256) { kind = 6; val = 0; }
+          else { uint32_t lt = s_len_tab[sym - 257]; kind = lt >> 9; val = lt & 0x1FFu; }
         }
-      } else if (sym == 256) {
-        if (br.consumed() > src_len * 8) { status = ZIPC_ERR_CORRUPTED; state = S_FINISH; }
-        else state = final_blk ? S_FINISH : S_HDR;
-      } else {
-        uint32_t lt = c_len_tab[sym - 257];
-        uint32_t eb = lt >> 9;
-        uint32_t length = (lt & 0x1FFu) + br.peek(eb);
-        br.drop(eb);
+        if (kind == 7) {                                                    // literal
+          if (br.loaded > src_bits && br.consumed() > src_bits) { status = ZIPC_ERR_CORRUPTED; state = S_FINISH; break; }
+          if (room == 0) { status = ZIPC_ERR_SIZE_EXCEEDED; state = S_FINISH; break; }
+          if (!COUNT_ONLY) myq[k * G + lane] = make_uint2(val, rel);
+          ntok = k + 1; rel++; room--;
+          hist = hist < 32768u ? hist + 1 : hist;
+          continue;
+        }
+        if (kind == 6) {                                                    // end of block
+          if (br.loaded > src_bits && br.consumed() > src_bits) { status = ZIPC_ERR_CORRUPTED; state = S_FINISH; }
+          else state = final_blk ? S_FINISH : S_HDR;
+          break;
+        }
+        uint32_t length = val + br.peek(kind);
+        br.drop(kind);
         br.refill();
         uint32_t e2 = dist_lut[br.peek(DB)];
-        int dsym;
-        if (e2 == ENT_LONG) dsym = canon_decode(br, dist_cnt, dist_syms);
-        else if (e2 == 0) dsym = -1;
-        else { dsym = (int)(e2 & 0x1FFu); br.drop(e2 >> 12); }
-        if (dsym < 0 || dsym > 29) { status = ZIPC_ERR_CORRUPTED; state = S_FINISH; }
-        else {
-          uint32_t dt = c_dist_tab[dsym];
-          uint32_t deb = dt >> 16;
-          uint32_t dist = (dt & 0xFFFFu) + br.peek(deb);
+        uint32_t dist;
+        if (e2 != 0 && e2 != ENT_LONG) {
+          br.drop(e2 & 15u);
+          uint32_t deb = (e2 >> 4) & 15u;
+          dist = (e2 >> 8) + br.peek(deb);
           br.drop(deb);
-          if (br.consumed() > src_len * 8 || (uint64_t)dist > out_pos) { status = ZIPC_ERR_CORRUPTED; state = S_FINISH; }
-          else if (out_pos + length > out_cap) { status = ZIPC_ERR_SIZE_EXCEEDED; state = S_FINISH; }
-          else {
-            if (!COUNT_ONLY) {
-              tok_len = length;
-              tok_dst = dst + out_pos;
-              tok_src = tok_dst - dist;
-              tok_per = dist < length ? dist : 0u;
-            }
-            out_pos += length;
-          }
+        } else {
+          int dsym = e2 ? canon_decode(br, dist_cnt, dist_syms) : -1;
+          if (dsym < 0 || dsym > 29) { status = ZIPC_ERR_CORRUPTED; state = S_FINISH; break; }
+          uint32_t dt = s_dist_tab[dsym];
+          dist = (dt & 0xFFFFu) + br.peek(dt >> 16);
+          br.drop(dt >> 16);
         }
+        if ((br.loaded > src_bits && br.consumed() > src_bits) || dist > hist) { status = ZIPC_ERR_CORRUPTED; state = S_FINISH; break; }
+        if (length > room) { status = ZIPC_ERR_SIZE_EXCEEDED; state = S_FINISH; break; }
+        if (!COUNT_ONLY) {
+          // a match is independent of this round when all of its source bytes precede the round
+          uint32_t reach = dist < length ? dist : length;                  // source bytes actually read
+          uint32_t dep = (dist < rel + reach) ? 0x80000000u : 0u;          // pos - dist + reach > batch_pos
+          myq[k * G + lane] = make_uint2(dep | (length << 16) | dist, rel);
+        }
+        ntok = k + 1; rel += length; room -= length;
+        hist = hist + length < 32768u ? hist + length : 32768u;
       }
-    } else if (state == S_STORED) {
-      // the whole stored block as one copy from the input (reference :678-680)
-      uint64_t pos = br.consumed() >> 3;
-      if (!COUNT_ONLY) {
-        tok_len = stored_left;
-        tok_dst = dst + out_pos;
-        tok_src = src + pos;
-        tok_per = 0;
-      }
-      out_pos += stored_left;
-      br.seek(src, src_len, pos + stored_left);
-      state = final_blk ? S_FINISH : S_HDR;
+      out_pos += rel;
     }
 
-    // ---- E: flattened warp copy of this round's tokens ----------------------------------------------------
+    // ---- E: the warp executes the queued tokens ------------------------------------------------------------
     if (!COUNT_ONLY) {
-      uint32_t incl = tok_len;
+      __syncwarp();
+      const unsigned long long base_ptr = (unsigned long long)(uintptr_t)(dst + batch_pos);
+      // E1: literals and matches whose source lies before this round: no ordering needed, so all their
+      // bytes are flattened over the lanes (QN tokens = 2 per lane for the prefix sum)
+      uint32_t l0, l1;
+      {
+        uint32_t n0 = __shfl_sync(0xffffffffu, ntok, lane & (G - 1));
+        uint32_t e0 = myq[lane].x, e1 = myq[lane + 32].x;
+        uint32_t j0 = lane / G, j1 = (lane + 32) / G;
+        l0 = (j0 < n0 && !(e0 >> 31)) ? (((e0 >> 16) & 0x1FFu) ? ((e0 >> 16) & 0x1FFu) : 1u) : 0u;
+        l1 = (j1 < n0 && !(e1 >> 31)) ? (((e1 >> 16) & 0x1FFu) ? ((e1 >> 16) & 0x1FFu) : 1u) : 0u;
+      }
+      uint32_t i0 = l0, i1 = l1;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
-        uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += v;
+        uint32_t v0 = __shfl_up_sync(0xffffffffu, i0, o), v1 = __shfl_up_sync(0xffffffffu, i1, o);
+        if (lane >= o) { i0 += v0; i1 += v1; }
       }
-      uint32_t excl = incl - tok_len;
-      uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-      for (uint32_t base = 0; base < total; base += 32) {
-        uint32_t g = base + lane;
-        // owner = number of lanes whose inclusive sum is <= g
-        uint32_t lo = 0;
+      const uint32_t tot0 = __shfl_sync(0xffffffffu, i0, 31);
+      const uint32_t total = tot0 + __shfl_sync(0xffffffffu, i1, 31);
+      tb[lane] = (uint16_t)(i0 - l0);
+      tb[lane + 32] = (uint16_t)(tot0 + i1 - l1);
+      if (lane == 0) tb[QN] = (uint16_t)total;
+      __syncwarp();
+      // four passes at a time: all loads are issued before the first store, so one L2 round trip
+      // covers 128 bytes of copies
+      for (uint32_t base = 0; base < total; base += 128) {
+        uint8_t val[4];
+        uint8_t *dq[4];
 #pragma unroll
-        for (int step = 16; step > 0; step >>= 1) {
-          uint32_t v = __shfl_sync(0xffffffffu, incl, (int)(lo + step - 1));
-          if (v <= g) lo += step;
+        for (int u = 0; u < 4; u++) {
+          uint32_t b = base + 32 * u + lane;
+          bool act = b < total;
+          uint32_t lo = 0;  // token i with tb[i] <= b < tb[i+1] (empty tokens are skipped)
+#pragma unroll
+          for (int step = QN / 2; step > 0; step >>= 1)
+            if ((uint32_t)tb[lo + step] <= b) lo += step;
+          uint32_t i = act ? lo : 0u;
+          uint32_t q = b - tb[i];
+          uint2 ent = myq[i];
+          unsigned long long d = __shfl_sync(0xffffffffu, base_ptr, (int)(i & (G - 1)));
+          uint8_t *dp = reinterpret_cast<uint8_t *>((uintptr_t)d) + ent.y;
+          uint32_t mlen = (ent.x >> 16) & 0x1FFu, mdist = ent.x & 0xFFFFu;
+          dq[u] = act ? dp + q : nullptr;
+          val[u] = (uint8_t)mdist;
+          if (act && mlen) {
+            const uint8_t *sp = dp - mdist + (mdist < mlen ? q % mdist : q);
+            unsigned int v;
+            asm volatile("ld.global.cg.u8 %0, [%1];" : "=r"(v) : "l"(sp) : "memory");
+            val[u] = (uint8_t)v;
+          }
         }
-        uint32_t t = lo & 31u;
-        uint32_t q = g - __shfl_sync(0xffffffffu, excl, (int)t);
-        unsigned long long s = __shfl_sync(0xffffffffu, (unsigned long long)(uintptr_t)tok_src, (int)t);
-        unsigned long long d = __shfl_sync(0xffffffffu, (unsigned long long)(uintptr_t)tok_dst, (int)t);
-        uint32_t per = __shfl_sync(0xffffffffu, tok_per, (int)t);
-        if (g < total) {
-          uint32_t idx = per ? q % per : q;
-          uint8_t b = *(reinterpret_cast<const volatile uint8_t *>((uintptr_t)s) + idx);
-          *(reinterpret_cast<uint8_t *>((uintptr_t)d) + q) = b;
-        }
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+          if (dq[u]) *dq[u] = val[u];
       }
+      __syncwarp();
+      // E2: matches that read bytes produced in this round, in token order (rare for text)
+      uint32_t maxtok = ntok;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) maxtok = max(maxtok, __shfl_xor_sync(0xffffffffu, maxtok, o));
+      for (uint32_t j = 1; j < maxtok; j++) {
+        uint2 ent2 = (leader && j < ntok) ? myq[j * G + lane] : make_uint2(0u, 0u);
+        uint32_t ent = ent2.x;
+        if (!__any_sync(0xffffffffu, ent >> 31)) continue;
+        uint32_t tlen = (ent >> 31) ? ((ent >> 16) & 0x1FFu) : 0u;
+        uint32_t pos = ent2.y;
+        uint32_t incl = tlen;
+#pragma unroll
+        for (int o = 1; o < G; o <<= 1) {
+          uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += v;
+        }
+        uint32_t excl = incl - tlen;
+        uint32_t tot = __shfl_sync(0xffffffffu, incl, G - 1);
+        for (uint32_t base = 0; base < tot; base += 32) {
+          uint32_t g = base + lane;
+          uint32_t lo = 0;  // owner = number of leaders whose inclusive sum is <= g
+#pragma unroll
+          for (int step = G / 2; step > 0; step >>= 1) {
+            uint32_t v = __shfl_sync(0xffffffffu, incl, (int)(lo + step - 1));
+            if (v <= g) lo += step;
+          }
+          uint32_t t = lo & (G - 1);
+          uint32_t q = g - __shfl_sync(0xffffffffu, excl, (int)t);
+          uint32_t oe = __shfl_sync(0xffffffffu, ent, (int)t);
+          uint32_t op = __shfl_sync(0xffffffffu, pos, (int)t);
+          unsigned long long d = __shfl_sync(0xffffffffu, base_ptr, (int)t);
+          if (g < tot) {
+            uint8_t *dp = reinterpret_cast<uint8_t *>((uintptr_t)d) + op;
+            uint32_t mlen = (oe >> 16) & 0x1FFu, mdist = oe & 0xFFFFu;
+            const uint8_t *sp = dp - mdist + (mdist < mlen ? q % mdist : q);
+            unsigned int v;
+            asm volatile("ld.global.cg.u8 %0, [%1];" : "=r"(v) : "l"(sp) : "memory");
+            dp[q] = (uint8_t)v;
+          }
+        }
+        __syncwarp();
+      }
+      // stored blocks: one coalesced copy from the input per leader (reference :678-680)
+      uint32_t sm = __ballot_sync(0xffffffffu, state == S_STORED);
+      while (sm) {
+        int L = __ffs(sm) - 1;
+        sm &= sm - 1;
+        uint32_t n = __shfl_sync(0xffffffffu, stored_len, L);
+        unsigned long long s = __shfl_sync(0xffffffffu, (unsigned long long)(uintptr_t)stored_src, L);
+        unsigned long long d = __shfl_sync(0xffffffffu, (unsigned long long)(uintptr_t)(dst + out_pos), L);
+        const uint8_t *sp = reinterpret_cast<const uint8_t *>((uintptr_t)s);
+        uint8_t *dp = reinterpret_cast<uint8_t *>((uintptr_t)d);
+        for (uint32_t i = lane; i < n; i += 32) dp[i] = sp[i];
+      }
+      __syncwarp();
     }
-    __syncwarp();
+    if (state == S_STORED) {
+      out_pos += stored_len;
+      state = final_blk ? S_FINISH : S_HDR;
+    }
 
     // ---- F: finished streams report ---------------------------------------------------------------------
     if (state == S_FINISH) {
@@ -502,12 +634,16 @@ int inflate_launch(zipc_b200_ctx *ctx, const InflateTask *d_tasks, uint32_t n, I
     ZB_CUDA(ctx, cudaFuncSetAttribute(inflate_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
     g_attr_set = true;
   }
-  uint32_t grid = (n + THREADS - 1) / THREADS;
-  if (grid > (uint32_t)ctx->sm_count) grid = (uint32_t)ctx->sm_count;
-  size_t sym_bytes = (size_t)(grid * THREADS + grid) * SYMS_PER_SLOT * sizeof(uint16_t);
+  // spread the streams over all SMs first (a CTA serves up to WARPS*G at a time)
+  uint32_t grid = (uint32_t)ctx->sm_count;
+  if (grid > n) grid = n;
+  size_t sym_bytes = (size_t)(grid * WARPS * G + grid) * SYMS_PER_SLOT * sizeof(uint16_t);
   if (int st = ctx->d_scratch.reserve(sym_bytes + 256)) return st;
   unsigned int *queue = reinterpret_cast<unsigned int *>(ctx->d_scratch.as<uint8_t>() + sym_bytes);
-  ZB_CUDA(ctx, cudaMemsetAsync(queue, 0, sizeof(unsigned int), ctx->stream));
+  {
+    unsigned int start = grid * WARPS * G;  // tasks [0, start) are assigned statically
+    ZB_CUDA(ctx, cudaMemcpyAsync(queue, &start, sizeof start, cudaMemcpyHostToDevice, ctx->stream));
+  }
   if (count_only)
     inflate_kernel<true><<<grid, THREADS, kSmemBytes, ctx->stream>>>(d_tasks, n, d_results, queue, ctx->d_scratch.as<uint16_t>());
   else
