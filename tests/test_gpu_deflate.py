@@ -1,0 +1,155 @@
+"""GPU parity: batched deflate.  The reference pins no deflate bytes, so the bar is:
+(1) every stream inflates bit-exactly through the oracle's inflate (stand-in for Zipc_deflate.inflate) and
+zlib, (2) checksums of the input are bit-exact, (3) compressed size within RATIO_TOLERANCE of the oracle
+per level, (4) the kernel's bytes equal the host model's (same algorithm run serially)."""
+import io
+import random
+import zipfile
+import zlib
+
+import numpy as np
+import pytest
+
+from oracle import zipc_oracle as zo
+import encoder_model as model
+from zipc_b200 import _lib, synth
+from zipc_b200 import zipc_deflate as zd
+
+pytestmark = pytest.mark.gpu
+RATIO_TOLERANCE = 1.05
+LEVELS = ("none", "fast", "default", "best")
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = zd.Context(0)
+    zd.set_default_context(c)
+    yield c
+    zd.set_default_context(None)
+    c.close()
+
+
+def test_deflate_trip(ctx):  # test/test.ml:28-43
+    strings = [b"", b"a", b"hellohello", b"abcdefghijklmnopqrstuvwxyzzyxwvutsrqponmlkjihgfedcba",
+               bytes((i + 1) % 255 for i in range(256))]
+    for level in LEVELS:
+        for s in strings:
+            cs = zd.deflate(s, level=level).get_ok()
+            assert zo.inflate(cs) == s and zlib.decompress(cs, -15) == s
+            assert zd.inflate(cs).get_ok() == s  # and back through our own decoder
+    assert zd.deflate(b"", level="none").get_ok().hex() == "010000ffff"
+    assert zd.deflate(b"").get_ok().hex() == "0300"
+    assert zd.deflate(b"a").get_ok().hex() == "4b0400"
+    assert zd.deflate(b"hellohello").get_ok().hex() == "cb48cdc9c9071300"
+
+
+def test_decompression_size_limits_on_our_stream(ctx):  # test/test.ml:45-55
+    src = b"Keep it to the limits."
+    csrc = zd.deflate(src).get_ok()
+    assert zo.inflate(csrc, len(src)) == src and zo.inflate(csrc, len(src) + 1) == src
+    with pytest.raises(zo.OracleError):
+        zo.inflate(csrc, len(src) - 1)
+
+
+def _corpus():
+    rnd = random.Random(5)
+    t = synth.text_v1(3, 100000).tobytes()
+    return {
+        "text": synth.text_v1(1007, 133120).tobytes(),
+        "text_big": synth.text_v1(11, 700001).tobytes(),
+        "random": rnd.randbytes(70000),
+        "mixed": t + rnd.randbytes(50000) + t,
+        "zeros": bytes(150000),
+        "runs": b"".join(bytes([rnd.randrange(256)]) * rnd.randrange(1, 600) for _ in range(500)),
+        "tiny": b"abc", "edge2047": t[:2047], "edge2048": t[:2048], "edge2049": t[:2049],
+        "edge61440": t[:61440], "edge61441": t[:61441], "blk": t[:65536] + t[:65536],
+    }
+
+
+@pytest.mark.parametrize("level", ["fast", "default", "best"])
+def test_corpus_roundtrip_ratio_and_model_equality(ctx, level):
+    corpus = _corpus()
+    names = list(corpus)
+    res = ctx.deflate_batch([corpus[k] for k in names], level, _lib.CK_CRC32)
+    zo.set_keep_codelen_freqs(False)
+    try:
+        for k, (st, cs, crc) in zip(names, res):
+            data = corpus[k]
+            cs = cs.tobytes()
+            assert st == 0, k
+            assert crc == zo.crc32(data), k
+            assert zo.inflate(cs) == data, k
+            assert zlib.decompress(cs, -15) == data, k
+            assert len(cs) <= RATIO_TOLERANCE * len(zo.deflate(data, level)) + 8, k
+            assert cs == model.deflate(data, level), k
+    finally:
+        zo.set_keep_codelen_freqs(True)
+
+
+def test_level_none_matches_reference_layout(ctx):
+    for data in (b"", b"x", synth.text_v1(2, 65535).tobytes(), synth.text_v1(2, 65536).tobytes(), synth.rand_v1(3, 200000).tobytes()):
+        cs = zd.deflate(data, level="none").get_ok()
+        assert zo.inflate(cs) == data and zlib.decompress(cs, -15) == data
+        assert len(cs) == len(data) + 5 * max(1, -(-len(data) // 65535))
+
+
+def test_fixture_redeflate_recode(ctx, zip_docs):  # test/test.ml:58-118 with the GPU codec in the loop
+    ms = [m for m in zo.zip_decode(zip_docs)]
+    out = []
+    for m in ms:
+        if m.is_dir:
+            out.append(m)
+            continue
+        s = zd.inflate_and_crc_32(zip_docs, start=m.start, len=m.compressed_size, decompressed_size=m.decompressed_size).get_ok()
+        assert s[1] == m.crc32
+        crc, cs = zd.crc_32_and_deflate(s[0], level="best").get_ok()
+        assert crc == m.crc32
+        out.append(zo.member_make(m.path, mode=m.mode, mtime=m.mtime, compression=8, compressed_bytes=cs,
+                                  decompressed_size=len(s[0]), crc32=crc))
+    recoded = zo.zip_encode(out)
+    back = {m.path: m for m in zo.zip_decode(recoded)}
+    assert back[b"zip-docs/rfc1951.txt"].crc32 == 0xFB4F3400 and back[b"zip-docs/APPNOTE.TXT"].crc32 == 0x39B029C4
+    for m in back.values():
+        if not m.is_dir:
+            zo.file_to_binary_string(m)  # inflate + CRC check by the oracle
+    assert zipfile.ZipFile(io.BytesIO(recoded)).testzip() is None
+
+
+def test_zlib_compress(ctx):
+    text = synth.text_v1(6, 100000).tobytes()
+    for level, hdr in (("none", "7801"), ("fast", "785e"), ("default", "789c"), ("best", "78da")):
+        ad, zs = zd.zlib_compress(text, level=level).get_ok()
+        assert zs[:2].hex() == hdr and ad == zlib.adler32(text) == zo.adler32(text)
+        assert zlib.decompress(zs) == text
+        assert zo.zlib_decompress(zs) == (text, ad)
+        assert zd.zlib_decompress(zs).get_ok() == (text, ad)
+    rnd = synth.rand_v1(8, 100000).tobytes()
+    ad, zs = zd.zlib_compress(rnd, level="default", adler_mode=_lib.ADLER_RFC1950).get_ok()
+    assert zlib.decompress(zs) == rnd and ad == zlib.adler32(rnd)
+    crc, ds = zd.adler_32_and_deflate(text).get_ok()
+    assert crc == zlib.adler32(text) and zo.inflate(ds) == text
+
+
+def test_many_members_ragged(ctx):
+    """C4 shape, scaled down: 400 members of 4-256 KiB (10 % incompressible), three levels."""
+    sizes = synth.member_sizes(400, seed=9)
+    datas = [(synth.rand_v1(2000 + i, int(n)) if i % 10 == 0 else synth.text_v1(2000 + i, int(n))) for i, n in enumerate(sizes)]
+    total = sum(d.size for d in datas)
+    zo.set_keep_codelen_freqs(False)
+    try:
+        for level in ("fast", "default", "best"):
+            res = ctx.deflate_batch(datas, level, _lib.CK_CRC32)
+            csum = 0
+            for d, (st, cs, crc) in zip(datas, res):
+                assert st == 0 and crc == zlib.crc32(d.tobytes())
+                assert zlib.decompress(cs.tobytes(), -15) == d.tobytes()
+                csum += cs.size
+            ref = sum(len(zo.deflate(d.tobytes(), level)) for d in datas[:40])
+            ours = sum(r[1].size for r in res[:40])
+            assert ours <= RATIO_TOLERANCE * ref
+            # and our own decoder reads them back bit-exactly
+            back = ctx.inflate_batch([r[1] for r in res], [d.size for d in datas], _lib.CK_CRC32)
+            for d, r, (st, out, crc) in zip(datas, res, back):
+                assert st == 0 and crc == r[2] and (out == d).all()
+    finally:
+        zo.set_keep_codelen_freqs(True)

@@ -47,15 +47,13 @@ int PinBuf::reserve(size_t bytes) {
 }
 void PinBuf::release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
 
-namespace {
-
-bool is_pinned(const void *p) {
+static bool is_pinned(const void *p) {
   cudaPointerAttributes a;
   if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
   return a.type == cudaMemoryTypeHost;
 }
 
-constexpr size_t kStageChunk = 16u << 20;
+static constexpr size_t kStageChunk = 16u << 20;
 
 // host -> device.  Pinned sources are DMA'd directly; pageable ones go through a double-buffered
 // pinned staging ring so that the CPU copy of chunk k+1 overlaps the DMA of chunk k.
@@ -128,7 +126,7 @@ int d2h(zipc_b200_ctx *ctx, void *h, const void *d, size_t bytes) {
   return rc;
 }
 
-inline size_t align_up(size_t v, size_t a) { return (v + a - 1) & ~(a - 1); }
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) & ~(a - 1); }
 
 // Uploads n host ranges into ctx->d_in and returns their device addresses.  When the ranges are
 // (nearly) one contiguous host span -- members of an in-memory archive -- the span is sent with one
@@ -174,7 +172,7 @@ int upload_ranges(zipc_b200_ctx *ctx, size_t n, const void *const *src, const si
   return ZIPC_OK;
 }
 
-__global__ void make_crc_segs_kernel(const InflateTask *tasks, const InflateResult *res, uint32_t n, CrcSeg *segs) {
+static __global__ void make_crc_segs_kernel(const InflateTask *tasks, const InflateResult *res, uint32_t n, CrcSeg *segs) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   CrcSeg s;
@@ -184,7 +182,7 @@ __global__ void make_crc_segs_kernel(const InflateTask *tasks, const InflateResu
   s._pad = 0;
   segs[i] = s;
 }
-__global__ void xor_ffffffff_kernel(uint32_t *v, uint32_t n) {
+static __global__ void xor_ffffffff_kernel(uint32_t *v, uint32_t n) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) v[i] ^= 0xFFFFFFFFu;
 }
@@ -248,7 +246,7 @@ int inflate_core(zipc_b200_ctx *ctx, int ck, int adler_mode, size_t n, const std
 }
 
 // Shared tail of the host-pointer batch calls: lay out the arena, run, copy back.
-int finish_to_host(zipc_b200_ctx *ctx, size_t n, const std::vector<size_t> &off, const size_t *len, size_t total,
+static int finish_to_host(zipc_b200_ctx *ctx, size_t n, const std::vector<size_t> &off, const size_t *len, size_t total,
                    void *dst, size_t dst_cap, size_t *dst_need, size_t *dst_off) {
   ctx->last_off = off;
   ctx->last_len.assign(len, len + n);
@@ -259,7 +257,6 @@ int finish_to_host(zipc_b200_ctx *ctx, size_t n, const std::vector<size_t> &off,
   return d2h(ctx, dst, ctx->d_out.p, total);
 }
 
-}  // namespace
 }  // namespace zb
 
 using namespace zb;
@@ -297,7 +294,7 @@ void zipc_b200_ctx_destroy(zipc_b200_ctx *ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   ctx->d_in.release(); ctx->d_out.release(); ctx->d_desc.release(); ctx->d_res.release();
-  ctx->d_scratch.release(); ctx->d_scratch2.release(); ctx->d_small.release();
+  ctx->d_scratch.release(); ctx->d_scratch2.release(); ctx->d_small.release(); ctx->d_slots.release(); ctx->d_desc2.release();
   ctx->h_stage.release(); ctx->h_res.release(); ctx->h_desc.release();
   if (ctx->d_crc_tabs) cudaFree(ctx->d_crc_tabs);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);

@@ -74,6 +74,24 @@ struct InflateResult {
   uint32_t _pad;
 };
 
+struct DeflateTask {  // one input to deflate (a ZIP member or an independent segment)
+  const uint8_t *src;
+  uint64_t src_len;   // < 2^32
+  uint8_t *dst;       // 4-byte aligned output slot
+  uint64_t dst_cap;
+};
+struct DeflateResult {
+  uint64_t out_len;
+  uint32_t status;
+  uint32_t blocks;
+};
+
+struct CopyDesc {     // gather: len bytes from src to dst
+  const uint8_t *src;
+  uint8_t *dst;
+  uint64_t len;
+};
+
 }  // namespace zb
 
 // ---- the context -------------------------------------------------------------------------------
@@ -87,7 +105,7 @@ struct zipc_b200_ctx {
   // constant tables on the device
   uint32_t *d_crc_tabs = nullptr;   // see crc32.cu: strided[4][256] | std[4][256] | xp16[32]
   // work buffers (grow-only)
-  zb::DevBuf d_in, d_out, d_desc, d_res, d_scratch, d_scratch2, d_small;
+  zb::DevBuf d_in, d_out, d_desc, d_res, d_scratch, d_scratch2, d_small, d_slots, d_desc2;
   zb::PinBuf h_stage, h_res, h_desc;
 
   // results of the last batch call kept for zipc_b200_fetch()
@@ -123,6 +141,21 @@ int adler32_launch_buffer(zipc_b200_ctx *ctx, const uint8_t *d_src, uint64_t len
 // per-range Adler-32 for n ranges given as (ptr,len) on the host; results (final values) to h_out
 int adler32_ranges(zipc_b200_ctx *ctx, const uint8_t *const *d_ptrs, const uint64_t *lens, size_t n, int mode,
                    uint32_t *h_out);
+// deflate.cu
+int deflate_launch(zipc_b200_ctx *ctx, const DeflateTask *d_tasks, uint32_t n, DeflateResult *d_results, int level);
+// zip_api.cu: n independent copies on the device (compaction of per-member output slots)
+int gather_launch(zipc_b200_ctx *ctx, const CopyDesc *d_descs, uint32_t n);
+// api.cu helpers shared with zip_api.cu
+int h2d(zipc_b200_ctx *ctx, void *d, const void *h, size_t bytes);
+int d2h(zipc_b200_ctx *ctx, void *h, const void *d, size_t bytes);
+int upload_ranges(zipc_b200_ctx *ctx, size_t n, const void *const *src, const size_t *len,
+                  std::vector<const uint8_t *> &d_ptr);
+int inflate_core(zipc_b200_ctx *ctx, int ck, int adler_mode, size_t n, const std::vector<const uint8_t *> &d_src,
+                 const size_t *src_len, const std::vector<uint8_t *> &d_dst, const std::vector<size_t> &cap,
+                 bool count_only, size_t *out_len, uint32_t *checksum, int *status);
+// host_util.cc
+int zip_assemble_impl(const zipc_b200_member *ms, size_t n, const char *first, void *out_v, size_t out_cap,
+                      size_t *out_len, bool copy_payload, uint64_t *payload_off);
 // inflate.cu
 int inflate_launch(zipc_b200_ctx *ctx, const InflateTask *d_tasks, uint32_t n, InflateResult *d_results,
                    bool count_only);

@@ -231,9 +231,15 @@ Hdr header_fields(const zipc_b200_member &m) {
 }
 }  // namespace
 
-int zipc_b200_zip_assemble(const zipc_b200_member *ms, size_t n, const char *first, void *out_v, size_t out_cap,
-                           size_t *out_len) {
-  if (!out_v || !out_len || (!ms && n)) return ZIPC_ERR_INVALID_ARG;
+}  // extern "C"
+
+namespace zb {
+// Archive layout engine behind zipc_b200_zip_assemble.  out_v == nullptr: compute *out_len and the
+// payload offsets only.  copy_payload == false: payloads are already in place (the GPU gathered them).
+// payload_off[i] (optional) receives the archive offset of member i's payload (members in caller order).
+int zip_assemble_impl(const zipc_b200_member *ms, size_t n, const char *first, void *out_v, size_t out_cap,
+                      size_t *out_len, bool copy_payload, uint64_t *payload_off) {
+  if (!out_len || (!ms && n)) return ZIPC_ERR_INVALID_ARG;
   if (!first) first = "mimetype";
   const size_t flen = std::strlen(first);
   std::vector<size_t> ord = map_order(ms, n);
@@ -249,6 +255,15 @@ int zipc_b200_zip_assemble(const zipc_b200_member *ms, size_t n, const char *fir
   }
   uint64_t total = 22;
   for (size_t k : ord) total += 30 + ms[k].path_len + (ms[k].is_dir ? 0 : ms[k].compressed_size) + 46 + ms[k].path_len;
+  if (payload_off) {
+    uint64_t at = 0;
+    for (size_t k : ord) {
+      at += 30 + ms[k].path_len;
+      payload_off[k] = at;
+      at += ms[k].is_dir ? 0 : ms[k].compressed_size;
+    }
+  }
+  if (!out_v) { *out_len = (size_t)total; return ZIPC_OK; }
   if (total > out_cap) { *out_len = (size_t)total; return ZIPC_ERR_DST_TOO_SMALL; }
   uint8_t *b = static_cast<uint8_t *>(out_v);
   std::vector<uint64_t> lfh_at(ord.size());
@@ -265,7 +280,7 @@ int zipc_b200_zip_assemble(const zipc_b200_member *ms, size_t n, const char *fir
     std::memcpy(b + pos + 30, m.path, m.path_len);
     pos += 30 + m.path_len;
     if (!m.is_dir && m.compressed_size) {
-      std::memcpy(b + pos, m.compressed_bytes + m.start, m.compressed_size);
+      if (copy_payload) std::memcpy(b + pos, m.compressed_bytes + m.start, m.compressed_size);
       pos += m.compressed_size;
     }
   }
@@ -296,6 +311,15 @@ int zipc_b200_zip_assemble(const zipc_b200_member *ms, size_t n, const char *fir
   wr16(b, pos + 20, 0);
   *out_len = (size_t)(pos + 22);
   return ZIPC_OK;
+}
+}  // namespace zb
+
+extern "C" {
+
+int zipc_b200_zip_assemble(const zipc_b200_member *ms, size_t n, const char *first, void *out_v, size_t out_cap,
+                           size_t *out_len) {
+  if (!out_v) return ZIPC_ERR_INVALID_ARG;
+  return zb::zip_assemble_impl(ms, n, first, out_v, out_cap, out_len, true, nullptr);
 }
 
 // ---- synthetic workloads -------------------------------------------------------------

@@ -1,10 +1,378 @@
-// zip_api.cu -- GPU-backed archive entry points (placeholder: extract/deflate-archive land with deflate).
+// zip_api.cu -- deflate / zlib-compress / archive entry points of the C ABI (host orchestration) and the
+// device gather that compacts per-member output slots.
+//
+//   zipc_b200_deflate_batch        <- Zipc_deflate.deflate / crc_32_and_deflate / adler_32_and_deflate
+//                                     (reference src/zipc_deflate.ml:1247-1259)
+//   zipc_b200_zlib_compress_batch  <- Zipc_deflate.zlib_compress (:1262-1277)
+//   zipc_b200_zip_extract_batch    <- Zipc.File.to_binary_string over parsed members (src/zipc.ml:205-225)
+//   zipc_b200_zip_deflate_archive  <- Zipc.File.deflate_of_binary_string + Zipc.to_binary_string
+//                                     (src/zipc.ml:179-185, 570-588)
+#include <algorithm>
+#include <cstring>
+#include <numeric>
+
 #include "common.cuh"
+
+namespace zb {
+namespace {
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) & ~(a - 1); }
+
+// one CTA per copy; 16-byte vectors when both ends allow it
+__global__ void __launch_bounds__(256) gather_kernel(const CopyDesc *__restrict__ descs, uint32_t n) {
+  for (uint32_t k = blockIdx.x; k < n; k += gridDim.x) {
+    const CopyDesc d = descs[k];
+    if (!d.len) continue;
+    if ((((uintptr_t)d.src | (uintptr_t)d.dst) & 15) == 0) {
+      const uint4 *s = reinterpret_cast<const uint4 *>(d.src);
+      uint4 *t = reinterpret_cast<uint4 *>(d.dst);
+      uint64_t nv = d.len >> 4;
+      for (uint64_t i = threadIdx.x; i < nv; i += blockDim.x) t[i] = s[i];
+      for (uint64_t i = (nv << 4) + threadIdx.x; i < d.len; i += blockDim.x) d.dst[i] = d.src[i];
+    } else if ((((uintptr_t)d.src ^ (uintptr_t)d.dst) & 3) == 0) {
+      // same misalignment: bytes up to a word boundary, then words
+      uint64_t head = (4 - ((uintptr_t)d.src & 3)) & 3;
+      if (head > d.len) head = d.len;
+      for (uint64_t i = threadIdx.x; i < head; i += blockDim.x) d.dst[i] = d.src[i];
+      const uint32_t *s = reinterpret_cast<const uint32_t *>(d.src + head);
+      uint32_t *t = reinterpret_cast<uint32_t *>(d.dst + head);
+      uint64_t nw = (d.len - head) >> 2;
+      for (uint64_t i = threadIdx.x; i < nw; i += blockDim.x) t[i] = s[i];
+      for (uint64_t i = head + (nw << 2) + threadIdx.x; i < d.len; i += blockDim.x) d.dst[i] = d.src[i];
+    } else {
+      for (uint64_t i = threadIdx.x; i < d.len; i += blockDim.x) d.dst[i] = d.src[i];
+    }
+  }
+}
+
+// Runs the encoder over n device-resident inputs.  Output of member i lands in a private slot
+// (d_slot[i], capacity slot_cap[i]); the caller compacts.  Checksums are of the INPUT (crc_op).
+int deflate_run(zipc_b200_ctx *ctx, int level, int ck, int adler_mode, size_t n,
+                const std::vector<const uint8_t *> &d_src, const size_t *src_len,
+                const std::vector<uint8_t *> &d_slot, const std::vector<size_t> &slot_cap,
+                size_t *out_len, uint32_t *checksum, int *status) {
+  if (!n) return ZIPC_OK;
+  if (n > 0xFFFFFFF0ull) return ZIPC_ERR_INVALID_ARG;
+  for (size_t i = 0; i < n; i++) if (src_len[i] > 0xFFFFFFFFull) return ZIPC_ERR_INVALID_ARG;
+  std::vector<uint32_t> order(n);
+  std::iota(order.begin(), order.end(), 0u);
+  std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return src_len[a] > src_len[b]; });
+  if (int st = ctx->h_desc.reserve(n * std::max(sizeof(DeflateTask), sizeof(CrcSeg)))) return st;
+  if (int st = ctx->d_desc.reserve(n * sizeof(DeflateTask))) return st;
+  if (int st = ctx->d_res.reserve(n * (sizeof(DeflateResult) + sizeof(uint32_t)))) return st;
+  if (int st = ctx->h_res.reserve(n * (sizeof(DeflateResult) + sizeof(uint32_t)))) return st;
+  DeflateTask *ht = ctx->h_desc.as<DeflateTask>();
+  for (size_t k = 0; k < n; k++) {
+    uint32_t i = order[k];
+    ht[k].src = d_src[i]; ht[k].src_len = src_len[i]; ht[k].dst = d_slot[i]; ht[k].dst_cap = slot_cap[i];
+  }
+  DeflateTask *dt = ctx->d_desc.as<DeflateTask>();
+  DeflateResult *dr = ctx->d_res.as<DeflateResult>();
+  ZB_CUDA(ctx, cudaMemcpyAsync(dt, ht, n * sizeof(DeflateTask), cudaMemcpyHostToDevice, ctx->stream));
+  if (int st = deflate_launch(ctx, dt, (uint32_t)n, dr, level)) return st;
+  DeflateResult *hr = ctx->h_res.as<DeflateResult>();
+  ZB_CUDA(ctx, cudaMemcpyAsync(hr, dr, n * sizeof(DeflateResult), cudaMemcpyDeviceToHost, ctx->stream));
+  ZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  for (size_t k = 0; k < n; k++) {
+    uint32_t i = order[k];
+    status[i] = (int)hr[k].status;
+    out_len[i] = (size_t)hr[k].out_len;
+  }
+  if (checksum) {
+    if (ck == ZIPC_CK_CRC32) {
+      if (int st = ctx->d_desc2.reserve(n * (sizeof(CrcSeg) + sizeof(uint32_t)))) return st;
+      CrcSeg *hs = ctx->h_desc.as<CrcSeg>();
+      for (size_t i = 0; i < n; i++) { hs[i].ptr = d_src[i]; hs[i].len = src_len[i]; hs[i].init = 0xFFFFFFFFu; hs[i]._pad = 0; }
+      CrcSeg *ds = ctx->d_desc2.as<CrcSeg>();
+      uint32_t *dc = reinterpret_cast<uint32_t *>(ds + n);
+      ZB_CUDA(ctx, cudaMemcpyAsync(ds, hs, n * sizeof(CrcSeg), cudaMemcpyHostToDevice, ctx->stream));
+      if (int st = crc32_launch_segments(ctx, ds, (uint32_t)n, dc)) return st;
+      ZB_CUDA(ctx, cudaMemcpyAsync(checksum, dc, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+      ZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+      for (size_t i = 0; i < n; i++) checksum[i] ^= 0xFFFFFFFFu;
+    } else if (ck == ZIPC_CK_ADLER32) {
+      std::vector<uint64_t> l(src_len, src_len + n);
+      if (int st = adler32_ranges(ctx, d_src.data(), l.data(), n, adler_mode, checksum)) return st;
+    } else {
+      for (size_t i = 0; i < n; i++) checksum[i] = 0;
+    }
+  }
+  return ZIPC_OK;
+}
+
+// Lays the n slots out in ctx->d_slots.
+int make_slots(zipc_b200_ctx *ctx, size_t n, const size_t *src_len, std::vector<uint8_t *> &d_slot,
+               std::vector<size_t> &slot_cap) {
+  d_slot.resize(n); slot_cap.resize(n);
+  size_t total = 0;
+  std::vector<size_t> off(n);
+  for (size_t i = 0; i < n; i++) { off[i] = total; slot_cap[i] = align_up(zipc_b200_deflate_bound(src_len[i]), 16); total += slot_cap[i]; }
+  if (int st = ctx->d_slots.reserve(total + 64)) return st;
+  for (size_t i = 0; i < n; i++) d_slot[i] = ctx->d_slots.as<uint8_t>() + off[i];
+  return ZIPC_OK;
+}
+
+// Compacts slot outputs into ctx->d_out at the given offsets.
+int compact(zipc_b200_ctx *ctx, size_t n, const std::vector<uint8_t *> &d_slot, const size_t *len,
+            const std::vector<size_t> &off, size_t total) {
+  if (int st = ctx->d_out.reserve(total + 64)) return st;
+  if (int st = ctx->h_desc.reserve(n * sizeof(CopyDesc))) return st;
+  if (int st = ctx->d_desc2.reserve(n * sizeof(CopyDesc))) return st;
+  CopyDesc *h = ctx->h_desc.as<CopyDesc>();
+  for (size_t i = 0; i < n; i++) { h[i].src = d_slot[i]; h[i].dst = ctx->d_out.as<uint8_t>() + off[i]; h[i].len = len[i]; }
+  ZB_CUDA(ctx, cudaMemcpyAsync(ctx->d_desc2.p, h, n * sizeof(CopyDesc), cudaMemcpyHostToDevice, ctx->stream));
+  return gather_launch(ctx, ctx->d_desc2.as<CopyDesc>(), (uint32_t)n);
+}
+
+}  // namespace
+
+int gather_launch(zipc_b200_ctx *ctx, const CopyDesc *d_descs, uint32_t n) {
+  if (!n) return ZIPC_OK;
+  uint32_t grid = std::min<uint32_t>(n, (uint32_t)ctx->sm_count * 8);
+  gather_kernel<<<grid, 256, 0, ctx->stream>>>(d_descs, n);
+  ctx->launches++;
+  ZB_CUDA(ctx, cudaGetLastError());
+  return ZIPC_OK;
+}
+
+}  // namespace zb
+
+using namespace zb;
+
 extern "C" {
-int zipc_b200_zip_extract_batch(zipc_b200_ctx *, const zipc_b200_member *, size_t, void *, size_t, size_t *, size_t *,
-                                size_t *, uint32_t *, int *) { return ZIPC_ERR_INVALID_ARG; }
-int zipc_b200_zip_deflate_archive(zipc_b200_ctx *, int, size_t, const char *const *, const uint32_t *, const void *const *,
-                                  const size_t *, const int32_t *, const int64_t *, const char *, void *, size_t, size_t *) {
-  return ZIPC_ERR_INVALID_ARG;
+
+size_t zipc_b200_deflate_bound(size_t src_len) { return src_len + 6 * (src_len / 61440 + 2) + 16; }
+
+int zipc_b200_deflate_batch(zipc_b200_ctx *ctx, int level, int ck, int adler_mode, size_t n, const void *const *src,
+                            const size_t *src_len, void *dst, size_t dst_cap, size_t *dst_need, size_t *dst_off,
+                            size_t *dst_len, uint32_t *checksum, int *status) {
+  if (!ctx || level < 0 || level > 3 || ck < 0 || ck > 2 || (n && (!src || !src_len || !dst_off || !dst_len || !status)))
+    return ZIPC_ERR_INVALID_ARG;
+  if (dst_need) *dst_need = 0;
+  if (!n) return ZIPC_OK;
+  DeviceGuard g(ctx->device);
+  std::vector<const uint8_t *> d_src;
+  if (int st = upload_ranges(ctx, n, src, src_len, d_src)) return st;
+  std::vector<uint8_t *> d_slot;
+  std::vector<size_t> cap;
+  if (int st = make_slots(ctx, n, src_len, d_slot, cap)) return st;
+  if (int st = deflate_run(ctx, level, ck, adler_mode, n, d_src, src_len, d_slot, cap, dst_len, checksum, status)) return st;
+  std::vector<size_t> off(n);
+  size_t total = 0;
+  for (size_t i = 0; i < n; i++) { off[i] = total; total += align_up(dst_len[i], 16); }
+  if (int st = compact(ctx, n, d_slot, dst_len, off, total)) return st;
+  ctx->last_off = off; ctx->last_len.assign(dst_len, dst_len + n); ctx->last_total = total;
+  for (size_t i = 0; i < n; i++) dst_off[i] = off[i];
+  if (dst_need) *dst_need = total;
+  if (!dst || dst_cap < total) { ZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); return ZIPC_ERR_DST_TOO_SMALL; }
+  return d2h(ctx, dst, ctx->d_out.p, total);
 }
+
+int zipc_b200_deflate_batch_dev(zipc_b200_ctx *ctx, int level, int ck, int adler_mode, size_t n, const void *d_src_v,
+                                const size_t *src_off, const size_t *src_len, void *d_dst_v, const size_t *dst_off,
+                                const size_t *dst_cap_each, size_t *dst_len, uint32_t *checksum, int *status) {
+  if (!ctx || level < 0 || level > 3 || ck < 0 || ck > 2 ||
+      (n && (!d_src_v || !src_off || !src_len || !d_dst_v || !dst_off || !dst_cap_each || !dst_len || !status)))
+    return ZIPC_ERR_INVALID_ARG;
+  if (!n) return ZIPC_OK;
+  DeviceGuard g(ctx->device);
+  std::vector<const uint8_t *> d_src(n);
+  std::vector<uint8_t *> d_slot(n);
+  std::vector<size_t> cap(n);
+  for (size_t i = 0; i < n; i++) {
+    d_src[i] = static_cast<const uint8_t *>(d_src_v) + src_off[i];
+    d_slot[i] = static_cast<uint8_t *>(d_dst_v) + dst_off[i];
+    if ((uintptr_t)d_slot[i] & 3) return ZIPC_ERR_INVALID_ARG;  // output slots are written as 32-bit words
+    cap[i] = dst_cap_each[i];
+  }
+  return deflate_run(ctx, level, ck, adler_mode, n, d_src, src_len, d_slot, cap, dst_len, checksum, status);
 }
+
+int zipc_b200_zlib_compress_batch(zipc_b200_ctx *ctx, int level, int adler_mode, size_t n, const void *const *src,
+                                  const size_t *src_len, void *dst, size_t dst_cap, size_t *dst_need, size_t *dst_off,
+                                  size_t *dst_len, uint32_t *adler, int *status) {
+  if (!ctx || level < 0 || level > 3 || (n && (!src || !src_len || !dst_off || !dst_len || !status)))
+    return ZIPC_ERR_INVALID_ARG;
+  if (dst_need) *dst_need = 0;
+  if (!n) return ZIPC_OK;
+  DeviceGuard g(ctx->device);
+  std::vector<const uint8_t *> d_src;
+  if (int st = upload_ranges(ctx, n, src, src_len, d_src)) return st;
+  std::vector<uint8_t *> d_slot;
+  std::vector<size_t> cap;
+  if (int st = make_slots(ctx, n, src_len, d_slot, cap)) return st;
+  std::vector<uint32_t> ad(n);
+  if (int st = deflate_run(ctx, level, ZIPC_CK_ADLER32, adler_mode, n, d_src, src_len, d_slot, cap, dst_len, ad.data(), status)) return st;
+  // framing: 2 header bytes, body, big-endian Adler-32 (reference :1264-1277)
+  std::vector<size_t> off(n), body_off(n);
+  size_t total = 0;
+  for (size_t i = 0; i < n; i++) { off[i] = total; body_off[i] = total + 2; total += align_up(dst_len[i] + 6, 16); }
+  if (int st = compact(ctx, n, d_slot, dst_len, body_off, total)) return st;
+  std::vector<size_t> flen(n);
+  for (size_t i = 0; i < n; i++) { flen[i] = dst_len[i] + 6; dst_off[i] = off[i]; }
+  ctx->last_off = off; ctx->last_len = flen; ctx->last_total = total;
+  // header and trailer bytes are written on the device copy so that fetch() sees complete streams
+  {
+    const unsigned cmf = 0x78, hdr = (cmf << 8) | ((unsigned)level << 6), flg = (hdr + 31 - hdr % 31) & 0xFF;
+    if (int st = ctx->h_res.reserve(n * 8)) return st;
+    uint8_t *hb = ctx->h_res.as<uint8_t>();
+    for (size_t i = 0; i < n; i++) {
+      hb[8 * i] = (uint8_t)cmf; hb[8 * i + 1] = (uint8_t)flg;
+      hb[8 * i + 2] = (uint8_t)(ad[i] >> 24); hb[8 * i + 3] = (uint8_t)(ad[i] >> 16);
+      hb[8 * i + 4] = (uint8_t)(ad[i] >> 8); hb[8 * i + 5] = (uint8_t)ad[i];
+    }
+    if (int st = ctx->d_res.reserve(n * 8)) return st;
+    ZB_CUDA(ctx, cudaMemcpyAsync(ctx->d_res.p, hb, n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    if (int st = ctx->h_desc.reserve(2 * n * sizeof(CopyDesc))) return st;
+    if (int st = ctx->d_desc.reserve(2 * n * sizeof(CopyDesc))) return st;
+    CopyDesc *h = ctx->h_desc.as<CopyDesc>();
+    for (size_t i = 0; i < n; i++) {
+      h[2 * i] = CopyDesc{ctx->d_res.as<uint8_t>() + 8 * i, ctx->d_out.as<uint8_t>() + off[i], 2};
+      h[2 * i + 1] = CopyDesc{ctx->d_res.as<uint8_t>() + 8 * i + 2, ctx->d_out.as<uint8_t>() + off[i] + 2 + dst_len[i], 4};
+    }
+    ZB_CUDA(ctx, cudaMemcpyAsync(ctx->d_desc.p, h, 2 * n * sizeof(CopyDesc), cudaMemcpyHostToDevice, ctx->stream));
+    if (int st = gather_launch(ctx, ctx->d_desc.as<CopyDesc>(), (uint32_t)(2 * n))) return st;
+  }
+  for (size_t i = 0; i < n; i++) { dst_len[i] = flen[i]; if (adler) adler[i] = ad[i]; }
+  if (dst_need) *dst_need = total;
+  if (!dst || dst_cap < total) { ZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); return ZIPC_ERR_DST_TOO_SMALL; }
+  return d2h(ctx, dst, ctx->d_out.p, total);
+}
+
+// ---- archive layer ---------------------------------------------------------------------------------------
+int zipc_b200_zip_extract_batch(zipc_b200_ctx *ctx, const zipc_b200_member *ms, size_t n, void *dst, size_t dst_cap,
+                                size_t *dst_need, size_t *dst_off, size_t *dst_len, uint32_t *found, int *status) {
+  if (!ctx || (n && (!ms || !dst_off || !dst_len || !status))) return ZIPC_ERR_INVALID_ARG;
+  if (dst_need) *dst_need = 0;
+  if (!n) return ZIPC_OK;
+  DeviceGuard g(ctx->device);
+  // classify (reference zipc.ml:205-217): encrypted -> error; Stored / Deflate handled; anything else -> error
+  std::vector<const void *> src(n, nullptr);
+  std::vector<size_t> slen(n, 0), cap(n, 0);
+  std::vector<int> kind(n, 0);  // 0 skip, 1 stored, 2 deflate
+  for (size_t i = 0; i < n; i++) {
+    const zipc_b200_member &m = ms[i];
+    status[i] = ZIPC_OK; dst_len[i] = 0;
+    if (found) found[i] = 0;
+    if (m.is_dir) continue;
+    if (m.gp_flags & 1) { status[i] = ZIPC_ERR_ZIP_ENCRYPTED; continue; }
+    if (m.compression != 0 && m.compression != 8) { status[i] = ZIPC_ERR_ZIP_FORMAT; continue; }
+    kind[i] = m.compression == 0 ? 1 : 2;
+    src[i] = m.compressed_bytes + m.start;
+    slen[i] = (size_t)m.compressed_size;
+    cap[i] = kind[i] == 1 ? (size_t)m.compressed_size : (size_t)m.decompressed_size;
+  }
+  std::vector<const uint8_t *> d_src;
+  if (int st = upload_ranges(ctx, n, src.data(), slen.data(), d_src)) return st;
+  std::vector<size_t> off(n);
+  size_t total = 0;
+  for (size_t i = 0; i < n; i++) { off[i] = total; total += align_up(cap[i], 16); }
+  if (int st = ctx->d_out.reserve(total + 64)) return st;
+  // deflate members through the inflate kernel (with CRC-32 of the output)
+  std::vector<uint32_t> idx;
+  for (size_t i = 0; i < n; i++) if (kind[i] == 2) idx.push_back((uint32_t)i);
+  if (!idx.empty()) {
+    size_t k = idx.size();
+    std::vector<const uint8_t *> s2(k);
+    std::vector<uint8_t *> d2(k);
+    std::vector<size_t> l2(k), c2(k), ol(k);
+    std::vector<uint32_t> ck(k);
+    std::vector<int> st2(k);
+    for (size_t j = 0; j < k; j++) { s2[j] = d_src[idx[j]]; d2[j] = ctx->d_out.as<uint8_t>() + off[idx[j]]; l2[j] = slen[idx[j]]; c2[j] = cap[idx[j]]; }
+    if (int st = inflate_core(ctx, ZIPC_CK_CRC32, 0, k, s2, l2.data(), d2, c2, false, ol.data(), ck.data(), st2.data())) return st;
+    for (size_t j = 0; j < k; j++) {
+      size_t i = idx[j];
+      status[i] = st2[j]; dst_len[i] = ol[j];
+      if (found) found[i] = ck[j];
+      if (st2[j] == ZIPC_OK && ck[j] != ms[i].crc32) status[i] = ZIPC_ERR_CHECKSUM;
+    }
+  }
+  // stored members: device copy + CRC-32
+  idx.clear();
+  for (size_t i = 0; i < n; i++) if (kind[i] == 1) idx.push_back((uint32_t)i);
+  if (!idx.empty()) {
+    size_t k = idx.size();
+    if (int st = ctx->h_desc.reserve(k * (sizeof(CopyDesc) + sizeof(CrcSeg)))) return st;
+    if (int st = ctx->d_desc2.reserve(k * (sizeof(CopyDesc) + sizeof(CrcSeg) + 4))) return st;
+    CopyDesc *hc = ctx->h_desc.as<CopyDesc>();
+    CrcSeg *hs = reinterpret_cast<CrcSeg *>(hc + k);
+    for (size_t j = 0; j < k; j++) {
+      size_t i = idx[j];
+      hc[j] = CopyDesc{d_src[i], ctx->d_out.as<uint8_t>() + off[i], slen[i]};
+      hs[j].ptr = d_src[i]; hs[j].len = slen[i]; hs[j].init = 0xFFFFFFFFu; hs[j]._pad = 0;
+    }
+    CopyDesc *dc = ctx->d_desc2.as<CopyDesc>();
+    CrcSeg *ds = reinterpret_cast<CrcSeg *>(dc + k);
+    uint32_t *dck = reinterpret_cast<uint32_t *>(ds + k);
+    ZB_CUDA(ctx, cudaMemcpyAsync(dc, hc, k * (sizeof(CopyDesc) + sizeof(CrcSeg)), cudaMemcpyHostToDevice, ctx->stream));
+    if (int st = gather_launch(ctx, dc, (uint32_t)k)) return st;
+    if (int st = crc32_launch_segments(ctx, ds, (uint32_t)k, dck)) return st;
+    std::vector<uint32_t> ck(k);
+    ZB_CUDA(ctx, cudaMemcpyAsync(ck.data(), dck, k * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    ZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (size_t j = 0; j < k; j++) {
+      size_t i = idx[j];
+      uint32_t c = ck[j] ^ 0xFFFFFFFFu;
+      dst_len[i] = slen[i];
+      if (found) found[i] = c;
+      if (c != ms[i].crc32) status[i] = ZIPC_ERR_CHECKSUM;
+    }
+  }
+  ctx->last_off = off; ctx->last_len.assign(dst_len, dst_len + n); ctx->last_total = total;
+  for (size_t i = 0; i < n; i++) dst_off[i] = off[i];
+  if (dst_need) *dst_need = total;
+  if (!dst || dst_cap < total) return ZIPC_ERR_DST_TOO_SMALL;
+  return d2h(ctx, dst, ctx->d_out.p, total);
+}
+
+int zipc_b200_zip_deflate_archive(zipc_b200_ctx *ctx, int level, size_t n, const char *const *paths,
+                                  const uint32_t *path_len, const void *const *src, const size_t *src_len,
+                                  const int32_t *mode, const int64_t *mtime, const char *first, void *out,
+                                  size_t out_cap, size_t *out_len) {
+  if (!ctx || level < 0 || level > 3 || !out_len || (n && (!paths || !path_len || !src || !src_len)))
+    return ZIPC_ERR_INVALID_ARG;
+  DeviceGuard g(ctx->device);
+  if (n > 0xFFFF) return ZIPC_ERR_ZIP_COUNT;  // zipc.ml:574
+  // Member.make path rules (zipc.ml:244-255): backslashes become slashes; sizes are checked by File.make
+  std::vector<std::string> norm(n);
+  for (size_t i = 0; i < n; i++) {
+    if (path_len[i] > 0xFFFF) return ZIPC_ERR_ZIP_PATH_LEN;
+    if (src_len[i] > 0xFFFFFFFFull) return ZIPC_ERR_ZIP_SIZE;
+    norm[i].assign(paths[i], path_len[i]);
+    for (char &c : norm[i]) if (c == '\\') c = '/';
+  }
+  std::vector<const uint8_t *> d_src;
+  if (int st = upload_ranges(ctx, n, src, src_len, d_src)) return st;
+  std::vector<uint8_t *> d_slot;
+  std::vector<size_t> cap;
+  if (int st = make_slots(ctx, n, src_len, d_slot, cap)) return st;
+  std::vector<size_t> clen(n);
+  std::vector<uint32_t> crc(n);
+  std::vector<int> st_m(n);
+  if (int st = deflate_run(ctx, level, ZIPC_CK_CRC32, 0, n, d_src, src_len, d_slot, cap, clen.data(), crc.data(), st_m.data())) return st;
+  for (size_t i = 0; i < n; i++) if (st_m[i]) return st_m[i];
+  std::vector<zipc_b200_member> ms(n);
+  for (size_t i = 0; i < n; i++) {
+    zipc_b200_member &m = ms[i];
+    std::memset(&m, 0, sizeof m);
+    m.path = norm[i].data(); m.path_len = (uint32_t)norm[i].size();
+    m.mode = mode ? mode[i] : 0644;
+    m.mtime = mtime ? std::max<int64_t>(mtime[i], 315532800) : 315532800;
+    m.version_made_by = 0x314; m.version_needed = 20; m.gp_flags = 0x800;  // File.make defaults (zipc.ml:138-143)
+    m.compression = 8;
+    m.compressed_size = clen[i]; m.decompressed_size = src_len[i]; m.crc32 = crc[i];
+  }
+  // layout first, then the GPU gathers every payload to its archive offset, then headers on the host
+  std::vector<uint64_t> poff(n, ~0ull);  // members shadowed by a later duplicate path keep ~0
+  size_t total = 0;
+  if (int st = zip_assemble_impl(ms.data(), n, first, nullptr, 0, &total, false, poff.data())) return st;
+  *out_len = total;
+  if (!out || out_cap < total) return ZIPC_ERR_DST_TOO_SMALL;
+  std::vector<size_t> off(n), glen(n);
+  for (size_t i = 0; i < n; i++) { bool in = poff[i] != ~0ull; off[i] = in ? (size_t)poff[i] : 0; glen[i] = in ? clen[i] : 0; }
+  if (int st = compact(ctx, n, d_slot, glen.data(), off, total)) return st;
+  if (int st = d2h(ctx, out, ctx->d_out.p, total)) return st;
+  return zip_assemble_impl(ms.data(), n, first, out, out_cap, out_len, false, nullptr);
+}
+
+}  // extern "C"
