@@ -88,6 +88,11 @@ const char *zipc_b200_last_error(const zipc_b200_ctx *ctx);
 void *zipc_b200_ctx_stream(zipc_b200_ctx *ctx);
 /* Number of kernels this ctx has launched so far (bench.py's gpu_launches). */
 uint64_t zipc_b200_ctx_launches(const zipc_b200_ctx *ctx);
+/* Diagnostics: when enabled, every call brackets its dominant kernel (CRC tiles / Adler chunks / inflate /
+ * deflate) with CUDA events on the ctx stream; zipc_b200_ctx_kernel_ms returns the duration of the last
+ * bracketed kernel in milliseconds (it waits for that kernel), or a negative value if none. */
+void zipc_b200_ctx_profile(zipc_b200_ctx *ctx, int enable);
+float zipc_b200_ctx_kernel_ms(zipc_b200_ctx *ctx);
 /* Pinned host memory helpers: buffers from here are DMA'd directly, others are staged. */
 int zipc_b200_host_alloc(size_t bytes, void **ptr);
 void zipc_b200_host_free(void *ptr);

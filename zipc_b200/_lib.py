@@ -24,6 +24,7 @@ SIZE_UNKNOWN = C.c_size_t(-1).value
 EXPORTS = [
     "zipc_b200_version", "zipc_b200_strerror", "zipc_b200_device_count", "zipc_b200_ctx_create",
     "zipc_b200_ctx_destroy", "zipc_b200_last_error", "zipc_b200_ctx_stream", "zipc_b200_ctx_launches",
+    "zipc_b200_ctx_profile", "zipc_b200_ctx_kernel_ms",
     "zipc_b200_host_alloc", "zipc_b200_host_free", "zipc_b200_dev_alloc", "zipc_b200_dev_free",
     "zipc_b200_memcpy_h2d", "zipc_b200_memcpy_d2h", "zipc_b200_sync",
     "zipc_b200_crc32", "zipc_b200_crc32_dev", "zipc_b200_crc32_dev_async", "zipc_b200_adler32",
@@ -58,6 +59,8 @@ def _declare(L):
         "zipc_b200_last_error": (C.c_char_p, [vp]),
         "zipc_b200_ctx_stream": (vp, [vp]),
         "zipc_b200_ctx_launches": (u64, [vp]),
+        "zipc_b200_ctx_profile": (None, [vp, i32]),
+        "zipc_b200_ctx_kernel_ms": (C.c_float, [vp]),
         "zipc_b200_host_alloc": (i32, [sz, vpp]),
         "zipc_b200_host_free": (None, [vp]),
         "zipc_b200_dev_alloc": (i32, [vp, sz, vpp]),

@@ -16,6 +16,7 @@
 //
 // Algorithmic bytes per launch: N.  Roofline: HBM.
 #include "common.cuh"
+#include "adler_core.cuh"
 
 namespace zb {
 namespace {
@@ -23,48 +24,6 @@ namespace {
 constexpr int kThreads = 512;
 constexpr int kWarps = kThreads / 32;
 constexpr uint32_t kChunk = 5552;
-
-__device__ __forceinline__ uint4 ldg_stream(const uint4 *p) {
-  uint4 v;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
-               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
-               : "l"(p));
-  return v;
-}
-
-// (A, B) of one range [ptr, ptr+n), n <= 5552, valid in lane 0
-__device__ __forceinline__ void adler_range_warp(const uint8_t *ptr, uint32_t n, int lane, uint32_t &A, uint32_t &B) {
-  uint32_t a = 0, b = 0;
-  uint32_t head = (uint32_t)((16 - ((uintptr_t)ptr & 15)) & 15);
-  if (head > n) head = n;
-  uint32_t nblk = (n - head) >> 4;
-  uint32_t tail_off = head + (nblk << 4);
-  if (lane == 0) {  // ragged ends, bytewise
-    for (uint32_t i = 0; i < head; i++) { uint32_t v = ptr[i]; a += v; b += (n - i) * v; }
-    for (uint32_t i = tail_off; i < n; i++) { uint32_t v = ptr[i]; a += v; b += (n - i) * v; }
-  }
-  const uint4 *p = reinterpret_cast<const uint4 *>(ptr + head);
-  for (uint32_t j = lane; j < nblk; j += 32) {
-    uint4 w = ldg_stream(p + j);
-    uint32_t sa = __dp4a(w.x, 0x01010101u, 0u);
-    sa = __dp4a(w.y, 0x01010101u, sa);
-    sa = __dp4a(w.z, 0x01010101u, sa);
-    sa = __dp4a(w.w, 0x01010101u, sa);
-    uint32_t sw = __dp4a(w.x, 0x0D0E0F10u, 0u);  // weights 16,15,14,13 for bytes 0..3
-    sw = __dp4a(w.y, 0x090A0B0Cu, sw);
-    sw = __dp4a(w.z, 0x05060708u, sw);
-    sw = __dp4a(w.w, 0x01020304u, sw);
-    uint32_t o = head + (j << 4);           // offset of the block in the range
-    a += sa;
-    b += (n - o - 16) * sa + sw;
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    a += __shfl_xor_sync(0xffffffffu, a, o);
-    b += __shfl_xor_sync(0xffffffffu, b, o);
-  }
-  A = a; B = b;
-}
 
 // chunk c of a single buffer: c == 0 -> [0, first), else [first + (c-1)*5552, +5552)   (first may
 // equal 5552 when len is a multiple of it; an empty first round is a no-op and is skipped)
@@ -75,7 +34,7 @@ adler_chunks_kernel(const uint8_t *__restrict__ src, uint32_t first, uint32_t nc
     uint64_t off = c == 0 ? 0 : (uint64_t)first + (uint64_t)(c - 1) * kChunk;
     uint32_t n = c == 0 ? first : kChunk;
     uint32_t A, B;
-    adler_range_warp(src + off, n, lane, A, B);
+    adler_range_warp<false>(src + off, n, lane, A, B);
     if (lane == 0) ab[c] = make_uint2(A, B);
   }
 }
@@ -86,27 +45,12 @@ adler_ranges_kernel(const AdlerSeg *__restrict__ segs, uint32_t nseg, uint2 *__r
   const int lane = threadIdx.x & 31;
   for (uint32_t c = blockIdx.x * kWarps + (threadIdx.x >> 5); c < nseg; c += gridDim.x * kWarps) {
     uint32_t A, B;
-    adler_range_warp(segs[c].ptr, segs[c].len, lane, A, B);
+    adler_range_warp<false>(segs[c].ptr, segs[c].len, lane, A, B);
     if (lane == 0) ab[c] = make_uint2(A, B);
   }
 }
 
 }  // namespace
-
-// The chunk recurrence of zipc_deflate.ml:181-197 over per-chunk partial sums.
-static inline void adler_fold_step(uint32_t &s1, uint32_t &s2, uint32_t n, uint32_t A, uint32_t B, int mode) {
-  uint32_t t2 = s2 + n * s1 + B;  // all int32-wrapping in the reference
-  uint32_t t1 = s1 + A;
-  if (mode == ZIPC_ADLER_REF_COMPAT) {
-    s1 = (uint32_t)((int32_t)t1 % 65521);
-    s2 = (uint32_t)((int32_t)t2 % 65521);
-  } else {
-    // RFC 1950: exact arithmetic.  n*s1 + B + s2 can exceed 2^32, so widen.
-    uint64_t w2 = (uint64_t)s2 + (uint64_t)n * s1 + B;
-    s1 = t1 % 65521u;
-    s2 = (uint32_t)(w2 % 65521u);
-  }
-}
 
 int adler32_launch_buffer(zipc_b200_ctx *ctx, const uint8_t *d_src, uint64_t len, int mode, uint32_t *h_out) {
   if (len == 0) { *h_out = 1; return ZIPC_OK; }
@@ -121,7 +65,10 @@ int adler32_launch_buffer(zipc_b200_ctx *ctx, const uint8_t *d_src, uint64_t len
   uint32_t grid = (nchunks + kWarps - 1) / kWarps;
   uint32_t maxgrid = (uint32_t)ctx->sm_count * 4;
   if (grid > maxgrid) grid = maxgrid;
-  adler_chunks_kernel<<<grid, kThreads, 0, ctx->stream>>>(d_src, first, nchunks, d_ab);
+  {
+    KernelTimer kt(ctx);
+    adler_chunks_kernel<<<grid, kThreads, 0, ctx->stream>>>(d_src, first, nchunks, d_ab);
+  }
   ctx->launches++;
   ZB_CUDA(ctx, cudaGetLastError());
   uint2 *h_ab = ctx->h_res.as<uint2>();

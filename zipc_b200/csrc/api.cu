@@ -214,7 +214,8 @@ int inflate_core(zipc_b200_ctx *ctx, int ck, int adler_mode, size_t n, const std
   InflateResult *dr = ctx->d_res.as<InflateResult>();
   uint32_t *dck = reinterpret_cast<uint32_t *>(dr + n);
   ZB_CUDA(ctx, cudaMemcpyAsync(dt, ht, n * sizeof(InflateTask), cudaMemcpyHostToDevice, ctx->stream));
-  if (int st = inflate_launch(ctx, dt, (uint32_t)n, dr, count_only)) return st;
+  const bool adler = !count_only && ck == ZIPC_CK_ADLER32;
+  if (int st = inflate_launch(ctx, dt, (uint32_t)n, dr, count_only, adler ? adler_mode : -1)) return st;
   bool crc = !count_only && ck == ZIPC_CK_CRC32;
   if (crc) {
     make_crc_segs_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(dt, dr, (uint32_t)n, dsegs);
@@ -234,14 +235,8 @@ int inflate_core(zipc_b200_ctx *ctx, int ck, int adler_mode, size_t n, const std
     out_len[i] = (size_t)hr[k].out_len;
     if (checksum) checksum[i] = crc && hr[k].status == ZIPC_OK ? hck[k] : 0u;
   }
-  if (!count_only && ck == ZIPC_CK_ADLER32 && checksum) {
-    std::vector<const uint8_t *> p(n);
-    std::vector<uint64_t> l(n);
-    for (size_t i = 0; i < n; i++) { p[i] = d_dst[i]; l[i] = status[i] == ZIPC_OK ? out_len[i] : 0; }
-    std::vector<uint32_t> a(n);
-    if (int st = adler32_ranges(ctx, p.data(), l.data(), n, adler_mode, a.data())) return st;
-    for (size_t i = 0; i < n; i++) checksum[i] = status[i] == ZIPC_OK ? a[i] : 0u;
-  }
+  if (adler && checksum)  // folded block by block inside the kernel (reference :682-690)
+    for (size_t k = 0; k < n; k++) checksum[order[k]] = hr[k].status == ZIPC_OK ? hr[k]._pad : 0u;
   return ZIPC_OK;
 }
 
@@ -297,6 +292,7 @@ void zipc_b200_ctx_destroy(zipc_b200_ctx *ctx) {
   ctx->d_scratch.release(); ctx->d_scratch2.release(); ctx->d_small.release(); ctx->d_slots.release(); ctx->d_desc2.release();
   ctx->h_stage.release(); ctx->h_res.release(); ctx->h_desc.release();
   if (ctx->d_crc_tabs) cudaFree(ctx->d_crc_tabs);
+  if (ctx->ev0) { cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); }
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -304,6 +300,23 @@ void zipc_b200_ctx_destroy(zipc_b200_ctx *ctx) {
 const char *zipc_b200_last_error(const zipc_b200_ctx *ctx) { return ctx ? ctx->last_error.c_str() : ""; }
 void *zipc_b200_ctx_stream(zipc_b200_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
 uint64_t zipc_b200_ctx_launches(const zipc_b200_ctx *ctx) { return ctx ? ctx->launches : 0; }
+void zipc_b200_ctx_profile(zipc_b200_ctx *ctx, int enable) {
+  if (!ctx) return;
+  DeviceGuard g(ctx->device);
+  if (enable && !ctx->ev0) { cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1); }
+  ctx->profile = enable != 0;
+  ctx->ev_valid = false;
+}
+float zipc_b200_ctx_kernel_ms(zipc_b200_ctx *ctx) {
+  if (!ctx || !ctx->ev_valid) return -1.0f;
+  DeviceGuard g(ctx->device);
+  float ms = -1.0f;
+  if (cudaEventSynchronize(ctx->ev1) != cudaSuccess || cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) != cudaSuccess) {
+    cudaGetLastError();
+    return -1.0f;
+  }
+  return ms;
+}
 
 int zipc_b200_host_alloc(size_t bytes, void **ptr) {
   if (!ptr) return ZIPC_ERR_INVALID_ARG;

@@ -71,7 +71,7 @@ struct InflateTask {  // one deflate stream to inflate
 struct InflateResult {
   uint64_t out_len;
   uint32_t status;
-  uint32_t _pad;
+  uint32_t _pad;      // fused Adler-32 of the output when the kernel was asked for it
 };
 
 struct DeflateTask {  // one input to deflate (a ZIP member or an independent segment)
@@ -101,6 +101,9 @@ struct zipc_b200_ctx {
   cudaStream_t stream = nullptr;
   std::string last_error;
   uint64_t launches = 0;
+  bool profile = false;           // bracket the dominant kernel of each call with events
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  bool ev_valid = false;
 
   // constant tables on the device
   uint32_t *d_crc_tabs = nullptr;   // see crc32.cu: strided[4][256] | std[4][256] | xp16[32]
@@ -121,6 +124,13 @@ int set_cuda_error(zipc_b200_ctx *ctx, cudaError_t e, const char *what);
     cudaError_t _e = (call);                                      \
     if (_e != cudaSuccess) return zb::set_cuda_error(ctx, _e, #call); \
   } while (0)
+
+// brackets one kernel launch with the ctx's profiling events (no-op unless enabled)
+struct KernelTimer {
+  zipc_b200_ctx *c;
+  explicit KernelTimer(zipc_b200_ctx *ctx) : c(ctx) { if (c->profile) cudaEventRecord(c->ev0, c->stream); }
+  ~KernelTimer() { if (c->profile) { cudaEventRecord(c->ev1, c->stream); c->ev_valid = true; } }
+};
 
 // RAII device guard
 struct DeviceGuard {
@@ -158,6 +168,6 @@ int zip_assemble_impl(const zipc_b200_member *ms, size_t n, const char *first, v
                       size_t *out_len, bool copy_payload, uint64_t *payload_off);
 // inflate.cu
 int inflate_launch(zipc_b200_ctx *ctx, const InflateTask *d_tasks, uint32_t n, InflateResult *d_results,
-                   bool count_only);
+                   bool count_only, int adler_mode /* -1: none */);
 
 }  // namespace zb

@@ -95,10 +95,25 @@ __device__ __forceinline__ uint4 ldg_stream(const uint4 *p) {
   return v;
 }
 
-// one word through the lane-replicated strided tables; rep = table base + lane
-__device__ __forceinline__ uint32_t step_rep(const uint32_t *__restrict__ rep, uint32_t u) {
-  return rep[3 * 8192 + ((u & 0xffu) << 5)] ^ rep[2 * 8192 + (((u >> 8) & 0xffu) << 5)] ^
-         rep[1 * 8192 + (((u >> 16) & 0xffu) << 5)] ^ rep[(u >> 24) << 5];
+// Shift amounts as multipliers (2^31, 2^23, 2^15) passed at run time: u >> s becomes the high half of
+// u * 2^(32-s), i.e. IMAD.HI on the FMA pipe.  The profile of the first version showed the ALU pipe
+// (LOP3/SHF) at 92 % and the FMA pipe idle; moving the four shifts over removes that bound.
+struct ShiftMul { uint32_t m1, m9, m17; };
+__device__ __forceinline__ uint32_t mulhi_rt(uint32_t a, uint32_t b) {
+  uint32_t r;
+  asm("mul.hi.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
+// one word through the lane-replicated strided tables.  rep is the (warp-uniform) table base, lane4 = lane * 4:
+// each index is "(byte * 128) | lane4", one LOP3 after the shift, and the base rides in the LDS address.
+__device__ __forceinline__ uint32_t step_rep(const uint32_t *__restrict__ rep, uint32_t lane4, uint32_t u, const ShiftMul k) {
+  const char *t = reinterpret_cast<const char *>(rep);
+  uint32_t i0 = ((u * 128u) & 0x7f80u) | lane4;            // (u & 0xff) * 128
+  uint32_t i1 = (mulhi_rt(u, k.m1) & 0x7f80u) | lane4;     // ((u >> 8) & 0xff) * 128
+  uint32_t i2 = (mulhi_rt(u, k.m9) & 0x7f80u) | lane4;     // ((u >> 16) & 0xff) * 128
+  uint32_t i3 = (mulhi_rt(u, k.m17) & 0x7f80u) | lane4;    // (u >> 24) * 128
+  return *reinterpret_cast<const uint32_t *>(t + 3 * 32768 + i0) ^ *reinterpret_cast<const uint32_t *>(t + 2 * 32768 + i1) ^
+         *reinterpret_cast<const uint32_t *>(t + 1 * 32768 + i2) ^ *reinterpret_cast<const uint32_t *>(t + i3);
 }
 // one word through the ordinary slice-by-4 tables (state valid right after the word)
 __device__ __forceinline__ uint32_t step_std(const uint32_t *__restrict__ st, uint32_t u) {
@@ -111,9 +126,10 @@ __device__ __forceinline__ uint32_t step_byte(const uint32_t *__restrict__ st, u
 
 // State after running seg.len bytes from seg.init; result valid in lane 0.
 __device__ uint32_t crc_segment_warp(const CrcSeg seg, int lane, const uint32_t *__restrict__ rep,
-                                     const uint32_t *__restrict__ st, const uint32_t *__restrict__ xp) {
+                                     const uint32_t *__restrict__ st, const uint32_t *__restrict__ xp, const ShiftMul sm) {
   const uint8_t *ptr = seg.ptr;
   uint64_t len = seg.len;
+  const uint32_t lane4 = (uint32_t)lane * 4u;
   if (len < 64) {  // tiny: one lane, bytewise
     uint32_t c = seg.init;
     if (lane == 0)
@@ -143,26 +159,26 @@ __device__ uint32_t crc_segment_warp(const CrcSeg seg, int lane, const uint32_t 
     for (int j = 0; j < 8; j++) w[j] = ldg_stream(p + 32 * (r + j));
 #pragma unroll
     for (int j = 0; j < 8; j++) {
-      c0 = step_rep(rep, c0 ^ w[j].x);
-      c1 = step_rep(rep, c1 ^ w[j].y);
-      c2 = step_rep(rep, c2 ^ w[j].z);
-      c3 = step_rep(rep, c3 ^ w[j].w);
+      c0 = step_rep(rep, lane4, c0 ^ w[j].x, sm);
+      c1 = step_rep(rep, lane4, c1 ^ w[j].y, sm);
+      c2 = step_rep(rep, lane4, c2 ^ w[j].z, sm);
+      c3 = step_rep(rep, lane4, c3 ^ w[j].w, sm);
     }
   }
   for (; r < R; r++) {
     uint4 w = ldg_stream(p + 32 * r);
-    c0 = step_rep(rep, c0 ^ w.x);
-    c1 = step_rep(rep, c1 ^ w.y);
-    c2 = step_rep(rep, c2 ^ w.z);
-    c3 = step_rep(rep, c3 ^ w.w);
+    c0 = step_rep(rep, lane4, c0 ^ w.x, sm);
+    c1 = step_rep(rep, lane4, c1 ^ w.y, sm);
+    c2 = step_rep(rep, lane4, c2 ^ w.z, sm);
+    c3 = step_rep(rep, lane4, c3 ^ w.w, sm);
   }
   bool has = false;
   if (rows >= 1) {  // row rows-1: last block of lanes >= k
     uint4 w = ldg_stream(p + 32 * (rows - 1));
     has = true;
     if (lane < k) {
-      c0 = step_rep(rep, c0 ^ w.x); c1 = step_rep(rep, c1 ^ w.y);
-      c2 = step_rep(rep, c2 ^ w.z); c3 = step_rep(rep, c3 ^ w.w);
+      c0 = step_rep(rep, lane4, c0 ^ w.x, sm); c1 = step_rep(rep, lane4, c1 ^ w.y, sm);
+      c2 = step_rep(rep, lane4, c2 ^ w.z, sm); c3 = step_rep(rep, lane4, c3 ^ w.w, sm);
     } else {
       c0 = step_std(st, c0 ^ w.x); c1 = step_std(st, c1 ^ w.y);
       c2 = step_std(st, c2 ^ w.z); c3 = step_std(st, c3 ^ w.w);
@@ -203,17 +219,17 @@ __device__ __forceinline__ void load_tables(const uint32_t *__restrict__ g_tabs,
 // Independent segments pulled from a queue, one warp each.
 __global__ void __launch_bounds__(kThreads, 1)
 crc32_segments_kernel(const CrcSeg *__restrict__ segs, uint32_t nseg, const uint32_t *__restrict__ g_tabs,
-                      uint32_t *__restrict__ states, unsigned int *__restrict__ queue) {
+                      uint32_t *__restrict__ states, unsigned int *__restrict__ queue, const ShiftMul sm) {
   extern __shared__ __align__(16) uint32_t smem[];
   load_tables(g_tabs, smem);
   const int lane = threadIdx.x & 31;
-  const uint32_t *rep = smem + lane, *st = smem + kRepWords, *xp = st + 1024;
+  const uint32_t *rep = smem, *st = smem + kRepWords, *xp = st + 1024;
   for (;;) {
     unsigned int s = 0;
     if (lane == 0) s = atomicAdd(queue, 1u);
     s = __shfl_sync(0xffffffffu, s, 0);
     if (s >= nseg) break;
-    uint32_t c = crc_segment_warp(segs[s], lane, rep, st, xp);
+    uint32_t c = crc_segment_warp(segs[s], lane, rep, st, xp, sm);
     if (lane == 0) states[s] = c;
   }
 }
@@ -222,18 +238,18 @@ crc32_segments_kernel(const CrcSeg *__restrict__ segs, uint32_t nseg, const uint
 // owns tile w.  Tile 0 starts from the CRC init value, the others from 0.
 __global__ void __launch_bounds__(kThreads, 1)
 crc32_tiles_kernel(const uint8_t *__restrict__ src, uint64_t len, uint64_t tile, uint32_t ntiles,
-                   const uint32_t *__restrict__ g_tabs, uint32_t *__restrict__ states) {
+                   const uint32_t *__restrict__ g_tabs, uint32_t *__restrict__ states, const ShiftMul sm) {
   extern __shared__ __align__(16) uint32_t smem[];
   load_tables(g_tabs, smem);
   const int lane = threadIdx.x & 31;
-  const uint32_t *rep = smem + lane, *st = smem + kRepWords, *xp = st + 1024;
+  const uint32_t *rep = smem, *st = smem + kRepWords, *xp = st + 1024;
   for (uint32_t t = blockIdx.x * kWarps + (threadIdx.x >> 5); t < ntiles; t += gridDim.x * kWarps) {
     CrcSeg seg;
     uint64_t off = (uint64_t)t * tile;
     seg.ptr = src + off;
     seg.len = len - off < tile ? len - off : tile;
     seg.init = t == 0 ? 0xFFFFFFFFu : 0u;
-    uint32_t c = crc_segment_warp(seg, lane, rep, st, xp);
+    uint32_t c = crc_segment_warp(seg, lane, rep, st, xp, sm);
     if (lane == 0) states[t] = c;
   }
 }
@@ -297,7 +313,7 @@ int crc32_launch_segments(zipc_b200_ctx *ctx, const CrcSeg *d_segs, uint32_t nse
   ZB_CUDA(ctx, cudaMemsetAsync(queue, 0, sizeof(unsigned int), ctx->stream));
   uint32_t grid = (nseg + kWarps - 1) / kWarps;
   if (grid > (uint32_t)ctx->sm_count) grid = (uint32_t)ctx->sm_count;
-  crc32_segments_kernel<<<grid, kThreads, kSmemBytes, ctx->stream>>>(d_segs, nseg, ctx->d_crc_tabs, d_states, queue);
+  crc32_segments_kernel<<<grid, kThreads, kSmemBytes, ctx->stream>>>(d_segs, nseg, ctx->d_crc_tabs, d_states, queue, ShiftMul{1u << 31, 1u << 23, 1u << 15});
   ctx->launches++;
   ZB_CUDA(ctx, cudaGetLastError());
   return ZIPC_OK;
@@ -323,7 +339,10 @@ int crc32_launch_buffer(zipc_b200_ctx *ctx, const uint8_t *d_src, uint64_t len, 
   if (int st = ctx->d_scratch2.reserve((size_t)(max_tiles + 1) * sizeof(uint32_t))) return st;
   uint32_t *d_states = ctx->d_scratch2.as<uint32_t>();
   uint32_t grid = (ntiles + kWarps - 1) / kWarps;
-  crc32_tiles_kernel<<<grid, kThreads, kSmemBytes, ctx->stream>>>(d_src, len, tile, ntiles, ctx->d_crc_tabs, d_states);
+  {
+    KernelTimer kt(ctx);
+    crc32_tiles_kernel<<<grid, kThreads, kSmemBytes, ctx->stream>>>(d_src, len, tile, ntiles, ctx->d_crc_tabs, d_states, ShiftMul{1u << 31, 1u << 23, 1u << 15});
+  }
   ctx->launches++;
   ZB_CUDA(ctx, cudaGetLastError());
   crc32_combine_tiles_kernel<<<1, kCombThreads, 0, ctx->stream>>>(d_states, F, G, gf_xpow8(last_len), cc, d_crc);

@@ -641,7 +641,10 @@ int deflate_launch(zipc_b200_ctx *ctx, const DeflateTask *d_tasks, uint32_t n, D
   if (int st = ctx->d_scratch.reserve(tok_bytes + 256)) return st;
   unsigned int *queue = reinterpret_cast<unsigned int *>(ctx->d_scratch.as<uint8_t>() + tok_bytes);
   ZB_CUDA(ctx, cudaMemsetAsync(queue, 0, sizeof(unsigned int), ctx->stream));
-  deflate_kernel<<<grid, THREADS, kSmemBytes, ctx->stream>>>(d_tasks, n, d_results, queue, ctx->d_scratch.as<uint32_t>(), level);
+  {
+    KernelTimer kt(ctx);
+    deflate_kernel<<<grid, THREADS, kSmemBytes, ctx->stream>>>(d_tasks, n, d_results, queue, ctx->d_scratch.as<uint32_t>(), level);
+  }
   ctx->launches++;
   ZB_CUDA(ctx, cudaGetLastError());
   return ZIPC_OK;

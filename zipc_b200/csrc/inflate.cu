@@ -25,6 +25,7 @@
 // Algorithmic bytes: C + U per stream (compressed read + uncompressed written).  The kernel is
 // issue/latency bound (serial bit parsing), not HBM bound: see DESIGN.md.
 #include "common.cuh"
+#include "adler_core.cuh"
 
 namespace zb {
 namespace {
@@ -219,7 +220,8 @@ __device__ void build_decoder_warp(WarpScratch &ws, int first, int n, int bits, 
 template <bool COUNT_ONLY>
 __global__ void __launch_bounds__(THREADS, 1)
 inflate_kernel(const InflateTask *__restrict__ tasks, uint32_t ntasks, InflateResult *__restrict__ results,
-               unsigned int *__restrict__ queue, uint16_t *__restrict__ g_syms) {
+               unsigned int *__restrict__ queue, uint16_t *__restrict__ g_syms, int adler_mode) {
+  // adler_mode: -1 = no checksum in this kernel, else ZIPC_ADLER_* (fused per-block Adler-32 of the output)
   extern __shared__ __align__(16) uint8_t smem_raw[];
   LaneTabs *tabs = reinterpret_cast<LaneTabs *>(smem_raw);                 // [WARPS*G] + fixed
   LaneTabs &fixed = tabs[WARPS * G];
@@ -265,6 +267,9 @@ inflate_kernel(const InflateTask *__restrict__ tasks, uint32_t ntasks, InflateRe
   uint32_t hlit = 0, hdist = 0;
   uint32_t stored_len = 0;
   const uint8_t *stored_src = nullptr;
+  uint32_t ad_state = 1;      // running Adler-32 (reference :558, :682-690)
+  uint64_t ad_from = 0;       // output offset up to which it is accounted
+  bool ad_pending = false;    // a block just ended: fold [ad_from, out_pos)
   const uint16_t *lit_lut = nullptr, *lit_cnt = nullptr, *dist_cnt = nullptr;
   const uint32_t *dist_lut = nullptr;
   const uint16_t *lit_syms = nullptr, *dist_syms = nullptr;
@@ -280,6 +285,7 @@ inflate_kernel(const InflateTask *__restrict__ tasks, uint32_t ntasks, InflateRe
         const InflateTask t = tasks[task];
         src = t.src; src_len = t.src_len; dst = t.dst; out_cap = t.dst_cap;
         out_pos = 0; status = ZIPC_OK; final_blk = false;
+        ad_state = 1; ad_from = 0; ad_pending = false;
         br.seek(src, src_len, 0);
         state = S_HDR;
       } else {
@@ -456,7 +462,7 @@ inflate_kernel(const InflateTask *__restrict__ tasks, uint32_t ntasks, InflateRe
         }
         if (kind == 6) {                                                    // end of block
           if (br.loaded > src_bits && br.consumed() > src_bits) { status = ZIPC_ERR_CORRUPTED; state = S_FINISH; }
-          else state = final_blk ? S_FINISH : S_HDR;
+          else { state = final_blk ? S_FINISH : S_HDR; ad_pending = true; }
           break;
         }
         uint32_t length = val + br.peek(kind);
@@ -608,14 +614,32 @@ inflate_kernel(const InflateTask *__restrict__ tasks, uint32_t ntasks, InflateRe
     if (state == S_STORED) {
       out_pos += stored_len;
       state = final_blk ? S_FINISH : S_HDR;
+      ad_pending = true;
     }
+
+    // ---- G: checksum of the block that just ended (reference inflated_block_crc, :682-690) ---------------------
+    // Adler-32 restarts its 5552-byte chunk grid at every block and, as written in the reference, reduces
+    // with a signed remainder, so it has to be folded block by block to stay bit-exact.
+    if (!COUNT_ONLY && adler_mode >= 0) {
+      uint32_t am = __ballot_sync(0xffffffffu, ad_pending);
+      while (am) {
+        int L = __ffs(am) - 1;
+        am &= am - 1;
+        unsigned long long p = __shfl_sync(0xffffffffu, (unsigned long long)(uintptr_t)(dst + ad_from), L);
+        unsigned long long n = __shfl_sync(0xffffffffu, (unsigned long long)(out_pos - ad_from), L);
+        uint32_t stt = __shfl_sync(0xffffffffu, ad_state, L);
+        uint32_t upd = adler_update_warp<true>(stt, reinterpret_cast<const uint8_t *>((uintptr_t)p), n, adler_mode, lane);
+        if (lane == L) { ad_state = upd; ad_from = out_pos; }
+      }
+    }
+    ad_pending = false;
 
     // ---- F: finished streams report ---------------------------------------------------------------------
     if (state == S_FINISH) {
       InflateResult r;
       r.out_len = status == ZIPC_OK ? out_pos : 0;
       r.status = status;
-      r._pad = 0;
+      r._pad = status == ZIPC_OK ? ad_state : 0;  // fused Adler-32 of the output (when requested)
       results[task] = r;
       state = S_IDLE;
     }
@@ -627,7 +651,7 @@ bool g_attr_set = false;
 }  // namespace
 
 int inflate_launch(zipc_b200_ctx *ctx, const InflateTask *d_tasks, uint32_t n, InflateResult *d_results,
-                   bool count_only) {
+                   bool count_only, int adler_mode) {
   if (n == 0) return ZIPC_OK;
   if (!g_attr_set) {
     ZB_CUDA(ctx, cudaFuncSetAttribute(inflate_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
@@ -644,10 +668,11 @@ int inflate_launch(zipc_b200_ctx *ctx, const InflateTask *d_tasks, uint32_t n, I
     unsigned int start = grid * WARPS * G;  // tasks [0, start) are assigned statically
     ZB_CUDA(ctx, cudaMemcpyAsync(queue, &start, sizeof start, cudaMemcpyHostToDevice, ctx->stream));
   }
+  KernelTimer kt(ctx);
   if (count_only)
-    inflate_kernel<true><<<grid, THREADS, kSmemBytes, ctx->stream>>>(d_tasks, n, d_results, queue, ctx->d_scratch.as<uint16_t>());
+    inflate_kernel<true><<<grid, THREADS, kSmemBytes, ctx->stream>>>(d_tasks, n, d_results, queue, ctx->d_scratch.as<uint16_t>(), -1);
   else
-    inflate_kernel<false><<<grid, THREADS, kSmemBytes, ctx->stream>>>(d_tasks, n, d_results, queue, ctx->d_scratch.as<uint16_t>());
+    inflate_kernel<false><<<grid, THREADS, kSmemBytes, ctx->stream>>>(d_tasks, n, d_results, queue, ctx->d_scratch.as<uint16_t>(), adler_mode);
   ctx->launches++;
   ZB_CUDA(ctx, cudaGetLastError());
   return ZIPC_OK;
