@@ -1,0 +1,145 @@
+"""GPU parity for the archive paths: Zipc.of_binary_string + File.to_binary_string (C3) and
+File.deflate_of_binary_string + Zipc.to_binary_string (C4), through the `zipc` mirror module."""
+import io
+import zipfile
+import zlib
+
+import numpy as np
+import pytest
+
+from oracle import zipc_oracle as zo
+from zipc_b200 import _lib, synth, zipc
+from zipc_b200 import zipc_deflate as zd
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = zd.Context(0)
+    zd.set_default_context(c)
+    yield c
+    zd.set_default_context(None)
+    c.close()
+
+
+def _assert_zip(archive, original):  # test/test.ml:74-108
+    z = zipc.of_binary_string(archive).get_ok()
+    d = zipc.find("zip-docs/", z)
+    assert d.kind is None and zo.ptime_to_date_time(d.mtime) == ((2023, 10, 21), (15, 6, 50)) and d.mode == 0o755
+    r = zipc.find("zip-docs/rfc1951.txt", z)
+    a = zipc.find("zip-docs/APPNOTE.TXT", z)
+    assert zo.ptime_to_date_time(r.mtime) == ((2023, 10, 21), (15, 6, 24)) and r.mode == 0o644
+    assert zo.ptime_to_date_time(a.mtime) == ((2023, 10, 21), (15, 6, 50)) and a.mode == 0o644
+    if original:
+        assert r.kind.compression == zipc.DEFLATE and r.kind.decompressed_size == 36944
+        assert a.kind.compression == zipc.DEFLATE and a.kind.decompressed_size == 174585
+    assert r.kind.decompressed_crc_32 == 0xFB4F3400 and a.kind.decompressed_crc_32 == 0x39B029C4
+    rs, as_ = zipc.File.to_binary_strings([r.kind, a.kind])
+    return z, rs.get_ok(), as_.get_ok()
+
+
+def test_crunched_trip(ctx, zip_docs):  # test/test.ml:57-118, every codec step on the GPU
+    z, r, a = _assert_zip(zip_docs, True)
+    ms = {m.path: m for m in zo.zip_decode(zip_docs)}
+    assert r == zo.file_to_binary_string(ms[b"zip-docs/rfc1951.txt"]) and a == zo.file_to_binary_string(ms[b"zip-docs/APPNOTE.TXT"])
+    # redeflate_recode (test.ml:58-73)
+    out = zipc.empty()
+    files = [m for m in z.values() if m.kind is not None and zipc.File.can_extract(m.kind)]
+    datas = [x.get_ok() for x in zipc.File.to_binary_strings([m.kind for m in files])]
+    news = zipc.File.deflate_of_binary_strings(datas, level="best")
+    for m in z.values():
+        if m.kind is None:
+            out = zipc.add(m, out)
+    for m, f in zip(files, news):
+        out = zipc.add(zipc.Member.make(m.path, f.get_ok(), mode=m.mode, mtime=m.mtime).get_ok(), out)
+    recoded = zipc.to_binary_string(out).get_ok()
+    assert len(recoded) == zipc.encoding_size(out)
+    _z2, r2, a2 = _assert_zip(recoded, True)
+    assert (r2, a2) == (r, a)
+    # the oracle (reference decoder) and Info-ZIP-compatible zipfile read it too
+    back = {m.path: m for m in zo.zip_decode(recoded)}
+    assert zo.file_to_binary_string(back[b"zip-docs/APPNOTE.TXT"]) == a
+    assert zipfile.ZipFile(io.BytesIO(recoded)).testzip() is None
+
+
+def test_archive_layout_bit_exact_given_same_payloads(ctx):
+    """X-2..X-4: with identical payloads the archive bytes equal the oracle's to_binary_string."""
+    datas = [synth.text_v1(50 + i, 3000 + 777 * i).tobytes() for i in range(12)]
+    files = [f.get_ok() for f in zipc.File.deflate_of_binary_strings(datas, level="default")]
+    z = zipc.empty()
+    oms = []
+    for i, (d, f) in enumerate(zip(datas, files)):
+        path = ("m/%05d.txt" % i) if i != 5 else "mimetype"
+        z = zipc.add(zipc.Member.make(path, f, mtime=1697900810 + i).get_ok(), z)
+        oms.append(zo.member_make(path.encode(), mtime=1697900810 + i, compression=8, compressed_bytes=bytes(f.compressed_bytes),
+                                  decompressed_size=len(d), crc32=f.decompressed_crc_32))
+    z = zipc.add(zipc.Member.make("dir\\sub", None).get_ok(), z)
+    oms.append(zo.member_make(b"dir\\sub", is_dir=True))
+    s = zipc.File.stored_of_binary_string(b"stored payload").get_ok()
+    z = zipc.add(zipc.Member.make("s.bin", s, mode=0o600).get_ok(), z)
+    oms.append(zo.member_make(b"s.bin", mode=0o600, **zo.file_stored_of_binary_string(b"stored payload")))
+    for first in (None, "s.bin"):
+        ours = zipc.to_binary_string(z, first=first).get_ok()
+        assert ours == zo.zip_encode(oms, first.encode() if first else None)
+    zf = zipfile.ZipFile(io.BytesIO(zipc.to_binary_string(z).get_ok()))
+    assert zf.testzip() is None and zf.read("m/00003.txt") == datas[3]
+
+
+def test_extract_statuses(ctx):
+    text = synth.text_v1(77, 50000).tobytes()
+    cs = zo.deflate(text, "default")
+    good = zipc.File.make(cs, compression=8, decompressed_size=len(text), decompressed_crc_32=zlib.crc32(text)).get_ok()
+    badcrc = zipc.File.make(cs, compression=8, decompressed_size=len(text), decompressed_crc_32=1).get_ok()
+    small = zipc.File.make(cs, compression=8, decompressed_size=len(text) - 1, decompressed_crc_32=zlib.crc32(text)).get_ok()
+    corrupt = zipc.File.make(cs[:100], compression=8, decompressed_size=len(text), decompressed_crc_32=0).get_ok()
+    enc = zipc.File.make(cs, compression=8, decompressed_size=len(text), decompressed_crc_32=0, gp_flags=0x801).get_ok()
+    lzma = zipc.File.make(cs, compression=14, decompressed_size=len(text), decompressed_crc_32=0).get_ok()
+    stored = zipc.File.stored_of_binary_string(text).get_ok()
+    storedbad = zipc.File.make(text, compression=0, decompressed_size=len(text), decompressed_crc_32=5).get_ok()
+    res = zipc.File.to_binary_strings([good, badcrc, small, corrupt, enc, lzma, stored, storedbad])
+    assert res[0].get_ok() == text and res[6].get_ok() == text
+    assert res[1].message == "Checksum mismatch, expected 1 found %x)" % zlib.crc32(text)
+    assert res[2].message == "deflate: Expected decompression size exceeded"
+    assert res[3].message == "deflate: Corrupted data stream"
+    assert res[4].message == "Encrypted file not supported"
+    assert res[5].message == "Compression lzma not supported"
+    assert res[7].message == "Checksum mismatch, expected 5 found %x)" % zlib.crc32(text)
+    # same verdicts from the oracle
+    for f, r in zip([good, badcrc, small, corrupt, stored, storedbad], [res[0], res[1], res[2], res[3], res[6], res[7]]):
+        m = zo.member_make(b"x", compression=f.compression, compressed_bytes=bytes(f.compressed_bytes),
+                           decompressed_size=f.decompressed_size, crc32=f.decompressed_crc_32)
+        try:
+            zo.file_to_binary_string(m); ok = True
+        except zo.OracleError as e:
+            ok = False
+            assert e.message == r.message
+        assert ok == r.is_ok()
+    assert zipc.File.to_binary_string_no_crc_check(badcrc).get_ok() == (text, zlib.crc32(text))
+
+
+def test_archive_of_binary_strings_c4_small(ctx):
+    """C4 scaled down: 300 members compressed on the GPU and assembled; framing bit-exact vs the oracle's
+    framing of the same payloads, every member inflates through the oracle, zipfile reads the archive."""
+    sizes = synth.member_sizes(300, seed=4)
+    datas = [synth.text_v1(3000 + i, int(n)).tobytes() for i, n in enumerate(sizes)]
+    paths = ["m/%05d.txt" % i for i in range(300)]
+    for level in ("fast", "default"):
+        arch = zipc.archive_of_binary_strings(paths, datas, level=level).get_ok()
+        ms = zo.zip_decode(arch)
+        assert [m.path.decode() for m in ms] == paths
+        assert zo.zip_encode(ms) == arch  # layout rules: re-encoding the decoded members reproduces the bytes
+        for m, d in list(zip(ms, datas))[::17]:
+            assert zo.file_to_binary_string(m) == d
+        zf = zipfile.ZipFile(io.BytesIO(arch))
+        assert zf.testzip() is None
+        # and back through our own archive decode + batch extract
+        z = zipc.of_binary_string(arch).get_ok()
+        outs = zipc.File.to_binary_strings([z[p.encode()].kind for p in paths])
+        assert all(o.get_ok() == d for o, d in zip(outs, datas))
+
+
+def test_of_binary_string_errors(ctx, zip_docs):
+    assert zipc.of_binary_string(b"").message == "File too short to be a ZIP archive"
+    assert zipc.of_binary_string(bytes(100)).message == "Likely not a ZIP archive: no end of central directory record found"
+    assert zipc.string_has_magic(zip_docs) and not zipc.string_has_magic(b"nope")

@@ -7,5 +7,6 @@ There is no CPU fallback: compute calls fail loudly without the library or witho
 from . import _lib  # noqa: F401
 from . import zipc_deflate  # noqa: F401
 from . import synth  # noqa: F401
+from . import zipc  # noqa: F401
 
-__all__ = ["_lib", "zipc_deflate", "synth"]
+__all__ = ["_lib", "zipc_deflate", "zipc", "synth"]
