@@ -457,6 +457,21 @@ def main():
                 del rr
             except Exception as e:  # never lose the headline line to a secondary workload
                 also[w] = {"error": repr(e)}
+        try:  # C1: one 64 MiB text-v1 stream, segment-independent deflate + indexed inflate, host buffers (e2e)
+            from zipc_b200 import synth
+            data = h.pinned(synth.text_v1(1, 64 << 20))
+            res = {}
+            for seg in (64 << 10, 256 << 10):
+                stream, index, crc = h.ctx.deflate_segmented(data, "default", seg)
+                t0 = time.perf_counter(); stream, index, crc = h.ctx.deflate_segmented(data, "default", seg); td = time.perf_counter() - t0
+                st, out, crc2 = h.ctx.inflate_segmented(stream, index)
+                t0 = time.perf_counter(); st, out, crc2 = h.ctx.inflate_segmented(stream, index); ti = time.perf_counter() - t0
+                assert st == 0 and crc2 == crc and out.size == data.size
+                res["seg_%dk" % (seg >> 10)] = {"deflate_e2e_GBps": round(data.size / td / 1e9, 3), "inflate_e2e_GBps": round(data.size / ti / 1e9, 3),
+                                               "ratio": round(stream.size / data.size, 4), "segments": int(index.shape[0] - 1)}
+            also["stream_c1"] = {"workload": "C1: 64 MiB text-v1(seed=1) as one RFC 1951 stream of independent segments + index; CRC-32 fused both ways", **res}
+        except Exception as e:
+            also["stream_c1"] = {"error": repr(e)}
         line["also"] = also
     if rank == 0:
         print(json.dumps(line))

@@ -182,6 +182,22 @@ int zipc_b200_zlib_compress_batch(zipc_b200_ctx *ctx, int level, int adler_mode,
                                   void *dst, size_t dst_cap, size_t *dst_need,
                                   size_t *dst_off, size_t *dst_len, uint32_t *adler, int *status);
 
+/* ---- one large stream as independent segments (BASELINE.json configs 1 and 5) ----------------------- */
+/* Zipc_deflate.crc_32_and_deflate for ONE large input, parallel inside the stream: the input is cut into
+ * segments of segment_size bytes, each compressed with a fresh window by one CTA; every segment but the last
+ * ends with an empty stored block, so the pieces are byte aligned and their concatenation is ONE valid
+ * RFC 1951 stream that Zipc_deflate.inflate reads.  index receives nseg + 1 pairs (compressed offset,
+ * uncompressed offset), the last pair being the totals.  last_piece = 0 keeps BFINAL off the last segment
+ * (the slice is a non-final piece of a stream spread over several GPUs).  crc32 = CRC-32 of the input. */
+int zipc_b200_deflate_segmented(zipc_b200_ctx *ctx, int level, const void *src, size_t len, size_t segment_size,
+                                int last_piece, void *dst, size_t dst_cap, size_t *dst_len, uint64_t *index,
+                                size_t index_cap_pairs, size_t *nseg, uint32_t *crc32);
+/* Zipc_deflate.inflate_and_crc_32 of such a stream WITH its index: segments are decoded in parallel (one
+ * decoder lane each).  status = ZIPC_OK or the status of the first bad segment.  Without the index the stream
+ * is an ordinary deflate stream (zipc_b200_inflate_batch decodes it serially). */
+int zipc_b200_inflate_segmented(zipc_b200_ctx *ctx, const void *src, size_t len, const uint64_t *index, size_t nseg,
+                                void *dst, size_t dst_cap, size_t *dst_len, uint32_t *crc32, int *status);
+
 /* ---- ZIP archive layer (zipc.ml) ------------------------------------------------------------ */
 /* One archive member: Zipc.Member.t + Zipc.File.t (zipc.ml:145-154,238-242). */
 typedef struct {

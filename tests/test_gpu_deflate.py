@@ -153,3 +153,46 @@ def test_many_members_ragged(ctx):
                 assert st == 0 and crc == r[2] and (out == d).all()
     finally:
         zo.set_keep_codelen_freqs(True)
+
+
+def test_segmented_single_stream(ctx):
+    """C1 / C5 shape, scaled down: one stream compressed as independent segments; the concatenation is ONE valid
+    RFC 1951 stream for the reference's inflate (oracle) and zlib, and the index lets us inflate it in parallel."""
+    data = synth.text_v1(1, (6 << 20) + 12345)
+    b = data.tobytes()
+    for seg in (64 << 10, 256 << 10, 1 << 20):
+        stream, index, crc = ctx.deflate_segmented(data, "default", seg)
+        assert crc == zlib.crc32(b)
+        assert index.shape[0] == -(-data.size // seg) + 1 and int(index[-1, 0]) == stream.size and int(index[-1, 1]) == data.size
+        s = stream.tobytes()
+        assert zlib.decompress(s, -15) == b
+        if seg == 256 << 10:
+            assert zo.inflate(s) == b                       # Zipc_deflate.inflate stand-in
+            out, ocrc = zo.inflate_and_crc_32(s, len(b))
+            assert ocrc == crc
+        st, out, crc2 = ctx.inflate_segmented(stream, index)
+        assert st == 0 and crc2 == crc and (out == data).all()
+        # serial decode of the same stream through the ordinary entry point
+        if seg == 1 << 20:
+            r = zd.inflate_and_crc_32(s, decompressed_size=len(b))
+            assert r.get_ok() == (b, crc)
+        ref = len(zlib.compress(b, 6))
+        assert stream.size <= 1.10 * ref
+    # pieces for several GPUs: non-final slices concatenate to one stream
+    half = data.size // 2 // 512 * 512
+    a, ia, ca = ctx.deflate_segmented(data[:half], "fast", 128 << 10, last_piece=False)
+    c, ic, cc = ctx.deflate_segmented(data[half:], "fast", 128 << 10, last_piece=True)
+    joined = a.tobytes() + c.tobytes()
+    assert zlib.decompress(joined, -15) == b and zo.inflate(joined) == b
+    assert _lib.lib().zipc_b200_crc32_combine(ca, cc, data.size - half) == zlib.crc32(b)
+    # edge cases
+    for n in (0, 1, 4096, 65536, 65537):
+        stream, index, crc = ctx.deflate_segmented(data[:n], "default", 64 << 10)
+        assert zlib.decompress(stream.tobytes(), -15) == b[:n] and crc == zlib.crc32(b[:n])
+        st, out, crc2 = ctx.inflate_segmented(stream, index)
+        assert st == 0 and out.tobytes() == b[:n]
+    # a damaged segment is reported, the call itself survives
+    stream, index, crc = ctx.deflate_segmented(data, "default", 256 << 10)
+    bad = stream.copy(); bad[int(index[3, 0]) + 100] ^= 0xFF
+    st, out, _ = ctx.inflate_segmented(bad, index)
+    assert st != 0 or out.tobytes() != b

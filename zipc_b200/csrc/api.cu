@@ -191,7 +191,7 @@ static __global__ void xor_ffffffff_kernel(uint32_t *v, uint32_t n) {
 // cap[i] == ZIPC_SIZE_UNKNOWN is not accepted here (the callers resolve sizes first).
 int inflate_core(zipc_b200_ctx *ctx, int ck, int adler_mode, size_t n, const std::vector<const uint8_t *> &d_src,
                  const size_t *src_len, const std::vector<uint8_t *> &d_dst, const std::vector<size_t> &cap,
-                 bool count_only, size_t *out_len, uint32_t *checksum, int *status) {
+                 bool count_only, size_t *out_len, uint32_t *checksum, int *status, uint32_t flags) {
   if (!n) return ZIPC_OK;
   if (n > 0xFFFFFFF0ull) return ZIPC_ERR_INVALID_ARG;
   // longest streams first: the tail of the dynamic queue is made of short ones
@@ -208,6 +208,7 @@ int inflate_core(zipc_b200_ctx *ctx, int ck, int adler_mode, size_t n, const std
     ht[k].src = d_src[i]; ht[k].src_len = src_len[i];
     ht[k].dst = count_only ? nullptr : d_dst[i];
     ht[k].dst_cap = cap[i] == ZIPC_SIZE_UNKNOWN ? ~0ull : (uint64_t)cap[i];
+    ht[k].flags = flags; ht[k]._pad = 0;
   }
   InflateTask *dt = ctx->d_desc.as<InflateTask>();
   CrcSeg *dsegs = reinterpret_cast<CrcSeg *>(dt + n);

@@ -67,7 +67,10 @@ struct InflateTask {  // one deflate stream to inflate
   uint64_t src_len;
   uint8_t *dst;       // may be null in count-only mode
   uint64_t dst_cap;   // ?decompressed_size, or ~0ull when unknown (count-only pass)
+  uint32_t flags;     // kInflateSegment: a piece of a segmented stream, ends where its input ends
+  uint32_t _pad;
 };
+constexpr uint32_t kInflateSegment = 1u;
 struct InflateResult {
   uint64_t out_len;
   uint32_t status;
@@ -79,7 +82,10 @@ struct DeflateTask {  // one input to deflate (a ZIP member or an independent se
   uint64_t src_len;   // < 2^32
   uint8_t *dst;       // 4-byte aligned output slot
   uint64_t dst_cap;
+  uint32_t flags;     // kDeflateNotFinal: no BFINAL, end with a byte-aligning empty stored block
+  uint32_t _pad;
 };
+constexpr uint32_t kDeflateNotFinal = 1u;
 struct DeflateResult {
   uint64_t out_len;
   uint32_t status;
@@ -162,7 +168,7 @@ int upload_ranges(zipc_b200_ctx *ctx, size_t n, const void *const *src, const si
                   std::vector<const uint8_t *> &d_ptr);
 int inflate_core(zipc_b200_ctx *ctx, int ck, int adler_mode, size_t n, const std::vector<const uint8_t *> &d_src,
                  const size_t *src_len, const std::vector<uint8_t *> &d_dst, const std::vector<size_t> &cap,
-                 bool count_only, size_t *out_len, uint32_t *checksum, int *status);
+                 bool count_only, size_t *out_len, uint32_t *checksum, int *status, uint32_t flags = 0);
 // host_util.cc
 int zip_assemble_impl(const zipc_b200_member *ms, size_t n, const char *first, void *out_v, size_t out_cap,
                       size_t *out_len, bool copy_payload, uint64_t *payload_off);

@@ -404,6 +404,7 @@ __device__ void encode_member(const Shared &sh, const DeflateTask t, int level, 
   uint32_t *out_words = reinterpret_cast<uint32_t *>(t.dst);
   const uint64_t out_cap_words = t.dst_cap / 4;
   const LevelParams lp = level_params(level);
+  const bool not_final = (t.flags & kDeflateNotFinal) != 0;
   const RingView ring{sh.ring};
   const PrevView prevv{sh.prev};
 
@@ -423,7 +424,15 @@ __device__ void encode_member(const Shared &sh, const DeflateTask t, int level, 
   for (uint32_t ts = 0; ts < n; ts += kTile) {
     const uint32_t te = min(ts + (uint32_t)kTile, n), want = min(n, te + (uint32_t)kTile);
     // 1. stage input
-    for (uint32_t i = loaded + tid; i < want; i += THREADS) sh.ringb[i & (kRing - 1)] = src[i];
+    if ((((uintptr_t)src) & 15) == 0 && (loaded & 15) == 0) {  // 16-byte vectors (slots of the packed arena are aligned)
+      const uint32_t nv = (want - loaded) >> 4;
+      const uint4 *sv = reinterpret_cast<const uint4 *>(src + loaded);
+      for (uint32_t i = tid; i < nv; i += THREADS)
+        *reinterpret_cast<uint4 *>(sh.ringb + ((loaded + 16 * i) & (kRing - 1))) = __ldg(sv + i);
+      for (uint32_t i = loaded + 16 * nv + tid; i < want; i += THREADS) sh.ringb[i & (kRing - 1)] = src[i];
+    } else {
+      for (uint32_t i = loaded + tid; i < want; i += THREADS) sh.ringb[i & (kRing - 1)] = src[i];
+    }
     loaded = want;
     __syncthreads();
     // 2a. hashes (0xFFFF = position cannot start a match)
@@ -492,11 +501,27 @@ __device__ void encode_member(const Shared &sh, const DeflateTask t, int level, 
     __syncthreads();
     // 3. longest match at every position (slot 0 carries position ts-1 from the previous tile)
     if (tid == 0) { sh.mlen[0] = (uint16_t)sh.sc[SC_CARRY_LEN]; sh.mdist[0] = (uint16_t)sh.sc[SC_CARRY_DIST]; }
-    for (int j = 0; j < PPT; j++) {
-      uint32_t i = tid + THREADS * j, p = ts + i, d = 0, l = 0;
-      if (p < te && p + 4 <= n) l = find_match(ring, prevv, p, n, sh.first[i], lp.depth, lp.nice, d);
-      sh.mlen[1 + i] = (uint16_t)l;
-      sh.mdist[1 + i] = (uint16_t)d;
+    {
+      // every lane owns PPT positions and walks their chains as ONE loop: when a position is finished the
+      // lane moves on to its next one instead of idling until the slowest lane of the warp is done with its
+      int j = 0;
+      MatchState ms;
+      ms.done = true;
+      bool have = false;
+      while (j < PPT) {
+        if (!have) {
+          uint32_t i = tid + THREADS * j, p = ts + i;
+          if (p < te && p + 4 <= n) { match_begin(ms, ring, p, n, sh.first[i], lp.depth); have = true; }
+          else { sh.mlen[1 + i] = 0; sh.mdist[1 + i] = 0; j++; }
+        } else if (ms.done) {
+          uint32_t i = tid + THREADS * j;
+          sh.mlen[1 + i] = (uint16_t)(ms.best >= (uint32_t)kMinMatch ? ms.best : 0);
+          sh.mdist[1 + i] = (uint16_t)ms.best_dist;
+          have = false; j++;
+        } else {
+          match_step(ms, ring, prevv, lp.nice);
+        }
+      }
     }
     __syncthreads();
     // 4. lazy parse by pointer jumping over nodes v = 2 * (p - ts) + kind; codes >= 2T are exits
@@ -520,6 +545,7 @@ __device__ void encode_member(const Shared &sh, const DeflateTask t, int level, 
         }
         __syncthreads();
         uint16_t *tmp = ja; ja = jb; jb = tmp;
+        if (ja[entry] >= 2 * kTile) break;  // the entry has left the tile: every node of the path is marked
       }
       const uint32_t ex = ja[entry] - 2 * kTile;  // after 2^11 >= T steps the entry has left the tile
       pos = te + (ex >> 1);
@@ -560,12 +586,30 @@ __device__ void encode_member(const Shared &sh, const DeflateTask t, int level, 
     if (tiles_in_block == kTilesPerBlock || last) {
       __syncthreads();
       const uint32_t blen = sh.sc[SC_BLK_SRCLEN];
-      finalize_block(sh, src, blk_src_start, ntok, toks, last, out_words, out_cap_words);
+      finalize_block(sh, src, blk_src_start, ntok, toks, last && !not_final, out_words, out_cap_words);
       blk_src_start += blen;
       ntok = 0; tiles_in_block = 0; nblocks++;
     }
   }
-  if (n == 0) { finalize_block(sh, src, 0, 0, toks, true, out_words, out_cap_words); nblocks++; }
+  if (n == 0) { finalize_block(sh, src, 0, 0, toks, !not_final, out_words, out_cap_words); nblocks++; }
+  if (not_final) {
+    // segment of a larger stream: close with an empty stored block (000, pad to a byte, LEN 0, NLEN ffff) so
+    // that the next segment starts byte aligned and the concatenation is one valid RFC 1951 stream
+    __syncthreads();
+    if (tid == 0) {
+      uint32_t pad = (8 - ((sh.sc[SC_CBITS] + 3) & 7)) & 7, k = 0;
+      sh.hdr_val[k] = 0; sh.hdr_nb[k++] = 3;
+      if (pad) { sh.hdr_val[k] = 0; sh.hdr_nb[k++] = (uint8_t)pad; }
+      sh.hdr_val[k] = 0; sh.hdr_nb[k++] = 16;
+      sh.hdr_val[k] = 0xFFFFu; sh.hdr_nb[k++] = 16;
+      sh.sc[SC_NHDR] = k;
+    }
+    __syncthreads();
+    const uint32_t nh = sh.sc[SC_NHDR];
+    const uint32_t *hv = sh.hdr_val;
+    const uint8_t *hn = sh.hdr_nb;
+    pack_items(sh, out_words, out_cap_words, nh, [&](uint32_t i, uint64_t &b, uint32_t &nn) { b = hv[i]; nn = hn[i]; });
+  }
   __syncthreads();
   if (tid == 0) {
     uint64_t outw = sh.sc[SC_OUTW];
@@ -612,7 +656,7 @@ stored_kernel(const DeflateTask *__restrict__ tasks, uint32_t ntasks, DeflateRes
   for (uint64_t b = threadIdx.x; b < nblk; b += blockDim.x) {
     uint64_t len = b + 1 < nblk ? 65535 : n - b * 65535;
     uint8_t *h = t.dst + b * 65540;
-    h[0] = b + 1 == nblk ? 1 : 0;
+    h[0] = (b + 1 == nblk && !(t.flags & kDeflateNotFinal)) ? 1 : 0;
     h[1] = (uint8_t)len; h[2] = (uint8_t)(len >> 8); h[3] = (uint8_t)~len; h[4] = (uint8_t)(~len >> 8);
   }
   for (uint64_t i = threadIdx.x; i < n; i += blockDim.x) t.dst[i + 5 * (i / 65535 + 1)] = t.src[i];

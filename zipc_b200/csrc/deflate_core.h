@@ -38,8 +38,8 @@ ZHD LevelParams level_params(int level) {
   // chain steps per position and the length at which the walk stops early
   LevelParams p;
   if (level <= 1) { p.depth = 4; p.nice = 32; }
-  else if (level == 2) { p.depth = 24; p.nice = 128; }
-  else { p.depth = 96; p.nice = 258; }
+  else if (level == 2) { p.depth = 12; p.nice = 128; }
+  else { p.depth = 48; p.nice = 258; }
   return p;
 }
 
@@ -97,45 +97,98 @@ ZHD uint32_t ring_load32(const Ring &ring, uint32_t pos) {
   return s ? (lo >> s) | (hi << (32 - s)) : lo;
 }
 
+template <class Ring>
+ZHD uint32_t ring_load8(const Ring &ring, uint32_t pos) {
+  uint32_t i = pos & (kRing - 1);
+  return (ring.word(i >> 2) >> ((i & 3u) * 8u)) & 0xFFu;
+}
+
+// The chain walk of one position as a resumable state machine, so that a GPU lane can interleave the
+// walks of its positions (a warp then waits for the slowest lane's TOTAL work, not for the slowest lane
+// of every position) while the host model simply runs it to completion.
+struct MatchState {
+  uint32_t p, max_len, best, best_dist, last_dist, reach, c;
+  uint32_t pw0, pw1;   // the 8 bytes at p
+  uint32_t chk;        // the byte at p + best: a candidate can only beat `best` if it matches there
+  int steps;
+  bool done;
+};
+
+template <class Ring>
+ZHD void match_begin(MatchState &m, const Ring &ring, uint32_t p, uint32_t n, uint32_t first_cand, int depth) {
+  m.p = p;
+  m.max_len = n - p < (uint32_t)kMaxMatch ? n - p : (uint32_t)kMaxMatch;
+  m.best = kMinMatch - 1; m.best_dist = 0; m.last_dist = 0;
+  m.reach = p < (uint32_t)kWindow ? p : (uint32_t)kWindow;
+  m.c = first_cand;
+  m.pw0 = ring_load32(ring, p);
+  m.pw1 = ring_load32(ring, p + 4);
+  m.chk = (m.pw0 >> 24) & 0xFFu;  // byte at p + 3
+  m.steps = depth;
+  m.done = depth <= 0;
+}
+
+// Evaluates one candidate of the chain.
+template <class Ring, class Prev>
+ZHD void match_step(MatchState &m, const Ring &ring, const Prev &prev, int nice) {
+  uint32_t dist = (m.p - m.c) & 0xFFFFu;
+  if (dist == 0 || dist > m.reach || dist <= m.last_dist) { m.done = true; return; }  // empty / out of window / stale
+  m.last_dist = dist;
+  uint32_t cp = m.p - dist;
+  if (m.best < m.max_len && ring_load8(ring, cp + m.best) == m.chk) {
+    uint32_t len;
+    uint32_t x = ring_load32(ring, cp) ^ m.pw0;
+    if (x) len = (uint32_t)
+#if defined(__CUDA_ARCH__)
+        (__ffs((int)x) - 1) >> 3;
+#else
+        __builtin_ctz(x) >> 3;
+#endif
+    else {
+      x = ring_load32(ring, cp + 4) ^ m.pw1;
+      if (x) len = 4 + ((uint32_t)
+#if defined(__CUDA_ARCH__)
+          (__ffs((int)x) - 1) >> 3);
+#else
+          __builtin_ctz(x) >> 3);
+#endif
+      else {
+        len = 8;
+        while (len < m.max_len) {
+          x = ring_load32(ring, cp + len) ^ ring_load32(ring, m.p + len);
+          if (x) {
+#if defined(__CUDA_ARCH__)
+            len += (uint32_t)(__ffs((int)x) - 1) >> 3;
+#else
+            len += (uint32_t)__builtin_ctz(x) >> 3;
+#endif
+            break;
+          }
+          len += 4;
+        }
+      }
+    }
+    if (len > m.max_len) len = m.max_len;
+    if (len > m.best) {
+      m.best = len; m.best_dist = dist;
+      if (len >= (uint32_t)nice || len == m.max_len) { m.done = true; return; }
+      m.chk = ring_load8(ring, m.p + len);
+    }
+  }
+  m.c = prev.link(cp);
+  if (--m.steps <= 0) m.done = true;
+}
+
 // Longest match for absolute position p (p + 4 <= n).  Returns len (0 if < 4) and sets dist.
 // first_cand is the chain head as it was just before p was inserted.
 template <class Ring, class Prev>
 ZHD uint32_t find_match(const Ring &ring, const Prev &prev, uint32_t p, uint32_t n, uint32_t first_cand,
                         int depth, int nice, uint32_t &dist_out) {
-  uint32_t max_len = n - p < (uint32_t)kMaxMatch ? n - p : (uint32_t)kMaxMatch;
-  uint32_t best = kMinMatch - 1, best_dist = 0, last_dist = 0;
-  uint32_t reach = p < (uint32_t)kWindow ? p : (uint32_t)kWindow;
-  uint32_t c = first_cand;
-  for (int step = 0; step < depth; step++) {
-    uint32_t dist = (p - c) & 0xFFFFu;
-    if (dist == 0 || dist > reach || dist <= last_dist) break;  // empty / out of window / stale link
-    last_dist = dist;
-    uint32_t cp = p - dist;
-    // cheap rejection: the 4 bytes ending at offset `best` must match to beat `best`
-    if (best + 1 <= max_len && ring_load32(ring, cp + best - 3) == ring_load32(ring, p + best - 3)) {
-      uint32_t len = 0;
-      while (len < max_len) {
-        uint32_t x = ring_load32(ring, cp + len) ^ ring_load32(ring, p + len);
-        if (x) {
-#if defined(__CUDA_ARCH__)
-          len += (uint32_t)(__ffs((int)x) - 1) >> 3;
-#else
-          len += (uint32_t)__builtin_ctz(x) >> 3;
-#endif
-          break;
-        }
-        len += 4;
-      }
-      if (len > max_len) len = max_len;
-      if (len > best) {
-        best = len; best_dist = dist;
-        if (len >= (uint32_t)nice || len == max_len) break;
-      }
-    }
-    c = prev.link(cp);
-  }
-  dist_out = best_dist;
-  return best >= (uint32_t)kMinMatch ? best : 0;
+  MatchState m;
+  match_begin(m, ring, p, n, first_cand, depth);
+  while (!m.done) match_step(m, ring, prev, nice);
+  dist_out = m.best_dist;
+  return m.best >= (uint32_t)kMinMatch ? m.best : 0;
 }
 
 // ---- lazy parse as a successor function ------------------------------------------------------------------

@@ -263,7 +263,7 @@ inflate_kernel(const InflateTask *__restrict__ tasks, uint32_t ntasks, InflateRe
   uint64_t src_len = 0;
   uint8_t *dst = nullptr;
   uint64_t out_pos = 0, out_cap = 0;
-  bool final_blk = false, need_build = false, first_task = true;
+  bool final_blk = false, need_build = false, first_task = true, segment = false;
   uint32_t hlit = 0, hdist = 0;
   uint32_t stored_len = 0;
   const uint8_t *stored_src = nullptr;
@@ -283,7 +283,7 @@ inflate_kernel(const InflateTask *__restrict__ tasks, uint32_t ntasks, InflateRe
       else task = atomicAdd(queue, 1u);
       if (task < ntasks) {
         const InflateTask t = tasks[task];
-        src = t.src; src_len = t.src_len; dst = t.dst; out_cap = t.dst_cap;
+        src = t.src; src_len = t.src_len; dst = t.dst; out_cap = t.dst_cap; segment = (t.flags & kInflateSegment) != 0;
         out_pos = 0; status = ZIPC_OK; final_blk = false;
         ad_state = 1; ad_from = 0; ad_pending = false;
         br.seek(src, src_len, 0);
@@ -295,6 +295,9 @@ inflate_kernel(const InflateTask *__restrict__ tasks, uint32_t ntasks, InflateRe
     if (__all_sync(0xffffffffu, state == S_EXIT)) break;
 
     // ---- B: block headers (reference :692-702, :623-661, :671-677) ------------------------------------
+    if (state == S_HDR && segment && br.consumed() == src_len * 8) {
+      state = S_FINISH;  // a segment ends at the block boundary where its input ends (byte aligned by construction)
+    }
     if (state == S_HDR) {
       br.refill();
       uint32_t h = br.peek(3);

@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(256) gather_kernel(const CopyDesc *__restrict_
 int deflate_run(zipc_b200_ctx *ctx, int level, int ck, int adler_mode, size_t n,
                 const std::vector<const uint8_t *> &d_src, const size_t *src_len,
                 const std::vector<uint8_t *> &d_slot, const std::vector<size_t> &slot_cap,
-                size_t *out_len, uint32_t *checksum, int *status) {
+                size_t *out_len, uint32_t *checksum, int *status, const std::vector<uint32_t> *flags = nullptr) {
   if (!n) return ZIPC_OK;
   if (n > 0xFFFFFFF0ull) return ZIPC_ERR_INVALID_ARG;
   for (size_t i = 0; i < n; i++) if (src_len[i] > 0xFFFFFFFFull) return ZIPC_ERR_INVALID_ARG;
@@ -65,6 +65,7 @@ int deflate_run(zipc_b200_ctx *ctx, int level, int ck, int adler_mode, size_t n,
   for (size_t k = 0; k < n; k++) {
     uint32_t i = order[k];
     ht[k].src = d_src[i]; ht[k].src_len = src_len[i]; ht[k].dst = d_slot[i]; ht[k].dst_cap = slot_cap[i];
+    ht[k].flags = flags ? (*flags)[i] : 0u; ht[k]._pad = 0;
   }
   DeflateTask *dt = ctx->d_desc.as<DeflateTask>();
   DeflateResult *dr = ctx->d_res.as<DeflateResult>();
@@ -237,6 +238,93 @@ int zipc_b200_zlib_compress_batch(zipc_b200_ctx *ctx, int level, int adler_mode,
   if (dst_need) *dst_need = total;
   if (!dst || dst_cap < total) { ZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); return ZIPC_ERR_DST_TOO_SMALL; }
   return d2h(ctx, dst, ctx->d_out.p, total);
+}
+
+// ---- segmented single stream -----------------------------------------------------------------------------
+int zipc_b200_deflate_segmented(zipc_b200_ctx *ctx, int level, const void *src, size_t len, size_t segment_size,
+                                int last_piece, void *dst, size_t dst_cap, size_t *dst_len, uint64_t *index,
+                                size_t index_cap_pairs, size_t *nseg_out, uint32_t *crc32) {
+  if (!ctx || level < 0 || level > 3 || (!src && len) || !dst_len || !nseg_out || segment_size < 4096 ||
+      segment_size > 0x7FFFFFFFull)
+    return ZIPC_ERR_INVALID_ARG;
+  DeviceGuard g(ctx->device);
+  const size_t nseg = len ? (len + segment_size - 1) / segment_size : 1;
+  *nseg_out = nseg;
+  if (index && index_cap_pairs < nseg + 1) return ZIPC_ERR_INVALID_ARG;
+  // input to the device (one copy), segments are slices of it
+  const size_t pre = (uintptr_t)src & 15;
+  if (int st = ctx->d_in.reserve(pre + len + 64)) return st;
+  uint8_t *d_base = ctx->d_in.as<uint8_t>() + pre;
+  if (int st = h2d(ctx, d_base, src, len)) return st;
+  std::vector<const uint8_t *> d_src(nseg);
+  std::vector<size_t> slen(nseg);
+  std::vector<uint32_t> flags(nseg, kDeflateNotFinal);
+  for (size_t i = 0; i < nseg; i++) { d_src[i] = d_base + i * segment_size; slen[i] = std::min(segment_size, len - i * segment_size); }
+  if (last_piece) flags[nseg - 1] = 0;
+  std::vector<uint8_t *> d_slot;
+  std::vector<size_t> cap, clen(nseg);
+  std::vector<int> st_m(nseg);
+  if (int st = make_slots(ctx, nseg, slen.data(), d_slot, cap)) return st;
+  if (int st = deflate_run(ctx, level, ZIPC_CK_NONE, 0, nseg, d_src, slen.data(), d_slot, cap, clen.data(), nullptr, st_m.data(), &flags)) return st;
+  for (size_t i = 0; i < nseg; i++) if (st_m[i]) return st_m[i];
+  if (crc32) {
+    if (int st = ctx->d_small.reserve(256)) return st;
+    uint32_t *d_crc = ctx->d_small.as<uint32_t>() + 32;
+    if (int st = crc32_launch_buffer(ctx, d_base, len, d_crc)) return st;
+    ZB_CUDA(ctx, cudaMemcpyAsync(crc32, d_crc, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  // the pieces are byte aligned: concatenate without gaps
+  std::vector<size_t> off(nseg);
+  size_t total = 0;
+  for (size_t i = 0; i < nseg; i++) { off[i] = total; total += clen[i]; }
+  if (index) {
+    for (size_t i = 0; i < nseg; i++) { index[2 * i] = off[i]; index[2 * i + 1] = (uint64_t)i * segment_size; }
+    index[2 * nseg] = total; index[2 * nseg + 1] = len;
+  }
+  if (int st = compact(ctx, nseg, d_slot, clen.data(), off, total)) return st;
+  ctx->last_off = off; ctx->last_len = clen; ctx->last_total = total;
+  *dst_len = total;
+  if (!dst || dst_cap < total) { ZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); return ZIPC_ERR_DST_TOO_SMALL; }
+  return d2h(ctx, dst, ctx->d_out.p, total);
+}
+
+int zipc_b200_inflate_segmented(zipc_b200_ctx *ctx, const void *src, size_t len, const uint64_t *index, size_t nseg,
+                                void *dst, size_t dst_cap, size_t *dst_len, uint32_t *crc32, int *status) {
+  if (!ctx || (!src && len) || !index || !nseg || !dst_len || !status) return ZIPC_ERR_INVALID_ARG;
+  DeviceGuard g(ctx->device);
+  const uint64_t ctotal = index[2 * nseg], utotal = index[2 * nseg + 1];
+  if (ctotal > len) return ZIPC_ERR_INVALID_ARG;
+  for (size_t i = 0; i < nseg; i++)
+    if (index[2 * i] > index[2 * i + 2] || index[2 * i + 1] > index[2 * i + 3]) return ZIPC_ERR_INVALID_ARG;
+  *dst_len = utotal;
+  const size_t pre = (uintptr_t)src & 15;
+  if (int st = ctx->d_in.reserve(pre + len + 64)) return st;
+  uint8_t *d_base = ctx->d_in.as<uint8_t>() + pre;
+  if (int st = h2d(ctx, d_base, src, len)) return st;
+  if (int st = ctx->d_out.reserve(utotal + 64)) return st;
+  std::vector<const uint8_t *> d_src(nseg);
+  std::vector<uint8_t *> d_dst(nseg);
+  std::vector<size_t> clen(nseg), cap(nseg), ol(nseg);
+  std::vector<int> st_m(nseg);
+  for (size_t i = 0; i < nseg; i++) {
+    d_src[i] = d_base + index[2 * i]; clen[i] = index[2 * i + 2] - index[2 * i];
+    d_dst[i] = ctx->d_out.as<uint8_t>() + index[2 * i + 1]; cap[i] = index[2 * i + 3] - index[2 * i + 1];
+  }
+  if (int st = inflate_core(ctx, ZIPC_CK_NONE, 0, nseg, d_src, clen.data(), d_dst, cap, false, ol.data(), nullptr, st_m.data(), kInflateSegment)) return st;
+  *status = ZIPC_OK;
+  for (size_t i = 0; i < nseg; i++) {
+    if (st_m[i]) { *status = st_m[i]; break; }
+    if (ol[i] != cap[i]) { *status = ZIPC_ERR_CORRUPTED; break; }  // the index promised more bytes
+  }
+  if (crc32) {
+    if (int st = ctx->d_small.reserve(256)) return st;
+    uint32_t *d_crc = ctx->d_small.as<uint32_t>() + 32;
+    if (int st = crc32_launch_buffer(ctx, ctx->d_out.as<uint8_t>(), utotal, d_crc)) return st;
+    ZB_CUDA(ctx, cudaMemcpyAsync(crc32, d_crc, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  ctx->last_off.assign(1, 0); ctx->last_len.assign(1, (size_t)utotal); ctx->last_total = utotal;
+  if (!dst || dst_cap < utotal) { ZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); return ZIPC_ERR_DST_TOO_SMALL; }
+  return d2h(ctx, dst, ctx->d_out.p, utotal);
 }
 
 // ---- archive layer ---------------------------------------------------------------------------------------

@@ -239,6 +239,36 @@ class Context:
         return [(stt[i], arena[off[i]:off[i] + ln[i]], ad[i]) for i in range(n)]
 
 
+    # -- one large stream as independent segments (configs 1 and 5)
+    def deflate_segmented(self, s, level: str = "default", segment_size: int = 256 << 10, last_piece: bool = True):
+        """-> (stream bytes-like, index ndarray[(nseg+1), 2] of (compressed, uncompressed) offsets, crc32 of s)"""
+        v = _as_view(s)
+        nseg_max = max(1, -(-v.size // segment_size))
+        index = np.zeros((nseg_max + 1, 2), dtype=np.uint64)
+        n, nseg, crc = C.c_size_t(), C.c_size_t(), C.c_uint32()
+        args = (self.h, LEVELS[level], v.ctypes.data if v.size else None, v.size, segment_size, int(last_piece))
+        st = self.L.zipc_b200_deflate_segmented(*args, None, 0, C.byref(n), index.ctypes.data_as(C.POINTER(C.c_uint64)),
+                                                nseg_max + 1, C.byref(nseg), C.byref(crc))
+        if st != _lib.ERR_DST_TOO_SMALL:
+            self._check(st, "deflate_segmented")
+        out = np.empty(max(n.value, 1), dtype=np.uint8)
+        self._check(self.L.zipc_b200_fetch(self.h, out.ctypes.data, out.size), "fetch")
+        return out[:n.value], index[:nseg.value + 1], crc.value
+
+    def inflate_segmented(self, stream, index):
+        """-> (status, output bytes-like, crc32 of the output)"""
+        v = _as_view(stream)
+        index = np.ascontiguousarray(index, dtype=np.uint64)
+        nseg = index.shape[0] - 1
+        out = np.empty(max(int(index[nseg, 1]), 1), dtype=np.uint8)
+        n, crc, st = C.c_size_t(), C.c_uint32(), C.c_int()
+        rc = self.L.zipc_b200_inflate_segmented(self.h, v.ctypes.data if v.size else None, v.size,
+                                                index.ctypes.data_as(C.POINTER(C.c_uint64)), nseg, out.ctypes.data, out.size,
+                                                C.byref(n), C.byref(crc), C.byref(st))
+        self._check(rc, "inflate_segmented")
+        return st.value, out[:n.value], crc.value
+
+
 _default: Context | None = None
 
 
