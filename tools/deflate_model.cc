@@ -17,6 +17,7 @@ struct Ring {
   std::vector<uint32_t> w;
   Ring() : w(kRing / 4, 0) {}
   uint32_t word(uint32_t a) const { return w[a]; }
+  uint32_t byte(uint32_t i) const { return reinterpret_cast<const uint8_t *>(w.data())[i]; }
   void put(uint32_t pos, uint8_t b) {
     uint32_t i = pos & (kRing - 1);
     reinterpret_cast<uint8_t *>(w.data())[i] = b;

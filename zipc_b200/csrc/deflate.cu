@@ -133,6 +133,7 @@ __device__ __forceinline__ Shared carve(uint8_t *base) {
 struct RingView {
   const uint32_t *w;
   __device__ __forceinline__ uint32_t word(uint32_t a) const { return w[a]; }
+  __device__ __forceinline__ uint32_t byte(uint32_t i) const { return reinterpret_cast<const uint8_t *>(w)[i]; }
 };
 struct PrevView {
   const uint16_t *l;
@@ -501,27 +502,12 @@ __device__ void encode_member(const Shared &sh, const DeflateTask t, int level, 
     __syncthreads();
     // 3. longest match at every position (slot 0 carries position ts-1 from the previous tile)
     if (tid == 0) { sh.mlen[0] = (uint16_t)sh.sc[SC_CARRY_LEN]; sh.mdist[0] = (uint16_t)sh.sc[SC_CARRY_DIST]; }
-    {
-      // every lane owns PPT positions and walks their chains as ONE loop: when a position is finished the
-      // lane moves on to its next one instead of idling until the slowest lane of the warp is done with its
-      int j = 0;
-      MatchState ms;
-      ms.done = true;
-      bool have = false;
-      while (j < PPT) {
-        if (!have) {
-          uint32_t i = tid + THREADS * j, p = ts + i;
-          if (p < te && p + 4 <= n) { match_begin(ms, ring, p, n, sh.first[i], lp.depth); have = true; }
-          else { sh.mlen[1 + i] = 0; sh.mdist[1 + i] = 0; j++; }
-        } else if (ms.done) {
-          uint32_t i = tid + THREADS * j;
-          sh.mlen[1 + i] = (uint16_t)(ms.best >= (uint32_t)kMinMatch ? ms.best : 0);
-          sh.mdist[1 + i] = (uint16_t)ms.best_dist;
-          have = false; j++;
-        } else {
-          match_step(ms, ring, prevv, lp.nice);
-        }
-      }
+    for (int j = 0; j < PPT; j++) {
+      // begin / store are uniform over the warp; only the chain steps diverge (lanes with short chains idle)
+      uint32_t i = tid + THREADS * j, p = ts + i, d = 0, l = 0;
+      if (p < te && p + 4 <= n) l = find_match(ring, prevv, p, n, sh.first[i], lp.depth, lp.nice, d);
+      sh.mlen[1 + i] = (uint16_t)l;
+      sh.mdist[1 + i] = (uint16_t)d;
     }
     __syncthreads();
     // 4. lazy parse by pointer jumping over nodes v = 2 * (p - ts) + kind; codes >= 2T are exits

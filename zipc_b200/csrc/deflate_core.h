@@ -94,13 +94,16 @@ ZHD uint32_t ring_load32(const Ring &ring, uint32_t pos) {
   uint32_t i = pos & (kRing - 1);
   uint32_t a = i >> 2, s = (i & 3u) * 8u;
   uint32_t lo = ring.word(a), hi = ring.word((a + 1) & (kRing / 4 - 1));
+#if defined(__CUDA_ARCH__)
+  return __funnelshift_r(lo, hi, s);
+#else
   return s ? (lo >> s) | (hi << (32 - s)) : lo;
+#endif
 }
 
 template <class Ring>
 ZHD uint32_t ring_load8(const Ring &ring, uint32_t pos) {
-  uint32_t i = pos & (kRing - 1);
-  return (ring.word(i >> 2) >> ((i & 3u) * 8u)) & 0xFFu;
+  return ring.byte(pos & (kRing - 1));
 }
 
 // The chain walk of one position as a resumable state machine, so that a GPU lane can interleave the

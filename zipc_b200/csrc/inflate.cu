@@ -24,6 +24,10 @@
 //
 // Algorithmic bytes: C + U per stream (compressed read + uncompressed written).  The kernel is
 // issue/latency bound (serial bit parsing), not HBM bound: see DESIGN.md.
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+
 #include "common.cuh"
 #include "adler_core.cuh"
 
@@ -59,8 +63,9 @@ struct __align__(16) WarpScratch {
 };
 
 constexpr int QN = K * G;      // tokens per warp round
+constexpr int kCompBytes = (QN + 34) * 2 + (QN + 32) + 4;  // per warp: cstart u16[QN+34], cidx u8[QN+32], padded to 4
 constexpr size_t kSmemBytes = sizeof(LaneTabs) * (WARPS * G + 1) + sizeof(WarpScratch) * WARPS +
-                              sizeof(uint32_t) * WARPS * QN * 2 + sizeof(uint16_t) * WARPS * (QN + 2) * 2 + 64 + 128 + 64;
+                              sizeof(uint32_t) * WARPS * QN * 2 + kCompBytes * WARPS + 64 + 128 + 64;
 
 enum : uint32_t { S_IDLE = 0, S_HDR = 1, S_DATA = 2, S_STORED = 3, S_FINISH = 4, S_EXIT = 5 };
 
@@ -85,6 +90,8 @@ struct BitReader {
   uint32_t n;            // valid bits in buf
   uint32_t ahead;        // the word after the ones in buf, already fetched (hides the load latency)
   uint64_t loaded;       // stream bits moved into buf so far (can exceed 8*len by < 64+32 bits)
+  uint64_t limit;        // 8 * len
+  bool tail;             // loaded > limit: only then can a token have run past the end of the input
   __device__ __forceinline__ uint32_t fetch() {
     uint32_t w = wp < wend ? *wp : 0u;
     wp++;
@@ -99,6 +106,8 @@ struct BitReader {
     buf = (uint64_t)(w >> (8 * a));
     n = 32 - 8 * a;
     loaded = byte_pos * 8 + n;
+    limit = len * 8;
+    tail = loaded > limit;
     ahead = fetch();
   }
   __device__ __forceinline__ void refill() {  // afterwards n >= 33
@@ -106,12 +115,14 @@ struct BitReader {
       buf |= (uint64_t)ahead << n;
       n += 32;
       loaded += 32;
+      tail = loaded > limit;
       ahead = fetch();
     }
   }
   __device__ __forceinline__ uint32_t peek(uint32_t cnt) const { return (uint32_t)buf & ((1u << cnt) - 1u); }
   __device__ __forceinline__ void drop(uint32_t cnt) { buf >>= cnt; n -= cnt; }
   __device__ __forceinline__ uint64_t consumed() const { return loaded - n; }
+  __device__ __forceinline__ bool overrun() const { return tail && loaded - n > limit; }
 };
 
 // ---- canonical walk for codes longer than the table (the reference's read_symbol, :584-591) --------
@@ -220,22 +231,23 @@ __device__ void build_decoder_warp(WarpScratch &ws, int first, int n, int bits, 
 template <bool COUNT_ONLY>
 __global__ void __launch_bounds__(THREADS, 1)
 inflate_kernel(const InflateTask *__restrict__ tasks, uint32_t ntasks, InflateResult *__restrict__ results,
-               unsigned int *__restrict__ queue, uint16_t *__restrict__ g_syms, int adler_mode) {
+               unsigned int *__restrict__ queue, uint16_t *__restrict__ g_syms, int adler_mode, int active_warps) {
   // adler_mode: -1 = no checksum in this kernel, else ZIPC_ADLER_* (fused per-block Adler-32 of the output)
   extern __shared__ __align__(16) uint8_t smem_raw[];
   LaneTabs *tabs = reinterpret_cast<LaneTabs *>(smem_raw);                 // [WARPS*G] + fixed
   LaneTabs &fixed = tabs[WARPS * G];
   WarpScratch *wss = reinterpret_cast<WarpScratch *>(tabs + WARPS * G + 1);
   uint32_t *tokq = reinterpret_cast<uint32_t *>(wss + WARPS);              // [WARPS][2][K][G]
-  uint16_t *tbq = reinterpret_cast<uint16_t *>(tokq + WARPS * QN * 2);     // [WARPS][2][QN+2] flattened byte bases
-  uint16_t *s_len_tab = tbq + WARPS * (QN + 2) * 2;
+  uint8_t *compq = reinterpret_cast<uint8_t *>(tokq + WARPS * QN * 2);     // [WARPS] compacted token lists
+  uint16_t *s_len_tab = reinterpret_cast<uint16_t *>(compq + ((WARPS * kCompBytes + 3) & ~3));
   uint32_t *s_dist_tab = reinterpret_cast<uint32_t *>(s_len_tab + 32);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   WarpScratch &ws = wss[warp];
   const bool leader = lane < G;
   LaneTabs &mine = tabs[warp * G + (leader ? lane : 0)];
   uint2 *myq = reinterpret_cast<uint2 *>(tokq + warp * QN * 2);  // [j*G+g]: x = dep << 31 | len << 16 | dist-or-byte, y = output offset inside the round
-  uint16_t *tb = tbq + warp * (QN + 2) * 2;       // exclusive byte offsets of the independent tokens
+  uint16_t *cstart = reinterpret_cast<uint16_t *>(compq + warp * kCompBytes);  // byte offset of compacted token c (+ end sentinel)
+  uint8_t *cidx = reinterpret_cast<uint8_t *>(cstart + QN + 34);                // queue slot of compacted token c
   const uint32_t slot = (blockIdx.x * WARPS + warp) * G + (leader ? lane : 0);
   uint16_t *my_syms = g_syms + (size_t)slot * SYMS_PER_SLOT;
   uint16_t *fixed_syms = g_syms + (size_t)(gridDim.x * WARPS * G + blockIdx.x) * SYMS_PER_SLOT;
@@ -256,6 +268,9 @@ inflate_kernel(const InflateTask *__restrict__ tasks, uint32_t ntasks, InflateRe
   }
   __syncthreads();
 
+  // Streams are packed into the first `active_warps` warps of every CTA (a warp's round costs the same
+  // whether 1 or G of its leaders are busy); the other warps only helped with the fixed tables.
+  if (warp >= active_warps) return;
   // per-leader decoder state (lanes >= G carry dead copies)
   uint32_t state = leader ? S_IDLE : S_EXIT, task = 0, status = ZIPC_OK;
   BitReader br{};
@@ -274,12 +289,18 @@ inflate_kernel(const InflateTask *__restrict__ tasks, uint32_t ntasks, InflateRe
   const uint32_t *dist_lut = nullptr;
   const uint16_t *lit_syms = nullptr, *dist_syms = nullptr;
 
+#ifdef ZB_INFLATE_TIMING
+  long long tA = 0, tD = 0, tE1 = 0, tE2 = 0, tG = 0, rounds = 0, ntoks = 0, t0 = clock64();
+#define ZB_TICK(acc) { long long t1 = clock64(); acc += t1 - t0; t0 = t1; }
+#else
+#define ZB_TICK(acc)
+#endif
   for (;;) {
     // ---- A: idle leaders pull work -------------------------------------------------------------------
     if (state == S_IDLE) {
       // first task: interleaved over the CTAs so the longest streams (sorted first) spread over all SMs;
       // afterwards from the shared queue, which starts behind the statically assigned ones
-      if (first_task) { task = (uint32_t)((lane * WARPS + warp) * gridDim.x + blockIdx.x); first_task = false; }
+      if (first_task) { task = (uint32_t)((lane * active_warps + warp) * gridDim.x + blockIdx.x); first_task = false; }
       else task = atomicAdd(queue, 1u);
       if (task < ntasks) {
         const InflateTask t = tasks[task];
@@ -435,19 +456,20 @@ inflate_kernel(const InflateTask *__restrict__ tasks, uint32_t ntasks, InflateRe
       }
     }
 
+    ZB_TICK(tA)
     // ---- D: leaders decode up to K tokens each (reference :593-616) -----------------------------------------
-    uint32_t ntok = 0;
+    uint32_t ntok = 0, depmask = 0;
     const uint64_t batch_pos = out_pos;  // output position of this leader's first queued token
     if (state == S_DATA) {
-      const uint64_t src_bits = src_len * 8;
       uint32_t rel = 0;                                                     // bytes produced in this round
       uint32_t hist = out_pos < 32768 ? (uint32_t)out_pos : 32768u;         // reachable history, capped
-      uint64_t room = out_cap - out_pos;
+      const uint64_t room64 = out_cap - out_pos;
+      uint32_t room = room64 > 0x7FFFFFFFull ? 0x7FFFFFFFu : (uint32_t)room64;  // a round produces < 2^12 bytes
       for (int k = 0; k < K; k++) {
         br.refill();
         uint32_t e = lit_lut[br.peek(LB)];
         uint32_t kind, val;
-        if (e != 0 && e != 0xFFFFu) { br.drop(e & 15u); kind = (e >> 4) & 7u; val = e >> 7; }
+        if ((uint16_t)(e + 1u) > 1u) { br.drop(e & 15u); kind = (e >> 4) & 7u; val = e >> 7; }   // neither 0 nor 0xFFFF
         else {
           int sym = e ? canon_decode(br, lit_cnt, lit_syms) : -1;
           if (sym < 0 || sym > 285) { status = ZIPC_ERR_CORRUPTED; state = S_FINISH; break; }
@@ -456,15 +478,15 @@ inflate_kernel(const InflateTask *__restrict__ tasks, uint32_t ntasks, InflateRe
           else { uint32_t lt = s_len_tab[sym - 257]; kind = lt >> 9; val = lt & 0x1FFu; }
         }
         if (kind == 7) {                                                    // literal
-          if (br.loaded > src_bits && br.consumed() > src_bits) { status = ZIPC_ERR_CORRUPTED; state = S_FINISH; break; }
+          if (br.overrun()) { status = ZIPC_ERR_CORRUPTED; state = S_FINISH; break; }
           if (room == 0) { status = ZIPC_ERR_SIZE_EXCEEDED; state = S_FINISH; break; }
           if (!COUNT_ONLY) myq[k * G + lane] = make_uint2(val, rel);
           ntok = k + 1; rel++; room--;
-          hist = hist < 32768u ? hist + 1 : hist;
+          hist = min(hist + 1u, 32768u);
           continue;
         }
         if (kind == 6) {                                                    // end of block
-          if (br.loaded > src_bits && br.consumed() > src_bits) { status = ZIPC_ERR_CORRUPTED; state = S_FINISH; }
+          if (br.overrun()) { status = ZIPC_ERR_CORRUPTED; state = S_FINISH; }
           else { state = final_blk ? S_FINISH : S_HDR; ad_pending = true; }
           break;
         }
@@ -473,7 +495,7 @@ inflate_kernel(const InflateTask *__restrict__ tasks, uint32_t ntasks, InflateRe
         br.refill();
         uint32_t e2 = dist_lut[br.peek(DB)];
         uint32_t dist;
-        if (e2 != 0 && e2 != ENT_LONG) {
+        if (e2 + 1u > 1u) {                                                 // neither 0 nor ENT_LONG
           br.drop(e2 & 15u);
           uint32_t deb = (e2 >> 4) & 15u;
           dist = (e2 >> 8) + br.peek(deb);
@@ -485,26 +507,34 @@ inflate_kernel(const InflateTask *__restrict__ tasks, uint32_t ntasks, InflateRe
           dist = (dt & 0xFFFFu) + br.peek(dt >> 16);
           br.drop(dt >> 16);
         }
-        if ((br.loaded > src_bits && br.consumed() > src_bits) || dist > hist) { status = ZIPC_ERR_CORRUPTED; state = S_FINISH; break; }
+        if (br.overrun() || dist > hist) { status = ZIPC_ERR_CORRUPTED; state = S_FINISH; break; }
         if (length > room) { status = ZIPC_ERR_SIZE_EXCEEDED; state = S_FINISH; break; }
         if (!COUNT_ONLY) {
           // a match is independent of this round when all of its source bytes precede the round
-          uint32_t reach = dist < length ? dist : length;                  // source bytes actually read
-          uint32_t dep = (dist < rel + reach) ? 0x80000000u : 0u;          // pos - dist + reach > batch_pos
-          myq[k * G + lane] = make_uint2(dep | (length << 16) | dist, rel);
+          uint32_t reach = min(dist, length);                               // source bytes actually read
+          bool dep = dist < rel + reach;                                    // pos - dist + reach > batch_pos
+          depmask |= dep ? (1u << k) : 0u;
+          myq[k * G + lane] = make_uint2((dep ? 0x80000000u : 0u) | (length << 16) | dist, rel);
         }
         ntok = k + 1; rel += length; room -= length;
-        hist = hist + length < 32768u ? hist + length : 32768u;
+        hist = min(hist + length, 32768u);
       }
       out_pos += rel;
     }
 
+    ZB_TICK(tD)
+#ifdef ZB_INFLATE_TIMING
+    rounds++; ntoks += ntok;
+#endif
     // ---- E: the warp executes the queued tokens ------------------------------------------------------------
     if (!COUNT_ONLY) {
       __syncwarp();
       const unsigned long long base_ptr = (unsigned long long)(uintptr_t)(dst + batch_pos);
       // E1: literals and matches whose source lies before this round: no ordering needed, so all their
-      // bytes are flattened over the lanes (QN tokens = 2 per lane for the prefix sum)
+      // bytes are flattened over the lanes.  The non-empty independent tokens are first compacted (QN queue
+      // slots, 2 per lane) so that a pass can find the owner of each byte with one warp OR-reduction:
+      // bit (end - base - 1) of M marks where a token ends inside the 32-byte window, and a byte's owner is
+      // the window's first token plus the number of ends before it.
       uint32_t l0, l1;
       {
         uint32_t n0 = __shfl_sync(0xffffffffu, ntok, lane & (G - 1));
@@ -521,27 +551,33 @@ inflate_kernel(const InflateTask *__restrict__ tasks, uint32_t ntasks, InflateRe
       }
       const uint32_t tot0 = __shfl_sync(0xffffffffu, i0, 31);
       const uint32_t total = tot0 + __shfl_sync(0xffffffffu, i1, 31);
-      tb[lane] = (uint16_t)(i0 - l0);
-      tb[lane + 32] = (uint16_t)(tot0 + i1 - l1);
-      if (lane == 0) tb[QN] = (uint16_t)total;
+      const uint32_t lt_mask = (1u << lane) - 1u;
+      const uint32_t b0 = __ballot_sync(0xffffffffu, l0 != 0), b1 = __ballot_sync(0xffffffffu, l1 != 0);
+      const uint32_t ncomp = __popc(b0) + __popc(b1);
+      if (l0) { uint32_t r = __popc(b0 & lt_mask); cstart[r] = (uint16_t)(i0 - l0); cidx[r] = (uint8_t)lane; }
+      if (l1) { uint32_t r = __popc(b0) + __popc(b1 & lt_mask); cstart[r] = (uint16_t)(tot0 + i1 - l1); cidx[r] = (uint8_t)(lane + 32); }
+      cstart[ncomp + lane] = lane == 0 ? (uint16_t)total : (uint16_t)0xFFFF;  // end sentinel, then "never ends"
+      if (lane < 2) cstart[ncomp + 32 + lane] = 0xFFFF;
       __syncwarp();
       // four passes at a time: all loads are issued before the first store, so one L2 round trip
       // covers 128 bytes of copies
+      uint32_t cbase = 0;  // first compacted token that reaches into the current window
       for (uint32_t base = 0; base < total; base += 128) {
         uint8_t val[4];
         uint8_t *dq[4];
 #pragma unroll
         for (int u = 0; u < 4; u++) {
-          uint32_t b = base + 32 * u + lane;
+          const uint32_t wb = base + 32 * u;                 // window [wb, wb + 32)
+          uint32_t b = wb + lane;
           bool act = b < total;
-          uint32_t lo = 0;  // token i with tb[i] <= b < tb[i+1] (empty tokens are skipped)
-#pragma unroll
-          for (int step = QN / 2; step > 0; step >>= 1)
-            if ((uint32_t)tb[lo + step] <= b) lo += step;
-          uint32_t i = act ? lo : 0u;
-          uint32_t q = b - tb[i];
-          uint2 ent = myq[i];
-          unsigned long long d = __shfl_sync(0xffffffffu, base_ptr, (int)(i & (G - 1)));
+          uint32_t endrel = (uint32_t)cstart[cbase + lane + 1] - wb;   // end of token cbase+lane, relative to the window
+          uint32_t M = __reduce_or_sync(0xffffffffu, (endrel - 1u) < 32u ? 1u << (endrel - 1u) : 0u);
+          uint32_t c = cbase + __popc(M & lt_mask);
+          cbase += __popc(M);
+          if (!act) c = 0;
+          uint32_t q = b - cstart[c];
+          uint2 ent = myq[cidx[c]];
+          unsigned long long d = __shfl_sync(0xffffffffu, base_ptr, (int)(cidx[c] & (G - 1)));
           uint8_t *dp = reinterpret_cast<uint8_t *>((uintptr_t)d) + ent.y;
           uint32_t mlen = (ent.x >> 16) & 0x1FFu, mdist = ent.x & 0xFFFFu;
           dq[u] = act ? dp + q : nullptr;
@@ -558,14 +594,14 @@ inflate_kernel(const InflateTask *__restrict__ tasks, uint32_t ntasks, InflateRe
           if (dq[u]) *dq[u] = val[u];
       }
       __syncwarp();
+      ZB_TICK(tE1)
       // E2: matches that read bytes produced in this round, in token order (rare for text)
-      uint32_t maxtok = ntok;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) maxtok = max(maxtok, __shfl_xor_sync(0xffffffffu, maxtok, o));
-      for (uint32_t j = 1; j < maxtok; j++) {
+      uint32_t levels = __reduce_or_sync(0xffffffffu, depmask);
+      while (levels) {
+        const uint32_t j = (uint32_t)__ffs((int)levels) - 1u;
+        levels &= levels - 1u;
         uint2 ent2 = (leader && j < ntok) ? myq[j * G + lane] : make_uint2(0u, 0u);
         uint32_t ent = ent2.x;
-        if (!__any_sync(0xffffffffu, ent >> 31)) continue;
         uint32_t tlen = (ent >> 31) ? ((ent >> 16) & 0x1FFu) : 0u;
         uint32_t pos = ent2.y;
         uint32_t incl = tlen;
@@ -600,6 +636,7 @@ inflate_kernel(const InflateTask *__restrict__ tasks, uint32_t ntasks, InflateRe
         }
         __syncwarp();
       }
+      ZB_TICK(tE2)
       // stored blocks: one coalesced copy from the input per leader (reference :678-680)
       uint32_t sm = __ballot_sync(0xffffffffu, state == S_STORED);
       while (sm) {
@@ -636,6 +673,7 @@ inflate_kernel(const InflateTask *__restrict__ tasks, uint32_t ntasks, InflateRe
       }
     }
     ad_pending = false;
+    ZB_TICK(tG)
 
     // ---- F: finished streams report ---------------------------------------------------------------------
     if (state == S_FINISH) {
@@ -647,6 +685,11 @@ inflate_kernel(const InflateTask *__restrict__ tasks, uint32_t ntasks, InflateRe
       state = S_IDLE;
     }
   }
+#ifdef ZB_INFLATE_TIMING
+  if ((blockIdx.x == 0 || blockIdx.x == 77) && lane == 0 && warp < 4)
+    printf("blk %d warp %d: hdr/build %lld  decode %lld  copyE1 %lld  copyE2 %lld  adler %lld  clk | rounds %lld tokens(lane0) %lld\n",
+           blockIdx.x, warp, tA, tD, tE1, tE2, tG, rounds, ntoks);
+#endif
 }
 
 bool g_attr_set = false;
@@ -665,17 +708,28 @@ int inflate_launch(zipc_b200_ctx *ctx, const InflateTask *d_tasks, uint32_t n, I
   uint32_t grid = (uint32_t)ctx->sm_count;
   if (grid > n) grid = n;
   size_t sym_bytes = (size_t)(grid * WARPS * G + grid) * SYMS_PER_SLOT * sizeof(uint16_t);
-  if (int st = ctx->d_scratch.reserve(sym_bytes + 256)) return st;
+  if (int st = ctx->d_scratch.reserve(sym_bytes + 256 + 4096)) return st;
   unsigned int *queue = reinterpret_cast<unsigned int *>(ctx->d_scratch.as<uint8_t>() + sym_bytes);
+  // how many warps per CTA take streams: enough for `oversub` streams per leader over the whole batch
+  int oversub = 1;
+  if (const char *e = getenv("ZIPC_B200_INFLATE_OVERSUB")) oversub = std::max(1, atoi(e));
+  // default: spread the streams over all warps (measured: the kernel is bound by per-warp latency, a warp
+  // with few busy leaders finishes its rounds sooner); ZIPC_B200_INFLATE_OVERSUB packs them instead
+  int active_warps = WARPS;
+  if (getenv("ZIPC_B200_INFLATE_OVERSUB")) {
+    active_warps = (int)((n + (size_t)grid * G * oversub - 1) / ((size_t)grid * G * oversub));
+    active_warps = std::max(1, std::min(active_warps, WARPS));
+  }
+  if (const char *e = getenv("ZIPC_B200_INFLATE_WARPS")) active_warps = std::max(1, std::min(atoi(e), WARPS));
   {
-    unsigned int start = grid * WARPS * G;  // tasks [0, start) are assigned statically
+    unsigned int start = grid * active_warps * G;  // tasks [0, start) are assigned statically
     ZB_CUDA(ctx, cudaMemcpyAsync(queue, &start, sizeof start, cudaMemcpyHostToDevice, ctx->stream));
   }
   KernelTimer kt(ctx);
   if (count_only)
-    inflate_kernel<true><<<grid, THREADS, kSmemBytes, ctx->stream>>>(d_tasks, n, d_results, queue, ctx->d_scratch.as<uint16_t>(), -1);
+    inflate_kernel<true><<<grid, THREADS, kSmemBytes, ctx->stream>>>(d_tasks, n, d_results, queue, ctx->d_scratch.as<uint16_t>(), -1, active_warps);
   else
-    inflate_kernel<false><<<grid, THREADS, kSmemBytes, ctx->stream>>>(d_tasks, n, d_results, queue, ctx->d_scratch.as<uint16_t>(), adler_mode);
+    inflate_kernel<false><<<grid, THREADS, kSmemBytes, ctx->stream>>>(d_tasks, n, d_results, queue, ctx->d_scratch.as<uint16_t>(), adler_mode, active_warps);
   ctx->launches++;
   ZB_CUDA(ctx, cudaGetLastError());
   return ZIPC_OK;
