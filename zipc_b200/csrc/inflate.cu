@@ -82,54 +82,58 @@ __constant__ uint32_t c_dist_tab[30] = {  // base | extra << 16   (reference :27
     4097 | 11 << 16, 6145 | 11 << 16, 8193 | 12 << 16,  12289 | 12 << 16, 16385 | 13 << 16, 24577 | 13 << 16};
 __constant__ uint8_t c_clen_order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
 
-// ---- bit reader: 64-bit buffer refilled with aligned 32-bit words --------------------------------
+// ---- bit reader: two 32-bit words + a bit offset; the next 32 stream bits are one funnel shift away ----------
+// After refill() at least 32 valid bits are visible; callers peek / drop at most 32 bits between refills.
 struct BitReader {
   const uint32_t *wp;    // next word to load into `ahead`
   const uint32_t *wend;  // first word not to load (words past the stream read as 0)
-  uint64_t buf;
-  uint32_t n;            // valid bits in buf
-  uint32_t ahead;        // the word after the ones in buf, already fetched (hides the load latency)
-  uint64_t loaded;       // stream bits moved into buf so far (can exceed 8*len by < 64+32 bits)
-  uint64_t limit;        // 8 * len
-  bool tail;             // loaded > limit: only then can a token have run past the end of the input
+  uint32_t lo, hi;       // current and next word
+  uint32_t pos;          // bit offset of the read position inside lo (may reach 63 before refill)
+  uint32_t ahead;        // the word after hi, already fetched (hides the load latency)
+  long long base;        // stream bit offset of bit 0 of lo (negative inside a leading partial word)
+  long long limit;       // 8 * len
+  bool tail;             // the visible window may reach past the end of the input
   __device__ __forceinline__ uint32_t fetch() {
     uint32_t w = wp < wend ? *wp : 0u;
     wp++;
     return w;
   }
-  __device__ __forceinline__ void seek(const uint8_t *base, uint64_t len, uint64_t byte_pos) {
-    const uint8_t *p = base + byte_pos;
+  __device__ __forceinline__ void seek(const uint8_t *src, uint64_t len, uint64_t byte_pos) {
+    const uint8_t *p = src + byte_pos;
     uint32_t a = (uint32_t)((uintptr_t)p & 3);
     wp = reinterpret_cast<const uint32_t *>(p - a);
-    wend = reinterpret_cast<const uint32_t *>(((uintptr_t)(base + len) + 3) & ~(uintptr_t)3);
-    uint32_t w = fetch();
-    buf = (uint64_t)(w >> (8 * a));
-    n = 32 - 8 * a;
-    loaded = byte_pos * 8 + n;
-    limit = len * 8;
-    tail = loaded > limit;
-    ahead = fetch();
+    wend = reinterpret_cast<const uint32_t *>(((uintptr_t)(src + len) + 3) & ~(uintptr_t)3);
+    lo = fetch(); hi = fetch(); ahead = fetch();
+    pos = 8 * a;
+    base = (long long)(byte_pos * 8) - 8 * a;
+    limit = (long long)(len * 8);
+    tail = base + 96 > limit;
   }
-  __device__ __forceinline__ void refill() {  // afterwards n >= 33
-    if (n <= 32) {
-      buf |= (uint64_t)ahead << n;
-      n += 32;
-      loaded += 32;
-      tail = loaded > limit;
+  __device__ __forceinline__ void refill() {  // afterwards pos < 32
+    if (pos >= 32) {
+      pos -= 32;
+      lo = hi; hi = ahead;
       ahead = fetch();
+      base += 32;
+      tail = base + 96 > limit;
     }
   }
-  __device__ __forceinline__ uint32_t peek(uint32_t cnt) const { return (uint32_t)buf & ((1u << cnt) - 1u); }
-  __device__ __forceinline__ void drop(uint32_t cnt) { buf >>= cnt; n -= cnt; }
-  __device__ __forceinline__ uint64_t consumed() const { return loaded - n; }
-  __device__ __forceinline__ bool overrun() const { return tail && loaded - n > limit; }
+  // pos may have run past 32 since the last refill (a code followed by its extra bits): then the window
+  // starts inside hi and continues in the prefetched word
+  __device__ __forceinline__ uint32_t window() const {
+    return pos < 32 ? __funnelshift_r(lo, hi, pos) : __funnelshift_r(hi, ahead, pos - 32);
+  }
+  __device__ __forceinline__ uint32_t peek(uint32_t cnt) const { return window() & ((1u << cnt) - 1u); }  // cnt < 32
+  __device__ __forceinline__ void drop(uint32_t cnt) { pos += cnt; }
+  __device__ __forceinline__ uint64_t consumed() const { return (uint64_t)(base + pos); }
+  __device__ __forceinline__ bool overrun() const { return tail && base + (long long)pos > limit; }
 };
 
 // ---- canonical walk for codes longer than the table (the reference's read_symbol, :584-591) --------
 // Returns the symbol and consumes its bits, or -1 (the reference would run off counts.(16)).
 __device__ __forceinline__ int canon_decode(BitReader &br, const uint16_t *cnt, const uint16_t *syms) {
   int len = 1, base = 0, offs = 0;
-  uint32_t bits = (uint32_t)br.buf;
+  uint32_t bits = br.window();
   for (; len <= 15; len++) {
     offs = 2 * offs + (int)(bits & 1u);
     bits >>= 1;
@@ -327,9 +331,9 @@ inflate_kernel(const InflateTask *__restrict__ tasks, uint32_t ntasks, InflateRe
       uint32_t type = h >> 1;
       if (br.consumed() > src_len * 8) { status = ZIPC_ERR_CORRUPTED; state = S_FINISH; }
       else if (type == 0) {
-        br.drop(br.n & 7u);  // to the byte boundary
+        br.drop((8u - ((uint32_t)br.consumed() & 7u)) & 7u);  // to the byte boundary
         br.refill();
-        uint32_t v = (uint32_t)br.buf;
+        uint32_t v = br.window();
         br.drop(32);
         uint32_t length = v & 0xFFFFu, inv = v >> 16;
         uint64_t pos = br.consumed() >> 3;
@@ -477,44 +481,41 @@ inflate_kernel(const InflateTask *__restrict__ tasks, uint32_t ntasks, InflateRe
           else if (sym == 256) { kind = 6; val = 0; }
           else { uint32_t lt = s_len_tab[sym - 257]; kind = lt >> 9; val = lt & 0x1FFu; }
         }
-        if (kind == 7) {                                                    // literal
-          if (br.overrun()) { status = ZIPC_ERR_CORRUPTED; state = S_FINISH; break; }
-          if (room == 0) { status = ZIPC_ERR_SIZE_EXCEEDED; state = S_FINISH; break; }
-          if (!COUNT_ONLY) myq[k * G + lane] = make_uint2(val, rel);
-          ntok = k + 1; rel++; room--;
-          hist = min(hist + 1u, 32768u);
-          continue;
-        }
         if (kind == 6) {                                                    // end of block
           if (br.overrun()) { status = ZIPC_ERR_CORRUPTED; state = S_FINISH; }
           else { state = final_blk ? S_FINISH : S_HDR; ad_pending = true; }
           break;
         }
-        uint32_t length = val + br.peek(kind);
-        br.drop(kind);
-        br.refill();
-        uint32_t e2 = dist_lut[br.peek(DB)];
-        uint32_t dist;
-        if (e2 + 1u > 1u) {                                                 // neither 0 nor ENT_LONG
-          br.drop(e2 & 15u);
-          uint32_t deb = (e2 >> 4) & 15u;
-          dist = (e2 >> 8) + br.peek(deb);
-          br.drop(deb);
-        } else {
-          int dsym = e2 ? canon_decode(br, dist_cnt, dist_syms) : -1;
-          if (dsym < 0 || dsym > 29) { status = ZIPC_ERR_CORRUPTED; state = S_FINISH; break; }
-          uint32_t dt = s_dist_tab[dsym];
-          dist = (dt & 0xFFFFu) + br.peek(dt >> 16);
-          br.drop(dt >> 16);
+        // literal and match lanes of the warp share everything below except the distance decode, so a round
+        // of mixed tokens does not pay for two copies of the checks / queue write / bookkeeping
+        uint32_t length = 1, dist = 0;
+        if (kind != 7) {
+          length = val + br.peek(kind);
+          br.drop(kind);
+          br.refill();
+          uint32_t e2 = dist_lut[br.peek(DB)];
+          if (e2 + 1u > 1u) {                                               // neither 0 nor ENT_LONG
+            br.drop(e2 & 15u);
+            uint32_t deb = (e2 >> 4) & 15u;
+            dist = (e2 >> 8) + br.peek(deb);
+            br.drop(deb);
+          } else {
+            int dsym = e2 ? canon_decode(br, dist_cnt, dist_syms) : -1;
+            if (dsym < 0 || dsym > 29) { status = ZIPC_ERR_CORRUPTED; state = S_FINISH; break; }
+            uint32_t dt = s_dist_tab[dsym];
+            dist = (dt & 0xFFFFu) + br.peek(dt >> 16);
+            br.drop(dt >> 16);
+          }
         }
         if (br.overrun() || dist > hist) { status = ZIPC_ERR_CORRUPTED; state = S_FINISH; break; }
         if (length > room) { status = ZIPC_ERR_SIZE_EXCEEDED; state = S_FINISH; break; }
         if (!COUNT_ONLY) {
           // a match is independent of this round when all of its source bytes precede the round
           uint32_t reach = min(dist, length);                               // source bytes actually read
-          bool dep = dist < rel + reach;                                    // pos - dist + reach > batch_pos
+          bool dep = kind != 7 && dist < rel + reach;                       // pos - dist + reach > batch_pos
           depmask |= dep ? (1u << k) : 0u;
-          myq[k * G + lane] = make_uint2((dep ? 0x80000000u : 0u) | (length << 16) | dist, rel);
+          uint32_t x = kind == 7 ? val : ((dep ? 0x80000000u : 0u) | (length << 16) | dist);
+          myq[k * G + lane] = make_uint2(x, rel);
         }
         ntok = k + 1; rel += length; room -= length;
         hist = min(hist + length, 32768u);
