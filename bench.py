@@ -173,8 +173,22 @@ def run_crc32(h: Harness, steps, warmup, rank):
     e2e_s = (time.perf_counter() - t0) / esteps
     check = zlib.crc32(host[: 64 << 20])  # cheap spot check of the generator + full check of the result below
     assert out.value == got, (hex(out.value), hex(got))
+    # Adler-32 over the same resident buffer (synchronous call: chunk kernel + device fold + 4-byte read back)
+    adler = {}
+    for name, mode in (("ref_compat", 0), ("rfc1950", 1)):
+        aout = C.c_uint32()
+        afn = lambda: h.L.zipc_b200_adler32_dev(h.ctx.h, d.data_ptr(), n, mode, C.byref(aout))
+        for _ in range(3):
+            assert afn() == 0
+        t0 = time.perf_counter()
+        for _ in range(10):
+            afn()
+        dt = (time.perf_counter() - t0) / 10
+        akms = h.kernel_ms(afn, 5)
+        adler[name] = {"value": "%08x" % aout.value, "GBps_per_call": round(n / dt / 1e9, 1), "chunk_kernel_ms": round(akms, 4) if akms else None}
+    assert int(adler["rfc1950"]["value"], 16) == zlib.adler32(host), adler
     return dict(units=n, total_ms=total_ms, launches=launches, kernel_ms=kms, algo_bytes=n, e2e_s=e2e_s,
-                h2d=n, d2h=4, result=got, host=host, extra={"crc32": "%08x" % got, "spot": "%08x" % check})
+                h2d=n, d2h=4, result=got, host=host, extra={"crc32": "%08x" % got, "spot": "%08x" % check, "adler32": adler})
 
 
 def _pack_device(h: Harness, items):

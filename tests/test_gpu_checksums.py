@@ -59,6 +59,35 @@ def test_adler32_quirk_kats(ctx):  # SURVEY.md 8a row A-n
         assert ctx.adler32(data, _lib.ADLER_RFC1950) == rfc
 
 
+def test_adler32_device_fold_adversarial(ctx):
+    """The fold of per-chunk sums runs on the device; inputs chosen so that every class of chunk occurs: certain
+    no-wrap, certain wrap-to-negative (0xFF runs), low-weight chunks after a negative state (zeros after 0xFF),
+    and chunks within 65521 of the 2^31 boundary (ramps)."""
+    rng = np.random.default_rng(7)
+    pieces = []
+    for i in range(400):
+        kind = i % 8
+        n = int(rng.integers(1, 40000))
+        if kind == 0: pieces.append(np.full(n, 0xFF, np.uint8))
+        elif kind == 1: pieces.append(np.zeros(n, np.uint8))
+        elif kind == 2: pieces.append(rng.integers(0, 256, n, dtype=np.uint8))
+        elif kind == 3: pieces.append(np.full(n, int(rng.integers(120, 136)), np.uint8))   # B near 2^31 per chunk
+        elif kind == 4: pieces.append(np.full(n, 1, np.uint8))
+        elif kind == 5: pieces.append((np.arange(n) % 251).astype(np.uint8))
+        elif kind == 6: pieces.append(rng.integers(100, 160, n, dtype=np.uint8))
+        else: pieces.append(np.full(n, int(rng.integers(0, 256)), np.uint8))
+    data = np.concatenate(pieces)
+    for lo, hi in [(0, len(data)), (1, len(data) - 3), (5552 * 7 + 11, 5552 * 900)]:
+        v = data[lo:hi]
+        b = v.tobytes()
+        assert ctx.adler32(v, _lib.ADLER_REF_COMPAT) == zo.adler32(b)
+        assert ctx.adler32(v, _lib.ADLER_RFC1950) == zlib.adler32(b)
+    for fill in (0x00, 0x80, 0x81, 0x7F, 0xFF):   # 0x80/0x81: every chunk sits at the wrap boundary
+        v = np.full(12 * 1024 * 1024 + 5, fill, np.uint8)
+        assert ctx.adler32(v, _lib.ADLER_REF_COMPAT) == zo.adler32(v.tobytes())
+        assert ctx.adler32(v, _lib.ADLER_RFC1950) == zlib.adler32(v.tobytes())
+
+
 def test_crc32_batch_ragged(ctx):
     rng = np.random.default_rng(5)
     items = [synth.rand_v1(i, int(s)).tobytes() for i, s in enumerate(rng.integers(0, 70000, size=300))]

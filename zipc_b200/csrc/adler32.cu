@@ -50,6 +50,209 @@ adler_ranges_kernel(const AdlerSeg *__restrict__ segs, uint32_t nseg, uint2 *__r
   }
 }
 
+
+// ---- device-side fold of the per-chunk partial sums ----------------------------------------------------------
+// s1 never wraps (s1 + A < 2^21), so s1 before chunk c is (1 + prefix sum of A) mod 65521: a scan.
+// s2' = srem(wrap32(s2 + W)), W = n * s1_before + B < 2^32.  Writing s2 as (residue r, negative?):
+//   M <= W < 2^31 - M   : no wrap whatever s2 is      -> r' = r + W,      result non-negative   ("L")
+//   W >= 2^31 + M       : always wraps to a negative  -> r' = r + W - K,  result negative       ("H"), K = 2^32 mod M
+//   W < M               : no wrap; stays non-negative if s2 was non-negative (a carry chain, resolved by a scan)
+//   anything else       : depends on the exact s2 -> resolved serially, in order ("U"; ~4e-4 of chunks on random data)
+// RFC 1950 mode is the same scan with every chunk treated as "L" and exact arithmetic.
+constexpr int kFoldThreads = 1024;
+constexpr int kFoldItems = 8;                         // consecutive chunks per thread -> 64-byte coalesced loads
+constexpr int kFoldTile = kFoldThreads * kFoldItems;  // chunks per pass of the CTA
+constexpr uint32_t kM = 65521u;
+constexpr int kFoldSmem = kFoldTile * 7;
+
+struct OpAddMod {
+  __device__ __forceinline__ uint32_t operator()(uint32_t earlier, uint32_t later) const {
+    uint32_t x = earlier + later;
+    return x >= kM ? x - kM : x;
+  }
+};
+// (g,p) in bits 1,0: g = "known non-negative afterwards", p = "sign passes through unchanged"
+struct OpCarry {
+  __device__ __forceinline__ uint32_t operator()(uint32_t earlier, uint32_t later) const {
+    uint32_t g = (later >> 1) | (later & (earlier >> 1) & 1u);
+    return (g & 1u) << 1 | (earlier & later & 1u);
+  }
+  static constexpr uint32_t identity = 1u;
+};
+
+// inclusive scan over the CTA (one value per thread); *total = reduction over all threads
+template <typename Op>
+__device__ __forceinline__ uint32_t block_scan(uint32_t v, uint32_t *scratch, uint32_t *total) {
+  Op op;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t x = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    uint32_t t = __shfl_up_sync(0xffffffffu, x, o);
+    if (lane >= o) x = op(t, x);
+  }
+  __syncthreads();  // scratch free again
+  if (lane == 31) scratch[warp] = x;
+  __syncthreads();
+  if (warp == 0) {
+    uint32_t w = scratch[lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      uint32_t t = __shfl_up_sync(0xffffffffu, w, o);
+      if (lane >= o) w = op(t, w);
+    }
+    scratch[32 + lane] = w;
+  }
+  __syncthreads();
+  *total = scratch[63];
+  return warp ? op(scratch[32 + warp - 1], x) : x;
+}
+
+__global__ void __launch_bounds__(kFoldThreads, 1)
+adler_fold_kernel(const uint2 *__restrict__ ab, uint32_t first, uint32_t nchunks, int mode, uint32_t *__restrict__ out) {
+  __shared__ uint32_t scratch[64];
+  extern __shared__ __align__(16) uint8_t fold_smem[];  // kFoldSmem bytes: per-chunk W, residue, class for the serial walk
+  uint32_t *smW = reinterpret_cast<uint32_t *>(fold_smem);
+  uint16_t *smR = reinterpret_cast<uint16_t *>(fold_smem + kFoldTile * 4);
+  uint8_t *smK = fold_smem + kFoldTile * 6;
+  __shared__ uint32_t smU[kFoldItems][32];
+  __shared__ uint32_t s_corr, s_neg;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t K = (uint32_t)((1ull << 32) % kM);
+  const bool quirk = mode == ZIPC_ADLER_REF_COMPAT;
+  uint32_t s1_carry = 1u;   // s1 before the tile
+  uint32_t r_carry = 0u;    // residue of s2 before the tile
+  uint32_t nn_carry = 1u;   // s2 known non-negative before the tile
+  if (tid == 0) s_neg = 0;  // sign of s2 before the tile (exact; used by the serial walk only)
+  for (uint32_t t0 = 0; t0 < nchunks; t0 += kFoldTile) {
+    const uint32_t base = t0 + tid * kFoldItems;
+    uint32_t A[kFoldItems], B[kFoldItems];
+    if (base + kFoldItems <= nchunks) {
+      const uint4 *p = reinterpret_cast<const uint4 *>(ab + base);  // 64-byte aligned: base is a multiple of 8
+#pragma unroll
+      for (int i = 0; i < kFoldItems / 2; i++) {
+        uint4 u = p[i];
+        A[2 * i] = u.x; B[2 * i] = u.y; A[2 * i + 1] = u.z; B[2 * i + 1] = u.w;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < kFoldItems; i++) {
+        uint2 e = base + i < nchunks ? ab[base + i] : make_uint2(0u, 0u);
+        A[i] = e.x; B[i] = e.y;
+      }
+    }
+    // s1 before every chunk
+    uint32_t pa[kFoldItems], asum = 0;
+#pragma unroll
+    for (int i = 0; i < kFoldItems; i++) { pa[i] = asum; asum += A[i] % kM; }
+    asum %= kM;
+    uint32_t atot;
+    uint32_t ainc = block_scan<OpAddMod>(asum, scratch, &atot);
+    const uint32_t s1_thread = (s1_carry + ainc + kM - asum) % kM;
+    // W, class
+    uint32_t W[kFoldItems], k[kFoldItems], gp = OpCarry::identity;
+#pragma unroll
+    for (int i = 0; i < kFoldItems; i++) {
+      uint32_t s1 = (s1_thread + pa[i]) % kM;
+      uint32_t n = base + i == 0 ? first : 5552u;
+      W[i] = n * s1 + B[i];  // < 2^32: 5552*65520 + 255*5552*5553/2
+      uint32_t c;
+      if (base + i >= nchunks) c = 4;                                    // past the end: identity
+      else if (!quirk) c = 0;                                            // exact arithmetic: every chunk is "L"
+      else if (W[i] >= kM && W[i] < 0x80000000u - kM) c = 0;             // L
+      else if (W[i] >= 0x80000000u + kM) c = 1;                          // H
+      else if (W[i] < kM) c = 2;                                         // low W
+      else c = 3;                                                        // U
+      k[i] = c;
+      if (c == 0) gp = 2u; else if (c == 1 || c == 3) gp = 0u;
+    }
+    uint32_t nn_in = nn_carry;
+    if (quirk) {
+      uint32_t gtot;
+      uint32_t ginc = block_scan<OpCarry>(gp, scratch, &gtot);
+      uint32_t gexc = __shfl_up_sync(0xffffffffu, ginc, 1);
+      if (lane == 0) gexc = warp ? scratch[32 + warp - 1] : OpCarry::identity;
+      nn_in = (gexc >> 1) | (gexc & nn_carry & 1u);
+      nn_carry = (gtot >> 1) | (gtot & nn_carry & 1u);
+    }
+    // resolve low-W chunks, deltas
+    uint32_t pd[kFoldItems], dsum = 0, has_u = 0;
+#pragma unroll
+    for (int i = 0; i < kFoldItems; i++) {
+      if (k[i] == 2) k[i] = nn_in ? 0u : 3u;
+      if (k[i] != 4) nn_in = k[i] == 0;
+      has_u |= k[i] == 3;
+      pd[i] = dsum;
+      uint32_t w = W[i] % kM;
+      dsum += k[i] == 0 ? w : k[i] == 1 ? (w + kM - K) % kM : 0u;
+    }
+    dsum %= kM;
+    uint32_t dtot;
+    uint32_t dinc = block_scan<OpAddMod>(dsum, scratch, &dtot);
+    const uint32_t r_thread = (r_carry + dinc + kM - dsum) % kM;
+    uint32_t corr = 0;
+    if (quirk) {
+      const uint32_t any_u = __syncthreads_or(has_u);
+      // sign after the last chunk of the tile, unless the walk below overrides it
+      {
+        int last = (int)min((uint32_t)kFoldTile, nchunks - t0) - 1;
+        if (last / kFoldItems == tid && !any_u) s_neg = k[last % kFoldItems] == 1;
+      }
+      if (any_u) {
+#pragma unroll
+        for (int i = 0; i < kFoldItems; i++) {
+          smW[i * kFoldThreads + tid] = W[i];  // [item][thread]: conflict-free
+          smR[i * kFoldThreads + tid] = (uint16_t)((r_thread + pd[i]) % kM);
+          smK[i * kFoldThreads + tid] = (uint8_t)k[i];
+          uint32_t bal = __ballot_sync(0xffffffffu, k[i] == 3);
+          if (lane == 0) smU[i][warp] = bal;
+        }
+        __syncthreads();
+        if (tid == 0) {
+          bool neg = s_neg != 0;   // sign before the tile
+          int last_idx = -1;       // last chunk whose sign `neg` describes (-1: the tile's predecessor)
+          uint32_t c = 0;
+          for (int w = 0; w < 32; w++) {
+            uint32_t any = 0;
+            for (int i = 0; i < kFoldItems; i++) any |= smU[i][w];
+            while (any) {
+              int l = __ffs(any) - 1;
+              any &= any - 1;
+              for (int i = 0; i < kFoldItems; i++) {
+                if (!((smU[i][w] >> l) & 1u)) continue;
+                const int th = w * 32 + l, j = th * kFoldItems + i, at = i * kFoldThreads + th;
+                if (last_idx != j - 1)  // j >= 1 here: last_idx == -1 covers j == 0
+                  neg = (i ? smK[at - kFoldThreads] : smK[(kFoldItems - 1) * kFoldThreads + th - 1]) == 1;
+                uint32_t r = (smR[at] + c) % kM;
+                long long v = (neg && r) ? (long long)r - kM : (long long)r;
+                long long X = v + (long long)smW[at];
+                long long Y = X >= (1ll << 31) ? X - (1ll << 32) : X;
+                uint32_t m = (uint32_t)(Y < 0 ? -Y : Y) % kM;  // |Y| < 2^31 + M
+                neg = Y < 0;
+                uint32_t r2 = neg && m ? kM - m : m;
+                c = (r2 + kM - smR[at]) % kM;
+                last_idx = j;
+              }
+            }
+          }
+          int last = (int)min((uint32_t)kFoldTile, nchunks - t0) - 1;
+          s_neg = last_idx == last ? (uint32_t)neg : (uint32_t)(smK[(last % kFoldItems) * kFoldThreads + last / kFoldItems] == 1);
+          s_corr = c;
+        }
+        __syncthreads();
+        corr = s_corr;
+      }
+    }
+    s1_carry = (s1_carry + atot) % kM;
+    r_carry = (r_carry + dtot + corr) % kM;
+    __syncthreads();
+  }
+  if (tid == 0) {
+    bool neg = quirk && s_neg;
+    uint32_t s2 = (neg && r_carry) ? r_carry - kM : r_carry;
+    *out = (s2 << 16) + s1_carry;
+  }
+}
 }  // namespace
 
 int adler32_launch_buffer(zipc_b200_ctx *ctx, const uint8_t *d_src, uint64_t len, int mode, uint32_t *h_out) {
@@ -59,8 +262,7 @@ int adler32_launch_buffer(zipc_b200_ctx *ctx, const uint8_t *d_src, uint64_t len
   uint64_t nchunks64 = 1 + (len - first) / kChunk;
   if (nchunks64 > 0xFFFFFFFFull) return ZIPC_ERR_INVALID_ARG;
   uint32_t nchunks = (uint32_t)nchunks64;
-  if (int st = ctx->d_scratch2.reserve((size_t)nchunks * sizeof(uint2))) return st;
-  if (int st = ctx->h_res.reserve((size_t)nchunks * sizeof(uint2))) return st;
+  if (int st = ctx->d_scratch2.reserve((size_t)nchunks * sizeof(uint2) + 64)) return st;
   uint2 *d_ab = ctx->d_scratch2.as<uint2>();
   uint32_t grid = (nchunks + kWarps - 1) / kWarps;
   uint32_t maxgrid = (uint32_t)ctx->sm_count * 4;
@@ -71,12 +273,14 @@ int adler32_launch_buffer(zipc_b200_ctx *ctx, const uint8_t *d_src, uint64_t len
   }
   ctx->launches++;
   ZB_CUDA(ctx, cudaGetLastError());
-  uint2 *h_ab = ctx->h_res.as<uint2>();
-  ZB_CUDA(ctx, cudaMemcpyAsync(h_ab, d_ab, (size_t)nchunks * sizeof(uint2), cudaMemcpyDeviceToHost, ctx->stream));
+  // fold on the device: one CTA, no host round trip of the partials
+  uint32_t *d_out = reinterpret_cast<uint32_t *>(d_ab + nchunks);
+  ZB_CUDA(ctx, cudaFuncSetAttribute(adler_fold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFoldSmem));  // per device
+  adler_fold_kernel<<<1, kFoldThreads, kFoldSmem, ctx->stream>>>(d_ab, first, nchunks, mode, d_out);
+  ctx->launches++;
+  ZB_CUDA(ctx, cudaGetLastError());
+  ZB_CUDA(ctx, cudaMemcpyAsync(h_out, d_out, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
   ZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  uint32_t s1 = 1, s2 = 0;
-  for (uint32_t c = 0; c < nchunks; c++) adler_fold_step(s1, s2, c == 0 ? first : kChunk, h_ab[c].x, h_ab[c].y, mode);
-  *h_out = (s2 << 16) + s1;
   return ZIPC_OK;
 }
 
