@@ -12,9 +12,10 @@
 //     are 512 bytes apart; its state is advanced with slice-by-4 tables that already contain the
 //     508 zero bytes between consecutive words:  T'_k[b] = T_k[b] * x^(8*508) mod P.
 //     That is 4 shared-memory lookups per 4 input bytes with no dependence between columns.
-//   * The 4 x 256 strided tables are replicated once per lane ( [k][byte][lane] ), so a warp's 32
+//   * The 4 x 256 strided tables are replicated once per lane ( [k/2][byte][k%2][lane] ), so a warp's 32
 //     simultaneous lookups always hit 32 different banks: the LDS pipe runs conflict-free at one
-//     lookup per lane per clock.  128 KiB of shared memory, one 1024-thread CTA per SM.
+//     lookup per lane per clock, and a lookup's address is one PRMT away from the data word.
+//     128 KiB of shared memory, one 1024-thread CTA per SM.
 //   * Each lane's last block is advanced with the ordinary tables, the four slots are merged
 //     (3 x "append 4 zero bytes"), lanes are aligned to the end of the body by one GF(2)[x]
 //     multiplication with x^(128*d), d in [0,31], and XOR-reduced over the warp.
@@ -95,25 +96,20 @@ __device__ __forceinline__ uint4 ldg_stream(const uint4 *p) {
   return v;
 }
 
-// Shift amounts as multipliers (2^31, 2^23, 2^15) passed at run time: u >> s becomes the high half of
-// u * 2^(32-s), i.e. IMAD.HI on the FMA pipe.  The profile of the first version showed the ALU pipe
-// (LOP3/SHF) at 92 % and the FMA pipe idle; moving the four shifts over removes that bound.
-struct ShiftMul { uint32_t m1, m9, m17; };
-__device__ __forceinline__ uint32_t mulhi_rt(uint32_t a, uint32_t b) {
-  uint32_t r;
-  asm("mul.hi.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
-  return r;
-}
-// one word through the lane-replicated strided tables.  rep is the (warp-uniform) table base, lane4 = lane * 4:
-// each index is "(byte * 128) | lane4", one LOP3 after the shift, and the base rides in the LDS address.
-__device__ __forceinline__ uint32_t step_rep(const uint32_t *__restrict__ rep, uint32_t lane4, uint32_t u, const ShiftMul k) {
+// One word through the lane-replicated strided tables.  Layout (bytes): table k, byte b, lane l at
+//   (k >> 1) * 65536 + b * 256 + (k & 1) * 128 + l * 4
+// so the variable part of an address is "b * 256 + l * 4": byte b of the word dropped into byte 1 of a register
+// whose byte 0 already holds l * 4 -- ONE PRMT per lookup (the first two versions spent a shift or IMAD.HI plus a
+// LOP3 per lookup and were bound by instruction issue, not by HBM).  The table/region offset rides in the LDS
+// immediate.  A warp's 32 lookups still hit 32 different banks.
+__device__ __forceinline__ uint32_t step_rep(const uint32_t *__restrict__ rep, uint32_t lane4, uint32_t u) {
   const char *t = reinterpret_cast<const char *>(rep);
-  uint32_t i0 = ((u * 128u) & 0x7f80u) | lane4;            // (u & 0xff) * 128
-  uint32_t i1 = (mulhi_rt(u, k.m1) & 0x7f80u) | lane4;     // ((u >> 8) & 0xff) * 128
-  uint32_t i2 = (mulhi_rt(u, k.m9) & 0x7f80u) | lane4;     // ((u >> 16) & 0xff) * 128
-  uint32_t i3 = (mulhi_rt(u, k.m17) & 0x7f80u) | lane4;    // (u >> 24) * 128
-  return *reinterpret_cast<const uint32_t *>(t + 3 * 32768 + i0) ^ *reinterpret_cast<const uint32_t *>(t + 2 * 32768 + i1) ^
-         *reinterpret_cast<const uint32_t *>(t + 1 * 32768 + i2) ^ *reinterpret_cast<const uint32_t *>(t + i3);
+  uint32_t i0 = __byte_perm(u, lane4, 0x5504);  // byte 0 of u -> T'_3
+  uint32_t i1 = __byte_perm(u, lane4, 0x5514);  // byte 1      -> T'_2
+  uint32_t i2 = __byte_perm(u, lane4, 0x5524);  // byte 2      -> T'_1
+  uint32_t i3 = __byte_perm(u, lane4, 0x5534);  // byte 3      -> T'_0
+  return *reinterpret_cast<const uint32_t *>(t + 65536 + 128 + i0) ^ *reinterpret_cast<const uint32_t *>(t + 65536 + i1) ^
+         *reinterpret_cast<const uint32_t *>(t + 128 + i2) ^ *reinterpret_cast<const uint32_t *>(t + i3);
 }
 // one word through the ordinary slice-by-4 tables (state valid right after the word)
 __device__ __forceinline__ uint32_t step_std(const uint32_t *__restrict__ st, uint32_t u) {
@@ -126,7 +122,7 @@ __device__ __forceinline__ uint32_t step_byte(const uint32_t *__restrict__ st, u
 
 // State after running seg.len bytes from seg.init; result valid in lane 0.
 __device__ uint32_t crc_segment_warp(const CrcSeg seg, int lane, const uint32_t *__restrict__ rep,
-                                     const uint32_t *__restrict__ st, const uint32_t *__restrict__ xp, const ShiftMul sm) {
+                                     const uint32_t *__restrict__ st, const uint32_t *__restrict__ xp) {
   const uint8_t *ptr = seg.ptr;
   uint64_t len = seg.len;
   const uint32_t lane4 = (uint32_t)lane * 4u;
@@ -152,6 +148,9 @@ __device__ uint32_t crc_segment_warp(const CrcSeg seg, int lane, const uint32_t 
   const uint4 *p = reinterpret_cast<const uint4 *>(body) + lane;
 
   // rows [0, rows-1): nobody's last block -> strided tables for every lane
+  // 8 rows (4 KiB per warp) are requested together, then consumed; with 32 warps per SM out of phase this keeps
+  // enough loads in flight (a software-pipelined variant measured the same: the LDS pipe, ~75 % busy, is the
+  // next limiter after HBM, not load latency).
   uint64_t R = rows > 0 ? rows - 1 : 0, r = 0;
   for (; r + 8 <= R; r += 8) {
     uint4 w[8];
@@ -159,26 +158,26 @@ __device__ uint32_t crc_segment_warp(const CrcSeg seg, int lane, const uint32_t 
     for (int j = 0; j < 8; j++) w[j] = ldg_stream(p + 32 * (r + j));
 #pragma unroll
     for (int j = 0; j < 8; j++) {
-      c0 = step_rep(rep, lane4, c0 ^ w[j].x, sm);
-      c1 = step_rep(rep, lane4, c1 ^ w[j].y, sm);
-      c2 = step_rep(rep, lane4, c2 ^ w[j].z, sm);
-      c3 = step_rep(rep, lane4, c3 ^ w[j].w, sm);
+      c0 = step_rep(rep, lane4, c0 ^ w[j].x);
+      c1 = step_rep(rep, lane4, c1 ^ w[j].y);
+      c2 = step_rep(rep, lane4, c2 ^ w[j].z);
+      c3 = step_rep(rep, lane4, c3 ^ w[j].w);
     }
   }
   for (; r < R; r++) {
     uint4 w = ldg_stream(p + 32 * r);
-    c0 = step_rep(rep, lane4, c0 ^ w.x, sm);
-    c1 = step_rep(rep, lane4, c1 ^ w.y, sm);
-    c2 = step_rep(rep, lane4, c2 ^ w.z, sm);
-    c3 = step_rep(rep, lane4, c3 ^ w.w, sm);
+    c0 = step_rep(rep, lane4, c0 ^ w.x);
+    c1 = step_rep(rep, lane4, c1 ^ w.y);
+    c2 = step_rep(rep, lane4, c2 ^ w.z);
+    c3 = step_rep(rep, lane4, c3 ^ w.w);
   }
   bool has = false;
   if (rows >= 1) {  // row rows-1: last block of lanes >= k
     uint4 w = ldg_stream(p + 32 * (rows - 1));
     has = true;
     if (lane < k) {
-      c0 = step_rep(rep, lane4, c0 ^ w.x, sm); c1 = step_rep(rep, lane4, c1 ^ w.y, sm);
-      c2 = step_rep(rep, lane4, c2 ^ w.z, sm); c3 = step_rep(rep, lane4, c3 ^ w.w, sm);
+      c0 = step_rep(rep, lane4, c0 ^ w.x); c1 = step_rep(rep, lane4, c1 ^ w.y);
+      c2 = step_rep(rep, lane4, c2 ^ w.z); c3 = step_rep(rep, lane4, c3 ^ w.w);
     } else {
       c0 = step_std(st, c0 ^ w.x); c1 = step_std(st, c1 ^ w.y);
       c2 = step_std(st, c2 ^ w.z); c3 = step_std(st, c3 ^ w.w);
@@ -210,8 +209,18 @@ __device__ uint32_t crc_segment_warp(const CrcSeg seg, int lane, const uint32_t 
 }
 
 __device__ __forceinline__ void load_tables(const uint32_t *__restrict__ g_tabs, uint32_t *smem) {
-  // replicate the strided tables per lane: rep[(k*256+b)*32 + lane]
-  for (int i = threadIdx.x; i < kRepWords; i += blockDim.x) smem[i] = g_tabs[i >> 5];
+  // replicate the strided tables per lane: word (k>>1)*16384 + b*64 + (k&1)*32 + lane  <-  TS[k][b].
+  // Thread t fetches TS entry t once; each warp then broadcasts its 32 entries by shuffle and stores them
+  // 32 lanes wide (conflict-free), instead of 32 dependent global loads per thread.
+  {
+    const int t = threadIdx.x, lane = t & 31;
+    const uint32_t v = g_tabs[t];  // blockDim.x == 1024 == number of TS entries
+#pragma unroll 8
+    for (int e = 0; e < 32; e++) {
+      int idx = (t & ~31) + e, k = idx >> 8, b = idx & 255;
+      smem[(k >> 1) * 16384 + b * 64 + (k & 1) * 32 + lane] = __shfl_sync(0xffffffffu, v, e);
+    }
+  }
   for (int i = threadIdx.x; i < 1024 + 32; i += blockDim.x) smem[kRepWords + i] = g_tabs[1024 + i];
   __syncthreads();
 }
@@ -219,7 +228,7 @@ __device__ __forceinline__ void load_tables(const uint32_t *__restrict__ g_tabs,
 // Independent segments pulled from a queue, one warp each.
 __global__ void __launch_bounds__(kThreads, 1)
 crc32_segments_kernel(const CrcSeg *__restrict__ segs, uint32_t nseg, const uint32_t *__restrict__ g_tabs,
-                      uint32_t *__restrict__ states, unsigned int *__restrict__ queue, const ShiftMul sm) {
+                      uint32_t *__restrict__ states, unsigned int *__restrict__ queue) {
   extern __shared__ __align__(16) uint32_t smem[];
   load_tables(g_tabs, smem);
   const int lane = threadIdx.x & 31;
@@ -229,7 +238,7 @@ crc32_segments_kernel(const CrcSeg *__restrict__ segs, uint32_t nseg, const uint
     if (lane == 0) s = atomicAdd(queue, 1u);
     s = __shfl_sync(0xffffffffu, s, 0);
     if (s >= nseg) break;
-    uint32_t c = crc_segment_warp(segs[s], lane, rep, st, xp, sm);
+    uint32_t c = crc_segment_warp(segs[s], lane, rep, st, xp);
     if (lane == 0) states[s] = c;
   }
 }
@@ -238,7 +247,7 @@ crc32_segments_kernel(const CrcSeg *__restrict__ segs, uint32_t nseg, const uint
 // owns tile w.  Tile 0 starts from the CRC init value, the others from 0.
 __global__ void __launch_bounds__(kThreads, 1)
 crc32_tiles_kernel(const uint8_t *__restrict__ src, uint64_t len, uint64_t tile, uint32_t ntiles,
-                   const uint32_t *__restrict__ g_tabs, uint32_t *__restrict__ states, const ShiftMul sm) {
+                   const uint32_t *__restrict__ g_tabs, uint32_t *__restrict__ states) {
   extern __shared__ __align__(16) uint32_t smem[];
   load_tables(g_tabs, smem);
   const int lane = threadIdx.x & 31;
@@ -249,7 +258,7 @@ crc32_tiles_kernel(const uint8_t *__restrict__ src, uint64_t len, uint64_t tile,
     seg.ptr = src + off;
     seg.len = len - off < tile ? len - off : tile;
     seg.init = t == 0 ? 0xFFFFFFFFu : 0u;
-    uint32_t c = crc_segment_warp(seg, lane, rep, st, xp, sm);
+    uint32_t c = crc_segment_warp(seg, lane, rep, st, xp);
     if (lane == 0) states[t] = c;
   }
 }
@@ -292,14 +301,14 @@ __global__ void crc32_finish_kernel(uint32_t *states, uint32_t n) {
   if (i < n) states[i] ^= 0xFFFFFFFFu;
 }
 
-bool g_attr_set = false;
+unsigned long long g_attr_devs = 0;  // bit d: attributes set on device d (function attributes are per device)
 int ensure_attrs(zipc_b200_ctx *ctx) {
-  if (g_attr_set) return ZIPC_OK;
+  if (g_attr_devs >> (ctx->device & 63) & 1ull) return ZIPC_OK;
   ZB_CUDA(ctx, cudaFuncSetAttribute(crc32_segments_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)kSmemBytes));
   ZB_CUDA(ctx, cudaFuncSetAttribute(crc32_tiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)kSmemBytes));
-  g_attr_set = true;
+  g_attr_devs |= 1ull << (ctx->device & 63);
   return ZIPC_OK;
 }
 
@@ -313,7 +322,7 @@ int crc32_launch_segments(zipc_b200_ctx *ctx, const CrcSeg *d_segs, uint32_t nse
   ZB_CUDA(ctx, cudaMemsetAsync(queue, 0, sizeof(unsigned int), ctx->stream));
   uint32_t grid = (nseg + kWarps - 1) / kWarps;
   if (grid > (uint32_t)ctx->sm_count) grid = (uint32_t)ctx->sm_count;
-  crc32_segments_kernel<<<grid, kThreads, kSmemBytes, ctx->stream>>>(d_segs, nseg, ctx->d_crc_tabs, d_states, queue, ShiftMul{1u << 31, 1u << 23, 1u << 15});
+  crc32_segments_kernel<<<grid, kThreads, kSmemBytes, ctx->stream>>>(d_segs, nseg, ctx->d_crc_tabs, d_states, queue);
   ctx->launches++;
   ZB_CUDA(ctx, cudaGetLastError());
   return ZIPC_OK;
@@ -325,6 +334,7 @@ int crc32_launch_buffer(zipc_b200_ctx *ctx, const uint8_t *d_src, uint64_t len, 
   // tile length: multiple of 512, at least 4 KiB so tiny buffers do not fan out pointlessly
   uint64_t tile = (len + max_tiles - 1) / max_tiles;
   if (tile < 4096) tile = 4096;
+  if (const char *e = getenv("ZIPC_B200_CRC_TILE")) { uint64_t v = strtoull(e, nullptr, 10); if (v >= 4096 && v < tile) tile = v; }  // tuning knob
   tile = (tile + 511) & ~511ull;
   uint32_t ntiles = len ? (uint32_t)((len + tile - 1) / tile) : 1;
   uint32_t F = ntiles - 1;
@@ -336,12 +346,13 @@ int crc32_launch_buffer(zipc_b200_ctx *ctx, const uint8_t *d_src, uint64_t len, 
   cc.xg[0] = gf_xpow8(tile);
   cc.xg[1] = gf_xpow8(tile * G);
   for (int l = 1; l < 11; l++) cc.xg[1 + l] = gf_mul(cc.xg[l], cc.xg[l]);
-  if (int st = ctx->d_scratch2.reserve((size_t)(max_tiles + 1) * sizeof(uint32_t))) return st;
+  if (int st = ctx->d_scratch2.reserve((size_t)(ntiles + 1) * sizeof(uint32_t))) return st;
   uint32_t *d_states = ctx->d_scratch2.as<uint32_t>();
   uint32_t grid = (ntiles + kWarps - 1) / kWarps;
+  if (grid > (uint32_t)ctx->sm_count) grid = (uint32_t)ctx->sm_count;
   {
     KernelTimer kt(ctx);
-    crc32_tiles_kernel<<<grid, kThreads, kSmemBytes, ctx->stream>>>(d_src, len, tile, ntiles, ctx->d_crc_tabs, d_states, ShiftMul{1u << 31, 1u << 23, 1u << 15});
+    crc32_tiles_kernel<<<grid, kThreads, kSmemBytes, ctx->stream>>>(d_src, len, tile, ntiles, ctx->d_crc_tabs, d_states);
   }
   ctx->launches++;
   ZB_CUDA(ctx, cudaGetLastError());

@@ -649,7 +649,7 @@ stored_kernel(const DeflateTask *__restrict__ tasks, uint32_t ntasks, DeflateRes
   if (threadIdx.x == 0) { results[task].out_len = need; results[task].status = ZIPC_OK; results[task].blocks = (uint32_t)nblk; }
 }
 
-bool g_attr_set = false;
+unsigned long long g_attr_devs = 0;  // bit d: attributes set on device d (function attributes are per device)
 
 }  // namespace
 
@@ -661,9 +661,9 @@ int deflate_launch(zipc_b200_ctx *ctx, const DeflateTask *d_tasks, uint32_t n, D
     ZB_CUDA(ctx, cudaGetLastError());
     return ZIPC_OK;
   }
-  if (!g_attr_set) {
+  if (!(g_attr_devs >> (ctx->device & 63) & 1ull)) {
     ZB_CUDA(ctx, cudaFuncSetAttribute(deflate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    g_attr_set = true;
+    g_attr_devs |= 1ull << (ctx->device & 63);
   }
   uint32_t grid = (uint32_t)ctx->sm_count;
   if (grid > n) grid = n;

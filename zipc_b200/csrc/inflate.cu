@@ -1,29 +1,37 @@
-// inflate.cu -- batched DEFLATE decoder for sm_100a: one *lane* per stream, warp-cooperative copies.
+// inflate.cu -- batched DEFLATE decoder for sm_100a: one *warp* per stream, speculative token decoding.
 //
 // Replaces the decode side of the reference (src/zipc_deflate.ml:532-718): read_bits (:564-579),
 // the bit-at-a-time read_symbol (:584-591), read_block_symbols (:593-616), the three block readers
 // (:618-680) and the driver inflate_and_crc (:692-709).  Results are bit-exact, including which of
 // the two errors ("Corrupted data stream" / "Expected decompression size exceeded") a bad stream
-// yields: checks happen in the reference's order token by token.
+// yields: checks are evaluated in the reference's order, token by token.
 //
 // Design (why it is not a translation):
-//   * Huffman decoding is serial per stream, so the parallelism is across streams: every lane of a
-//     warp runs the decoder state machine of its own stream (10k ZIP members = 10k independent
-//     streams).  A finished lane pulls the next stream from a global queue.
-//   * Symbols are decoded through per-stream lookup tables in shared memory (2^LB entries for
-//     literal/length, 2^DB for distance, 16-bit entries); codes longer than the table fall back to
-//     the canonical walk over per-length counts.  The fixed-Huffman tables are built once per CTA.
-//   * A round decodes one token per lane (uniform control flow), then the 32 tokens' bytes are
-//     flattened over the warp: lane j of pass p moves byte 32p+j of the concatenated copies, so a
-//     258-byte match costs 9 coalesced passes rather than stalling 31 lanes.  Back-references read
-//     the stream's own earlier output from global memory (L1/L2 resident, at most 32 KiB back).
-//   * Dynamic-block headers are parsed by the owning lanes, then the warp builds that lane's tables
-//     cooperatively.
-// The checksum of the output is produced by the CRC-32 / Adler-32 kernels over the freshly written
-// (L2-warm) output, see api.cu.
+//   * Huffman decoding is serial per stream: a token's position is known only after the previous token
+//     is decoded.  The first version ran one decoder state machine per lane (8 per warp); its profile
+//     showed the SM waiting on that dependent chain (~2000 clk per token and stream, 55 % issue
+//     utilisation, a 256 KiB member bounding the whole batch).  This version breaks the chain:
+//       - D1 (speculate): the warp looks at a window of 32*NB bits.  Lane l decodes, for each of its NB
+//         bit offsets, the complete token that WOULD start there (literal, or length + distance with
+//         their extra bits: two table lookups, branch free, NB independent chains per lane) and posts
+//         (token, bit length) in shared memory.
+//       - D2 (walk): every lane follows the chain start -> start + bits -> ... through that table (one
+//         LDS + add per token); lane i keeps token i in registers.  Up to 32 tokens per round.
+//       - checks (distance, size, input overrun) run in parallel, one token per lane; the first failing
+//         token cuts the round and decides the error, as the serial reference would.
+//   * E (copy): the round's literal bytes and match bytes whose source precedes the round are flattened
+//     over the 32 lanes (byte b of the round's independent bytes -> lane b % 32); matches that read
+//     bytes of the same round follow in order.  Back-references read the stream's own earlier output
+//     from global memory through L2 (ld.global.cg), at most 32 KiB back.
+//   * Compressed input is staged in a 256-byte ring per warp, refilled with coalesced 128-byte loads
+//     that are issued one refill ahead.
+//   * Lookup tables: 2^LB literal/length entries (16 bit) and 2^DB distance entries (32 bit) per warp in
+//     shared memory; longer codes (rare) take the canonical walk.  The fixed-Huffman tables are built
+//     once per CTA; dynamic tables are built cooperatively by the warp.
+//   * 16 warps per CTA, one CTA per SM, streams handed out through a global queue (longest first).
 //
 // Algorithmic bytes: C + U per stream (compressed read + uncompressed written).  The kernel is
-// issue/latency bound (serial bit parsing), not HBM bound: see DESIGN.md.
+// issue/latency bound (bit parsing), not HBM bound: see DESIGN.md.
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
@@ -34,21 +42,22 @@
 namespace zb {
 namespace {
 
-constexpr int LB = 9;        // literal/length table bits
-constexpr int DB = 7;        // distance table bits (>= 6: the area also hosts the 128-entry code-length table)
-constexpr int G = 8;         // streams (decoder state machines) per warp: lanes 0..G-1 lead
-constexpr int K = 8;         // tokens a leader decodes per round
-constexpr int WARPS = 16;    // warps per CTA (one CTA per SM: tables fill shared memory)
+constexpr int LB = 11;       // literal/length table bits
+constexpr int DB = 9;        // distance table bits (>= 7: the area also hosts the 128-entry code-length table)
+constexpr int NB = 4;        // candidate bit offsets per lane
+constexpr int NB_LOG = 2;
+constexpr int WBITS = 32 * NB;  // speculation window
+constexpr int WARPS = 16;    // warps per CTA (one CTA per SM)
 constexpr int THREADS = WARPS * 32;
+constexpr int ROUND_TOKENS = 32;  // one token per lane
 constexpr uint32_t ENT_LONG = 0xFFFFFFFFu;  // code longer than the table: canonical walk (0xFFFF in 16-bit tables)
 constexpr int SYMS_PER_SLOT = 320;     // sorted symbols: 288 litlen + 32 dist
 
-// per-lane shared memory record
 // lit entry  (16 bit): [3:0] code length, [6:4] kind (0..5 = length symbol with that many extra bits,
 //                       6 = end of block, 7 = literal), [15:7] value (literal byte / length base)
 // dist entry (32 bit): [3:0] code length, [7:4] extra bits, [31:8] distance base
 // 0 = invalid code (corrupt stream); all ones = code longer than the table (canonical walk)
-struct __align__(16) LaneTabs {
+struct __align__(16) WarpTabs {
   uint16_t lit[1 << LB];
   uint32_t dist[1 << DB];
   uint16_t lit_cnt[16];
@@ -61,11 +70,16 @@ struct __align__(16) WarpScratch {
   uint16_t symoff[16];
   int err;
 };
+// candidate table entry: x = token (literal byte, or length << 16 | distance),
+//                        y = [7:0] bits the token occupies, [8] end of block, [31:16] bytes it produces;
+//                        y & 0xFFFF == 0: not decodable through the tables (long code or invalid)
+struct __align__(16) WarpWork {
+  uint2 cand[WBITS];      // [ (o % NB) * 32 + o / NB ]
+  uint32_t ring[64];      // compressed input, words [w0, w0 + 64) of the stream
+  uint8_t cidx[32];       // E1: lane holding the r-th independent token
+};
 
-constexpr int QN = K * G;      // tokens per warp round
-constexpr int kCompBytes = (QN + 34) * 2 + (QN + 32) + 4;  // per warp: cstart u16[QN+34], cidx u8[QN+32], padded to 4
-constexpr size_t kSmemBytes = sizeof(LaneTabs) * (WARPS * G + 1) + sizeof(WarpScratch) * WARPS +
-                              sizeof(uint32_t) * WARPS * QN * 2 + kCompBytes * WARPS + 64 + 128 + 64;
+constexpr size_t kSmemBytes = sizeof(WarpTabs) * (WARPS + 1) + sizeof(WarpScratch) * WARPS + sizeof(WarpWork) * WARPS + 64 + 128 + 64;
 
 enum : uint32_t { S_IDLE = 0, S_HDR = 1, S_DATA = 2, S_STORED = 3, S_FINISH = 4, S_EXIT = 5 };
 
@@ -82,67 +96,76 @@ __constant__ uint32_t c_dist_tab[30] = {  // base | extra << 16   (reference :27
     4097 | 11 << 16, 6145 | 11 << 16, 8193 | 12 << 16,  12289 | 12 << 16, 16385 | 13 << 16, 24577 | 13 << 16};
 __constant__ uint8_t c_clen_order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
 
-// ---- bit reader: two 32-bit words + a bit offset; the next 32 stream bits are one funnel shift away ----------
-// After refill() at least 32 valid bits are visible; callers peek / drop at most 32 bits between refills.
-struct BitReader {
-  const uint32_t *wp;    // next word to load into `ahead`
-  const uint32_t *wend;  // first word not to load (words past the stream read as 0)
-  uint32_t lo, hi;       // current and next word
-  uint32_t pos;          // bit offset of the read position inside lo (may reach 63 before refill)
-  uint32_t ahead;        // the word after hi, already fetched (hides the load latency)
-  long long base;        // stream bit offset of bit 0 of lo (negative inside a leading partial word)
-  long long limit;       // 8 * len
-  bool tail;             // the visible window may reach past the end of the input
-  __device__ __forceinline__ uint32_t fetch() {
-    uint32_t w = wp < wend ? *wp : 0u;
-    wp++;
+// ---- compressed input: a 64-word ring per warp, all state warp-uniform -----------------------------------------
+struct Input {
+  uint32_t *ring;          // shared memory, [64]
+  const uint32_t *srcw;    // word-aligned base (at or before the first stream byte)
+  uint32_t nwords;         // words that may be read
+  uint32_t w0;             // ring holds words [w0, w0 + 64), w0 % 32 == 0
+  uint32_t pre;            // word w0 + 64 + lane, requested one refill ahead
+  uint64_t P;              // read position in bits from srcw
+  uint64_t limit;          // first bit past the stream
+  uint32_t skew;           // bits between srcw and the stream start (0, 8, 16, 24)
+  __device__ __forceinline__ uint32_t load(uint32_t k) const {
+    uint32_t w = 0;
+    if (k < nwords) asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(w) : "l"(srcw + k));
     return w;
   }
-  __device__ __forceinline__ void seek(const uint8_t *src, uint64_t len, uint64_t byte_pos) {
-    const uint8_t *p = src + byte_pos;
-    uint32_t a = (uint32_t)((uintptr_t)p & 3);
-    wp = reinterpret_cast<const uint32_t *>(p - a);
-    wend = reinterpret_cast<const uint32_t *>(((uintptr_t)(src + len) + 3) & ~(uintptr_t)3);
-    lo = fetch(); hi = fetch(); ahead = fetch();
-    pos = 8 * a;
-    base = (long long)(byte_pos * 8) - 8 * a;
-    limit = (long long)(len * 8);
-    tail = base + 96 > limit;
+  __device__ __forceinline__ void seek_bits(uint64_t bitpos, int lane) {
+    P = bitpos;
+    w0 = (uint32_t)(bitpos >> 5) & ~31u;
+    __syncwarp();
+    ring[lane] = load(w0 + lane);          // w0 % 64 may be 32: slot of word k is k & 63
+    ring[32 + lane] = load(w0 + 32 + lane);
+    if (w0 & 32u) { uint32_t t = ring[lane]; ring[lane] = ring[32 + lane]; ring[32 + lane] = t; }
+    pre = load(w0 + 64 + lane);
+    __syncwarp();
   }
-  __device__ __forceinline__ void refill() {  // afterwards pos < 32
-    if (pos >= 32) {
-      pos -= 32;
-      lo = hi; hi = ahead;
-      ahead = fetch();
-      base += 32;
-      tail = base + 96 > limit;
+  __device__ __forceinline__ void open(const uint8_t *src, uint64_t len, int lane) {
+    uint32_t a = (uint32_t)((uintptr_t)src & 3);
+    srcw = reinterpret_cast<const uint32_t *>(src - a);
+    nwords = (uint32_t)((a + len + 3) >> 2);
+    skew = 8 * a;
+    limit = (uint64_t)skew + 8 * len;
+    seek_bits(skew, lane);
+  }
+  // afterwards words [P >> 5, (P >> 5) + 32] are in the ring
+  __device__ __forceinline__ void ensure(int lane) {
+    while ((uint32_t)(P >> 5) >= w0 + 32) {
+      __syncwarp();
+      ring[(w0 & 32u) + lane] = pre;
+      w0 += 32;
+      pre = load(w0 + 64 + lane);
+      __syncwarp();
     }
   }
-  // pos may have run past 32 since the last refill (a code followed by its extra bits): then the window
-  // starts inside hi and continues in the prefetched word
-  __device__ __forceinline__ uint32_t window() const {
-    return pos < 32 ? __funnelshift_r(lo, hi, pos) : __funnelshift_r(hi, ahead, pos - 32);
+  __device__ __forceinline__ uint32_t peek32() const {  // the next 32 bits (uniform: broadcast reads)
+    uint32_t k = (uint32_t)(P >> 5);
+    return __funnelshift_r(ring[k & 63], ring[(k + 1) & 63], (uint32_t)P & 31u);
   }
-  __device__ __forceinline__ uint32_t peek(uint32_t cnt) const { return window() & ((1u << cnt) - 1u); }  // cnt < 32
-  __device__ __forceinline__ void drop(uint32_t cnt) { pos += cnt; }
-  __device__ __forceinline__ uint64_t consumed() const { return (uint64_t)(base + pos); }
-  __device__ __forceinline__ bool overrun() const { return tail && base + (long long)pos > limit; }
+  __device__ __forceinline__ uint32_t get(uint32_t n, int lane) {  // n <= 16
+    ensure(lane);
+    uint32_t v = peek32() & ((1u << n) - 1u);
+    P += n;
+    return v;
+  }
+  __device__ __forceinline__ uint64_t consumed() const { return P - skew; }   // stream bits read
+  __device__ __forceinline__ bool overrun() const { return P > limit; }
 };
 
 // ---- canonical walk for codes longer than the table (the reference's read_symbol, :584-591) --------
-// Returns the symbol and consumes its bits, or -1 (the reference would run off counts.(16)).
-__device__ __forceinline__ int canon_decode(BitReader &br, const uint16_t *cnt, const uint16_t *syms) {
-  int len = 1, base = 0, offs = 0;
-  uint32_t bits = br.window();
-  for (; len <= 15; len++) {
+// Returns the symbol and its length, or -1 (the reference would run off counts.(16)).
+__device__ __forceinline__ int canon_decode(uint32_t bits, const uint16_t *cnt, const uint16_t *syms, uint32_t &len_out) {
+  int base = 0, offs = 0;
+  for (int len = 1; len <= 15; len++) {
     offs = 2 * offs + (int)(bits & 1u);
     bits >>= 1;
     int count = cnt[len];
-    if (offs < count) { br.drop(len); return syms[base + offs]; }
+    if (offs < count) { len_out = (uint32_t)len; return syms[base + offs]; }
     base += count;
     offs -= count;
   }
-  br.drop(15);
+  len_out = 15;
   return -1;
 }
 
@@ -229,32 +252,26 @@ __device__ void build_decoder_warp(WarpScratch &ws, int first, int n, int bits, 
 }
 
 // ---- the kernel ------------------------------------------------------------------------------------------
-// Each warp serves G streams: lanes 0..G-1 ("leaders") run one decoder state machine each and decode up to
-// K tokens per round into a small queue; then all 32 lanes execute the queued tokens, token index by token
-// index, with the bytes of the G concurrent tokens flattened over the lanes.
 template <bool COUNT_ONLY>
 __global__ void __launch_bounds__(THREADS, 1)
 inflate_kernel(const InflateTask *__restrict__ tasks, uint32_t ntasks, InflateResult *__restrict__ results,
-               unsigned int *__restrict__ queue, uint16_t *__restrict__ g_syms, int adler_mode, int active_warps) {
+               unsigned int *__restrict__ queue, uint16_t *__restrict__ g_syms, int adler_mode) {
   // adler_mode: -1 = no checksum in this kernel, else ZIPC_ADLER_* (fused per-block Adler-32 of the output)
   extern __shared__ __align__(16) uint8_t smem_raw[];
-  LaneTabs *tabs = reinterpret_cast<LaneTabs *>(smem_raw);                 // [WARPS*G] + fixed
-  LaneTabs &fixed = tabs[WARPS * G];
-  WarpScratch *wss = reinterpret_cast<WarpScratch *>(tabs + WARPS * G + 1);
-  uint32_t *tokq = reinterpret_cast<uint32_t *>(wss + WARPS);              // [WARPS][2][K][G]
-  uint8_t *compq = reinterpret_cast<uint8_t *>(tokq + WARPS * QN * 2);     // [WARPS] compacted token lists
-  uint16_t *s_len_tab = reinterpret_cast<uint16_t *>(compq + ((WARPS * kCompBytes + 3) & ~3));
+  WarpTabs *tabs = reinterpret_cast<WarpTabs *>(smem_raw);                  // [WARPS] + fixed
+  WarpTabs &fixed = tabs[WARPS];
+  WarpScratch *wss = reinterpret_cast<WarpScratch *>(tabs + WARPS + 1);
+  WarpWork *works = reinterpret_cast<WarpWork *>(wss + WARPS);
+  uint16_t *s_len_tab = reinterpret_cast<uint16_t *>(works + WARPS);
   uint32_t *s_dist_tab = reinterpret_cast<uint32_t *>(s_len_tab + 32);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   WarpScratch &ws = wss[warp];
-  const bool leader = lane < G;
-  LaneTabs &mine = tabs[warp * G + (leader ? lane : 0)];
-  uint2 *myq = reinterpret_cast<uint2 *>(tokq + warp * QN * 2);  // [j*G+g]: x = dep << 31 | len << 16 | dist-or-byte, y = output offset inside the round
-  uint16_t *cstart = reinterpret_cast<uint16_t *>(compq + warp * kCompBytes);  // byte offset of compacted token c (+ end sentinel)
-  uint8_t *cidx = reinterpret_cast<uint8_t *>(cstart + QN + 34);                // queue slot of compacted token c
-  const uint32_t slot = (blockIdx.x * WARPS + warp) * G + (leader ? lane : 0);
+  WarpTabs &mine = tabs[warp];
+  WarpWork &wk = works[warp];
+  const uint32_t slot = blockIdx.x * WARPS + warp;
   uint16_t *my_syms = g_syms + (size_t)slot * SYMS_PER_SLOT;
-  uint16_t *fixed_syms = g_syms + (size_t)(gridDim.x * WARPS * G + blockIdx.x) * SYMS_PER_SLOT;
+  uint16_t *fixed_syms = g_syms + (size_t)(gridDim.x * WARPS + blockIdx.x) * SYMS_PER_SLOT;
+  const uint32_t lt_mask = (1u << lane) - 1u;
 
   if (threadIdx.x < 29) s_len_tab[threadIdx.x] = c_len_tab[threadIdx.x];
   if (threadIdx.x < 30) s_dist_tab[threadIdx.x] = c_dist_tab[threadIdx.x];
@@ -272,18 +289,15 @@ inflate_kernel(const InflateTask *__restrict__ tasks, uint32_t ntasks, InflateRe
   }
   __syncthreads();
 
-  // Streams are packed into the first `active_warps` warps of every CTA (a warp's round costs the same
-  // whether 1 or G of its leaders are busy); the other warps only helped with the fixed tables.
-  if (warp >= active_warps) return;
-  // per-leader decoder state (lanes >= G carry dead copies)
-  uint32_t state = leader ? S_IDLE : S_EXIT, task = 0, status = ZIPC_OK;
-  BitReader br{};
+  // decoder state: identical in all lanes of the warp (no broadcasts needed, branches are uniform)
+  uint32_t state = S_IDLE, task = 0, status = ZIPC_OK;
+  Input in{};
+  in.ring = wk.ring;
   const uint8_t *src = nullptr;
   uint64_t src_len = 0;
   uint8_t *dst = nullptr;
   uint64_t out_pos = 0, out_cap = 0;
-  bool final_blk = false, need_build = false, first_task = true, segment = false;
-  uint32_t hlit = 0, hdist = 0;
+  bool final_blk = false, first_task = true, segment = false;
   uint32_t stored_len = 0;
   const uint8_t *stored_src = nullptr;
   uint32_t ad_state = 1;      // running Adler-32 (reference :558, :682-690)
@@ -293,58 +307,46 @@ inflate_kernel(const InflateTask *__restrict__ tasks, uint32_t ntasks, InflateRe
   const uint32_t *dist_lut = nullptr;
   const uint16_t *lit_syms = nullptr, *dist_syms = nullptr;
 
-#ifdef ZB_INFLATE_TIMING
-  long long tA = 0, tD = 0, tE1 = 0, tE2 = 0, tG = 0, rounds = 0, ntoks = 0, t0 = clock64();
-#define ZB_TICK(acc) { long long t1 = clock64(); acc += t1 - t0; t0 = t1; }
-#else
-#define ZB_TICK(acc)
-#endif
   for (;;) {
-    // ---- A: idle leaders pull work -------------------------------------------------------------------
+    // ---- A: pull work -----------------------------------------------------------------------------------
     if (state == S_IDLE) {
       // first task: interleaved over the CTAs so the longest streams (sorted first) spread over all SMs;
       // afterwards from the shared queue, which starts behind the statically assigned ones
-      if (first_task) { task = (uint32_t)((lane * active_warps + warp) * gridDim.x + blockIdx.x); first_task = false; }
-      else task = atomicAdd(queue, 1u);
-      if (task < ntasks) {
-        const InflateTask t = tasks[task];
-        src = t.src; src_len = t.src_len; dst = t.dst; out_cap = t.dst_cap; segment = (t.flags & kInflateSegment) != 0;
-        out_pos = 0; status = ZIPC_OK; final_blk = false;
-        ad_state = 1; ad_from = 0; ad_pending = false;
-        br.seek(src, src_len, 0);
-        state = S_HDR;
-      } else {
-        state = S_EXIT;
+      if (first_task) { task = (uint32_t)warp * gridDim.x + blockIdx.x; first_task = false; }
+      else {
+        if (lane == 0) task = atomicAdd(queue, 1u);
+        task = __shfl_sync(0xffffffffu, task, 0);
       }
+      if (task >= ntasks) break;
+      const InflateTask t = tasks[task];
+      src = t.src; src_len = t.src_len; dst = t.dst; out_cap = t.dst_cap; segment = (t.flags & kInflateSegment) != 0;
+      out_pos = 0; status = ZIPC_OK; final_blk = false;
+      ad_state = 1; ad_from = 0; ad_pending = false;
+      in.open(src, src_len, lane);
+      state = S_HDR;
     }
-    if (__all_sync(0xffffffffu, state == S_EXIT)) break;
 
-    // ---- B: block headers (reference :692-702, :623-661, :671-677) ------------------------------------
-    if (state == S_HDR && segment && br.consumed() == src_len * 8) {
+    // ---- B: block header (reference :692-702, :623-661, :671-677) ------------------------------------------
+    if (state == S_HDR && segment && in.consumed() == src_len * 8) {
       state = S_FINISH;  // a segment ends at the block boundary where its input ends (byte aligned by construction)
     }
     if (state == S_HDR) {
-      br.refill();
-      uint32_t h = br.peek(3);
-      br.drop(3);
+      uint32_t h = in.get(3, lane);
       final_blk = h & 1u;
       uint32_t type = h >> 1;
-      if (br.consumed() > src_len * 8) { status = ZIPC_ERR_CORRUPTED; state = S_FINISH; }
+      if (in.overrun()) { status = ZIPC_ERR_CORRUPTED; state = S_FINISH; }
       else if (type == 0) {
-        br.drop((8u - ((uint32_t)br.consumed() & 7u)) & 7u);  // to the byte boundary
-        br.refill();
-        uint32_t v = br.window();
-        br.drop(32);
-        uint32_t length = v & 0xFFFFu, inv = v >> 16;
-        uint64_t pos = br.consumed() >> 3;
-        if (br.consumed() > src_len * 8 || length != ((~inv) & 0xFFFFu) || src_len - pos < length) {
+        in.P += (8u - ((uint32_t)in.consumed() & 7u)) & 7u;  // to the byte boundary
+        uint32_t length = in.get(16, lane), inv = in.get(16, lane);
+        uint64_t pos = in.consumed() >> 3;
+        if (in.overrun() || length != ((~inv) & 0xFFFFu) || src_len - pos < length) {
           status = ZIPC_ERR_CORRUPTED; state = S_FINISH;
         } else if (out_pos + length > out_cap) {
           status = ZIPC_ERR_SIZE_EXCEEDED; state = S_FINISH;
         } else {
           stored_len = length;
           stored_src = src + pos;
-          br.seek(src, src_len, pos + length);
+          in.seek_bits((uint64_t)in.skew + 8 * (pos + length), lane);
           state = S_STORED;
         }
       } else if (type == 1) {
@@ -352,19 +354,15 @@ inflate_kernel(const InflateTask *__restrict__ tasks, uint32_t ntasks, InflateRe
         lit_syms = fixed_syms; dist_syms = fixed_syms + 288;
         state = S_DATA;
       } else if (type == 2) {
-        br.refill();
-        hlit = 257 + br.peek(5); br.drop(5);
-        hdist = 1 + br.peek(5); br.drop(5);
-        uint32_t hclen = 4 + br.peek(4); br.drop(4);
+        // every lane parses the header redundantly (uniform control flow, broadcast reads of the ring)
+        uint32_t hlit = 257 + in.get(5, lane);
+        uint32_t hdist = 1 + in.get(5, lane);
+        uint32_t hclen = 4 + in.get(4, lane);
         bool bad = hlit > 286 || hdist > 30;
         // code length code lengths, 3 bits per symbol, packed by symbol
         uint64_t clc = 0;
-        for (uint32_t i = 0; i < hclen; i++) {
-          br.refill();
-          clc |= (uint64_t)br.peek(3) << (3 * c_clen_order[i]);
-          br.drop(3);
-        }
-        if (br.consumed() > src_len * 8) bad = true;
+        for (uint32_t i = 0; i < hclen; i++) clc |= (uint64_t)in.get(3, lane) << (3 * c_clen_order[i]);
+        if (in.overrun()) bad = true;
         // code-length decoder (7-bit table in the distance area, 8-bit entries: len << 5 | sym)
         uint8_t *cl_lut = reinterpret_cast<uint8_t *>(mine.dist);
         uint64_t next = 0;  // next code per length, 8 bits each
@@ -389,270 +387,280 @@ inflate_kernel(const InflateTask *__restrict__ tasks, uint32_t ntasks, InflateRe
             bad = true;
         }
         if (!bad) {
-          uint32_t *z = reinterpret_cast<uint32_t *>(cl_lut);
-          for (int i = 0; i < 32; i++) z[i] = 0;
-          for (int s = 0; s < 19; s++) {
-            uint32_t l = (uint32_t)(clc >> (3 * s)) & 7u;
-            if (!l) continue;
-            uint32_t code = (uint32_t)(next >> (8 * l)) & 0xffu;
-            next += 1ull << (8 * l);
-            uint32_t rev = __brev(code) >> (32 - l);
-            for (uint32_t k = rev; k < 128; k += (1u << l)) cl_lut[k] = (uint8_t)((l << 5) | s);
+          __syncwarp();
+          reinterpret_cast<uint32_t *>(cl_lut)[lane] = 0;
+          __syncwarp();
+          if (lane == 0) {
+            for (int s = 0; s < 19; s++) {
+              uint32_t l = (uint32_t)(clc >> (3 * s)) & 7u;
+              if (!l) continue;
+              uint32_t code = (uint32_t)(next >> (8 * l)) & 0xffu;
+              next += 1ull << (8 * l);
+              uint32_t rev = __brev(code) >> (32 - l);
+              for (uint32_t k = rev; k < 128; k += (1u << l)) cl_lut[k] = (uint8_t)((l << 5) | s);
+            }
           }
-          // decode hlit + hdist code lengths into the (currently unused) literal table area
-          uint8_t *lens = reinterpret_cast<uint8_t *>(mine.lit);
+          __syncwarp();
+          // decode hlit + hdist code lengths straight into the build scratch
           uint32_t num = 0, total = hlit + hdist, prev = 0;
           while (num < total && !bad) {
-            br.refill();
-            uint32_t e = cl_lut[br.peek(7)];
+            in.ensure(lane);
+            uint32_t w = in.peek32();
+            uint32_t e = cl_lut[w & 127u];
             if (!e) { bad = true; break; }
-            br.drop(e >> 5);
+            uint32_t used = e >> 5;
             uint32_t sym = e & 31u, rep = 1, val = sym;
             if (sym == 16) {
               if (num == 0) { bad = true; break; }
-              rep = 3 + br.peek(2); br.drop(2); val = prev;
-            } else if (sym == 17) { rep = 3 + br.peek(3); br.drop(3); val = 0; }
-            else if (sym == 18) { rep = 11 + br.peek(7); br.drop(7); val = 0; }
+              rep = 3 + ((w >> used) & 3u); used += 2; val = prev;
+            } else if (sym == 17) { rep = 3 + ((w >> used) & 7u); used += 3; val = 0; }
+            else if (sym == 18) { rep = 11 + ((w >> used) & 127u); used += 7; val = 0; }
+            in.P += used;
             if (rep > total - num) { bad = true; break; }
-            for (uint32_t r = 0; r < rep; r++) lens[num++] = (uint8_t)val;
+            if (lane == 0)
+              for (uint32_t r = 0; r < rep; r++) ws.len[num + r] = (uint8_t)val;
+            num += rep;
             prev = val;
           }
-          if (br.consumed() > src_len * 8) bad = true;
+          if (in.overrun()) bad = true;
+          __syncwarp();
+          if (!bad) {
+            for (uint32_t i = total + lane; i < 320; i += 32) ws.len[i] = 0;
+            if (lane == 0) ws.err = 0;
+            __syncwarp();
+            if (ws.len[256] == 0) bad = true;  // no end-of-block code (:662)
+            __syncwarp();
+            if (!bad) build_decoder_warp<false>(ws, 0, (int)hlit, LB, mine.lit, mine.lit_cnt, my_syms, s_len_tab, s_dist_tab, lane);
+            __syncwarp();
+            if (!bad && !ws.err) build_decoder_warp<true>(ws, (int)hlit, (int)hdist, DB, mine.dist, mine.dist_cnt, my_syms + 288, s_len_tab, s_dist_tab, lane);
+            __syncwarp();
+            if (ws.err) bad = true;
+          }
         }
         if (bad) { status = ZIPC_ERR_CORRUPTED; state = S_FINISH; }
-        else { need_build = true; }
+        else {
+          lit_lut = mine.lit; dist_lut = mine.dist; lit_cnt = mine.lit_cnt; dist_cnt = mine.dist_cnt;
+          lit_syms = my_syms; dist_syms = my_syms + 288;
+          state = S_DATA;
+        }
       } else {
         status = ZIPC_ERR_CORRUPTED; state = S_FINISH;
       }
     }
 
-    // ---- C: cooperative table builds ---------------------------------------------------------------
-    {
-      uint32_t m = __ballot_sync(0xffffffffu, need_build);
-      while (m) {
-        int L = __ffs(m) - 1;
-        m &= m - 1;
-        LaneTabs &lt = tabs[warp * G + L];
-        uint32_t nl = __shfl_sync(0xffffffffu, hlit, L), nd = __shfl_sync(0xffffffffu, hdist, L);
-        uint16_t *syms = g_syms + (size_t)((blockIdx.x * WARPS + warp) * G + L) * SYMS_PER_SLOT;
-        const uint8_t *lens = reinterpret_cast<const uint8_t *>(lt.lit);
-        __syncwarp();
-        for (uint32_t i = lane; i < 320; i += 32) ws.len[i] = i < nl + nd ? lens[i] : 0;
-        if (lane == 0) ws.err = 0;
-        __syncwarp();
-        if (ws.len[256] == 0) { if (lane == 0) ws.err = 1; }  // no end-of-block code (:662)
-        __syncwarp();
-        if (!ws.err) build_decoder_warp<false>(ws, 0, (int)nl, LB, lt.lit, lt.lit_cnt, syms, s_len_tab, s_dist_tab, lane);
-        __syncwarp();
-        if (!ws.err) build_decoder_warp<true>(ws, (int)nl, (int)nd, DB, lt.dist, lt.dist_cnt, syms + 288, s_len_tab, s_dist_tab, lane);
-        __syncwarp();
-        int err = ws.err;
-        if (lane == L) {
-          need_build = false;
-          if (err) { status = ZIPC_ERR_CORRUPTED; state = S_FINISH; }
-          else {
-            lit_lut = mine.lit; dist_lut = mine.dist; lit_cnt = mine.lit_cnt; dist_cnt = mine.dist_cnt;
-            lit_syms = my_syms; dist_syms = my_syms + 288;
-            state = S_DATA;
-          }
-        }
-        __syncwarp();
-      }
-    }
-
-    ZB_TICK(tA)
-    // ---- D: leaders decode up to K tokens each (reference :593-616) -----------------------------------------
-    uint32_t ntok = 0, depmask = 0;
-    const uint64_t batch_pos = out_pos;  // output position of this leader's first queued token
+    // ---- D: one round of up to 32 tokens (reference :593-616) ---------------------------------------------------
     if (state == S_DATA) {
-      uint32_t rel = 0;                                                     // bytes produced in this round
-      uint32_t hist = out_pos < 32768 ? (uint32_t)out_pos : 32768u;         // reachable history, capped
-      const uint64_t room64 = out_cap - out_pos;
-      uint32_t room = room64 > 0x7FFFFFFFull ? 0x7FFFFFFFu : (uint32_t)room64;  // a round produces < 2^12 bytes
-      for (int k = 0; k < K; k++) {
-        br.refill();
-        uint32_t e = lit_lut[br.peek(LB)];
-        uint32_t kind, val;
-        if ((uint16_t)(e + 1u) > 1u) { br.drop(e & 15u); kind = (e >> 4) & 7u; val = e >> 7; }   // neither 0 nor 0xFFFF
-        else {
-          int sym = e ? canon_decode(br, lit_cnt, lit_syms) : -1;
-          if (sym < 0 || sym > 285) { status = ZIPC_ERR_CORRUPTED; state = S_FINISH; break; }
-          if (sym < 256) { kind = 7; val = (uint32_t)sym; }
-          else if (sym == 256) { kind = 6; val = 0; }
-          else { uint32_t lt = s_len_tab[sym - 257]; kind = lt >> 9; val = lt & 0x1FFu; }
-        }
-        if (kind == 6) {                                                    // end of block
-          if (br.overrun()) { status = ZIPC_ERR_CORRUPTED; state = S_FINISH; }
-          else { state = final_blk ? S_FINISH : S_HDR; ad_pending = true; }
-          break;
-        }
-        // literal and match lanes of the warp share everything below except the distance decode, so a round
-        // of mixed tokens does not pay for two copies of the checks / queue write / bookkeeping
-        uint32_t length = 1, dist = 0;
-        if (kind != 7) {
-          length = val + br.peek(kind);
-          br.drop(kind);
-          br.refill();
-          uint32_t e2 = dist_lut[br.peek(DB)];
-          if (e2 + 1u > 1u) {                                               // neither 0 nor ENT_LONG
-            br.drop(e2 & 15u);
-            uint32_t deb = (e2 >> 4) & 15u;
-            dist = (e2 >> 8) + br.peek(deb);
-            br.drop(deb);
-          } else {
-            int dsym = e2 ? canon_decode(br, dist_cnt, dist_syms) : -1;
-            if (dsym < 0 || dsym > 29) { status = ZIPC_ERR_CORRUPTED; state = S_FINISH; break; }
-            uint32_t dt = s_dist_tab[dsym];
-            dist = (dt & 0xFFFFu) + br.peek(dt >> 16);
-            br.drop(dt >> 16);
+      uint32_t n = 0, rel = 0;                 // tokens and bytes of this round (uniform)
+      uint32_t tx = 0, trel = 0, tend = 0;     // lane i: token i, its output offset in the round, its end in the input
+      const uint64_t P0 = in.P;
+      uint32_t stop = 0;                       // 1 = end of block, 2 = token needs the slow path
+      uint32_t eob_bits = 0;
+      do {
+        in.ensure(lane);
+        // D1: speculative decode of the tokens starting at bits P + NB*lane + j
+        {
+          const uint32_t pb = ((uint32_t)in.P & 31u) + NB * lane;
+          const uint32_t wi = (uint32_t)(in.P >> 5) + (pb >> 5);
+          const uint32_t sh0 = pb & 31u;
+          const uint32_t a0 = wk.ring[wi & 63], a1 = wk.ring[(wi + 1) & 63], a2 = wk.ring[(wi + 2) & 63], a3 = wk.ring[(wi + 3) & 63];
+#pragma unroll
+          for (int j = 0; j < NB; j++) {
+            const uint32_t s = sh0 + j;
+            const bool up = s >= 32;
+            const uint32_t x0 = up ? a1 : a0, x1 = up ? a2 : a1, x2 = up ? a3 : a2;
+            const uint32_t lo = __funnelshift_r(x0, x1, s & 31u), hi = __funnelshift_r(x1, x2, s & 31u);
+            const uint32_t e = lit_lut[lo & ((1u << LB) - 1u)];
+            const uint32_t clen = e & 15u, kind = (e >> 4) & 7u, val = e >> 7;
+            const uint32_t p = clen + (kind < 6 ? kind : 0u);                   // code + length extra bits (<= 20)
+            const uint32_t mlen = val + ((lo >> clen) & ((1u << kind) - 1u));   // meaningful when kind < 6
+            const uint32_t d32 = __funnelshift_r(lo, hi, p);
+            const uint32_t e2 = dist_lut[d32 & ((1u << DB) - 1u)];
+            const uint32_t dl = e2 & 15u, deb = (e2 >> 4) & 15u;
+            const uint32_t dist = (e2 >> 8) + ((d32 >> dl) & ((1u << deb) - 1u));
+            const bool ok1 = (uint16_t)(e + 1u) > 1u, ok2 = e2 + 1u > 1u;
+            uint32_t cx, cy;
+            if (kind == 7) { cx = val; cy = (1u << 16) | clen; }
+            else if (kind == 6) { cx = 0; cy = 0x100u | clen; }
+            else { cx = (mlen << 16) | dist; cy = ok2 ? (mlen << 16) | (p + dl + deb) : 0u; }
+            if (!ok1) cy = 0;
+            wk.cand[j * 32 + lane] = make_uint2(cx, cy);
           }
         }
-        if (br.overrun() || dist > hist) { status = ZIPC_ERR_CORRUPTED; state = S_FINISH; break; }
-        if (length > room) { status = ZIPC_ERR_SIZE_EXCEEDED; state = S_FINISH; break; }
-        if (!COUNT_ONLY) {
-          // a match is independent of this round when all of its source bytes precede the round
-          uint32_t reach = min(dist, length);                               // source bytes actually read
-          bool dep = kind != 7 && dist < rel + reach;                       // pos - dist + reach > batch_pos
-          depmask |= dep ? (1u << k) : 0u;
-          uint32_t x = kind == 7 ? val : ((dep ? 0x80000000u : 0u) | (length << 16) | dist);
-          myq[k * G + lane] = make_uint2(x, rel);
+        __syncwarp();
+        // D2: follow the chain of real tokens through the candidates
+        uint32_t o = 0;
+        const uint32_t pbase = (uint32_t)(in.P - P0);
+        while (o < WBITS && n < ROUND_TOKENS) {
+          const uint2 c = wk.cand[((o & (NB - 1)) << 5) | (o >> NB_LOG)];
+          const uint32_t t = c.y & 0xFFFFu;
+          if (t - 1u >= 255u) { stop = t ? 1u : 2u; eob_bits = t & 0xFFu; break; }
+          if (lane == (int)n) { tx = c.x; trel = rel; tend = pbase + o + t; }
+          rel += c.y >> 16; n++; o += t;
         }
-        ntok = k + 1; rel += length; room -= length;
-        hist = min(hist + length, 32768u);
-      }
-      out_pos += rel;
-    }
+        in.P += o;
+        __syncwarp();
+      } while (!stop && n < ROUND_TOKENS - 8);
 
-    ZB_TICK(tD)
-#ifdef ZB_INFLATE_TIMING
-    rounds++; ntoks += ntok;
-#endif
-    // ---- E: the warp executes the queued tokens ------------------------------------------------------------
-    if (!COUNT_ONLY) {
-      __syncwarp();
-      const unsigned long long base_ptr = (unsigned long long)(uintptr_t)(dst + batch_pos);
-      // E1: literals and matches whose source lies before this round: no ordering needed, so all their
-      // bytes are flattened over the lanes.  The non-empty independent tokens are first compacted (QN queue
-      // slots, 2 per lane) so that a pass can find the owner of each byte with one warp OR-reduction:
-      // bit (end - base - 1) of M marks where a token ends inside the 32-byte window, and a byte's owner is
-      // the window's first token plus the number of ends before it.
-      uint32_t l0, l1;
-      {
-        uint32_t n0 = __shfl_sync(0xffffffffu, ntok, lane & (G - 1));
-        uint32_t e0 = myq[lane].x, e1 = myq[lane + 32].x;
-        uint32_t j0 = lane / G, j1 = (lane + 32) / G;
-        l0 = (j0 < n0 && !(e0 >> 31)) ? (((e0 >> 16) & 0x1FFu) ? ((e0 >> 16) & 0x1FFu) : 1u) : 0u;
-        l1 = (j1 < n0 && !(e1 >> 31)) ? (((e1 >> 16) & 0x1FFu) ? ((e1 >> 16) & 0x1FFu) : 1u) : 0u;
-      }
-      uint32_t i0 = l0, i1 = l1;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        uint32_t v0 = __shfl_up_sync(0xffffffffu, i0, o), v1 = __shfl_up_sync(0xffffffffu, i1, o);
-        if (lane >= o) { i0 += v0; i1 += v1; }
-      }
-      const uint32_t tot0 = __shfl_sync(0xffffffffu, i0, 31);
-      const uint32_t total = tot0 + __shfl_sync(0xffffffffu, i1, 31);
-      const uint32_t lt_mask = (1u << lane) - 1u;
-      const uint32_t b0 = __ballot_sync(0xffffffffu, l0 != 0), b1 = __ballot_sync(0xffffffffu, l1 != 0);
-      const uint32_t ncomp = __popc(b0) + __popc(b1);
-      if (l0) { uint32_t r = __popc(b0 & lt_mask); cstart[r] = (uint16_t)(i0 - l0); cidx[r] = (uint8_t)lane; }
-      if (l1) { uint32_t r = __popc(b0) + __popc(b1 & lt_mask); cstart[r] = (uint16_t)(tot0 + i1 - l1); cidx[r] = (uint8_t)(lane + 32); }
-      cstart[ncomp + lane] = lane == 0 ? (uint16_t)total : (uint16_t)0xFFFF;  // end sentinel, then "never ends"
-      if (lane < 2) cstart[ncomp + 32 + lane] = 0xFFFF;
-      __syncwarp();
-      // four passes at a time: all loads are issued before the first store, so one L2 round trip
-      // covers 128 bytes of copies
-      uint32_t cbase = 0;  // first compacted token that reaches into the current window
-      for (uint32_t base = 0; base < total; base += 128) {
-        uint8_t val[4];
-        uint8_t *dq[4];
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-          const uint32_t wb = base + 32 * u;                 // window [wb, wb + 32)
-          uint32_t b = wb + lane;
-          bool act = b < total;
-          uint32_t endrel = (uint32_t)cstart[cbase + lane + 1] - wb;   // end of token cbase+lane, relative to the window
-          uint32_t M = __reduce_or_sync(0xffffffffu, (endrel - 1u) < 32u ? 1u << (endrel - 1u) : 0u);
-          uint32_t c = cbase + __popc(M & lt_mask);
-          cbase += __popc(M);
-          if (!act) c = 0;
-          uint32_t q = b - cstart[c];
-          uint2 ent = myq[cidx[c]];
-          unsigned long long d = __shfl_sync(0xffffffffu, base_ptr, (int)(cidx[c] & (G - 1)));
-          uint8_t *dp = reinterpret_cast<uint8_t *>((uintptr_t)d) + ent.y;
-          uint32_t mlen = (ent.x >> 16) & 0x1FFu, mdist = ent.x & 0xFFFFu;
-          dq[u] = act ? dp + q : nullptr;
-          val[u] = (uint8_t)mdist;
-          if (act && mlen) {
-            const uint8_t *sp = dp - mdist + (mdist < mlen ? q % mdist : q);
-            unsigned int v;
-            asm volatile("ld.global.cg.u8 %0, [%1];" : "=r"(v) : "l"(sp) : "memory");
-            val[u] = (uint8_t)v;
+      // a token the tables cannot decode, at the head of the round: serial decode of that one token
+      if (stop == 2 && n == 0) {
+        in.ensure(lane);
+        uint32_t w = in.peek32();
+        uint32_t e = lit_lut[w & ((1u << LB) - 1u)];
+        uint32_t kind = 8, val = 0, used = 0;
+        if ((uint16_t)(e + 1u) > 1u) { used = e & 15u; kind = (e >> 4) & 7u; val = e >> 7; }
+        else if (e) {
+          int sym = canon_decode(w, lit_cnt, lit_syms, used);
+          if (sym >= 0 && sym <= 285) {
+            if (sym < 256) { kind = 7; val = (uint32_t)sym; }
+            else if (sym == 256) { kind = 6; val = 0; }
+            else { uint32_t lt = s_len_tab[sym - 257]; kind = lt >> 9; val = lt & 0x1FFu; }
           }
         }
-#pragma unroll
-        for (int u = 0; u < 4; u++)
-          if (dq[u]) *dq[u] = val[u];
-      }
-      __syncwarp();
-      ZB_TICK(tE1)
-      // E2: matches that read bytes produced in this round, in token order (rare for text)
-      uint32_t levels = __reduce_or_sync(0xffffffffu, depmask);
-      while (levels) {
-        const uint32_t j = (uint32_t)__ffs((int)levels) - 1u;
-        levels &= levels - 1u;
-        uint2 ent2 = (leader && j < ntok) ? myq[j * G + lane] : make_uint2(0u, 0u);
-        uint32_t ent = ent2.x;
-        uint32_t tlen = (ent >> 31) ? ((ent >> 16) & 0x1FFu) : 0u;
-        uint32_t pos = ent2.y;
-        uint32_t incl = tlen;
-#pragma unroll
-        for (int o = 1; o < G; o <<= 1) {
-          uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
-          if (lane >= o) incl += v;
-        }
-        uint32_t excl = incl - tlen;
-        uint32_t tot = __shfl_sync(0xffffffffu, incl, G - 1);
-        for (uint32_t base = 0; base < tot; base += 32) {
-          uint32_t g = base + lane;
-          uint32_t lo = 0;  // owner = number of leaders whose inclusive sum is <= g
-#pragma unroll
-          for (int step = G / 2; step > 0; step >>= 1) {
-            uint32_t v = __shfl_sync(0xffffffffu, incl, (int)(lo + step - 1));
-            if (v <= g) lo += step;
+        in.P += used;
+        if (kind == 8) { status = ZIPC_ERR_CORRUPTED; state = S_FINISH; }
+        else if (kind == 6) { stop = 1; eob_bits = 0; }
+        else if (kind == 7) { if (lane == 0) { tx = val; trel = 0; } rel = 1; n = 1; stop = 0; }
+        else {
+          in.ensure(lane);
+          w = in.peek32();
+          uint32_t mlen = val + (w & ((1u << kind) - 1u));
+          in.P += kind;
+          in.ensure(lane);
+          w = in.peek32();
+          uint32_t e2 = dist_lut[w & ((1u << DB) - 1u)];
+          uint32_t dist = 0;
+          bool okd = true;
+          if (e2 + 1u > 1u) {
+            uint32_t dl = e2 & 15u, deb = (e2 >> 4) & 15u;
+            dist = (e2 >> 8) + ((w >> dl) & ((1u << deb) - 1u));
+            in.P += dl + deb;
+          } else {
+            uint32_t dl = 0;
+            int dsym = e2 ? canon_decode(w, dist_cnt, dist_syms, dl) : -1;
+            if (dsym < 0 || dsym > 29) okd = false;
+            else {
+              in.P += dl;
+              in.ensure(lane);
+              w = in.peek32();
+              uint32_t dt = s_dist_tab[dsym];
+              dist = (dt & 0xFFFFu) + (w & ((1u << (dt >> 16)) - 1u));
+              in.P += dt >> 16;
+            }
           }
-          uint32_t t = lo & (G - 1);
-          uint32_t q = g - __shfl_sync(0xffffffffu, excl, (int)t);
-          uint32_t oe = __shfl_sync(0xffffffffu, ent, (int)t);
-          uint32_t op = __shfl_sync(0xffffffffu, pos, (int)t);
-          unsigned long long d = __shfl_sync(0xffffffffu, base_ptr, (int)t);
-          if (g < tot) {
-            uint8_t *dp = reinterpret_cast<uint8_t *>((uintptr_t)d) + op;
-            uint32_t mlen = (oe >> 16) & 0x1FFu, mdist = oe & 0xFFFFu;
-            const uint8_t *sp = dp - mdist + (mdist < mlen ? q % mdist : q);
+          if (!okd) { status = ZIPC_ERR_CORRUPTED; state = S_FINISH; }
+          else { if (lane == 0) { tx = (mlen << 16) | dist; trel = 0; } rel = mlen; n = 1; stop = 0; }
+        }
+        if (lane == 0) tend = (uint32_t)(in.P - P0);
+      }
+
+      // checks, one token per lane, in the reference's order: input overrun / distance -> corrupted, then size
+      if (state == S_DATA) {
+        const bool have = lane < (int)n;
+        const uint32_t mlen = tx >> 16, mdist = tx & 0xFFFFu;
+        const uint32_t tlen = mlen ? mlen : 1u;
+        const uint32_t hist0 = out_pos < 32768 ? (uint32_t)out_pos : 32768u;
+        const uint64_t room64 = out_cap - out_pos;
+        const uint32_t room0 = room64 > 0x7FFFFFFFull ? 0x7FFFFFFFu : (uint32_t)room64;
+        const bool corrupt = have && ((mlen && mdist > min(hist0 + trel, 32768u)) || P0 + tend > in.limit);
+        const bool exceed = have && trel + tlen > room0;
+        const uint32_t fm = __ballot_sync(0xffffffffu, corrupt || exceed);
+        if (fm) {
+          const int f = __ffs((int)fm) - 1;
+          n = (uint32_t)f;
+          rel = __shfl_sync(0xffffffffu, trel, f);
+          status = __shfl_sync(0xffffffffu, (int)corrupt, f) ? ZIPC_ERR_CORRUPTED : ZIPC_ERR_SIZE_EXCEEDED;
+          state = S_FINISH;
+          stop = 0;
+        }
+      }
+      if (stop == 1 && state == S_DATA) {  // end of block
+        in.P += eob_bits;
+        if (in.overrun()) { status = ZIPC_ERR_CORRUPTED; state = S_FINISH; }
+        else { state = final_blk ? S_FINISH : S_HDR; ad_pending = true; }
+      }
+
+      // ---- E: execute the round's tokens -------------------------------------------------------------------
+      if (!COUNT_ONLY && n) {
+        const bool have = lane < (int)n;
+        const uint32_t mlen = have ? tx >> 16 : 0u, mdist = tx & 0xFFFFu;
+        const uint32_t tlen = have ? (mlen ? mlen : 1u) : 0u;
+        // a match is independent of this round when all of its source bytes precede the round
+        const bool dep = mlen && mdist < trel + min(mdist, mlen);
+        uint8_t *const obase = dst + out_pos;
+        // E1: literals and independent matches, bytes flattened over the lanes
+        const uint32_t li = dep ? 0u : tlen;
+        uint32_t incI = li;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          uint32_t v = __shfl_up_sync(0xffffffffu, incI, o);
+          if (lane >= o) incI += v;
+        }
+        const uint32_t totalI = __shfl_sync(0xffffffffu, incI, 31);
+        const uint32_t bI = __ballot_sync(0xffffffffu, li != 0);
+        if (li) wk.cidx[__popc(bI & lt_mask)] = (uint8_t)lane;
+        __syncwarp();
+        const uint32_t istart = incI - li;
+        uint32_t rbase = 0;  // independent tokens that end before the current window
+        for (uint32_t base = 0; base < totalI; base += 64) {
+          uint8_t val[2];
+          uint8_t *dq[2];
+#pragma unroll
+          for (int u = 0; u < 2; u++) {
+            const uint32_t wb = base + 32 * u;
+            const uint32_t b = wb + lane;
+            const bool act = b < totalI;
+            const uint32_t endrel = incI - wb;   // end of my token relative to the window
+            const uint32_t M = __reduce_or_sync(0xffffffffu, (li && (endrel - 1u) < 32u) ? 1u << (endrel - 1u) : 0u);
+            const uint32_t r = rbase + __popc(M & lt_mask);
+            rbase += __popc(M);
+            const int own = act ? (int)wk.cidx[r] : 0;
+            const uint32_t ox = __shfl_sync(0xffffffffu, tx, own);
+            const uint32_t orel = __shfl_sync(0xffffffffu, trel, own);
+            const uint32_t q = b - __shfl_sync(0xffffffffu, istart, own);
+            uint8_t *dp = obase + orel;
+            const uint32_t olen = ox >> 16, odist = ox & 0xFFFFu;
+            dq[u] = act ? dp + q : nullptr;
+            val[u] = (uint8_t)ox;
+            if (act && olen) {
+              const uint8_t *sp = dp - odist + (odist < olen ? q % odist : q);
+              unsigned int v;
+              asm volatile("ld.global.cg.u8 %0, [%1];" : "=r"(v) : "l"(sp) : "memory");
+              val[u] = (uint8_t)v;
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 2; u++)
+            if (dq[u]) *dq[u] = val[u];
+        }
+        __syncwarp();
+        // E2: matches that read bytes produced in this round, in token order
+        uint32_t dm = __ballot_sync(0xffffffffu, dep);
+        while (dm) {
+          const int t = __ffs((int)dm) - 1;
+          dm &= dm - 1;
+          const uint32_t ox = __shfl_sync(0xffffffffu, tx, t);
+          const uint32_t orel = __shfl_sync(0xffffffffu, trel, t);
+          const uint32_t olen = ox >> 16, odist = ox & 0xFFFFu;
+          uint8_t *dp = obase + orel;
+          for (uint32_t q = lane; q < olen; q += 32) {
+            const uint8_t *sp = dp - odist + (odist < olen ? q % odist : q);
             unsigned int v;
             asm volatile("ld.global.cg.u8 %0, [%1];" : "=r"(v) : "l"(sp) : "memory");
             dp[q] = (uint8_t)v;
           }
+          __syncwarp();
         }
+      }
+      out_pos += rel;
+    }
+
+    // ---- stored block: one coalesced copy from the input (reference :678-680) ------------------------------------
+    if (state == S_STORED) {
+      if (!COUNT_ONLY) {
+        uint8_t *dp = dst + out_pos;
+        for (uint32_t i = lane; i < stored_len; i += 32) dp[i] = stored_src[i];
         __syncwarp();
       }
-      ZB_TICK(tE2)
-      // stored blocks: one coalesced copy from the input per leader (reference :678-680)
-      uint32_t sm = __ballot_sync(0xffffffffu, state == S_STORED);
-      while (sm) {
-        int L = __ffs(sm) - 1;
-        sm &= sm - 1;
-        uint32_t n = __shfl_sync(0xffffffffu, stored_len, L);
-        unsigned long long s = __shfl_sync(0xffffffffu, (unsigned long long)(uintptr_t)stored_src, L);
-        unsigned long long d = __shfl_sync(0xffffffffu, (unsigned long long)(uintptr_t)(dst + out_pos), L);
-        const uint8_t *sp = reinterpret_cast<const uint8_t *>((uintptr_t)s);
-        uint8_t *dp = reinterpret_cast<uint8_t *>((uintptr_t)d);
-        for (uint32_t i = lane; i < n; i += 32) dp[i] = sp[i];
-      }
-      __syncwarp();
-    }
-    if (state == S_STORED) {
       out_pos += stored_len;
       state = final_blk ? S_FINISH : S_HDR;
       ad_pending = true;
@@ -661,76 +669,57 @@ inflate_kernel(const InflateTask *__restrict__ tasks, uint32_t ntasks, InflateRe
     // ---- G: checksum of the block that just ended (reference inflated_block_crc, :682-690) ---------------------
     // Adler-32 restarts its 5552-byte chunk grid at every block and, as written in the reference, reduces
     // with a signed remainder, so it has to be folded block by block to stay bit-exact.
-    if (!COUNT_ONLY && adler_mode >= 0) {
-      uint32_t am = __ballot_sync(0xffffffffu, ad_pending);
-      while (am) {
-        int L = __ffs(am) - 1;
-        am &= am - 1;
-        unsigned long long p = __shfl_sync(0xffffffffu, (unsigned long long)(uintptr_t)(dst + ad_from), L);
-        unsigned long long n = __shfl_sync(0xffffffffu, (unsigned long long)(out_pos - ad_from), L);
-        uint32_t stt = __shfl_sync(0xffffffffu, ad_state, L);
-        uint32_t upd = adler_update_warp<true>(stt, reinterpret_cast<const uint8_t *>((uintptr_t)p), n, adler_mode, lane);
-        if (lane == L) { ad_state = upd; ad_from = out_pos; }
+    if (ad_pending) {
+      if (!COUNT_ONLY && adler_mode >= 0) {
+        __syncwarp();
+        ad_state = adler_update_warp<true>(ad_state, dst + ad_from, out_pos - ad_from, adler_mode, lane);
+        ad_state = __shfl_sync(0xffffffffu, ad_state, 0);
+        ad_from = out_pos;
       }
+      ad_pending = false;
     }
-    ad_pending = false;
-    ZB_TICK(tG)
 
-    // ---- F: finished streams report ---------------------------------------------------------------------
+    // ---- F: report -------------------------------------------------------------------------------------------
     if (state == S_FINISH) {
-      InflateResult r;
-      r.out_len = status == ZIPC_OK ? out_pos : 0;
-      r.status = status;
-      r._pad = status == ZIPC_OK ? ad_state : 0;  // fused Adler-32 of the output (when requested)
-      results[task] = r;
+      if (lane == 0) {
+        InflateResult r;
+        r.out_len = status == ZIPC_OK ? out_pos : 0;
+        r.status = status;
+        r._pad = status == ZIPC_OK ? ad_state : 0;  // fused Adler-32 of the output (when requested)
+        results[task] = r;
+      }
       state = S_IDLE;
     }
   }
-#ifdef ZB_INFLATE_TIMING
-  if ((blockIdx.x == 0 || blockIdx.x == 77) && lane == 0 && warp < 4)
-    printf("blk %d warp %d: hdr/build %lld  decode %lld  copyE1 %lld  copyE2 %lld  adler %lld  clk | rounds %lld tokens(lane0) %lld\n",
-           blockIdx.x, warp, tA, tD, tE1, tE2, tG, rounds, ntoks);
-#endif
 }
 
-bool g_attr_set = false;
+unsigned long long g_attr_devs = 0;  // bit d: attributes set on device d (function attributes are per device)
 
 }  // namespace
 
 int inflate_launch(zipc_b200_ctx *ctx, const InflateTask *d_tasks, uint32_t n, InflateResult *d_results,
                    bool count_only, int adler_mode) {
   if (n == 0) return ZIPC_OK;
-  if (!g_attr_set) {
+  if (!(g_attr_devs >> (ctx->device & 63) & 1ull)) {
     ZB_CUDA(ctx, cudaFuncSetAttribute(inflate_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
     ZB_CUDA(ctx, cudaFuncSetAttribute(inflate_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-    g_attr_set = true;
+    g_attr_devs |= 1ull << (ctx->device & 63);
   }
-  // spread the streams over all SMs first (a CTA serves up to WARPS*G at a time)
+  // one warp per stream; spread the streams over all SMs first
   uint32_t grid = (uint32_t)ctx->sm_count;
   if (grid > n) grid = n;
-  size_t sym_bytes = (size_t)(grid * WARPS * G + grid) * SYMS_PER_SLOT * sizeof(uint16_t);
+  size_t sym_bytes = (size_t)(grid * WARPS + grid) * SYMS_PER_SLOT * sizeof(uint16_t);
   if (int st = ctx->d_scratch.reserve(sym_bytes + 256 + 4096)) return st;
   unsigned int *queue = reinterpret_cast<unsigned int *>(ctx->d_scratch.as<uint8_t>() + sym_bytes);
-  // how many warps per CTA take streams: enough for `oversub` streams per leader over the whole batch
-  int oversub = 1;
-  if (const char *e = getenv("ZIPC_B200_INFLATE_OVERSUB")) oversub = std::max(1, atoi(e));
-  // default: spread the streams over all warps (measured: the kernel is bound by per-warp latency, a warp
-  // with few busy leaders finishes its rounds sooner); ZIPC_B200_INFLATE_OVERSUB packs them instead
-  int active_warps = WARPS;
-  if (getenv("ZIPC_B200_INFLATE_OVERSUB")) {
-    active_warps = (int)((n + (size_t)grid * G * oversub - 1) / ((size_t)grid * G * oversub));
-    active_warps = std::max(1, std::min(active_warps, WARPS));
-  }
-  if (const char *e = getenv("ZIPC_B200_INFLATE_WARPS")) active_warps = std::max(1, std::min(atoi(e), WARPS));
   {
-    unsigned int start = grid * active_warps * G;  // tasks [0, start) are assigned statically
+    unsigned int start = grid * WARPS;  // tasks [0, start) are assigned statically
     ZB_CUDA(ctx, cudaMemcpyAsync(queue, &start, sizeof start, cudaMemcpyHostToDevice, ctx->stream));
   }
   KernelTimer kt(ctx);
   if (count_only)
-    inflate_kernel<true><<<grid, THREADS, kSmemBytes, ctx->stream>>>(d_tasks, n, d_results, queue, ctx->d_scratch.as<uint16_t>(), -1, active_warps);
+    inflate_kernel<true><<<grid, THREADS, kSmemBytes, ctx->stream>>>(d_tasks, n, d_results, queue, ctx->d_scratch.as<uint16_t>(), -1);
   else
-    inflate_kernel<false><<<grid, THREADS, kSmemBytes, ctx->stream>>>(d_tasks, n, d_results, queue, ctx->d_scratch.as<uint16_t>(), adler_mode, active_warps);
+    inflate_kernel<false><<<grid, THREADS, kSmemBytes, ctx->stream>>>(d_tasks, n, d_results, queue, ctx->d_scratch.as<uint16_t>(), adler_mode);
   ctx->launches++;
   ZB_CUDA(ctx, cudaGetLastError());
   return ZIPC_OK;
