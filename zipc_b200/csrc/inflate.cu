@@ -44,8 +44,7 @@ namespace {
 
 constexpr int LB = 11;       // literal/length table bits
 constexpr int DB = 9;        // distance table bits (>= 7: the area also hosts the 128-entry code-length table)
-constexpr int NB = 4;        // candidate bit offsets per lane
-constexpr int NB_LOG = 2;
+constexpr int NB = 8;        // candidate bit offsets per lane: lane l owns offsets l, l + 32, ...
 constexpr int WBITS = 32 * NB;  // speculation window
 constexpr int WARPS = 16;    // warps per CTA (one CTA per SM)
 constexpr int THREADS = WARPS * 32;
@@ -71,10 +70,13 @@ struct __align__(16) WarpScratch {
   int err;
 };
 // candidate table entry: x = token (literal byte, or length << 16 | distance),
-//                        y = [7:0] bits the token occupies, [8] end of block, [31:16] bytes it produces;
-//                        y & 0xFFFF == 0: not decodable through the tables (long code or invalid)
+//                        y = 8 * (bits the token occupies) << 16 | bytes it produces   (bit 31 clear)
+//                        y = kCandEob | code length: end of block;  y = kCandSlow: not decodable through the
+//                        tables (long code or invalid code)
+constexpr uint32_t kCandEob = 0x80000000u, kCandSlow = 0xFFFFFFFFu;
 struct __align__(16) WarpWork {
-  uint2 cand[WBITS];      // [ (o % NB) * 32 + o / NB ]
+  uint2 cand[WBITS];      // by bit offset from the round's start
+  uint2 tokq[ROUND_TOKENS];  // the round's tokens in order: x = token, y = output offset | input end << 16
   uint32_t ring[64];      // compressed input, words [w0, w0 + 64) of the stream
   uint8_t cidx[32];       // E1: lane holding the r-th independent token
 };
@@ -455,51 +457,61 @@ inflate_kernel(const InflateTask *__restrict__ tasks, uint32_t ntasks, InflateRe
       const uint64_t P0 = in.P;
       uint32_t stop = 0;                       // 1 = end of block, 2 = token needs the slow path
       uint32_t eob_bits = 0;
-      do {
-        in.ensure(lane);
-        // D1: speculative decode of the tokens starting at bits P + NB*lane + j
-        {
-          const uint32_t pb = ((uint32_t)in.P & 31u) + NB * lane;
-          const uint32_t wi = (uint32_t)(in.P >> 5) + (pb >> 5);
-          const uint32_t sh0 = pb & 31u;
-          const uint32_t a0 = wk.ring[wi & 63], a1 = wk.ring[(wi + 1) & 63], a2 = wk.ring[(wi + 2) & 63], a3 = wk.ring[(wi + 3) & 63];
+      in.ensure(lane);
+      // D1: speculative decode of the tokens that would start at bits P + lane + 32 j.  Straight-line code: both
+      // table lookups are made for every candidate and the token kind only selects among the results.
+      {
+        const uint32_t sh = ((uint32_t)in.P & 31u) + lane;
+        const uint32_t wi = (uint32_t)(in.P >> 5) + (sh >> 5);
+        const uint32_t s = sh & 31u;
+        uint32_t a[NB + 2];
 #pragma unroll
-          for (int j = 0; j < NB; j++) {
-            const uint32_t s = sh0 + j;
-            const bool up = s >= 32;
-            const uint32_t x0 = up ? a1 : a0, x1 = up ? a2 : a1, x2 = up ? a3 : a2;
-            const uint32_t lo = __funnelshift_r(x0, x1, s & 31u), hi = __funnelshift_r(x1, x2, s & 31u);
-            const uint32_t e = lit_lut[lo & ((1u << LB) - 1u)];
-            const uint32_t clen = e & 15u, kind = (e >> 4) & 7u, val = e >> 7;
-            const uint32_t p = clen + (kind < 6 ? kind : 0u);                   // code + length extra bits (<= 20)
-            const uint32_t mlen = val + ((lo >> clen) & ((1u << kind) - 1u));   // meaningful when kind < 6
-            const uint32_t d32 = __funnelshift_r(lo, hi, p);
-            const uint32_t e2 = dist_lut[d32 & ((1u << DB) - 1u)];
-            const uint32_t dl = e2 & 15u, deb = (e2 >> 4) & 15u;
-            const uint32_t dist = (e2 >> 8) + ((d32 >> dl) & ((1u << deb) - 1u));
-            const bool ok1 = (uint16_t)(e + 1u) > 1u, ok2 = e2 + 1u > 1u;
-            uint32_t cx, cy;
-            if (kind == 7) { cx = val; cy = (1u << 16) | clen; }
-            else if (kind == 6) { cx = 0; cy = 0x100u | clen; }
-            else { cx = (mlen << 16) | dist; cy = ok2 ? (mlen << 16) | (p + dl + deb) : 0u; }
-            if (!ok1) cy = 0;
-            wk.cand[j * 32 + lane] = make_uint2(cx, cy);
+        for (int t = 0; t < NB + 2; t++) a[t] = wk.ring[(wi + t) & 63];
+#pragma unroll
+        for (int j = 0; j < NB; j++) {
+          const uint32_t lo = __funnelshift_r(a[j], a[j + 1], s), hi = __funnelshift_r(a[j + 1], a[j + 2], s);
+          const uint32_t e = lit_lut[lo & ((1u << LB) - 1u)];
+          const uint32_t clen = e & 15u, kind = (e >> 4) & 7u, val = e >> 7;
+          const bool is_len = kind < 6;
+          const uint32_t p = clen + (is_len ? kind : 0u);                     // code + length extra bits (<= 20)
+          const uint32_t mlen = val + ((lo >> clen) & ~(0xFFFFFFFFu << kind));  // meaningful when is_len
+          const uint32_t d32 = __funnelshift_r(lo, hi, p);
+          uint32_t e2;
+          {  // volatile: keeps the load out of a branch, the point is NB independent chains
+            const uint32_t *dp = dist_lut + (d32 & ((1u << DB) - 1u));
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(e2) : "r"((uint32_t)__cvta_generic_to_shared(dp)));
           }
+          const uint32_t dl = e2 & 15u, deb = (e2 >> 4) & 15u;
+          const uint32_t dist = (e2 >> 8) + ((d32 >> dl) & ~(0xFFFFFFFFu << deb));
+          const bool ok1 = (uint16_t)(e + 1u) > 1u, ok2 = e2 + 1u > 1u;
+          const uint32_t cx = is_len ? (mlen << 16) | dist : val;
+          uint32_t cy = is_len ? ((p + dl + deb) << 19) | mlen : (clen << 19) | 1u;
+          cy = kind == 6 ? kCandEob | clen : cy;
+          cy = (!ok1 || (is_len && !ok2)) ? kCandSlow : cy;
+          wk.cand[j * 32 + lane] = make_uint2(cx, cy);
         }
-        __syncwarp();
-        // D2: follow the chain of real tokens through the candidates
-        uint32_t o = 0;
-        const uint32_t pbase = (uint32_t)(in.P - P0);
-        while (o < WBITS && n < ROUND_TOKENS) {
-          const uint2 c = wk.cand[((o & (NB - 1)) << 5) | (o >> NB_LOG)];
-          const uint32_t t = c.y & 0xFFFFu;
-          if (t - 1u >= 255u) { stop = t ? 1u : 2u; eob_bits = t & 0xFFu; break; }
-          if (lane == (int)n) { tx = c.x; trel = rel; tend = pbase + o + t; }
-          rel += c.y >> 16; n++; o += t;
+      }
+      __syncwarp();
+      // D2: follow the chain of real tokens through the candidates (all lanes alike; the queue write is one store)
+      {
+        uint32_t o8 = 0;  // 8 * bit offset: the byte offset into cand[]
+        const char *cb = reinterpret_cast<const char *>(wk.cand);
+        for (;;) {
+          const uint2 c = *reinterpret_cast<const uint2 *>(cb + o8);
+          if ((int)c.y < 0) { stop = c.y == kCandSlow ? 2u : 1u; eob_bits = c.y & 0xFFu; break; }
+          o8 += c.y >> 16;
+          wk.tokq[n] = make_uint2(c.x, rel | (o8 << 13));
+          rel += c.y & 0xFFFFu;
+          n++;
+          if (o8 >= WBITS * 8 || n >= ROUND_TOKENS) break;
         }
-        in.P += o;
-        __syncwarp();
-      } while (!stop && n < ROUND_TOKENS - 8);
+        in.P += o8 >> 3;
+      }
+      __syncwarp();
+      if (lane < (int)n) {
+        const uint2 q = wk.tokq[lane];
+        tx = q.x; trel = q.y & 0xFFFFu; tend = q.y >> 16;
+      }
 
       // a token the tables cannot decode, at the head of the round: serial decode of that one token
       if (stop == 2 && n == 0) {
