@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libzipc_b200.so")
+# ZIPC_B200_LIB: A/B testing of alternative builds of the same library (tuning only)
+LIB_PATH = os.environ.get("ZIPC_B200_LIB") or os.path.join(_HERE, "libzipc_b200.so")
 
 # status codes (include/zipc_b200.h)
 OK, ERR_CORRUPTED, ERR_SIZE_EXCEEDED, ERR_ZLIB_METHOD, ERR_ZLIB_WINDOW, ERR_ZLIB_DICT = 0, 1, 2, 3, 4, 5

@@ -46,7 +46,10 @@ constexpr int LB = 11;       // literal/length table bits
 constexpr int DB = 9;        // distance table bits (>= 7: the area also hosts the 128-entry code-length table)
 constexpr int NB = 8;        // candidate bit offsets per lane: lane l owns offsets l, l + 32, ...
 constexpr int WBITS = 32 * NB;  // speculation window
-constexpr int WARPS = 16;    // warps per CTA (one CTA per SM)
+#ifndef ZB_INFLATE_WARPS
+#define ZB_INFLATE_WARPS 24
+#endif
+constexpr int WARPS = ZB_INFLATE_WARPS;    // warps per CTA (one CTA per SM)
 constexpr int THREADS = WARPS * 32;
 constexpr int ROUND_TOKENS = 32;  // one token per lane
 constexpr uint32_t ENT_LONG = 0xFFFFFFFFu;  // code longer than the table: canonical walk (0xFFFF in 16-bit tables)
@@ -74,14 +77,30 @@ struct __align__(16) WarpScratch {
 //                        y = kCandEob | code length: end of block;  y = kCandSlow: not decodable through the
 //                        tables (long code or invalid code)
 constexpr uint32_t kCandEob = 0x80000000u, kCandSlow = 0xFFFFFFFFu;
+// per-stream values that are read a few times per round at most live in shared memory, not in registers
+// (the kernel runs 24 warps per SM: 80 registers per thread)
+struct WarpState {
+  const uint32_t *srcw;    // word-aligned base of the input (at or before the first stream byte)
+  const uint8_t *src;
+  uint64_t src_len, out_cap;
+  uint64_t ad_from;        // output offset up to which the Adler-32 is accounted
+  uint64_t limit;          // first input bit past the stream, counted from srcw
+  uint32_t nwords;         // words that may be read
+  uint32_t skew;           // bits between srcw and the stream start (0, 8, 16, 24)
+};
 struct __align__(16) WarpWork {
-  uint2 cand[WBITS];      // by bit offset from the round's start
+  WarpState st;
+  union {
+    uint2 cand[WBITS];    // by bit offset from the round's start
+    WarpScratch build;    // table construction never overlaps a decoding round
+  };
   uint2 tokq[ROUND_TOKENS];  // the round's tokens in order: x = token, y = output offset | input end << 16
   uint32_t ring[64];      // compressed input, words [w0, w0 + 64) of the stream
   uint8_t cidx[32];       // E1: lane holding the r-th independent token
 };
 
-constexpr size_t kSmemBytes = sizeof(WarpTabs) * (WARPS + 1) + sizeof(WarpScratch) * WARPS + sizeof(WarpWork) * WARPS + 64 + 128 + 64;
+static_assert(sizeof(WarpScratch) <= sizeof(uint2) * WBITS, "build scratch must fit the candidate table");
+constexpr size_t kSmemBytes = sizeof(WarpTabs) * (WARPS + 1) + sizeof(WarpWork) * WARPS + 64 + 128 + 64;
 
 enum : uint32_t { S_IDLE = 0, S_HDR = 1, S_DATA = 2, S_STORED = 3, S_FINISH = 4, S_EXIT = 5 };
 
@@ -100,59 +119,58 @@ __constant__ uint8_t c_clen_order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4
 
 // ---- compressed input: a 64-word ring per warp, all state warp-uniform -----------------------------------------
 struct Input {
-  uint32_t *ring;          // shared memory, [64]
-  const uint32_t *srcw;    // word-aligned base (at or before the first stream byte)
-  uint32_t nwords;         // words that may be read
   uint32_t w0;             // ring holds words [w0, w0 + 64), w0 % 32 == 0
   uint32_t pre;            // word w0 + 64 + lane, requested one refill ahead
-  uint64_t P;              // read position in bits from srcw
-  uint64_t limit;          // first bit past the stream
-  uint32_t skew;           // bits between srcw and the stream start (0, 8, 16, 24)
-  __device__ __forceinline__ uint32_t load(uint32_t k) const {
+  uint64_t P;              // read position in bits from st.srcw
+  __device__ __forceinline__ uint32_t load(const WarpState &st, uint32_t k) const {
     uint32_t w = 0;
-    if (k < nwords) asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(w) : "l"(srcw + k));
+    if (k < st.nwords) asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(w) : "l"(st.srcw + k));
     return w;
   }
-  __device__ __forceinline__ void seek_bits(uint64_t bitpos, int lane) {
+  __device__ __forceinline__ void seek_bits(WarpWork &wk, uint64_t bitpos, int lane) {
     P = bitpos;
     w0 = (uint32_t)(bitpos >> 5) & ~31u;
     __syncwarp();
-    ring[lane] = load(w0 + lane);          // w0 % 64 may be 32: slot of word k is k & 63
-    ring[32 + lane] = load(w0 + 32 + lane);
-    if (w0 & 32u) { uint32_t t = ring[lane]; ring[lane] = ring[32 + lane]; ring[32 + lane] = t; }
-    pre = load(w0 + 64 + lane);
+    const uint32_t x = load(wk.st, w0 + lane), y = load(wk.st, w0 + 32 + lane);
+    wk.ring[(w0 & 32u) + lane] = x;          // slot of word k is k & 63
+    wk.ring[((w0 & 32u) ^ 32u) + lane] = y;
+    pre = load(wk.st, w0 + 64 + lane);
     __syncwarp();
   }
-  __device__ __forceinline__ void open(const uint8_t *src, uint64_t len, int lane) {
-    uint32_t a = (uint32_t)((uintptr_t)src & 3);
-    srcw = reinterpret_cast<const uint32_t *>(src - a);
-    nwords = (uint32_t)((a + len + 3) >> 2);
-    skew = 8 * a;
-    limit = (uint64_t)skew + 8 * len;
-    seek_bits(skew, lane);
+  // st.src / st.src_len are set: derive the rest (lane 0 writes) and fill the ring
+  __device__ __forceinline__ void open(WarpWork &wk, int lane) {
+    if (lane == 0) {
+      const uint32_t a = (uint32_t)((uintptr_t)wk.st.src & 3);
+      wk.st.srcw = reinterpret_cast<const uint32_t *>(wk.st.src - a);
+      wk.st.nwords = (uint32_t)((a + wk.st.src_len + 3) >> 2);
+      wk.st.skew = 8 * a;
+      wk.st.limit = (uint64_t)(8 * a) + 8 * wk.st.src_len;
+    }
+    __syncwarp();
+    seek_bits(wk, wk.st.skew, lane);
   }
   // afterwards words [P >> 5, (P >> 5) + 32] are in the ring
-  __device__ __forceinline__ void ensure(int lane) {
+  __device__ __forceinline__ void ensure(WarpWork &wk, int lane) {
     while ((uint32_t)(P >> 5) >= w0 + 32) {
       __syncwarp();
-      ring[(w0 & 32u) + lane] = pre;
+      wk.ring[(w0 & 32u) + lane] = pre;
       w0 += 32;
-      pre = load(w0 + 64 + lane);
+      pre = load(wk.st, w0 + 64 + lane);
       __syncwarp();
     }
   }
-  __device__ __forceinline__ uint32_t peek32() const {  // the next 32 bits (uniform: broadcast reads)
+  __device__ __forceinline__ uint32_t peek32(const WarpWork &wk) const {  // the next 32 bits (uniform: broadcast reads)
     uint32_t k = (uint32_t)(P >> 5);
-    return __funnelshift_r(ring[k & 63], ring[(k + 1) & 63], (uint32_t)P & 31u);
+    return __funnelshift_r(wk.ring[k & 63], wk.ring[(k + 1) & 63], (uint32_t)P & 31u);
   }
-  __device__ __forceinline__ uint32_t get(uint32_t n, int lane) {  // n <= 16
-    ensure(lane);
-    uint32_t v = peek32() & ((1u << n) - 1u);
+  __device__ __forceinline__ uint32_t get(WarpWork &wk, uint32_t n, int lane) {  // n <= 16
+    ensure(wk, lane);
+    uint32_t v = peek32(wk) & ((1u << n) - 1u);
     P += n;
     return v;
   }
-  __device__ __forceinline__ uint64_t consumed() const { return P - skew; }   // stream bits read
-  __device__ __forceinline__ bool overrun() const { return P > limit; }
+  __device__ __forceinline__ uint64_t consumed(const WarpWork &wk) const { return P - wk.st.skew; }   // stream bits read
+  __device__ __forceinline__ bool overrun(const WarpWork &wk) const { return P > wk.st.limit; }
 };
 
 // ---- canonical walk for codes longer than the table (the reference's read_symbol, :584-591) --------
@@ -262,14 +280,13 @@ inflate_kernel(const InflateTask *__restrict__ tasks, uint32_t ntasks, InflateRe
   extern __shared__ __align__(16) uint8_t smem_raw[];
   WarpTabs *tabs = reinterpret_cast<WarpTabs *>(smem_raw);                  // [WARPS] + fixed
   WarpTabs &fixed = tabs[WARPS];
-  WarpScratch *wss = reinterpret_cast<WarpScratch *>(tabs + WARPS + 1);
-  WarpWork *works = reinterpret_cast<WarpWork *>(wss + WARPS);
+  WarpWork *works = reinterpret_cast<WarpWork *>(tabs + WARPS + 1);
   uint16_t *s_len_tab = reinterpret_cast<uint16_t *>(works + WARPS);
   uint32_t *s_dist_tab = reinterpret_cast<uint32_t *>(s_len_tab + 32);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  WarpScratch &ws = wss[warp];
   WarpTabs &mine = tabs[warp];
   WarpWork &wk = works[warp];
+  WarpScratch &ws = wk.build;
   const uint32_t slot = blockIdx.x * WARPS + warp;
   uint16_t *my_syms = g_syms + (size_t)slot * SYMS_PER_SLOT;
   uint16_t *fixed_syms = g_syms + (size_t)(gridDim.x * WARPS + blockIdx.x) * SYMS_PER_SLOT;
@@ -294,20 +311,14 @@ inflate_kernel(const InflateTask *__restrict__ tasks, uint32_t ntasks, InflateRe
   // decoder state: identical in all lanes of the warp (no broadcasts needed, branches are uniform)
   uint32_t state = S_IDLE, task = 0, status = ZIPC_OK;
   Input in{};
-  in.ring = wk.ring;
-  const uint8_t *src = nullptr;
-  uint64_t src_len = 0;
+  WarpState &st = wk.st;
   uint8_t *dst = nullptr;
-  uint64_t out_pos = 0, out_cap = 0;
-  bool final_blk = false, first_task = true, segment = false;
+  uint64_t out_pos = 0;
+  bool final_blk = false, first_task = true, segment = false, use_fixed = false;
   uint32_t stored_len = 0;
-  const uint8_t *stored_src = nullptr;
+  uint64_t stored_at = 0;     // stream offset of the stored block's bytes
   uint32_t ad_state = 1;      // running Adler-32 (reference :558, :682-690)
-  uint64_t ad_from = 0;       // output offset up to which it is accounted
-  bool ad_pending = false;    // a block just ended: fold [ad_from, out_pos)
-  const uint16_t *lit_lut = nullptr, *lit_cnt = nullptr, *dist_cnt = nullptr;
-  const uint32_t *dist_lut = nullptr;
-  const uint16_t *lit_syms = nullptr, *dist_syms = nullptr;
+  bool ad_pending = false;    // a block just ended: fold [st.ad_from, out_pos)
 
   for (;;) {
     // ---- A: pull work -----------------------------------------------------------------------------------
@@ -321,50 +332,51 @@ inflate_kernel(const InflateTask *__restrict__ tasks, uint32_t ntasks, InflateRe
       }
       if (task >= ntasks) break;
       const InflateTask t = tasks[task];
-      src = t.src; src_len = t.src_len; dst = t.dst; out_cap = t.dst_cap; segment = (t.flags & kInflateSegment) != 0;
+      __syncwarp();
+      if (lane == 0) { st.src = t.src; st.src_len = t.src_len; st.out_cap = t.dst_cap; st.ad_from = 0; }
+      dst = t.dst; segment = (t.flags & kInflateSegment) != 0;
       out_pos = 0; status = ZIPC_OK; final_blk = false;
-      ad_state = 1; ad_from = 0; ad_pending = false;
-      in.open(src, src_len, lane);
+      ad_state = 1; ad_pending = false;
+      in.open(wk, lane);
       state = S_HDR;
     }
 
     // ---- B: block header (reference :692-702, :623-661, :671-677) ------------------------------------------
-    if (state == S_HDR && segment && in.consumed() == src_len * 8) {
+    if (state == S_HDR && segment && in.consumed(wk) == st.src_len * 8) {
       state = S_FINISH;  // a segment ends at the block boundary where its input ends (byte aligned by construction)
     }
     if (state == S_HDR) {
-      uint32_t h = in.get(3, lane);
+      uint32_t h = in.get(wk, 3, lane);
       final_blk = h & 1u;
       uint32_t type = h >> 1;
-      if (in.overrun()) { status = ZIPC_ERR_CORRUPTED; state = S_FINISH; }
+      if (in.overrun(wk)) { status = ZIPC_ERR_CORRUPTED; state = S_FINISH; }
       else if (type == 0) {
-        in.P += (8u - ((uint32_t)in.consumed() & 7u)) & 7u;  // to the byte boundary
-        uint32_t length = in.get(16, lane), inv = in.get(16, lane);
-        uint64_t pos = in.consumed() >> 3;
-        if (in.overrun() || length != ((~inv) & 0xFFFFu) || src_len - pos < length) {
+        in.P += (8u - ((uint32_t)in.consumed(wk) & 7u)) & 7u;  // to the byte boundary
+        uint32_t length = in.get(wk, 16, lane), inv = in.get(wk, 16, lane);
+        uint64_t pos = in.consumed(wk) >> 3;
+        if (in.overrun(wk) || length != ((~inv) & 0xFFFFu) || st.src_len - pos < length) {
           status = ZIPC_ERR_CORRUPTED; state = S_FINISH;
-        } else if (out_pos + length > out_cap) {
+        } else if (out_pos + length > st.out_cap) {
           status = ZIPC_ERR_SIZE_EXCEEDED; state = S_FINISH;
         } else {
           stored_len = length;
-          stored_src = src + pos;
-          in.seek_bits((uint64_t)in.skew + 8 * (pos + length), lane);
+          stored_at = pos;
+          in.seek_bits(wk, (uint64_t)st.skew + 8 * (pos + length), lane);
           state = S_STORED;
         }
       } else if (type == 1) {
-        lit_lut = fixed.lit; dist_lut = fixed.dist; lit_cnt = fixed.lit_cnt; dist_cnt = fixed.dist_cnt;
-        lit_syms = fixed_syms; dist_syms = fixed_syms + 288;
+        use_fixed = true;
         state = S_DATA;
       } else if (type == 2) {
         // every lane parses the header redundantly (uniform control flow, broadcast reads of the ring)
-        uint32_t hlit = 257 + in.get(5, lane);
-        uint32_t hdist = 1 + in.get(5, lane);
-        uint32_t hclen = 4 + in.get(4, lane);
+        uint32_t hlit = 257 + in.get(wk, 5, lane);
+        uint32_t hdist = 1 + in.get(wk, 5, lane);
+        uint32_t hclen = 4 + in.get(wk, 4, lane);
         bool bad = hlit > 286 || hdist > 30;
         // code length code lengths, 3 bits per symbol, packed by symbol
         uint64_t clc = 0;
-        for (uint32_t i = 0; i < hclen; i++) clc |= (uint64_t)in.get(3, lane) << (3 * c_clen_order[i]);
-        if (in.overrun()) bad = true;
+        for (uint32_t i = 0; i < hclen; i++) clc |= (uint64_t)in.get(wk, 3, lane) << (3 * c_clen_order[i]);
+        if (in.overrun(wk)) bad = true;
         // code-length decoder (7-bit table in the distance area, 8-bit entries: len << 5 | sym)
         uint8_t *cl_lut = reinterpret_cast<uint8_t *>(mine.dist);
         uint64_t next = 0;  // next code per length, 8 bits each
@@ -406,8 +418,8 @@ inflate_kernel(const InflateTask *__restrict__ tasks, uint32_t ntasks, InflateRe
           // decode hlit + hdist code lengths straight into the build scratch
           uint32_t num = 0, total = hlit + hdist, prev = 0;
           while (num < total && !bad) {
-            in.ensure(lane);
-            uint32_t w = in.peek32();
+            in.ensure(wk, lane);
+            uint32_t w = in.peek32(wk);
             uint32_t e = cl_lut[w & 127u];
             if (!e) { bad = true; break; }
             uint32_t used = e >> 5;
@@ -424,7 +436,7 @@ inflate_kernel(const InflateTask *__restrict__ tasks, uint32_t ntasks, InflateRe
             num += rep;
             prev = val;
           }
-          if (in.overrun()) bad = true;
+          if (in.overrun(wk)) bad = true;
           __syncwarp();
           if (!bad) {
             for (uint32_t i = total + lane; i < 320; i += 32) ws.len[i] = 0;
@@ -441,8 +453,7 @@ inflate_kernel(const InflateTask *__restrict__ tasks, uint32_t ntasks, InflateRe
         }
         if (bad) { status = ZIPC_ERR_CORRUPTED; state = S_FINISH; }
         else {
-          lit_lut = mine.lit; dist_lut = mine.dist; lit_cnt = mine.lit_cnt; dist_cnt = mine.dist_cnt;
-          lit_syms = my_syms; dist_syms = my_syms + 288;
+          use_fixed = false;
           state = S_DATA;
         }
       } else {
@@ -452,12 +463,15 @@ inflate_kernel(const InflateTask *__restrict__ tasks, uint32_t ntasks, InflateRe
 
     // ---- D: one round of up to 32 tokens (reference :593-616) ---------------------------------------------------
     if (state == S_DATA) {
+      const WarpTabs &T = use_fixed ? fixed : mine;
+      const uint16_t *lit_lut = T.lit;
+      const uint32_t *dist_lut = T.dist;
       uint32_t n = 0, rel = 0;                 // tokens and bytes of this round (uniform)
       uint32_t tx = 0, trel = 0, tend = 0;     // lane i: token i, its output offset in the round, its end in the input
       const uint64_t P0 = in.P;
       uint32_t stop = 0;                       // 1 = end of block, 2 = token needs the slow path
       uint32_t eob_bits = 0;
-      in.ensure(lane);
+      in.ensure(wk, lane);
       // D1: speculative decode of the tokens that would start at bits P + lane + 32 j.  Straight-line code: both
       // table lookups are made for every candidate and the token kind only selects among the results.
       {
@@ -515,13 +529,13 @@ inflate_kernel(const InflateTask *__restrict__ tasks, uint32_t ntasks, InflateRe
 
       // a token the tables cannot decode, at the head of the round: serial decode of that one token
       if (stop == 2 && n == 0) {
-        in.ensure(lane);
-        uint32_t w = in.peek32();
+        in.ensure(wk, lane);
+        uint32_t w = in.peek32(wk);
         uint32_t e = lit_lut[w & ((1u << LB) - 1u)];
         uint32_t kind = 8, val = 0, used = 0;
         if ((uint16_t)(e + 1u) > 1u) { used = e & 15u; kind = (e >> 4) & 7u; val = e >> 7; }
         else if (e) {
-          int sym = canon_decode(w, lit_cnt, lit_syms, used);
+          int sym = canon_decode(w, T.lit_cnt, use_fixed ? fixed_syms : my_syms, used);
           if (sym >= 0 && sym <= 285) {
             if (sym < 256) { kind = 7; val = (uint32_t)sym; }
             else if (sym == 256) { kind = 6; val = 0; }
@@ -533,12 +547,12 @@ inflate_kernel(const InflateTask *__restrict__ tasks, uint32_t ntasks, InflateRe
         else if (kind == 6) { stop = 1; eob_bits = 0; }
         else if (kind == 7) { if (lane == 0) { tx = val; trel = 0; } rel = 1; n = 1; stop = 0; }
         else {
-          in.ensure(lane);
-          w = in.peek32();
+          in.ensure(wk, lane);
+          w = in.peek32(wk);
           uint32_t mlen = val + (w & ((1u << kind) - 1u));
           in.P += kind;
-          in.ensure(lane);
-          w = in.peek32();
+          in.ensure(wk, lane);
+          w = in.peek32(wk);
           uint32_t e2 = dist_lut[w & ((1u << DB) - 1u)];
           uint32_t dist = 0;
           bool okd = true;
@@ -548,12 +562,12 @@ inflate_kernel(const InflateTask *__restrict__ tasks, uint32_t ntasks, InflateRe
             in.P += dl + deb;
           } else {
             uint32_t dl = 0;
-            int dsym = e2 ? canon_decode(w, dist_cnt, dist_syms, dl) : -1;
+            int dsym = e2 ? canon_decode(w, T.dist_cnt, (use_fixed ? fixed_syms : my_syms) + 288, dl) : -1;
             if (dsym < 0 || dsym > 29) okd = false;
             else {
               in.P += dl;
-              in.ensure(lane);
-              w = in.peek32();
+              in.ensure(wk, lane);
+              w = in.peek32(wk);
               uint32_t dt = s_dist_tab[dsym];
               dist = (dt & 0xFFFFu) + (w & ((1u << (dt >> 16)) - 1u));
               in.P += dt >> 16;
@@ -571,9 +585,9 @@ inflate_kernel(const InflateTask *__restrict__ tasks, uint32_t ntasks, InflateRe
         const uint32_t mlen = tx >> 16, mdist = tx & 0xFFFFu;
         const uint32_t tlen = mlen ? mlen : 1u;
         const uint32_t hist0 = out_pos < 32768 ? (uint32_t)out_pos : 32768u;
-        const uint64_t room64 = out_cap - out_pos;
+        const uint64_t room64 = st.out_cap - out_pos;
         const uint32_t room0 = room64 > 0x7FFFFFFFull ? 0x7FFFFFFFu : (uint32_t)room64;
-        const bool corrupt = have && ((mlen && mdist > min(hist0 + trel, 32768u)) || P0 + tend > in.limit);
+        const bool corrupt = have && ((mlen && mdist > min(hist0 + trel, 32768u)) || P0 + tend > st.limit);
         const bool exceed = have && trel + tlen > room0;
         const uint32_t fm = __ballot_sync(0xffffffffu, corrupt || exceed);
         if (fm) {
@@ -587,7 +601,7 @@ inflate_kernel(const InflateTask *__restrict__ tasks, uint32_t ntasks, InflateRe
       }
       if (stop == 1 && state == S_DATA) {  // end of block
         in.P += eob_bits;
-        if (in.overrun()) { status = ZIPC_ERR_CORRUPTED; state = S_FINISH; }
+        if (in.overrun(wk)) { status = ZIPC_ERR_CORRUPTED; state = S_FINISH; }
         else { state = final_blk ? S_FINISH : S_HDR; ad_pending = true; }
       }
 
@@ -670,7 +684,8 @@ inflate_kernel(const InflateTask *__restrict__ tasks, uint32_t ntasks, InflateRe
     if (state == S_STORED) {
       if (!COUNT_ONLY) {
         uint8_t *dp = dst + out_pos;
-        for (uint32_t i = lane; i < stored_len; i += 32) dp[i] = stored_src[i];
+        const uint8_t *sp = st.src + stored_at;
+        for (uint32_t i = lane; i < stored_len; i += 32) dp[i] = sp[i];
         __syncwarp();
       }
       out_pos += stored_len;
@@ -684,9 +699,11 @@ inflate_kernel(const InflateTask *__restrict__ tasks, uint32_t ntasks, InflateRe
     if (ad_pending) {
       if (!COUNT_ONLY && adler_mode >= 0) {
         __syncwarp();
-        ad_state = adler_update_warp<true>(ad_state, dst + ad_from, out_pos - ad_from, adler_mode, lane);
+        ad_state = adler_update_warp<true>(ad_state, dst + st.ad_from, out_pos - st.ad_from, adler_mode, lane);
         ad_state = __shfl_sync(0xffffffffu, ad_state, 0);
-        ad_from = out_pos;
+        __syncwarp();
+        if (lane == 0) st.ad_from = out_pos;
+        __syncwarp();
       }
       ad_pending = false;
     }
