@@ -42,23 +42,33 @@
 namespace zb {
 namespace {
 
-constexpr int LB = 11;       // literal/length table bits
-constexpr int DB = 9;        // distance table bits (>= 7: the area also hosts the 128-entry code-length table)
+#ifndef ZB_INFLATE_LB
+#define ZB_INFLATE_LB 11
+#endif
+constexpr int LB = ZB_INFLATE_LB;       // literal/length table bits
+#ifndef ZB_INFLATE_DB
+#define ZB_INFLATE_DB 8
+#endif
+constexpr int DB = ZB_INFLATE_DB;        // distance table bits (>= 7: the area also hosts the 128-entry code-length table)
 constexpr int NB = 8;        // candidate bit offsets per lane: lane l owns offsets l, l + 32, ...
 constexpr int WBITS = 32 * NB;  // speculation window
 #ifndef ZB_INFLATE_WARPS
-#define ZB_INFLATE_WARPS 24
+#define ZB_INFLATE_WARPS 32
 #endif
 constexpr int WARPS = ZB_INFLATE_WARPS;    // warps per CTA (one CTA per SM)
 constexpr int THREADS = WARPS * 32;
 constexpr int ROUND_TOKENS = 32;  // one token per lane
-constexpr uint32_t ENT_LONG = 0xFFFFFFFFu;  // code longer than the table: canonical walk (0xFFFF in 16-bit tables)
 constexpr int SYMS_PER_SLOT = 320;     // sorted symbols: 288 litlen + 32 dist
 
-// lit entry  (16 bit): [3:0] code length, [6:4] kind (0..5 = length symbol with that many extra bits,
-//                       6 = end of block, 7 = literal), [15:7] value (literal byte / length base)
-// dist entry (32 bit): [3:0] code length, [7:4] extra bits, [31:8] distance base
-// 0 = invalid code (corrupt stream); all ones = code longer than the table (canonical walk)
+// lit entry  (16 bit): [15] stop, [14] length symbol, [13:9] bits the symbol occupies INCLUDING the length's extra
+//                       bits, [8:0] literal byte | length symbol - 257 | stop kind (kStopEob / kStopInvalid / kStopLong)
+// dist entry (32 bit): [31] stop ([30]: code longer than the table, else invalid), [23:9] distance base,
+//                       [8:5] code length, [4:0] code length + extra bits
+// The speculative pass (D1) only needs "how many bits, or stop": one mask per table.
+constexpr uint32_t kLitStop = 0x8000u, kLitIsLen = 0x4000u;
+constexpr uint32_t kStopEob = 1, kStopInvalid = 2, kStopLong = 3;
+constexpr uint16_t kLitInvalid = (uint16_t)(kLitStop | kStopInvalid), kLitLong = (uint16_t)(kLitStop | kStopLong);
+constexpr uint32_t kDistInvalid = 0x80000000u, kDistLong = 0xC0000000u;
 struct __align__(16) WarpTabs {
   uint16_t lit[1 << LB];
   uint32_t dist[1 << DB];
@@ -72,13 +82,12 @@ struct __align__(16) WarpScratch {
   uint16_t symoff[16];
   int err;
 };
-// candidate table entry: x = token (literal byte, or length << 16 | distance),
-//                        y = 8 * (bits the token occupies) << 16 | bytes it produces   (bit 31 clear)
-//                        y = kCandEob | code length: end of block;  y = kCandSlow: not decodable through the
-//                        tables (long code or invalid code)
-constexpr uint32_t kCandEob = 0x80000000u, kCandSlow = 0xFFFFFFFFu;
+// candidate table entry (8 bit): bits the token starting at this offset occupies (1..48);
+//                                kCandEob | code length: end of block;  kCandSlow: not decodable through the
+//                                tables (long or invalid code).  Bit 7 set = the walk stops here.
+constexpr uint32_t kCandEob = 0x80u, kCandSlow = 0xFFu;
 // per-stream values that are read a few times per round at most live in shared memory, not in registers
-// (the kernel runs 24 warps per SM: 80 registers per thread)
+// (the kernel runs many warps per SM: 64..80 registers per thread)
 struct WarpState {
   const uint32_t *srcw;    // word-aligned base of the input (at or before the first stream byte)
   const uint8_t *src;
@@ -91,15 +100,16 @@ struct WarpState {
 struct __align__(16) WarpWork {
   WarpState st;
   union {
-    uint2 cand[WBITS];    // by bit offset from the round's start
+    uint8_t cand[WBITS];  // by bit offset from the round's start
     WarpScratch build;    // table construction never overlaps a decoding round
   };
-  uint2 tokq[ROUND_TOKENS];  // the round's tokens in order: x = token, y = output offset | input end << 16
+  uint16_t tokq[ROUND_TOKENS];  // bit offsets of the round's tokens, in order (bit 15: decoded by the slow path)
+  uint32_t slow_tx[ROUND_TOKENS];   // slow path tokens: the token ...
+  uint16_t slow_end[ROUND_TOKENS];  // ... and the bit offset where it ends
   uint32_t ring[64];      // compressed input, words [w0, w0 + 64) of the stream
   uint8_t cidx[32];       // E1: lane holding the r-th independent token
 };
 
-static_assert(sizeof(WarpScratch) <= sizeof(uint2) * WBITS, "build scratch must fit the candidate table");
 constexpr size_t kSmemBytes = sizeof(WarpTabs) * (WARPS + 1) + sizeof(WarpWork) * WARPS + 64 + 128 + 64;
 
 enum : uint32_t { S_IDLE = 0, S_HDR = 1, S_DATA = 2, S_STORED = 3, S_FINISH = 4, S_EXIT = 5 };
@@ -163,6 +173,10 @@ struct Input {
     uint32_t k = (uint32_t)(P >> 5);
     return __funnelshift_r(wk.ring[k & 63], wk.ring[(k + 1) & 63], (uint32_t)P & 31u);
   }
+  __device__ __forceinline__ static uint32_t peek32_at(const WarpWork &wk, uint64_t pos) {
+    uint32_t k = (uint32_t)(pos >> 5);
+    return __funnelshift_r(wk.ring[k & 63], wk.ring[(k + 1) & 63], (uint32_t)pos & 31u);
+  }
   __device__ __forceinline__ uint32_t get(WarpWork &wk, uint32_t n, int lane) {  // n <= 16
     ensure(wk, lane);
     uint32_t v = peek32(wk) & ((1u << n) - 1u);
@@ -207,7 +221,7 @@ __device__ void build_decoder_warp(WarpScratch &ws, int first, int n, int bits, 
   }
   {  // clear the table: 0 = invalid
     const int words = IS_DIST ? (1 << bits) : (1 << bits) / 2;
-    for (int i = lane; i < words; i += 32) lut32[i] = 0;
+    for (int i = lane; i < words; i += 32) lut32[i] = IS_DIST ? kDistInvalid : (uint32_t)kLitInvalid * 0x10001u;
   }
   __syncwarp();
   if (lane == 0) {
@@ -253,22 +267,73 @@ __device__ void build_decoder_warp(WarpScratch &ws, int first, int n, int bits, 
     uint32_t rev = __brev(code) >> (32 - l);
     if (l <= bits) {
       if (IS_DIST) {
-        uint32_t e = 0;                                   // 30, 31 never occur in valid data (:608)
-        if (sym <= 29) { uint32_t dt = s_dist_tab[sym]; e = ((dt & 0xFFFFu) << 8) | ((dt >> 16) << 4) | (uint32_t)l; }
+        uint32_t e = kDistInvalid;                        // 30, 31 never occur in valid data (:608)
+        if (sym <= 29) { uint32_t dt = s_dist_tab[sym]; e = ((dt & 0xFFFFu) << 9) | ((uint32_t)l << 5) | ((uint32_t)l + (dt >> 16)); }
         for (uint32_t k = rev; k < (1u << bits); k += (1u << l)) lut32[k] = e;
       } else {
-        uint16_t e = 0;                                   // 286, 287 never occur in valid data (:598)
-        if (sym < 256) e = (uint16_t)((sym << 7) | (7 << 4) | l);
-        else if (sym == 256) e = (uint16_t)((6 << 4) | l);
-        else if (sym <= 285) { uint32_t lt = s_len_tab[sym - 257]; e = (uint16_t)(((lt & 0x1FFu) << 7) | ((lt >> 9) << 4) | (uint32_t)l); }
+        uint16_t e = kLitInvalid;                         // 286, 287 never occur in valid data (:598)
+        if (sym < 256) e = (uint16_t)((l << 9) | sym);
+        else if (sym == 256) e = (uint16_t)(kLitStop | (l << 9) | kStopEob);
+        else if (sym <= 285) { uint32_t lt = s_len_tab[sym - 257]; e = (uint16_t)(kLitIsLen | ((l + (lt >> 9)) << 9) | (uint32_t)(sym - 257)); }
         for (uint32_t k = rev; k < (1u << bits); k += (1u << l)) lut16[k] = e;
       }
     } else {
-      if (IS_DIST) lut32[rev & ((1u << bits) - 1u)] = ENT_LONG;
-      else lut16[rev & ((1u << bits) - 1u)] = 0xFFFF;
+      if (IS_DIST) lut32[rev & ((1u << bits) - 1u)] = kDistLong;
+      else lut16[rev & ((1u << bits) - 1u)] = kLitLong;
     }
   }
   __syncwarp();
+}
+
+// ---- one token through the canonical walk (codes longer than the tables), all lanes alike --------------------------
+// pos: bit position of the token (the ring covers at least 1024 bits from the round's start).
+// Returns 0 = token (tx, bits set), 1 = end of block (bits set), 2 = corrupt.
+__device__ __noinline__ uint32_t slow_token(const WarpWork &wk, const WarpTabs &T, const uint16_t *syms,
+                                            const uint16_t *s_len_tab, const uint32_t *s_dist_tab, uint64_t pos,
+                                            uint32_t &tx, uint32_t &bits) {
+  uint32_t w = Input::peek32_at(wk, pos);
+  const uint32_t e = T.lit[w & ((1u << LB) - 1u)];
+  int sym = -1;          // literal/length symbol
+  uint32_t used = 0;     // bits of its code
+  if (!(e & kLitStop)) {
+    const uint32_t p = (e >> 9) & 31u;
+    if (e & kLitIsLen) { sym = 257 + (int)(e & 31u); used = p - (s_len_tab[e & 31u] >> 9); }
+    else { sym = (int)(e & 0xFFu); used = p; }
+  } else if ((e & 0x1FFu) == kStopLong) {
+    sym = canon_decode(w, T.lit_cnt, syms, used);
+    if (sym > 285) sym = -1;
+  } else if ((e & 0x1FFu) == kStopEob) {
+    sym = 256; used = (e >> 9) & 31u;
+  }  // kStopInvalid: sym stays -1
+  bits = used;
+  if (sym < 0) return 2;
+  if (sym == 256) return 1;
+  if (sym < 256) { tx = (uint32_t)sym; return 0; }
+  const uint32_t lt = s_len_tab[sym - 257];
+  const uint32_t ebits = lt >> 9;
+  w = Input::peek32_at(wk, pos + used);
+  const uint32_t mlen = (lt & 0x1FFu) + (w & ((1u << ebits) - 1u));
+  used += ebits;
+  w = Input::peek32_at(wk, pos + used);
+  const uint32_t e2 = T.dist[w & ((1u << DB) - 1u)];
+  uint32_t dist;
+  if (!(e2 >> 31)) {
+    const uint32_t dl = (e2 >> 5) & 15u, dtot = e2 & 31u;
+    dist = ((e2 >> 9) & 0x7FFFu) + ((w >> dl) & ~(0xFFFFFFFFu << (dtot - dl)));
+    used += dtot;
+  } else {
+    uint32_t dl = 0;
+    int dsym = e2 == kDistLong ? canon_decode(w, T.dist_cnt, syms + 288, dl) : -1;
+    if (dsym < 0 || dsym > 29) { bits = used; return 2; }
+    used += dl;
+    w = Input::peek32_at(wk, pos + used);
+    const uint32_t dt = s_dist_tab[dsym];
+    dist = (dt & 0xFFFFu) + (w & ((1u << (dt >> 16)) - 1u));
+    used += dt >> 16;
+  }
+  tx = (mlen << 16) | dist;
+  bits = used;
+  return 0;
 }
 
 // ---- the kernel ------------------------------------------------------------------------------------------
@@ -469,11 +534,12 @@ inflate_kernel(const InflateTask *__restrict__ tasks, uint32_t ntasks, InflateRe
       uint32_t n = 0, rel = 0;                 // tokens and bytes of this round (uniform)
       uint32_t tx = 0, trel = 0, tend = 0;     // lane i: token i, its output offset in the round, its end in the input
       const uint64_t P0 = in.P;
-      uint32_t stop = 0;                       // 1 = end of block, 2 = token needs the slow path
+      uint32_t stop = 0;                       // 1 = end of block, 3 = undecodable token (corrupt stream)
       uint32_t eob_bits = 0;
       in.ensure(wk, lane);
-      // D1: speculative decode of the tokens that would start at bits P + lane + 32 j.  Straight-line code: both
-      // table lookups are made for every candidate and the token kind only selects among the results.
+      // D1: how many bits would a token starting at bit P + lane + 32 j occupy?  Straight-line code: both table
+      // lookups are made for every candidate (NB independent chains per lane); values are decoded later, and only
+      // for the offsets that turn out to be real token starts.
       {
         const uint32_t sh = ((uint32_t)in.P & 31u) + lane;
         const uint32_t wi = (uint32_t)(in.P >> 5) + (sh >> 5);
@@ -485,99 +551,90 @@ inflate_kernel(const InflateTask *__restrict__ tasks, uint32_t ntasks, InflateRe
         for (int j = 0; j < NB; j++) {
           const uint32_t lo = __funnelshift_r(a[j], a[j + 1], s), hi = __funnelshift_r(a[j + 1], a[j + 2], s);
           const uint32_t e = lit_lut[lo & ((1u << LB) - 1u)];
-          const uint32_t clen = e & 15u, kind = (e >> 4) & 7u, val = e >> 7;
-          const bool is_len = kind < 6;
-          const uint32_t p = clen + (is_len ? kind : 0u);                     // code + length extra bits (<= 20)
-          const uint32_t mlen = val + ((lo >> clen) & ~(0xFFFFFFFFu << kind));  // meaningful when is_len
+          const uint32_t p = (e >> 9) & 31u;
           const uint32_t d32 = __funnelshift_r(lo, hi, p);
           uint32_t e2;
-          {  // volatile: keeps the load out of a branch, the point is NB independent chains
+          {  // volatile: keeps the load out of a branch
             const uint32_t *dp = dist_lut + (d32 & ((1u << DB) - 1u));
             asm volatile("ld.shared.u32 %0, [%1];" : "=r"(e2) : "r"((uint32_t)__cvta_generic_to_shared(dp)));
           }
-          const uint32_t dl = e2 & 15u, deb = (e2 >> 4) & 15u;
-          const uint32_t dist = (e2 >> 8) + ((d32 >> dl) & ~(0xFFFFFFFFu << deb));
-          const bool ok1 = (uint16_t)(e + 1u) > 1u, ok2 = e2 + 1u > 1u;
-          const uint32_t cx = is_len ? (mlen << 16) | dist : val;
-          uint32_t cy = is_len ? ((p + dl + deb) << 19) | mlen : (clen << 19) | 1u;
-          cy = kind == 6 ? kCandEob | clen : cy;
-          cy = (!ok1 || (is_len && !ok2)) ? kCandSlow : cy;
-          wk.cand[j * 32 + lane] = make_uint2(cx, cy);
+          const bool is_len = (e & kLitIsLen) != 0;
+          uint32_t c = p + (is_len ? e2 & 31u : 0u);
+          c = (is_len && (int)e2 < 0) ? kCandSlow : c;
+          if (e & kLitStop) c = (e & 0x1FFu) == kStopEob ? kCandEob | p : kCandSlow;
+          wk.cand[j * 32 + lane] = (uint8_t)c;
         }
       }
       __syncwarp();
-      // D2: follow the chain of real tokens through the candidates (all lanes alike; the queue write is one store)
+      // D2: follow the chain of real tokens through the candidates.  All lanes walk alike; the only per-token
+      // work is the chain itself (load, add) and one store of the token's offset.
       {
-        uint32_t o8 = 0;  // 8 * bit offset: the byte offset into cand[]
-        const char *cb = reinterpret_cast<const char *>(wk.cand);
+        uint32_t o = 0;
         for (;;) {
-          const uint2 c = *reinterpret_cast<const uint2 *>(cb + o8);
-          if ((int)c.y < 0) { stop = c.y == kCandSlow ? 2u : 1u; eob_bits = c.y & 0xFFu; break; }
-          o8 += c.y >> 16;
-          wk.tokq[n] = make_uint2(c.x, rel | (o8 << 13));
-          rel += c.y & 0xFFFFu;
+          uint32_t c = wk.cand[o];
+          if (c & 0x80u) {
+            if (c != kCandSlow) { stop = 1; eob_bits = c & 0x7Fu; break; }
+            // long or invalid code: decode this one token serially and go on
+            uint32_t stx = 0, sbits = 0;
+            const uint32_t r = slow_token(wk, T, use_fixed ? fixed_syms : my_syms, s_len_tab, s_dist_tab, P0 + o, stx, sbits);
+            if (r) { stop = r == 1 ? 1u : 3u; eob_bits = sbits; break; }
+            wk.slow_tx[n] = stx;
+            wk.slow_end[n] = (uint16_t)(o + sbits);
+            wk.tokq[n] = (uint16_t)(o | 0x8000u);
+            c = sbits;
+          } else {
+            wk.tokq[n] = (uint16_t)o;
+          }
+          o += c;
           n++;
-          if (o8 >= WBITS * 8 || n >= ROUND_TOKENS) break;
+          if (o >= WBITS || n >= ROUND_TOKENS) break;
         }
-        in.P += o8 >> 3;
+        in.P += o;
       }
       __syncwarp();
-      if (lane < (int)n) {
-        const uint2 q = wk.tokq[lane];
-        tx = q.x; trel = q.y & 0xFFFFu; tend = q.y >> 16;
-      }
-
-      // a token the tables cannot decode, at the head of the round: serial decode of that one token
-      if (stop == 2 && n == 0) {
-        in.ensure(wk, lane);
-        uint32_t w = in.peek32(wk);
-        uint32_t e = lit_lut[w & ((1u << LB) - 1u)];
-        uint32_t kind = 8, val = 0, used = 0;
-        if ((uint16_t)(e + 1u) > 1u) { used = e & 15u; kind = (e >> 4) & 7u; val = e >> 7; }
-        else if (e) {
-          int sym = canon_decode(w, T.lit_cnt, use_fixed ? fixed_syms : my_syms, used);
-          if (sym >= 0 && sym <= 285) {
-            if (sym < 256) { kind = 7; val = (uint32_t)sym; }
-            else if (sym == 256) { kind = 6; val = 0; }
-            else { uint32_t lt = s_len_tab[sym - 257]; kind = lt >> 9; val = lt & 0x1FFu; }
-          }
-        }
-        in.P += used;
-        if (kind == 8) { status = ZIPC_ERR_CORRUPTED; state = S_FINISH; }
-        else if (kind == 6) { stop = 1; eob_bits = 0; }
-        else if (kind == 7) { if (lane == 0) { tx = val; trel = 0; } rel = 1; n = 1; stop = 0; }
-        else {
-          in.ensure(wk, lane);
-          w = in.peek32(wk);
-          uint32_t mlen = val + (w & ((1u << kind) - 1u));
-          in.P += kind;
-          in.ensure(wk, lane);
-          w = in.peek32(wk);
-          uint32_t e2 = dist_lut[w & ((1u << DB) - 1u)];
-          uint32_t dist = 0;
-          bool okd = true;
-          if (e2 + 1u > 1u) {
-            uint32_t dl = e2 & 15u, deb = (e2 >> 4) & 15u;
-            dist = (e2 >> 8) + ((w >> dl) & ((1u << deb) - 1u));
-            in.P += dl + deb;
+      // lane i decodes token i (table entries are known to be plain ones); output offsets by a scan over the lengths
+      {
+        uint32_t tlen = 0;
+        const uint32_t oq = lane < (int)n ? wk.tokq[lane] : 0u;
+        if (oq & 0x8000u) {
+          tx = wk.slow_tx[lane];
+          tlen = (tx >> 16) ? tx >> 16 : 1u;
+          tend = wk.slow_end[lane];
+        } else if (lane < (int)n) {
+          const uint32_t o = oq;
+          const uint64_t pb = P0 + o;
+          const uint32_t k = (uint32_t)(pb >> 5), sb = (uint32_t)pb & 31u;
+          const uint32_t w0 = wk.ring[k & 63], w1 = wk.ring[(k + 1) & 63], w2 = wk.ring[(k + 2) & 63];
+          const uint32_t lo = __funnelshift_r(w0, w1, sb), hi = __funnelshift_r(w1, w2, sb);
+          const uint32_t e = lit_lut[lo & ((1u << LB) - 1u)];
+          const uint32_t p = (e >> 9) & 31u;
+          if (e & kLitIsLen) {
+            const uint32_t lt = s_len_tab[e & 31u];
+            const uint32_t ebits = lt >> 9;
+            const uint32_t mlen = (lt & 0x1FFu) + ((lo >> (p - ebits)) & ~(0xFFFFFFFFu << ebits));
+            const uint32_t d32 = __funnelshift_r(lo, hi, p);
+            const uint32_t e2 = dist_lut[d32 & ((1u << DB) - 1u)];
+            const uint32_t dl = (e2 >> 5) & 15u, dtot = e2 & 31u;
+            const uint32_t dist = ((e2 >> 9) & 0x7FFFu) + ((d32 >> dl) & ~(0xFFFFFFFFu << (dtot - dl)));
+            tx = (mlen << 16) | dist;
+            tlen = mlen;
+            tend = o + p + dtot;
           } else {
-            uint32_t dl = 0;
-            int dsym = e2 ? canon_decode(w, T.dist_cnt, (use_fixed ? fixed_syms : my_syms) + 288, dl) : -1;
-            if (dsym < 0 || dsym > 29) okd = false;
-            else {
-              in.P += dl;
-              in.ensure(wk, lane);
-              w = in.peek32(wk);
-              uint32_t dt = s_dist_tab[dsym];
-              dist = (dt & 0xFFFFu) + (w & ((1u << (dt >> 16)) - 1u));
-              in.P += dt >> 16;
-            }
+            tx = e & 0xFFu;
+            tlen = 1;
+            tend = o + p;
           }
-          if (!okd) { status = ZIPC_ERR_CORRUPTED; state = S_FINISH; }
-          else { if (lane == 0) { tx = (mlen << 16) | dist; trel = 0; } rel = mlen; n = 1; stop = 0; }
         }
-        if (lane == 0) tend = (uint32_t)(in.P - P0);
+        uint32_t inc = tlen;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          uint32_t v = __shfl_up_sync(0xffffffffu, inc, d);
+          if (lane >= d) inc += v;
+        }
+        trel = inc - tlen;
+        rel = __shfl_sync(0xffffffffu, inc, 31);
       }
+      __syncwarp();  // cand / tokq are rewritten by the next round
 
       // checks, one token per lane, in the reference's order: input overrun / distance -> corrupted, then size
       if (state == S_DATA) {
@@ -599,6 +656,7 @@ inflate_kernel(const InflateTask *__restrict__ tasks, uint32_t ntasks, InflateRe
           stop = 0;
         }
       }
+      if (stop == 3 && state == S_DATA) { status = ZIPC_ERR_CORRUPTED; state = S_FINISH; }
       if (stop == 1 && state == S_DATA) {  // end of block
         in.P += eob_bits;
         if (in.overrun(wk)) { status = ZIPC_ERR_CORRUPTED; state = S_FINISH; }
