@@ -536,6 +536,7 @@ inflate_kernel(const InflateTask *__restrict__ tasks, uint32_t ntasks, InflateRe
       const uint64_t P0 = in.P;
       uint32_t stop = 0;                       // 1 = end of block, 3 = undecodable token (corrupt stream)
       uint32_t eob_bits = 0;
+      uint32_t slowmask = 0;                   // bit k: token k went through the slow path
       in.ensure(wk, lane);
       // D1: how many bits would a token starting at bit P + lane + 32 j occupy?  Straight-line code: both table
       // lookups are made for every candidate (NB independent chains per lane); values are decoded later, and only
@@ -544,6 +545,7 @@ inflate_kernel(const InflateTask *__restrict__ tasks, uint32_t ntasks, InflateRe
         const uint32_t sh = ((uint32_t)in.P & 31u) + lane;
         const uint32_t wi = (uint32_t)(in.P >> 5) + (sh >> 5);
         const uint32_t s = sh & 31u;
+        const uint32_t dist_sa = (uint32_t)__cvta_generic_to_shared(dist_lut);
         uint32_t a[NB + 2];
 #pragma unroll
         for (int t = 0; t < NB + 2; t++) a[t] = wk.ring[(wi + t) & 63];
@@ -553,11 +555,8 @@ inflate_kernel(const InflateTask *__restrict__ tasks, uint32_t ntasks, InflateRe
           const uint32_t e = lit_lut[lo & ((1u << LB) - 1u)];
           const uint32_t p = (e >> 9) & 31u;
           const uint32_t d32 = __funnelshift_r(lo, hi, p);
-          uint32_t e2;
-          {  // volatile: keeps the load out of a branch
-            const uint32_t *dp = dist_lut + (d32 & ((1u << DB) - 1u));
-            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(e2) : "r"((uint32_t)__cvta_generic_to_shared(dp)));
-          }
+          uint32_t e2;  // volatile: keeps the load out of a branch
+          asm volatile("ld.shared.u32 %0, [%1];" : "=r"(e2) : "r"(dist_sa + 4u * (d32 & ((1u << DB) - 1u))));
           const bool is_len = (e & kLitIsLen) != 0;
           uint32_t c = p + (is_len ? e2 & 31u : 0u);
           c = (is_len && (int)e2 < 0) ? kCandSlow : c;
@@ -569,34 +568,62 @@ inflate_kernel(const InflateTask *__restrict__ tasks, uint32_t ntasks, InflateRe
       // D2: follow the chain of real tokens through the candidates.  All lanes walk alike; the only per-token
       // work is the chain itself (load, add) and one store of the token's offset.
       {
-        uint32_t o = 0;
+        // The loop body is the per-token cost of the whole decoder, so it is kept to: load, test, store, two adds,
+        // two compares.  Everything else (end of block, long codes) happens outside of it.
+        // Written in PTX: the compiler's version of this loop carried 15 instructions per token.
+        const uint32_t cand_sa = (uint32_t)__cvta_generic_to_shared(wk.cand);
+        const uint32_t tokq_sa = (uint32_t)__cvta_generic_to_shared(wk.tokq);
+        uint32_t ca = cand_sa, qa = tokq_sa;  // shared addresses of the current candidate / the next queue slot
+        // the queue keeps the low 16 bits of a token's candidate address: offset = (entry - cand_sa) mod 2^16
+        const uint32_t ca_end = cand_sa + WBITS, qa_end = tokq_sa + 2 * ROUND_TOKENS;
         for (;;) {
-          uint32_t c = wk.cand[o];
-          if (c & 0x80u) {
-            if (c != kCandSlow) { stop = 1; eob_bits = c & 0x7Fu; break; }
-            // long or invalid code: decode this one token serially and go on
-            uint32_t stx = 0, sbits = 0;
-            const uint32_t r = slow_token(wk, T, use_fixed ? fixed_syms : my_syms, s_len_tab, s_dist_tab, P0 + o, stx, sbits);
-            if (r) { stop = r == 1 ? 1u : 3u; eob_bits = sbits; break; }
-            wk.slow_tx[n] = stx;
-            wk.slow_end[n] = (uint16_t)(o + sbits);
-            wk.tokq[n] = (uint16_t)(o | 0x8000u);
-            c = sbits;
-          } else {
-            wk.tokq[n] = (uint16_t)o;
-          }
-          o += c;
-          n++;
-          if (o >= WBITS || n >= ROUND_TOKENS) break;
+          uint32_t c;
+          asm volatile(
+              "{\n"
+              ".reg .pred p;\n"
+              ".reg .u32 t;\n"
+              "WALK:\n"
+              "  ld.shared.u8 %0, [%1];\n"
+              "  and.b32 t, %0, 0x80;\n"
+              "  setp.ne.u32 p, t, 0;\n"
+              "  @p bra WALK_DONE;\n"
+              "  st.shared.u16 [%2], %1;\n"
+              "  add.u32 %1, %1, %0;\n"
+              "  add.u32 %2, %2, 2;\n"
+              "  setp.lt.u32 p, %1, %3;\n"
+              "  setp.lt.and.u32 p, %2, %4, p;\n"
+              "  @p bra WALK;\n"
+              "  mov.u32 %0, 0;\n"
+              "WALK_DONE:\n"
+              "}\n"
+              : "=&r"(c), "+r"(ca), "+r"(qa)
+              : "r"(ca_end), "r"(qa_end)
+              : "memory");
+          if (c == 0) break;
+          if (c != kCandSlow) { stop = 1; eob_bits = c & 0x7Fu; break; }
+          // long or invalid code: decode this one token serially and go on
+          uint32_t stx = 0, sbits = 0;
+          const uint32_t o = ca - cand_sa, k = (qa - tokq_sa) >> 1;
+          const uint32_t r = slow_token(wk, T, use_fixed ? fixed_syms : my_syms, s_len_tab, s_dist_tab, P0 + o, stx, sbits);
+          if (r) { stop = r == 1 ? 1u : 3u; eob_bits = sbits; break; }
+          wk.slow_tx[k] = stx;
+          wk.slow_end[k] = (uint16_t)(o + sbits);
+          wk.tokq[k] = (uint16_t)ca;
+          slowmask |= 1u << k;
+          ca += sbits;
+          qa += 2;
+          if (ca >= ca_end || qa >= qa_end) break;
         }
+        n = (qa - tokq_sa) >> 1;
+        const uint32_t o = ca - cand_sa;
         in.P += o;
       }
       __syncwarp();
       // lane i decodes token i (table entries are known to be plain ones); output offsets by a scan over the lengths
       {
         uint32_t tlen = 0;
-        const uint32_t oq = lane < (int)n ? wk.tokq[lane] : 0u;
-        if (oq & 0x8000u) {
+        const uint32_t oq = (wk.tokq[lane] - (uint32_t)__cvta_generic_to_shared(wk.cand)) & 0xFFFFu;
+        if ((slowmask >> lane) & 1u) {
           tx = wk.slow_tx[lane];
           tlen = (tx >> 16) ? tx >> 16 : 1u;
           tend = wk.slow_end[lane];
