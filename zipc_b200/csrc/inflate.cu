@@ -604,7 +604,7 @@ inflate_kernel(const InflateTask *__restrict__ tasks, uint32_t ntasks, InflateRe
           // long or invalid code: decode this one token serially and go on
           uint32_t stx = 0, sbits = 0;
           const uint32_t o = ca - cand_sa, k = (qa - tokq_sa) >> 1;
-          const uint32_t r = slow_token(wk, T, use_fixed ? fixed_syms : my_syms, s_len_tab, s_dist_tab, P0 + o, stx, sbits);
+          const uint32_t r = slow_token(wk, T, g_syms + (size_t)(use_fixed ? gridDim.x * WARPS + blockIdx.x : slot) * SYMS_PER_SLOT, s_len_tab, s_dist_tab, P0 + o, stx, sbits);
           if (r) { stop = r == 1 ? 1u : 3u; eob_bits = sbits; break; }
           wk.slow_tx[k] = stx;
           wk.slow_end[k] = (uint16_t)(o + sbits);
