@@ -43,6 +43,15 @@ WORKLOAD_DESC = {
 }
 
 
+def ncu_traffic(which):
+    """DRAM bytes per launch of the dominant kernel, from the committed ncu capture of this command (profiles/)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            return int(json.load(f)[which]["traffic_bytes"])
+    except Exception:
+        return None
+
+
 def measured_peak_gbs():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -456,7 +465,7 @@ def main():
     if r["kernel_ms"]:
         ach = r["algo_bytes"] / (r["kernel_ms"] / 1e3) / 1e9
         roof = {"bound": "hbm", "achieved": round(ach, 1), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4),
-                "traffic": None, "kernel": {"crc32": "crc32_tiles_kernel", "inflate": "inflate_kernel<false>", "deflate": "deflate_kernel"}[which],
+                "traffic": ncu_traffic(which), "kernel": {"crc32": "crc32_tiles_kernel", "inflate": "inflate_kernel<false>", "deflate": "deflate_kernel"}[which],
                 "kernel_ms": round(r["kernel_ms"], 4), "algorithmic_bytes": r["algo_bytes"], "peak_source": peak_src}
     line = {"metric": METRIC[which], "value": round(value, 2), "unit": "GB/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(r["total_ms_max"] / args.steps, 4), "higher_is_better": True,

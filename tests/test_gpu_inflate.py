@@ -108,6 +108,54 @@ def test_oracle_made_streams(ctx):
     _check_batch(ctx, streams, sizes)
 
 
+def test_extreme_code_shapes(ctx):
+    """Streams chosen for the speculative decoder: 15-bit and 1-bit Huffman codes (geometric byte
+    distributions), runs of one byte (1-bit literal / 258-byte matches at distance 1, more than 32 tokens per
+    256-bit window), far distances with long distance codes, and many short blocks with changing tables."""
+    rng = np.random.default_rng(11)
+    datas = []
+    # geometric distributions: P(b) ~ 2^-k -> code lengths 1..15
+    for scale in (0.35, 0.7, 1.4, 3.0):
+        datas.append(np.minimum(rng.exponential(scale, 300000), 255).astype(np.uint8).tobytes())
+    datas.append(bytes(300000))                                            # one symbol
+    datas.append((b"\x00" * 1000 + b"\x01") * 300)                      # near-degenerate code
+    datas.append(bytes(rng.integers(0, 2, 200000, dtype=np.uint8)))        # two symbols: 1-bit literals
+    datas.append(bytes(rng.integers(0, 4, 200000, dtype=np.uint8)))
+    far = rng.integers(0, 256, 33000, dtype=np.uint8).tobytes()
+    datas.append(far + far[:5000] + far[20000:29000] + far[:33000])        # distances up to 32768
+    words = [bytes(rng.integers(97, 123, int(rng.integers(2, 12)), dtype=np.uint8)) for _ in range(5000)]
+    datas.append(b" ".join(words[int(i)] for i in rng.zipf(1.3, 60000) % 5000))
+    streams, sizes = [], []
+    for d in datas:
+        for lvl, strategy in ((9, zlib.Z_DEFAULT_STRATEGY), (1, zlib.Z_DEFAULT_STRATEGY), (6, zlib.Z_HUFFMAN_ONLY),
+                              (6, zlib.Z_RLE), (6, zlib.Z_FILTERED), (6, zlib.Z_FIXED)):
+            c = zlib.compressobj(lvl, zlib.DEFLATED, -15, 9, strategy)
+            streams.append(c.compress(d) + c.flush()); sizes.append(len(d))
+        for lvl in ("fast", "best"):
+            streams.append(zo.deflate(d, lvl)); sizes.append(len(d))
+        # many short blocks, tables change every 1000 bytes
+        c = zlib.compressobj(6, zlib.DEFLATED, -15, 1)
+        out = b"".join(c.compress(d[i:i + 1000]) + c.flush(zlib.Z_FULL_FLUSH if (i // 1000) % 2 else zlib.Z_SYNC_FLUSH)
+                       for i in range(0, min(len(d), 60000), 1000)) + c.flush()
+        streams.append(out); sizes.append(min(len(d), 60000))
+    got = ctx.inflate_batch(streams, sizes, _lib.CK_CRC32)
+    k = 0
+    for d in datas:
+        for _ in range(9):
+            st, out, ck = got[k]
+            exp = d[:sizes[k]]
+            assert st == 0, (k, st)
+            assert out.tobytes() == exp, k
+            assert ck == zlib.crc32(exp), k
+            k += 1
+    # unknown sizes (count pass) and a too-small limit on every stream
+    got = ctx.inflate_batch(streams, None, _lib.CK_ADLER32)
+    for k, (st, out, ck) in enumerate(got):
+        assert st == 0 and len(out) == sizes[k], k
+    got = ctx.inflate_batch(streams, [max(0, n - 1) for n in sizes], _lib.CK_NONE)
+    assert all(st == _lib.ERR_SIZE_EXCEEDED for st, _, _ in got)
+
+
 def test_multi_member_sync_flush_streams(ctx):
     # many small blocks incl. empty stored blocks (Z_SYNC_FLUSH) and block type changes
     data = synth.text_v1(9, 200000).tobytes()
