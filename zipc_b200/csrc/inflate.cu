@@ -698,8 +698,10 @@ inflate_kernel(const InflateTask *__restrict__ tasks, uint32_t ntasks, InflateRe
         // a match is independent of this round when all of its source bytes precede the round
         const bool dep = mlen && mdist < trel + min(mdist, mlen);
         uint8_t *const obase = dst + out_pos;
-        // E1: literals and independent matches, bytes flattened over the lanes
-        const uint32_t li = dep ? 0u : tlen;
+        // E1: literals go straight out, one lane each (no loads involved)
+        if (have && !mlen) obase[trel] = (uint8_t)tx;
+        // independent matches: their bytes flattened over the lanes
+        const uint32_t li = (dep || !mlen) ? 0u : tlen;
         uint32_t incI = li;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
