@@ -208,11 +208,20 @@ adler_fold_kernel(const uint2 *__restrict__ ab, uint32_t first, uint32_t nchunks
           if (lane == 0) smU[i][warp] = bal;
         }
         __syncthreads();
+        // warp 0 finds the warps that own uncertain chunks (one lane per warp), lane 0 walks only those
+        uint32_t warps_u = 0;
+        if (warp == 0) {
+          uint32_t mine = 0;
+          for (int i = 0; i < kFoldItems; i++) mine |= smU[i][lane];
+          warps_u = __ballot_sync(0xffffffffu, mine != 0);
+        }
         if (tid == 0) {
           bool neg = s_neg != 0;   // sign before the tile
           int last_idx = -1;       // last chunk whose sign `neg` describes (-1: the tile's predecessor)
           uint32_t c = 0;
-          for (int w = 0; w < 32; w++) {
+          while (warps_u) {
+            const int w = __ffs(warps_u) - 1;
+            warps_u &= warps_u - 1;
             uint32_t any = 0;
             for (int i = 0; i < kFoldItems; i++) any |= smU[i][w];
             while (any) {
