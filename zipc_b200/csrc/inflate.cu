@@ -50,7 +50,10 @@ constexpr int LB = ZB_INFLATE_LB;       // literal/length table bits
 #define ZB_INFLATE_DB 8
 #endif
 constexpr int DB = ZB_INFLATE_DB;        // distance table bits (>= 7: the area also hosts the 128-entry code-length table)
-constexpr int NB = 8;        // candidate bit offsets per lane: lane l owns offsets l, l + 32, ...
+#ifndef ZB_INFLATE_NB
+#define ZB_INFLATE_NB 10
+#endif
+constexpr int NB = ZB_INFLATE_NB;        // candidate bit offsets per lane: lane l owns offsets l, l + 32, ...
 constexpr int WBITS = 32 * NB;  // speculation window
 #ifndef ZB_INFLATE_WARPS
 #define ZB_INFLATE_WARPS 32
