@@ -296,11 +296,6 @@ crc32_combine_tiles_kernel(const uint32_t *__restrict__ states, uint32_t F, uint
   if (q == 0) *out = (gf_mul(v[0], xl) ^ states[F]) ^ 0xFFFFFFFFu;
 }
 
-__global__ void crc32_finish_kernel(uint32_t *states, uint32_t n) {
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) states[i] ^= 0xFFFFFFFFu;
-}
-
 unsigned long long g_attr_devs = 0;  // bit d: attributes set on device d (function attributes are per device)
 int ensure_attrs(zipc_b200_ctx *ctx) {
   if (g_attr_devs >> (ctx->device & 63) & 1ull) return ZIPC_OK;

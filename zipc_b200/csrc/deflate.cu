@@ -512,11 +512,22 @@ __device__ void encode_member(const Shared &sh, const DeflateTask t, int level, 
     __syncthreads();
     // 4. lazy parse by pointer jumping over nodes v = 2 * (p - ts) + kind; codes >= 2T are exits
     if (pos < te) {
-      for (int j = 0; j < 2 * PPT; j++) {
-        uint32_t v = tid + THREADS * j, i = v >> 1, k = v & 1u, p = ts + i, nk, em;
-        uint32_t np = lazy_next(p, k, sh.mlen[1 + i], sh.mlen[i], nk, em);
-        sh.jumpA[v] = (uint16_t)(np < te ? 2 * (np - ts) + nk : 2 * kTile + 2 * (np - te) + nk);
-        sh.mark[v] = 0;
+      // both nodes of a position are handled by one thread: their jump codes share a 32-bit word and their
+      // marks a 16-bit word, which saves a third of the shared-memory operations of every round
+      uint32_t *jA32 = reinterpret_cast<uint32_t *>(sh.jumpA);
+      uint16_t *mk16 = reinterpret_cast<uint16_t *>(sh.mark);
+      for (int j = 0; j < PPT; j++) {
+        const uint32_t i = tid + THREADS * j, p = ts + i;
+        const uint32_t ml = sh.mlen[1 + i], mp = sh.mlen[i];
+        uint32_t code[2];
+#pragma unroll
+        for (uint32_t k = 0; k < 2; k++) {
+          uint32_t nk, em;
+          const uint32_t np = lazy_next(p, k, ml, mp, nk, em);
+          code[k] = np < te ? 2 * (np - ts) + nk : 2 * kTile + 2 * (np - te) + nk;
+        }
+        jA32[i] = code[0] | (code[1] << 16);
+        mk16[i] = 0;
       }
       __syncthreads();
       const uint32_t entry = 2 * (pos - ts) + kind;
@@ -524,10 +535,16 @@ __device__ void encode_member(const Shared &sh, const DeflateTask t, int level, 
       __syncthreads();
       uint16_t *ja = sh.jumpA, *jb = sh.jumpB;
       for (int r = 0; r < 11; r++) {
-        for (int j = 0; j < 2 * PPT; j++) {
-          uint32_t v = tid + THREADS * j, w = ja[v];
-          if (sh.mark[v] && w < 2 * kTile) sh.mark[w] = 1;
-          jb[v] = w < 2 * kTile ? ja[w] : (uint16_t)w;
+        const uint32_t *ja32 = reinterpret_cast<const uint32_t *>(ja);
+        uint32_t *jb32 = reinterpret_cast<uint32_t *>(jb);
+        for (int j = 0; j < PPT; j++) {
+          const uint32_t i = tid + THREADS * j;
+          const uint32_t jj = ja32[i], mm = mk16[i];
+          const uint32_t w0 = jj & 0xFFFFu, w1 = jj >> 16;
+          if ((mm & 0xFFu) && w0 < 2 * kTile) sh.mark[w0] = 1;
+          if ((mm >> 8) && w1 < 2 * kTile) sh.mark[w1] = 1;
+          const uint32_t n0 = w0 < 2 * kTile ? ja[w0] : w0, n1 = w1 < 2 * kTile ? ja[w1] : w1;
+          jb32[i] = n0 | (n1 << 16);
         }
         __syncthreads();
         uint16_t *tmp = ja; ja = jb; jb = tmp;
