@@ -130,6 +130,19 @@ __device__ __forceinline__ Shared carve(uint8_t *base) {
   return s;
 }
 
+// lanes of the warp whose key equals mine, from one ballot per key bit (match.any takes a hardware loop over
+// the distinct values: ~400 clk for 32 different hashes; this is BITS ballots + logic ops)
+template <int BITS>
+__device__ __forceinline__ uint32_t match_any_bits(uint32_t key) {
+  uint32_t m = 0xffffffffu;
+#pragma unroll
+  for (int b = 0; b < BITS; b++) {
+    const uint32_t v = __ballot_sync(0xffffffffu, (key >> b) & 1u);
+    m &= ((key >> b) & 1u) ? v : ~v;
+  }
+  return m;
+}
+
 struct RingView {
   const uint32_t *w;
   __device__ __forceinline__ uint32_t word(uint32_t a) const { return w[a]; }
@@ -450,8 +463,7 @@ __device__ void encode_member(const Shared &sh, const DeflateTask t, int level, 
       uint32_t i = warp * 128 + b * 32 + lane;
       uint32_t h = sh.hsh[i];
       bool valid = h != 0xFFFFu;
-      uint32_t key = valid ? (h & 15u) : (32u + lane);
-      uint32_t m = __match_any_sync(0xffffffffu, key);
+      uint32_t m = match_any_bits<4>(h & 15u) & __ballot_sync(0xffffffffu, valid);  // valid lanes of my class
       uint32_t below = m & ((1u << lane) - 1u);
       uint32_t base = valid ? sh.cnt[warp * 16 + (h & 15u)] : 0;
       lrank[b] = base + __popc(below);
@@ -485,8 +497,8 @@ __device__ void encode_member(const Shared &sh, const DeflateTask t, int level, 
         uint32_t k = base + lane;
         bool valid = k < c1;
         uint32_t i = valid ? sh.poslist[k] : 0, p = ts + i;
-        uint32_t h = valid ? sh.hsh[i] : (0x10000u + lane);
-        uint32_t m = __match_any_sync(0xffffffffu, h);
+        uint32_t h = valid ? sh.hsh[i] : 0u;
+        uint32_t m = match_any_bits<kHashBits>(h) & __ballot_sync(0xffffffffu, valid);  // valid lanes with my hash
         uint32_t below = m & ((1u << lane) - 1u);
         int srcl = below ? 31 - __clz(below) : 0;
         uint32_t pp = __shfl_sync(0xffffffffu, p, srcl);
