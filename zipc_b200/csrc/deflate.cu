@@ -35,11 +35,20 @@ namespace {
 
 using namespace dfl;
 
-constexpr int THREADS = 512;
+#ifndef ZB_DEFLATE_THREADS
+#define ZB_DEFLATE_THREADS 1024
+#endif
+constexpr int THREADS = ZB_DEFLATE_THREADS;   // 512 or 1024
 constexpr int NWARPS = THREADS / 32;
-constexpr int PPT = kTile / THREADS;  // positions per thread per tile (4)
+constexpr int PPT = kTile / THREADS;  // positions per thread per tile
+constexpr int kClasses = NWARPS;      // hash classes of the chain insertion: one warp each
+constexpr int kClassBits = NWARPS == 32 ? 5 : 4;
+constexpr int PPW = kTile / NWARPS;   // positions a warp ranks in the partition step
+constexpr int SORTN = 512;            // keys of the literal/length frequency sort
+static_assert(THREADS == 512 || THREADS == 1024, "the kernel is written for 16 or 32 warps");
 constexpr int kTokCap = 65536;        // tokens per block scratch (block source <= 61440 + 258)
-constexpr int kChunk = 2048;          // items per bit-packer chunk (4 per thread)
+constexpr int kChunk = 2048;          // items per bit-packer chunk
+constexpr int IPT = kChunk / THREADS; // items per thread per chunk
 constexpr int kStageWords = kChunk * 48 / 32 + 8;
 
 // ---- shared memory map ------------------------------------------------------------------------------------
@@ -53,7 +62,7 @@ constexpr int Y_BYTES = kTile * 2 + (kTile + 8) * 2 * 2 + kTile * 2;  // first, 
 constexpr int OFF_HIST = OFF_Y + Y_BYTES;                    // u32[288] lit, u32[32] dist
 constexpr int OFF_CODE = OFF_HIST + 320 * 4;                 // u32[288] lit codes, u32[32] dist codes
 constexpr int OFF_MISC = OFF_CODE + 320 * 4;                 // class counters, scan scratch, scalars
-constexpr int MISC_BYTES = 2048;
+constexpr int MISC_BYTES = 4096;
 constexpr int kSmemBytes = OFF_MISC + MISC_BYTES;
 static_assert(kStageWords * 4 + 704 * 5 + 64 <= X_BYTES, "bit staging + header items must fit the parse area");
 static_assert(512 * 4 * 2 + 320 * 2 + 1024 <= Y_BYTES, "finalize scratch must fit the tile area");
@@ -77,8 +86,8 @@ struct Shared {
   uint8_t *ll, *dl, *both, *cl;
   uint32_t *dkeys, *dscratch, *ckeys, *cscratch, *cfreq;
   uint32_t *hist_l, *hist_d, *lcode, *dcode;
-  uint16_t *cnt;     // [NWARPS][16] per-warp class counts, then offsets
-  uint16_t *cstart;  // [17] class starts
+  uint16_t *cnt;     // [NWARPS][kClasses] per-warp class counts, then offsets
+  uint16_t *cstart;  // [kClasses + 1] class starts
   uint32_t *scan;    // [NWARPS + 1]
   uint32_t *sc;      // scalars
 };
@@ -124,8 +133,8 @@ __device__ __forceinline__ Shared carve(uint8_t *base) {
   s.dcode = s.lcode + 288;
   uint8_t *m = base + OFF_MISC;
   s.cnt = reinterpret_cast<uint16_t *>(m);
-  s.cstart = s.cnt + NWARPS * 16;
-  s.scan = reinterpret_cast<uint32_t *>(m + 640);
+  s.cstart = s.cnt + NWARPS * kClasses;
+  s.scan = reinterpret_cast<uint32_t *>(m + 2048 + 128);
   s.sc = s.scan + 40;
   return s;
 }
@@ -186,11 +195,11 @@ template <class Fetch>
 __device__ void pack_items(const Shared &sh, uint32_t *out_words, uint64_t out_cap_words, uint32_t count, Fetch fetch) {
   const int tid = threadIdx.x;
   for (uint32_t c0 = 0; c0 < count; c0 += kChunk) {
-    uint64_t bits[4];
-    uint32_t nb[4], mine = 0;
+    uint64_t bits[IPT];
+    uint32_t nb[IPT], mine = 0;
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
-      uint32_t i = c0 + tid * 4 + k;
+    for (int k = 0; k < IPT; k++) {
+      uint32_t i = c0 + tid * IPT + k;
       bits[k] = 0; nb[k] = 0;
       if (i < count) fetch(i, bits[k], nb[k]);
       mine += nb[k];
@@ -203,7 +212,7 @@ __device__ void pack_items(const Shared &sh, uint32_t *out_words, uint64_t out_c
     __syncthreads();
     off += cbits;
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
+    for (int k = 0; k < IPT; k++) {
       if (!nb[k]) continue;
       uint32_t w = off >> 5, s = off & 31;
       uint64_t lo = bits[k] << s;
@@ -246,19 +255,19 @@ __device__ void finalize_block(const Shared &sh, const uint8_t *src, uint64_t bl
   if (tid == 0) sh.hist_l[256] += 1;  // end of block symbol (reference :1088-1092)
   __syncthreads();
   // -- literal/length frequencies: bitonic sort of 512 keys (freq << 9 | sym; unused symbols sort last)
-  sh.keys[tid] = (tid < kNumLit && sh.hist_l[tid]) ? ((sh.hist_l[tid] << 9) | (uint32_t)tid) : 0xFFFFFFFFu;
+  if (tid < SORTN) sh.keys[tid] = (tid < kNumLit && sh.hist_l[tid]) ? ((sh.hist_l[tid] << 9) | (uint32_t)tid) : 0xFFFFFFFFu;
   __syncthreads();
-  for (int k = 2; k <= THREADS; k <<= 1)
+  for (int k = 2; k <= SORTN; k <<= 1)
     for (int j = k >> 1; j > 0; j >>= 1) {
       int partner = tid ^ j;
-      if (partner > tid) {
+      if (tid < SORTN && partner > tid) {
         uint32_t a = sh.keys[tid], b = sh.keys[partner];
         bool up = (tid & k) == 0;
         if ((a > b) == up) { sh.keys[tid] = b; sh.keys[partner] = a; }
       }
       __syncthreads();
     }
-  if (sh.keys[tid] != 0xFFFFFFFFu && (tid == THREADS - 1 || sh.keys[tid + 1] == 0xFFFFFFFFu)) sh.sc[SC_M_L] = tid + 1;
+  if (tid < SORTN && sh.keys[tid] != 0xFFFFFFFFu && (tid == SORTN - 1 || sh.keys[tid + 1] == 0xFFFFFFFFu)) sh.sc[SC_M_L] = tid + 1;
   // -- distance frequencies: one warp, shuffle bitonic sort of 32 keys
   if (warp == 1) {
     uint32_t key = (lane < kNumDist && sh.hist_d[lane]) ? ((sh.hist_d[lane] << 9) | (uint32_t)lane) : 0xFFFFFFFFu;
@@ -454,40 +463,42 @@ __device__ void encode_member(const Shared &sh, const DeflateTask t, int level, 
       uint32_t i = tid + THREADS * j, p = ts + i;
       sh.hsh[i] = (p < te && p + 4 <= n) ? (uint16_t)hash4(ring_load32(ring, p)) : (uint16_t)0xFFFF;
     }
-    for (int i = tid; i < NWARPS * 16; i += THREADS) sh.cnt[i] = 0;
+    for (int i = tid; i < NWARPS * kClasses; i += THREADS) sh.cnt[i] = 0;
     __syncthreads();
-    // 2b. partition the tile's positions by hash class (low 4 bits), keeping position order:
-    //     warp w ranks its 128 consecutive positions, 32 at a time
-    uint32_t lrank[4];
-    for (int b = 0; b < 4; b++) {
-      uint32_t i = warp * 128 + b * 32 + lane;
+    // 2b. partition the tile's positions by hash class (low bits), keeping position order:
+    //     warp w ranks its PPW consecutive positions, 32 at a time
+    uint32_t lrank[PPW / 32];
+    for (int b = 0; b < PPW / 32; b++) {
+      uint32_t i = warp * PPW + b * 32 + lane;
       uint32_t h = sh.hsh[i];
       bool valid = h != 0xFFFFu;
-      uint32_t m = match_any_bits<4>(h & 15u) & __ballot_sync(0xffffffffu, valid);  // valid lanes of my class
+      const uint32_t cls = h & (kClasses - 1);
+      uint32_t m = match_any_bits<kClassBits>(cls) & __ballot_sync(0xffffffffu, valid);  // valid lanes of my class
       uint32_t below = m & ((1u << lane) - 1u);
-      uint32_t base = valid ? sh.cnt[warp * 16 + (h & 15u)] : 0;
+      uint32_t base = valid ? sh.cnt[warp * kClasses + cls] : 0;
       lrank[b] = base + __popc(below);
       __syncwarp();
-      if (valid && below == 0) sh.cnt[warp * 16 + (h & 15u)] = (uint16_t)(base + __popc(m));
+      if (valid && below == 0) sh.cnt[warp * kClasses + cls] = (uint16_t)(base + __popc(m));
       __syncwarp();
     }
     __syncthreads();
-    if (tid < 16) {  // per class: exclusive offsets over the warps, then the class total
+    if (tid < kClasses) {  // per class: exclusive offsets over the warps, then the class total
       uint32_t run = 0;
-      for (int w = 0; w < NWARPS; w++) { uint32_t c = sh.cnt[w * 16 + tid]; sh.cnt[w * 16 + tid] = (uint16_t)run; run += c; }
+      for (int w = 0; w < NWARPS; w++) { uint32_t c = sh.cnt[w * kClasses + tid]; sh.cnt[w * kClasses + tid] = (uint16_t)run; run += c; }
       sh.cstart[tid + 1] = (uint16_t)run;
     }
     __syncthreads();
     if (tid == 0) {
       uint32_t run = 0;
-      for (int c = 0; c < 16; c++) { uint32_t v = sh.cstart[c + 1]; sh.cstart[c] = (uint16_t)run; run += v; }
-      sh.cstart[16] = (uint16_t)run;
+      for (int c = 0; c < kClasses; c++) { uint32_t v = sh.cstart[c + 1]; sh.cstart[c] = (uint16_t)run; run += v; }
+      sh.cstart[kClasses] = (uint16_t)run;
     }
     __syncthreads();
-    for (int b = 0; b < 4; b++) {
-      uint32_t i = warp * 128 + b * 32 + lane;
+    for (int b = 0; b < PPW / 32; b++) {
+      uint32_t i = warp * PPW + b * 32 + lane;
       uint32_t h = sh.hsh[i];
-      if (h != 0xFFFFu) sh.poslist[sh.cstart[h & 15u] + sh.cnt[warp * 16 + (h & 15u)] + lrank[b]] = (uint16_t)i;
+      const uint32_t cls = h & (kClasses - 1);
+      if (h != 0xFFFFu) sh.poslist[sh.cstart[cls] + sh.cnt[warp * kClasses + cls] + lrank[b]] = (uint16_t)i;
     }
     __syncthreads();
     // 2c. chain insertion: warp w owns hash class w, walks its positions in order, 32 per step
@@ -565,10 +576,10 @@ __device__ void encode_member(const Shared &sh, const DeflateTask t, int level, 
       const uint32_t ex = ja[entry] - 2 * kTile;  // after 2^11 >= T steps the entry has left the tile
       pos = te + (ex >> 1);
       kind = ex & 1u;
-      // 5. tokens of the visited nodes, in position order (8 consecutive nodes per thread)
-      uint32_t tk[8], cnt = 0, srcsum = 0;
-      for (int j = 0; j < 8; j++) {
-        uint32_t v = tid * 8 + j, i = v >> 1, k = v & 1u, p = ts + i;
+      // 5. tokens of the visited nodes, in position order (2 * PPT consecutive nodes per thread)
+      uint32_t tk[2 * PPT], cnt = 0, srcsum = 0;
+      for (int j = 0; j < 2 * PPT; j++) {
+        uint32_t v = tid * (2 * PPT) + j, i = v >> 1, k = v & 1u, p = ts + i;
         if (!sh.mark[v] || p >= te) continue;
         uint32_t nk, em;
         uint32_t mp = sh.mlen[i];
