@@ -94,7 +94,7 @@ struct Shared {
 
 // scalar slots in sh.sc
 enum { SC_TASK = 0, SC_OUTW, SC_CARRY, SC_CBITS, SC_OVERFLOW, SC_M_L, SC_M_D, SC_NHDR, SC_BTYPE, SC_HLIT, SC_HDIST,
-       SC_EXIT, SC_CARRY_LEN, SC_CARRY_DIST, SC_SUMDYN, SC_SUMFIX, SC_BLK_SRCLEN, SC_NRSYM, SC_HCLEN, SC_HDRBITS };
+       SC_EXIT, SC_CARRY_LEN, SC_CARRY_DIST, SC_SUMDYN, SC_SUMFIX, SC_BLK_SRCLEN, SC_NRSYM, SC_HCLEN, SC_HDRBITS, SC_BATCH };
 
 __device__ __forceinline__ Shared carve(uint8_t *base) {
   Shared s;
@@ -464,6 +464,7 @@ __device__ void encode_member(const Shared &sh, const DeflateTask t, int level, 
       sh.hsh[i] = (p < te && p + 4 <= n) ? (uint16_t)hash4(ring_load32(ring, p)) : (uint16_t)0xFFFF;
     }
     for (int i = tid; i < NWARPS * kClasses; i += THREADS) sh.cnt[i] = 0;
+    if (tid == 0) sh.sc[SC_BATCH] = 0;
     __syncthreads();
     // 2b. partition the tile's positions by hash class (low bits), keeping position order:
     //     warp w ranks its PPW consecutive positions, 32 at a time
@@ -509,7 +510,7 @@ __device__ void encode_member(const Shared &sh, const DeflateTask t, int level, 
         bool valid = k < c1;
         uint32_t i = valid ? sh.poslist[k] : 0, p = ts + i;
         uint32_t h = valid ? sh.hsh[i] : 0u;
-        uint32_t m = match_any_bits<kHashBits>(h) & __ballot_sync(0xffffffffu, valid);  // valid lanes with my hash
+        uint32_t m = match_any_bits<kHashBits - kClassBits>(h >> kClassBits) & __ballot_sync(0xffffffffu, valid);  // valid lanes with my hash (the class bits are equal anyway)
         uint32_t below = m & ((1u << lane) - 1u);
         int srcl = below ? 31 - __clz(below) : 0;
         uint32_t pp = __shfl_sync(0xffffffffu, p, srcl);
@@ -525,9 +526,15 @@ __device__ void encode_member(const Shared &sh, const DeflateTask t, int level, 
     __syncthreads();
     // 3. longest match at every position (slot 0 carries position ts-1 from the previous tile)
     if (tid == 0) { sh.mlen[0] = (uint16_t)sh.sc[SC_CARRY_LEN]; sh.mdist[0] = (uint16_t)sh.sc[SC_CARRY_DIST]; }
-    for (int j = 0; j < PPT; j++) {
+    // batches of 32 consecutive positions are handed out through a counter: chains are much longer in some
+    // stretches of the input than in others, and with two fixed batches per warp the CTA waited for its slowest warp
+    for (;;) {
       // begin / store are uniform over the warp; only the chain steps diverge (lanes with short chains idle)
-      uint32_t i = tid + THREADS * j, p = ts + i, d = 0, l = 0;
+      uint32_t b = 0;
+      if (lane == 0) b = atomicAdd(&sh.sc[SC_BATCH], 1u);
+      b = __shfl_sync(0xffffffffu, b, 0);
+      if (b >= kTile / 32) break;
+      uint32_t i = b * 32 + lane, p = ts + i, d = 0, l = 0;
       if (p < te && p + 4 <= n) l = find_match(ring, prevv, p, n, sh.first[i], lp.depth, lp.nice, d);
       sh.mlen[1 + i] = (uint16_t)l;
       sh.mdist[1 + i] = (uint16_t)d;
