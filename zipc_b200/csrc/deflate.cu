@@ -514,8 +514,10 @@ __device__ void encode_member(const Shared &sh, const DeflateTask t, int level, 
         uint32_t below = m & ((1u << lane) - 1u);
         int srcl = below ? 31 - __clz(below) : 0;
         uint32_t pp = __shfl_sync(0xffffffffu, p, srcl);
+        uint16_t cand = 0;
+        if (valid) cand = below ? (uint16_t)pp : sh.head[h];
+        __syncwarp();  // every head is read before any head of this batch is replaced
         if (valid) {
-          uint16_t cand = below ? (uint16_t)pp : sh.head[h];
           sh.first[i] = cand;
           sh.prev[p & (kWindow - 1)] = cand;
           if ((m >> lane) == 1u) sh.head[h] = (uint16_t)p;  // highest lane of the group
@@ -564,6 +566,9 @@ __device__ void encode_member(const Shared &sh, const DeflateTask t, int level, 
       if (tid == 0) sh.mark[entry] = 1;
       __syncthreads();
       uint16_t *ja = sh.jumpA, *jb = sh.jumpB;
+      // Marks only ever move along the path (a marked node marks J_r of itself), so a mark that becomes visible
+      // within the round it is written (there is no barrier between the reads and the writes of sh.mark) can
+      // only mark further path nodes early: the race is benign and the final set is exactly the path.
       for (int r = 0; r < 11; r++) {
         const uint32_t *ja32 = reinterpret_cast<const uint32_t *>(ja);
         uint32_t *jb32 = reinterpret_cast<uint32_t *>(jb);
