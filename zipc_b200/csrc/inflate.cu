@@ -63,15 +63,16 @@ constexpr int THREADS = WARPS * 32;
 constexpr int ROUND_TOKENS = 32;  // one token per lane
 constexpr int SYMS_PER_SLOT = 320;     // sorted symbols: 288 litlen + 32 dist
 
-// lit entry  (16 bit): [15] stop, [14] length symbol, [13:9] bits the symbol occupies INCLUDING the length's extra
-//                       bits, [8:0] literal byte | length symbol - 257 | stop kind (kStopEob / kStopInvalid / kStopLong)
-// dist entry (32 bit): [31] stop ([30]: code longer than the table, else invalid), [23:9] distance base,
-//                       [8:5] code length, [4:0] code length + extra bits
-// The speculative pass (D1) only needs "how many bits, or stop": one mask per table.
-constexpr uint32_t kLitStop = 0x8000u, kLitIsLen = 0x4000u;
-constexpr uint32_t kStopEob = 1, kStopInvalid = 2, kStopLong = 3;
-constexpr uint16_t kLitInvalid = (uint16_t)(kLitStop | kStopInvalid), kLitLong = (uint16_t)(kLitStop | kStopLong);
-constexpr uint32_t kDistInvalid = 0x80000000u, kDistLong = 0xC0000000u;
+// Table entries are laid out for the speculative pass (D1), whose only question is "how many bits, or stop":
+// lit entry  (16 bit): [7:0] candidate byte, [15:8] literal byte | length symbol - 257
+//     candidate byte: literal -> code length;  length symbol -> kCbIsLen | (code length + the length's extra bits);
+//                     end of block -> kCbStop | code length;  kCbInvalid / kCbLong (both >= kCbSlow)
+// dist entry (32 bit): [7:0] code length + extra bits, or kDbInvalid / kDbLong (then the sum with any length part is
+//                      >= kCbSlow);  [11:8] code length;  [26:12] distance base
+constexpr uint32_t kCbIsLen = 0x40u, kCbStop = 0x80u, kCbSlow = 0xC0u, kCbInvalid = 0xFEu, kCbLong = 0xFFu;
+constexpr uint16_t kLitInvalid = (uint16_t)kCbInvalid, kLitLong = (uint16_t)kCbLong;
+constexpr uint32_t kDbInvalid = 0xC0u, kDbLong = 0xC1u;   // + (<= 20 bits of the length part) stays below 0x100
+constexpr uint32_t kDistInvalid = kDbInvalid, kDistLong = kDbLong;
 struct __align__(16) WarpTabs {
   uint16_t lit[1 << LB];
   uint32_t dist[1 << DB];
@@ -86,9 +87,8 @@ struct __align__(16) WarpScratch {
   int err;
 };
 // candidate table entry (8 bit): bits the token starting at this offset occupies (1..48);
-//                                kCandEob | code length: end of block;  kCandSlow: not decodable through the
-//                                tables (long or invalid code).  Bit 7 set = the walk stops here.
-constexpr uint32_t kCandEob = 0x80u, kCandSlow = 0xFFu;
+//                                kCbStop | code length (< kCbSlow): end of block;  >= kCbSlow: not decodable through
+//                                the tables (long or invalid code).  Bit 7 set = the walk stops here.
 // per-stream values that are read a few times per round at most live in shared memory, not in registers
 // (the kernel runs many warps per SM: 64..80 registers per thread)
 struct WarpState {
@@ -271,13 +271,13 @@ __device__ void build_decoder_warp(WarpScratch &ws, int first, int n, int bits, 
     if (l <= bits) {
       if (IS_DIST) {
         uint32_t e = kDistInvalid;                        // 30, 31 never occur in valid data (:608)
-        if (sym <= 29) { uint32_t dt = s_dist_tab[sym]; e = ((dt & 0xFFFFu) << 9) | ((uint32_t)l << 5) | ((uint32_t)l + (dt >> 16)); }
+        if (sym <= 29) { uint32_t dt = s_dist_tab[sym]; e = ((dt & 0xFFFFu) << 12) | ((uint32_t)l << 8) | ((uint32_t)l + (dt >> 16)); }
         for (uint32_t k = rev; k < (1u << bits); k += (1u << l)) lut32[k] = e;
       } else {
         uint16_t e = kLitInvalid;                         // 286, 287 never occur in valid data (:598)
-        if (sym < 256) e = (uint16_t)((l << 9) | sym);
-        else if (sym == 256) e = (uint16_t)(kLitStop | (l << 9) | kStopEob);
-        else if (sym <= 285) { uint32_t lt = s_len_tab[sym - 257]; e = (uint16_t)(kLitIsLen | ((l + (lt >> 9)) << 9) | (uint32_t)(sym - 257)); }
+        if (sym < 256) e = (uint16_t)((sym << 8) | l);
+        else if (sym == 256) e = (uint16_t)(kCbStop | l);
+        else if (sym <= 285) { uint32_t lt = s_len_tab[sym - 257]; e = (uint16_t)(((sym - 257) << 8) | kCbIsLen | (l + (lt >> 9))); }
         for (uint32_t k = rev; k < (1u << bits); k += (1u << l)) lut16[k] = e;
       }
     } else {
@@ -298,16 +298,17 @@ __device__ __noinline__ uint32_t slow_token(const WarpWork &wk, const WarpTabs &
   const uint32_t e = T.lit[w & ((1u << LB) - 1u)];
   int sym = -1;          // literal/length symbol
   uint32_t used = 0;     // bits of its code
-  if (!(e & kLitStop)) {
-    const uint32_t p = (e >> 9) & 31u;
-    if (e & kLitIsLen) { sym = 257 + (int)(e & 31u); used = p - (s_len_tab[e & 31u] >> 9); }
-    else { sym = (int)(e & 0xFFu); used = p; }
-  } else if ((e & 0x1FFu) == kStopLong) {
+  const uint32_t cb = e & 0xFFu;
+  if (!(cb & kCbStop)) {
+    const uint32_t p = cb & 31u;
+    if (cb & kCbIsLen) { sym = 257 + (int)(e >> 8); used = p - (s_len_tab[e >> 8] >> 9); }
+    else { sym = (int)(e >> 8); used = p; }
+  } else if (cb == kCbLong) {
     sym = canon_decode(w, T.lit_cnt, syms, used);
     if (sym > 285) sym = -1;
-  } else if ((e & 0x1FFu) == kStopEob) {
-    sym = 256; used = (e >> 9) & 31u;
-  }  // kStopInvalid: sym stays -1
+  } else if (cb < kCbSlow) {
+    sym = 256; used = cb & 31u;
+  }  // kCbInvalid: sym stays -1
   bits = used;
   if (sym < 0) return 2;
   if (sym == 256) return 1;
@@ -320,9 +321,9 @@ __device__ __noinline__ uint32_t slow_token(const WarpWork &wk, const WarpTabs &
   w = Input::peek32_at(wk, pos + used);
   const uint32_t e2 = T.dist[w & ((1u << DB) - 1u)];
   uint32_t dist;
-  if (!(e2 >> 31)) {
-    const uint32_t dl = (e2 >> 5) & 15u, dtot = e2 & 31u;
-    dist = ((e2 >> 9) & 0x7FFFu) + ((w >> dl) & ~(0xFFFFFFFFu << (dtot - dl)));
+  if ((e2 & 0xFFu) < kDbInvalid) {
+    const uint32_t dl = (e2 >> 8) & 15u, dtot = e2 & 0xFFu;
+    dist = (e2 >> 12) + ((w >> dl) & ~(0xFFFFFFFFu << (dtot - dl)));
     used += dtot;
   } else {
     uint32_t dl = 0;
@@ -556,14 +557,13 @@ inflate_kernel(const InflateTask *__restrict__ tasks, uint32_t ntasks, InflateRe
         for (int j = 0; j < NB; j++) {
           const uint32_t lo = __funnelshift_r(a[j], a[j + 1], s), hi = __funnelshift_r(a[j + 1], a[j + 2], s);
           const uint32_t e = lit_lut[lo & ((1u << LB) - 1u)];
-          const uint32_t p = (e >> 9) & 31u;
+          const uint32_t p = e & 31u;
           const uint32_t d32 = __funnelshift_r(lo, hi, p);
           uint32_t e2;  // volatile: keeps the load out of a branch
           asm volatile("ld.shared.u32 %0, [%1];" : "=r"(e2) : "r"(dist_sa + 4u * (d32 & ((1u << DB) - 1u))));
-          const bool is_len = (e & kLitIsLen) != 0;
-          uint32_t c = p + (is_len ? e2 & 31u : 0u);
-          c = (is_len && (int)e2 < 0) ? kCandSlow : c;
-          if (e & kLitStop) c = (e & 0x1FFu) == kStopEob ? kCandEob | p : kCandSlow;
+          // length symbol (and not a stop entry): bits of the whole token, >= kCbSlow if the distance part is not
+          // decodable;  anything else: the candidate byte as stored in the table
+          const uint32_t c = (e & 0xC0u) == kCbIsLen ? p + (e2 & 0xFFu) : e;
           wk.cand[j * 32 + lane] = (uint8_t)c;
         }
       }
@@ -603,7 +603,7 @@ inflate_kernel(const InflateTask *__restrict__ tasks, uint32_t ntasks, InflateRe
               : "r"(ca_end), "r"(qa_end)
               : "memory");
           if (c == 0) break;
-          if (c != kCandSlow) { stop = 1; eob_bits = c & 0x7Fu; break; }
+          if (c < kCbSlow) { stop = 1; eob_bits = c & 31u; break; }
           // long or invalid code: decode this one token serially and go on
           uint32_t stx = 0, sbits = 0;
           const uint32_t o = ca - cand_sa, k = (qa - tokq_sa) >> 1;
@@ -637,20 +637,20 @@ inflate_kernel(const InflateTask *__restrict__ tasks, uint32_t ntasks, InflateRe
           const uint32_t w0 = wk.ring[k & 63], w1 = wk.ring[(k + 1) & 63], w2 = wk.ring[(k + 2) & 63];
           const uint32_t lo = __funnelshift_r(w0, w1, sb), hi = __funnelshift_r(w1, w2, sb);
           const uint32_t e = lit_lut[lo & ((1u << LB) - 1u)];
-          const uint32_t p = (e >> 9) & 31u;
-          if (e & kLitIsLen) {
-            const uint32_t lt = s_len_tab[e & 31u];
+          const uint32_t p = e & 31u;
+          if (e & kCbIsLen) {
+            const uint32_t lt = s_len_tab[e >> 8];
             const uint32_t ebits = lt >> 9;
             const uint32_t mlen = (lt & 0x1FFu) + ((lo >> (p - ebits)) & ~(0xFFFFFFFFu << ebits));
             const uint32_t d32 = __funnelshift_r(lo, hi, p);
             const uint32_t e2 = dist_lut[d32 & ((1u << DB) - 1u)];
-            const uint32_t dl = (e2 >> 5) & 15u, dtot = e2 & 31u;
-            const uint32_t dist = ((e2 >> 9) & 0x7FFFu) + ((d32 >> dl) & ~(0xFFFFFFFFu << (dtot - dl)));
+            const uint32_t dl = (e2 >> 8) & 15u, dtot = e2 & 0xFFu;
+            const uint32_t dist = (e2 >> 12) + ((d32 >> dl) & ~(0xFFFFFFFFu << (dtot - dl)));
             tx = (mlen << 16) | dist;
             tlen = mlen;
             tend = o + p + dtot;
           } else {
-            tx = e & 0xFFu;
+            tx = e >> 8;
             tlen = 1;
             tend = o + p;
           }
