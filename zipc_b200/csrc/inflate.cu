@@ -584,11 +584,9 @@ inflate_kernel(const InflateTask *__restrict__ tasks, uint32_t ntasks, InflateRe
           asm volatile(
               "{\n"
               ".reg .pred p;\n"
-              ".reg .u32 t;\n"
               "WALK:\n"
               "  ld.shared.u8 %0, [%1];\n"
-              "  and.b32 t, %0, 0x80;\n"
-              "  setp.ne.u32 p, t, 0;\n"
+              "  setp.ge.u32 p, %0, 0x80;\n"
               "  @p bra WALK_DONE;\n"
               "  st.shared.u16 [%2], %1;\n"
               "  add.u32 %1, %1, %0;\n"
