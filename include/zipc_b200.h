@@ -193,7 +193,7 @@ int zipc_b200_deflate_segmented(zipc_b200_ctx *ctx, int level, const void *src, 
                                 int last_piece, void *dst, size_t dst_cap, size_t *dst_len, uint64_t *index,
                                 size_t index_cap_pairs, size_t *nseg, uint32_t *crc32);
 /* Zipc_deflate.inflate_and_crc_32 of such a stream WITH its index: segments are decoded in parallel (one
- * decoder lane each).  status = ZIPC_OK or the status of the first bad segment.  Without the index the stream
+ * warp each).  status = ZIPC_OK or the status of the first bad segment.  Without the index the stream
  * is an ordinary deflate stream (zipc_b200_inflate_batch decodes it serially). */
 int zipc_b200_inflate_segmented(zipc_b200_ctx *ctx, const void *src, size_t len, const uint64_t *index, size_t nseg,
                                 void *dst, size_t dst_cap, size_t *dst_len, uint32_t *crc32, int *status);
