@@ -715,11 +715,12 @@ inflate_kernel(const InflateTask *__restrict__ tasks, uint32_t ntasks, InflateRe
         __syncwarp();
         const uint32_t istart = incI - li;
         uint32_t rbase = 0;  // independent tokens that end before the current window
-        for (uint32_t base = 0; base < totalI; base += 64) {
-          uint8_t val[2];
-          uint8_t *dq[2];
+        constexpr int kPasses = 4;  // loads of up to 128 bytes are in flight before the first store
+        for (uint32_t base = 0; base < totalI; base += 32 * kPasses) {
+          uint8_t val[kPasses];
+          uint8_t *dq[kPasses];
 #pragma unroll
-          for (int u = 0; u < 2; u++) {
+          for (int u = 0; u < kPasses; u++) {
             const uint32_t wb = base + 32 * u;
             const uint32_t b = wb + lane;
             const bool act = b < totalI;
@@ -743,7 +744,7 @@ inflate_kernel(const InflateTask *__restrict__ tasks, uint32_t ntasks, InflateRe
             }
           }
 #pragma unroll
-          for (int u = 0; u < 2; u++)
+          for (int u = 0; u < kPasses; u++)
             if (dq[u]) *dq[u] = val[u];
         }
         __syncwarp();
