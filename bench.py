@@ -215,6 +215,45 @@ def _pack_device(h: Harness, items):
     return hp, h.torch.from_numpy(hp).to(f"cuda:{h.device}"), offs, lens
 
 
+def run_inflate_foreign(h: Harness, count=10000):
+    """C3 with a FOREIGN encoder: the same members compressed by zlib -6 on the host (longer matches, ~16k-symbol
+    blocks, occasional stored / fixed blocks) and inflated on the GPU, device-resident."""
+    import zlib
+    P = lambda a, t: a.ctypes.data_as(C.POINTER(t))
+    datas = make_members(count, 1000)
+
+    def comp(d):
+        c = zlib.compressobj(6, zlib.DEFLATED, -15)
+        return np.frombuffer(c.compress(d.tobytes()) + c.flush(), dtype=np.uint8)
+    with ThreadPoolExecutor(max_workers=os.cpu_count() or 4) as ex:
+        streams = list(ex.map(comp, datas))
+    crcs = np.array([zlib.crc32(d.tobytes()) for d in datas[:200]], dtype=np.uint32)
+    n = len(datas)
+    U = int(sum(d.size for d in datas)); Cb = int(sum(x.size for x in streams))
+    _, dcs, coff, clen = _pack_device(h, streams)
+    soff = np.concatenate([[0], np.cumsum([(d.size + 15) & ~15 for d in datas])[:-1]]).astype(np.uint64)
+    slen = np.array([d.size for d in datas], dtype=np.uint64)
+    ddst = h.torch.empty(int(soff[-1] + slen[-1]) + 64, dtype=h.torch.uint8, device=f"cuda:{h.device}")
+    dl = np.zeros(n, dtype=np.uint64); ck = np.zeros(n, dtype=np.uint32); st = np.zeros(n, dtype=np.int32)
+
+    def fn():
+        rc = h.L.zipc_b200_inflate_batch_dev(h.ctx.h, 2, 0, n, dcs.data_ptr(), P(coff, C.c_size_t), P(clen, C.c_size_t),
+                                             ddst.data_ptr(), P(soff, C.c_size_t), P(slen, C.c_size_t), P(dl, C.c_size_t),
+                                             P(ck, C.c_uint32), P(st, C.c_int))
+        assert rc == 0, rc
+    for _ in range(3):
+        fn()
+    h.torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        fn()
+    h.torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / 3
+    assert (st == 0).all() and (dl == slen).all() and (ck[:200] == crcs).all(), "parity lost on zlib-made streams"
+    return {"workload": "C3 members compressed by zlib -6 on the host (foreign encoder), batch inflate + CRC-32, device-resident",
+            "metric": "inflate_GBps_uncompressed", "value": round(U / dt / 1e9, 2), "unit": "GB/s", "ratio": round(Cb / U, 4), "members": n}
+
+
 def run_archive(h: Harness, count=10000):
     """ZIP archive layer end to end (host buffers): Zipc.File.deflate_of_binary_string x n + Zipc.to_binary_string
     in one call, then Zipc.of_binary_string + File.to_binary_string x n (CRC-32 checked) in two."""
@@ -362,8 +401,11 @@ def cpu_crc32(host: np.ndarray, budget_s=10.0):
         if time.perf_counter() - t0 > budget_s or reps >= 8:
             break
     dt = time.perf_counter() - t0
+    import zlib
+    t1 = time.perf_counter(); zlib.crc32(host[: 256 << 20]); tz = time.perf_counter() - t1   # a familiar yardstick
     return {"value": round(n * reps / dt / 1e9, 3), "unit": "GB/s", "cores": 1, "kind": "port",
-            "sample": f"{reps} x full 1 GiB buffer, Crc_32.string restated in C (oracle/zipc_oracle.c), 1 thread: the reference hashes one string on one core"}
+            "sample": f"{reps} x full 1 GiB buffer, Crc_32.string restated in C (oracle/zipc_oracle.c), 1 thread: the reference hashes one string on one core",
+            "zlib_crc32_yardstick_GBps": round((256 << 20) / tz / 1e9, 3)}
 
 
 def cpu_codec(which, datas, streams, level="default", budget_s=12.0):
@@ -549,6 +591,10 @@ def main():
                 del rr
             except Exception as e:  # never lose the headline line to a secondary workload
                 also[w] = {"error": repr(e)}
+        try:
+            also["inflate_foreign_zlib6"] = run_inflate_foreign(h)
+        except Exception as e:
+            also["inflate_foreign_zlib6"] = {"error": repr(e)}
         try:
             also["archive"] = run_archive(h)
         except Exception as e:
