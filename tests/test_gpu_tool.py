@@ -90,3 +90,31 @@ def test_file_codecs_and_crc(tmp_path, capsys):
     assert int(capsys.readouterr().out.strip(), 16) == zlib.adler32(data)
     c.write_bytes(b"\x78\x9c\x00garbage")
     assert zipc_tool.main(["decompress", "--zlib", str(c), str(d)]) == zipc_tool.EXIT_SOME
+
+
+def test_foreign_archives_and_unsupported_members(tmp_path):
+    """Archives written by another implementation (python zipfile): deflate at several levels, stored, a directory,
+    and a bzip2 member, which the reference (and this tool) report as unsupported (exit 3) unless skipped."""
+    import bz2  # noqa: F401  (zipfile needs it for ZIP_BZIP2)
+    rnd = os.urandom(70000)
+    text = b"".join(b"line %d of some text\n" % i for i in range(20000))
+    p = tmp_path / "foreign.zip"
+    with zipfile.ZipFile(str(p), "w") as z:
+        z.writestr(zipfile.ZipInfo("odd/"), b"")    # directory without the directory attribute: a file member to zipc
+        z.mkdir("dir")
+        z.writestr("dir/text1", text, compress_type=zipfile.ZIP_DEFLATED, compresslevel=1)
+        z.writestr("dir/text9", text, compress_type=zipfile.ZIP_DEFLATED, compresslevel=9)
+        z.writestr("rnd.stored", rnd, compress_type=zipfile.ZIP_STORED)
+        z.writestr("rnd.deflated", rnd, compress_type=zipfile.ZIP_DEFLATED)
+        z.writestr("empty", b"", compress_type=zipfile.ZIP_DEFLATED)
+    assert zipc_tool.main(["unzip", "-t", str(p)]) == zipc_tool.EXIT_OK
+    assert zipc_tool.main(["recode", "--deflate", "--level", "best", "-t", str(p)]) == zipc_tool.EXIT_OK
+    q = tmp_path / "with_bz2.zip"
+    with zipfile.ZipFile(str(q), "w") as z:
+        z.writestr("ok", text, compress_type=zipfile.ZIP_DEFLATED)
+        z.writestr("nope.bz2", text, compress_type=zipfile.ZIP_BZIP2)
+    assert zipc_tool.main(["unzip", "-t", str(q)]) == zipc_tool.EXIT_UNSUPPORTED
+    assert zipc_tool.main(["unzip", "-t", "-u", str(q)]) == zipc_tool.EXIT_OK
+    out = tmp_path / "x"
+    assert zipc_tool.main(["unzip", "-d", str(out), str(p)]) == 0
+    assert (out / "dir" / "text9").read_bytes() == text and (out / "rnd.stored").read_bytes() == rnd

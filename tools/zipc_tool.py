@@ -187,6 +187,9 @@ def cmd_unzip(a) -> int:
             code = EXIT_CORRUPTED
             continue
         dst = os.path.join(root, p)
+        if p.endswith("/"):  # a directory written as an empty file member (no directory attribute): some zippers do
+            os.makedirs(dst, exist_ok=True)
+            continue
         os.makedirs(os.path.dirname(dst) or ".", exist_ok=True)
         with open(dst, "wb") as f:
             f.write(r.get_ok())
