@@ -101,6 +101,21 @@ ZHD uint32_t ring_load32(const Ring &ring, uint32_t pos) {
 #endif
 }
 
+// 8 bytes at pos as two little-endian words
+template <class Ring>
+ZHD void ring_load64(const Ring &ring, uint32_t pos, uint32_t &w0, uint32_t &w1) {
+  uint32_t i = pos & (kRing - 1);
+  uint32_t a = i >> 2, s = (i & 3u) * 8u;
+  uint32_t x0 = ring.word(a), x1 = ring.word((a + 1) & (kRing / 4 - 1)), x2 = ring.word((a + 2) & (kRing / 4 - 1));
+#if defined(__CUDA_ARCH__)
+  w0 = __funnelshift_r(x0, x1, s);
+  w1 = __funnelshift_r(x1, x2, s);
+#else
+  w0 = s ? (x0 >> s) | (x1 << (32 - s)) : x0;
+  w1 = s ? (x1 >> s) | (x2 << (32 - s)) : x1;
+#endif
+}
+
 template <class Ring>
 ZHD uint32_t ring_load8(const Ring &ring, uint32_t pos) {
   return ring.byte(pos & (kRing - 1));
@@ -140,7 +155,11 @@ ZHD void match_step(MatchState &m, const Ring &ring, const Prev &prev, int nice)
   uint32_t cp = m.p - dist;
   if (m.best < m.max_len && ring_load8(ring, cp + m.best) == m.chk) {
     uint32_t len;
-    uint32_t x = ring_load32(ring, cp) ^ m.pw0;
+    // candidates of one chain nearly always share the first 4 bytes (same hash), so both words are fetched at
+    // once: 3 aligned loads for 8 bytes instead of 2 + 2
+    uint32_t w0, w1;
+    ring_load64(ring, cp, w0, w1);
+    uint32_t x = w0 ^ m.pw0;
     if (x) len = (uint32_t)
 #if defined(__CUDA_ARCH__)
         (__ffs((int)x) - 1) >> 3;
@@ -148,7 +167,7 @@ ZHD void match_step(MatchState &m, const Ring &ring, const Prev &prev, int nice)
         __builtin_ctz(x) >> 3;
 #endif
     else {
-      x = ring_load32(ring, cp + 4) ^ m.pw1;
+      x = w1 ^ m.pw1;
       if (x) len = 4 + ((uint32_t)
 #if defined(__CUDA_ARCH__)
           (__ffs((int)x) - 1) >> 3);
