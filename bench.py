@@ -514,6 +514,7 @@ def main():
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--no-also", action="store_true", help="skip the secondary workloads in the default run")
     ap.add_argument("--members", type=int, default=10000)
+    ap.add_argument("--level", choices=["fast", "default", "best"], default="default", help="deflate level of the codec workloads")
     args = ap.parse_args()
     if args.steps is None:
         args.steps = 20 if args.workload == "crc32" else 5
@@ -541,7 +542,7 @@ def main():
     def run(which, steps, warmup):
         barrier()
         with ClockSampler(local) as cs:
-            r = run_crc32(h, steps, warmup, rank) if which == "crc32" else run_codec(h, which, steps, warmup, rank, args.members)
+            r = run_crc32(h, steps, warmup, rank) if which == "crc32" else run_codec(h, which, steps, warmup, rank, args.members, args.level)
         barrier()
         r["clocks"] = cs.summary()
         # max over ranks of the device time and of the end-to-end time; units summed over ranks
@@ -566,7 +567,7 @@ def main():
     line = {"metric": METRIC[which], "value": round(value, 2), "unit": "GB/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(r["total_ms_max"] / args.steps, 4), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": WORKLOAD_DESC[which], "l2": "inputs larger than L2 (>= 1 GiB per step), no flush needed",
+            "config": {"workload": WORKLOAD_DESC[which].replace("level default", "level " + args.level), "l2": "inputs larger than L2 (>= 1 GiB per step), no flush needed",
                        "per_gpu_bytes": int(r["units"]), **r["extra"]},
             "clocks": r["clocks"],
             "e2e": {"value": round(e2e, 3), "unit": "GB/s", "h2d_bytes_per_step": int(r["h2d"]), "d2h_bytes_per_step": int(r["d2h"]),
