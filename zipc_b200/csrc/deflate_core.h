@@ -139,8 +139,7 @@ ZHD void match_begin(MatchState &m, const Ring &ring, uint32_t p, uint32_t n, ui
   m.best = kMinMatch - 1; m.best_dist = 0; m.last_dist = 0;
   m.reach = p < (uint32_t)kWindow ? p : (uint32_t)kWindow;
   m.c = first_cand;
-  m.pw0 = ring_load32(ring, p);
-  m.pw1 = ring_load32(ring, p + 4);
+  ring_load64(ring, p, m.pw0, m.pw1);
   m.chk = (m.pw0 >> 24) & 0xFFu;  // byte at p + 3
   m.steps = depth;
   m.done = depth <= 0;
