@@ -722,6 +722,7 @@ inflate_kernel(const InflateTask *__restrict__ tasks, uint32_t ntasks, InflateRe
 #pragma unroll
           for (int u = 0; u < kPasses; u++) {
             const uint32_t wb = base + 32 * u;
+            if (wb >= totalI) { dq[u] = nullptr; val[u] = 0; continue; }   // (uniform) nothing left for this pass
             const uint32_t b = wb + lane;
             const bool act = b < totalI;
             const uint32_t endrel = incI - wb;   // end of my token relative to the window
