@@ -86,11 +86,57 @@ def test_corpus_roundtrip_ratio_and_model_equality(ctx, level):
         zo.set_keep_codelen_freqs(True)
 
 
-def test_level_none_matches_reference_layout(ctx):
-    for data in (b"", b"x", synth.text_v1(2, 65535).tobytes(), synth.text_v1(2, 65536).tobytes(), synth.rand_v1(3, 200000).tobytes()):
+def test_level_none_matches_reference_bytes(ctx):
+    """`None: stored blocks of 65,534 source bytes (zipc_deflate.ml:747-750, :1106-1116) -- byte-identical to the oracle"""
+    for data in (b"", b"x", synth.text_v1(2, 65534).tobytes(), synth.text_v1(2, 65535).tobytes(), synth.text_v1(2, 65536).tobytes(),
+                 synth.rand_v1(3, 200000).tobytes()):
         cs = zd.deflate(data, level="none").get_ok()
+        assert cs == zo.deflate(data, "none")
         assert zo.inflate(cs) == data and zlib.decompress(cs, -15) == data
-        assert len(cs) == len(data) + 5 * max(1, -(-len(data) // 65535))
+        assert len(cs) == len(data) + 5 * max(1, -(-len(data) // 65534))
+
+
+def _quirk_corpus():
+    """inputs on which the reference's signed Int32.rem Adler-32 differs from RFC 1950 (mean byte >= 115 per chunk), so
+    that the per-block fold and the re-packed state between blocks matter (zipc_deflate.ml:175-198, :1081-1086)"""
+    t = np.frombuffer(synth.text_v1(21, 300000).tobytes(), dtype=np.uint8)
+    rnd = synth.rand_v1(22, 250001).tobytes()
+    return {
+        "text_bit7": (t | 0x80).tobytes(),
+        "rand": rnd,
+        "ff_runs": b"\xff" * 200000 + rnd[:5000] + b"\xff" * 70000,
+        "mix": (t[:90000] | 0x80).tobytes() + rnd[:70000] + bytes(range(256)) * 300 + b"\xfe" * 65534 + t[:50000].tobytes(),
+        "ramp": bytes(range(256)) * 1000,
+        "short_ff": b"\xff" * 5552,
+        "empty": b"",
+    }
+
+
+@pytest.mark.parametrize("level", LEVELS)
+def test_zlib_compress_ref_compat_round_trips_through_the_reference(ctx, level):
+    """Z-2 / D-1: in REF_COMPAT mode the trailer (and adler_32_and_deflate's value) is the Adler-32 folded over the
+    encoder's own blocks, i.e. exactly what the reference's zlib_decompress recomputes from the stream."""
+    corpus = _quirk_corpus()
+    names = list(corpus)
+    res = ctx.zlib_compress_batch([corpus[k] for k in names], level, _lib.ADLER_REF_COMPAT)
+    quirk_seen = 0
+    for k, (st, zs, ad) in zip(names, res):
+        data, zs = corpus[k], zs.tobytes()
+        assert st == 0, k
+        out, found = zo.zlib_decompress(zs)              # raises on "Checksum mismatch"
+        assert out == data and found == ad, k
+        assert int.from_bytes(zs[-4:], "big") == ad, k
+        assert zd.zlib_decompress(zs).get_ok() == (data, ad), k   # and our own decoder agrees
+        quirk_seen += ad != zlib.adler32(data)
+    assert quirk_seen >= 3  # the corpus does exercise the quirk
+    # adler_32_and_deflate returns the same per-block value
+    res = ctx.deflate_batch([corpus[k] for k in names], level, _lib.CK_ADLER32, _lib.ADLER_REF_COMPAT)
+    for k, (st, ds, ad) in zip(names, res):
+        assert st == 0 and zo.inflate_and_adler_32(ds.tobytes()) == (corpus[k], ad), k
+    # RFC 1950 mode is the standard checksum: zlib reads the streams
+    res = ctx.zlib_compress_batch([corpus[k] for k in names], level, _lib.ADLER_RFC1950)
+    for k, (st, zs, ad) in zip(names, res):
+        assert st == 0 and ad == zlib.adler32(corpus[k]) and zlib.decompress(zs.tobytes()) == corpus[k], k
 
 
 def test_fixture_redeflate_recode(ctx, zip_docs):  # test/test.ml:58-118 with the GPU codec in the loop

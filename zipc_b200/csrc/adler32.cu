@@ -337,4 +337,59 @@ int adler32_ranges(zipc_b200_ctx *ctx, const uint8_t *const *d_ptrs, const uint6
   return ZIPC_OK;
 }
 
+int adler32_blocked(zipc_b200_ctx *ctx, const uint8_t *const *d_ptrs, const uint32_t *nblk, const uint32_t *blk_len,
+                    size_t n, int mode, uint32_t *h_out) {
+  // every block is chunked on its own grid (first chunk = block length mod 5552), exactly what Adler_32.string_update
+  // does when the reference calls it once per block with the packed state of the previous block
+  size_t total = 0, nb = 0;
+  for (size_t i = 0; i < n; i++)
+    for (uint32_t b = 0; b < nblk[i]; b++, nb++) total += blk_len[nb] ? 1 + (blk_len[nb] - 1) / kChunk : 0;
+  if (total > 0xFFFFFFFFull) return ZIPC_ERR_INVALID_ARG;
+  if (total == 0) { for (size_t i = 0; i < n; i++) h_out[i] = 1; return ZIPC_OK; }
+  if (int st = ctx->h_desc.reserve(total * sizeof(AdlerSeg))) return st;
+  if (int st = ctx->d_desc.reserve(total * sizeof(AdlerSeg))) return st;
+  if (int st = ctx->d_scratch2.reserve(total * sizeof(uint2))) return st;
+  if (int st = ctx->h_res.reserve(total * sizeof(uint2))) return st;
+  AdlerSeg *h = ctx->h_desc.as<AdlerSeg>();
+  size_t k = 0;
+  nb = 0;
+  for (size_t i = 0; i < n; i++) {
+    uint64_t off = 0;
+    for (uint32_t b = 0; b < nblk[i]; b++, nb++) {
+      const uint32_t len = blk_len[nb];
+      if (!len) continue;
+      uint32_t m = len % kChunk;
+      if (m == 0) m = kChunk;
+      for (uint32_t done = 0; done < len; done += m, m = kChunk) { h[k].ptr = d_ptrs[i] + off + done; h[k].len = m; h[k]._pad = 0; k++; }
+      off += len;
+    }
+  }
+  ZB_CUDA(ctx, cudaMemcpyAsync(ctx->d_desc.p, h, total * sizeof(AdlerSeg), cudaMemcpyHostToDevice, ctx->stream));
+  uint32_t grid = (uint32_t)((total + kWarps - 1) / kWarps);
+  uint32_t maxgrid = (uint32_t)ctx->sm_count * 4;
+  if (grid > maxgrid) grid = maxgrid;
+  adler_ranges_kernel<<<grid, kThreads, 0, ctx->stream>>>(ctx->d_desc.as<AdlerSeg>(), (uint32_t)total, ctx->d_scratch2.as<uint2>());
+  ctx->launches++;
+  ZB_CUDA(ctx, cudaGetLastError());
+  uint2 *h_ab = ctx->h_res.as<uint2>();
+  ZB_CUDA(ctx, cudaMemcpyAsync(h_ab, ctx->d_scratch2.p, total * sizeof(uint2), cudaMemcpyDeviceToHost, ctx->stream));
+  ZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  k = 0;
+  nb = 0;
+  for (size_t i = 0; i < n; i++) {
+    uint32_t state = 1;
+    for (uint32_t b = 0; b < nblk[i]; b++, nb++) {
+      const uint32_t len = blk_len[nb];
+      if (!len) continue;
+      uint32_t s1 = state & 0xFFFFu, s2 = state >> 16;  // the state is re-packed between blocks (zipc_deflate.ml:178,198)
+      uint32_t m = len % kChunk;
+      if (m == 0) m = kChunk;
+      for (uint32_t done = 0; done < len; done += m, m = kChunk, k++) adler_fold_step(s1, s2, m, h_ab[k].x, h_ab[k].y, mode);
+      state = (s2 << 16) + s1;
+    }
+    h_out[i] = state;
+  }
+  return ZIPC_OK;
+}
+
 }  // namespace zb

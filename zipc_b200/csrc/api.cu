@@ -128,29 +128,48 @@ int d2h(zipc_b200_ctx *ctx, void *h, const void *d, size_t bytes) {
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) & ~(a - 1); }
 
-// Uploads n host ranges into ctx->d_in and returns their device addresses.  When the ranges are
-// (nearly) one contiguous host span -- members of an in-memory archive -- the span is sent with one
-// copy; otherwise ranges are packed back to back (4-byte aligned).
+// Uploads n host ranges into ctx->d_in and returns their device addresses.  Never reads a byte of host memory that
+// lies in a page none of the ranges touches: the ranges are sent as ONE span only when, in address order, every gap
+// between neighbours is smaller than a page (then each gap byte shares a page with the end of one range or the
+// start of the next -- members of an in-memory archive, separated by their local headers) and both ends of the
+// span have the same kind of memory (pinned or pageable).  Otherwise every range is copied on its own: pinned ranges
+// by DMA, pageable ones packed through the staging buffer.
 int upload_ranges(zipc_b200_ctx *ctx, size_t n, const void *const *src, const size_t *len,
                   std::vector<const uint8_t *> &d_ptr) {
   d_ptr.assign(n, nullptr);
   if (!n) return ZIPC_OK;
   uintptr_t lo = ~(uintptr_t)0, hi = 0;
-  size_t sum = 0;
+  size_t sum = 0, live = 0;
   for (size_t i = 0; i < n; i++) {
     if (!len[i]) continue;
     if (!src[i]) return ZIPC_ERR_INVALID_ARG;
     uintptr_t a = (uintptr_t)src[i];
+    if (a + len[i] < a) return ZIPC_ERR_INVALID_ARG;
     lo = std::min(lo, a); hi = std::max(hi, a + len[i]);
-    sum += len[i];
+    sum += len[i]; live++;
   }
   if (!sum) {
     if (int st = ctx->d_in.reserve(64)) return st;
     for (size_t i = 0; i < n; i++) d_ptr[i] = ctx->d_in.as<uint8_t>();
     return ZIPC_OK;
   }
-  size_t span = hi - lo;
-  if (span <= sum + sum / 4 + 65536) {
+  constexpr uintptr_t kMaxGap = 4096;  // < the smallest page size: a gap this small never contains a whole page
+  const size_t span = hi - lo;
+  bool one_span = span <= sum + live * (kMaxGap - 1);
+  if (one_span) {
+    std::vector<uint32_t> order;
+    order.reserve(live);
+    for (size_t i = 0; i < n; i++) if (len[i]) order.push_back((uint32_t)i);
+    std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return (uintptr_t)src[a] < (uintptr_t)src[b]; });
+    uintptr_t end = (uintptr_t)src[order[0]] + len[order[0]];
+    for (size_t k = 1; k < order.size() && one_span; k++) {
+      const uintptr_t a = (uintptr_t)src[order[k]];
+      if (a > end && a - end >= kMaxGap) one_span = false;
+      end = std::max(end, a + len[order[k]]);
+    }
+    if (one_span && is_pinned((const void *)lo) != is_pinned((const void *)(hi - 1))) one_span = false;
+  }
+  if (one_span) {
     size_t pre = lo & 15;  // keep the host alignment so 16-byte paths stay aligned
     if (int st = ctx->d_in.reserve(pre + span + 64)) return st;
     uint8_t *base = ctx->d_in.as<uint8_t>() + pre;
@@ -158,17 +177,57 @@ int upload_ranges(zipc_b200_ctx *ctx, size_t n, const void *const *src, const si
     for (size_t i = 0; i < n; i++) d_ptr[i] = len[i] ? base + ((uintptr_t)src[i] - lo) : base;
     return ZIPC_OK;
   }
-  size_t total = 0;
+  size_t total = 0, pageable = 0;
   std::vector<size_t> off(n);
-  for (size_t i = 0; i < n; i++) { off[i] = total; total += align_up(len[i], 16); }
+  std::vector<char> pin(n, 0);
+  for (size_t i = 0; i < n; i++) {
+    off[i] = total; total += align_up(len[i], 16);
+    if (len[i]) { pin[i] = is_pinned(src[i]) && is_pinned(static_cast<const uint8_t *>(src[i]) + len[i] - 1); if (!pin[i]) pageable += align_up(len[i], 16); }
+  }
   if (int st = ctx->d_in.reserve(total + 64)) return st;
-  // pack into pinned memory first, then one DMA
-  if (int st = ctx->h_stage.reserve(std::max(total, 2 * kStageChunk))) return st;
-  uint8_t *hs = ctx->h_stage.as<uint8_t>();
-  for (size_t i = 0; i < n; i++) if (len[i]) std::memcpy(hs + off[i], src[i], len[i]);
-  ZB_CUDA(ctx, cudaMemcpyAsync(ctx->d_in.p, hs, total, cudaMemcpyHostToDevice, ctx->stream));
-  ZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  for (size_t i = 0; i < n; i++) d_ptr[i] = ctx->d_in.as<uint8_t>() + off[i];
+  uint8_t *dbase = ctx->d_in.as<uint8_t>();
+  // pageable ranges: packed into pinned staging chunk by chunk (CPU copy of chunk k+1 overlaps the DMA of chunk k);
+  // consecutive pageable ranges keep consecutive device offsets, so a staged run is one DMA
+  if (pageable) {
+    if (int st = ctx->h_stage.reserve(2 * kStageChunk)) return st;
+    cudaEvent_t ev[2];
+    ZB_CUDA(ctx, cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming));
+    ZB_CUDA(ctx, cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming));
+    bool used[2] = {false, false};
+    int k = 0, rc = ZIPC_OK;
+    size_t i = 0, done_in_i = 0;  // next range / bytes of it already staged
+    while (rc == ZIPC_OK) {
+      while (i < n && (!len[i] || pin[i])) { i++; done_in_i = 0; }
+      if (i >= n) break;
+      uint8_t *s = ctx->h_stage.as<uint8_t>() + (size_t)k * kStageChunk;
+      if (used[k]) cudaEventSynchronize(ev[k]);
+      // fill this staging buffer with a run of device-contiguous pageable bytes
+      const size_t dev_start = off[i] + done_in_i;
+      size_t fill = 0;
+      while (i < n && fill < kStageChunk) {
+        if (!len[i]) { i++; done_in_i = 0; continue; }
+        if (pin[i] || off[i] + done_in_i != dev_start + fill) break;
+        const size_t m = std::min(len[i] - done_in_i, kStageChunk - fill);
+        std::memcpy(s + fill, static_cast<const uint8_t *>(src[i]) + done_in_i, m);
+        fill += m; done_in_i += m;
+        if (done_in_i == len[i]) {
+          const size_t padto = std::min(align_up(len[i], 16) - len[i], kStageChunk - fill);
+          std::memset(s + fill, 0, padto);
+          if (padto == align_up(len[i], 16) - len[i]) { fill += padto; i++; done_in_i = 0; } else break;
+        }
+      }
+      cudaError_t e = cudaMemcpyAsync(dbase + dev_start, s, fill, cudaMemcpyHostToDevice, ctx->stream);
+      if (e != cudaSuccess) { rc = set_cuda_error(ctx, e, "upload_ranges staging"); break; }
+      cudaEventRecord(ev[k], ctx->stream);
+      used[k] = true;
+      k ^= 1;
+    }
+    for (int j = 0; j < 2; j++) { if (used[j]) cudaEventSynchronize(ev[j]); cudaEventDestroy(ev[j]); }
+    if (rc) return rc;
+  }
+  for (size_t i = 0; i < n; i++)
+    if (len[i] && pin[i]) ZB_CUDA(ctx, cudaMemcpyAsync(dbase + off[i], src[i], len[i], cudaMemcpyHostToDevice, ctx->stream));
+  for (size_t i = 0; i < n; i++) d_ptr[i] = dbase + off[i];
   return ZIPC_OK;
 }
 
@@ -290,7 +349,7 @@ void zipc_b200_ctx_destroy(zipc_b200_ctx *ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   ctx->d_in.release(); ctx->d_out.release(); ctx->d_desc.release(); ctx->d_res.release();
-  ctx->d_scratch.release(); ctx->d_scratch2.release(); ctx->d_small.release(); ctx->d_slots.release(); ctx->d_desc2.release();
+  ctx->d_scratch.release(); ctx->d_scratch2.release(); ctx->d_small.release(); ctx->d_slots.release(); ctx->d_desc2.release(); ctx->d_blk.release();
   ctx->h_stage.release(); ctx->h_res.release(); ctx->h_desc.release();
   if (ctx->d_crc_tabs) cudaFree(ctx->d_crc_tabs);
   if (ctx->ev0) { cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); }
@@ -500,6 +559,7 @@ int zipc_b200_zlib_decompress_batch(zipc_b200_ctx *ctx, int adler_mode, size_t n
     const uint8_t *s = static_cast<const uint8_t *>(src[i]);
     size_t len = src_len[i];
     body[i] = s; blen[i] = 0;
+    if (len && !s) return ZIPC_ERR_INVALID_ARG;
     if (len < 6) { pre[i] = ZIPC_ERR_CORRUPTED; continue; }
     unsigned cmf = s[0], flg = s[1];
     if ((256 * cmf + flg) % 31 != 0) { pre[i] = ZIPC_ERR_CORRUPTED; continue; }

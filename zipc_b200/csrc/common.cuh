@@ -83,7 +83,7 @@ struct DeflateTask {  // one input to deflate (a ZIP member or an independent se
   uint8_t *dst;       // 4-byte aligned output slot
   uint64_t dst_cap;
   uint32_t flags;     // kDeflateNotFinal: no BFINAL, end with a byte-aligning empty stored block
-  uint32_t _pad;
+  uint32_t blk_off;   // index of this member's first entry in the launch's block-length list (see deflate_launch)
 };
 constexpr uint32_t kDeflateNotFinal = 1u;
 struct DeflateResult {
@@ -114,7 +114,7 @@ struct zipc_b200_ctx {
   // constant tables on the device
   uint32_t *d_crc_tabs = nullptr;   // see crc32.cu: strided[4][256] | std[4][256] | xp16[32]
   // work buffers (grow-only)
-  zb::DevBuf d_in, d_out, d_desc, d_res, d_scratch, d_scratch2, d_small, d_slots, d_desc2;
+  zb::DevBuf d_in, d_out, d_desc, d_res, d_scratch, d_scratch2, d_small, d_slots, d_desc2, d_blk;
   zb::PinBuf h_stage, h_res, h_desc;
 
   // results of the last batch call kept for zipc_b200_fetch()
@@ -157,8 +157,19 @@ int adler32_launch_buffer(zipc_b200_ctx *ctx, const uint8_t *d_src, uint64_t len
 // per-range Adler-32 for n ranges given as (ptr,len) on the host; results (final values) to h_out
 int adler32_ranges(zipc_b200_ctx *ctx, const uint8_t *const *d_ptrs, const uint64_t *lens, size_t n, int mode,
                    uint32_t *h_out);
+// Adler-32 of n inputs, each folded block by block as the reference does on both codec sides (state re-packed and the
+// 5552-byte chunk grid restarted at every block, :682-690, :1081-1086): member i consists of nblk[i] consecutive
+// blocks whose lengths follow each other in blk_len
+int adler32_blocked(zipc_b200_ctx *ctx, const uint8_t *const *d_ptrs, const uint32_t *nblk, const uint32_t *blk_len,
+                    size_t n, int mode, uint32_t *h_out);
 // deflate.cu
-int deflate_launch(zipc_b200_ctx *ctx, const DeflateTask *d_tasks, uint32_t n, DeflateResult *d_results, int level);
+// d_blk_lens (may be null): receives the source length of every deflate block of member i at
+// d_blk_lens[task.blk_off + b], b < result.blocks -- the ranges the reference checksums one by one (:1081-1086)
+int deflate_launch(zipc_b200_ctx *ctx, const DeflateTask *d_tasks, uint32_t n, DeflateResult *d_results, int level,
+                   uint32_t *d_blk_lens = nullptr);
+// upper bound of the number of deflate blocks the encoder emits for an input of src_len bytes
+inline uint32_t deflate_max_blocks(uint64_t src_len) { return (uint32_t)(src_len / 61440) + 2; }
+constexpr uint32_t kStoredBlock = 65534;  // source bytes per block at level `None (reference :747-750, :1106-1116)
 // zip_api.cu: n independent copies on the device (compaction of per-member output slots)
 int gather_launch(zipc_b200_ctx *ctx, const CopyDesc *d_descs, uint32_t n);
 // api.cu helpers shared with zip_api.cu

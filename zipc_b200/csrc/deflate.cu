@@ -420,7 +420,8 @@ __device__ void finalize_block(const Shared &sh, const uint8_t *src, uint64_t bl
 }
 
 // ---- one member ----------------------------------------------------------------------------------------------
-__device__ void encode_member(const Shared &sh, const DeflateTask t, int level, uint32_t *toks, DeflateResult *res) {
+__device__ void encode_member(const Shared &sh, const DeflateTask t, int level, uint32_t *toks, DeflateResult *res,
+                              uint32_t *blk_lens) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint8_t *src = t.src;
   const uint32_t n = (uint32_t)t.src_len;
@@ -625,11 +626,16 @@ __device__ void encode_member(const Shared &sh, const DeflateTask t, int level, 
       __syncthreads();
       const uint32_t blen = sh.sc[SC_BLK_SRCLEN];
       finalize_block(sh, src, blk_src_start, ntok, toks, last && !not_final, out_words, out_cap_words);
+      if (tid == 0 && blk_lens) blk_lens[t.blk_off + nblocks] = blen;
       blk_src_start += blen;
       ntok = 0; tiles_in_block = 0; nblocks++;
     }
   }
-  if (n == 0) { finalize_block(sh, src, 0, 0, toks, !not_final, out_words, out_cap_words); nblocks++; }
+  if (n == 0) {
+    finalize_block(sh, src, 0, 0, toks, !not_final, out_words, out_cap_words);
+    if (tid == 0 && blk_lens) blk_lens[t.blk_off] = 0;
+    nblocks++;
+  }
   if (not_final) {
     // segment of a larger stream: close with an empty stored block (000, pad to a byte, LEN 0, NLEN ffff) so
     // that the next segment starts byte aligned and the concatenation is one valid RFC 1951 stream
@@ -666,7 +672,8 @@ __device__ void encode_member(const Shared &sh, const DeflateTask t, int level, 
 
 __global__ void __launch_bounds__(THREADS, 1)
 deflate_kernel(const DeflateTask *__restrict__ tasks, uint32_t ntasks, DeflateResult *__restrict__ results,
-               unsigned int *__restrict__ queue, uint32_t *__restrict__ tok_scratch, int level) {
+               unsigned int *__restrict__ queue, uint32_t *__restrict__ tok_scratch, int level,
+               uint32_t *__restrict__ blk_lens) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   const Shared sh = carve(smem_raw);
   uint32_t *toks = tok_scratch + (size_t)blockIdx.x * kTokCap;
@@ -676,28 +683,30 @@ deflate_kernel(const DeflateTask *__restrict__ tasks, uint32_t ntasks, DeflateRe
     __syncthreads();
     const uint32_t task = sh.sc[SC_TASK];
     if (task >= ntasks) break;
-    encode_member(sh, tasks[task], level, toks, &results[task]);
+    encode_member(sh, tasks[task], level, toks, &results[task], blk_lens);
   }
 }
 
-// level `None (reference :1106-1116): stored blocks only, one CTA per member.  Blocks hold 65535 bytes.
+// level `None (reference :1106-1116): stored blocks only, one CTA per member.  Blocks hold 65534 bytes as in the
+// reference (:747-750), so the output is byte-identical to Zipc_deflate.deflate ~level:`None.
 __global__ void __launch_bounds__(256)
 stored_kernel(const DeflateTask *__restrict__ tasks, uint32_t ntasks, DeflateResult *__restrict__ results) {
   const uint32_t task = blockIdx.x;
   if (task >= ntasks) return;
   const DeflateTask t = tasks[task];
-  const uint64_t n = t.src_len, nblk = n ? (n + 65534) / 65535 : 1, need = n + 5 * nblk;
+  constexpr uint64_t B = kStoredBlock;
+  const uint64_t n = t.src_len, nblk = n ? (n + B - 1) / B : 1, need = n + 5 * nblk;
   if (need > t.dst_cap) {
     if (threadIdx.x == 0) { results[task].out_len = 0; results[task].status = ZIPC_ERR_DST_TOO_SMALL; results[task].blocks = 0; }
     return;
   }
   for (uint64_t b = threadIdx.x; b < nblk; b += blockDim.x) {
-    uint64_t len = b + 1 < nblk ? 65535 : n - b * 65535;
-    uint8_t *h = t.dst + b * 65540;
+    uint64_t len = b + 1 < nblk ? B : n - b * B;
+    uint8_t *h = t.dst + b * (B + 5);
     h[0] = (b + 1 == nblk && !(t.flags & kDeflateNotFinal)) ? 1 : 0;
     h[1] = (uint8_t)len; h[2] = (uint8_t)(len >> 8); h[3] = (uint8_t)~len; h[4] = (uint8_t)(~len >> 8);
   }
-  for (uint64_t i = threadIdx.x; i < n; i += blockDim.x) t.dst[i + 5 * (i / 65535 + 1)] = t.src[i];
+  for (uint64_t i = threadIdx.x; i < n; i += blockDim.x) t.dst[i + 5 * (i / B + 1)] = t.src[i];
   if (threadIdx.x == 0) { results[task].out_len = need; results[task].status = ZIPC_OK; results[task].blocks = (uint32_t)nblk; }
 }
 
@@ -705,7 +714,8 @@ unsigned long long g_attr_devs = 0;  // bit d: attributes set on device d (funct
 
 }  // namespace
 
-int deflate_launch(zipc_b200_ctx *ctx, const DeflateTask *d_tasks, uint32_t n, DeflateResult *d_results, int level) {
+int deflate_launch(zipc_b200_ctx *ctx, const DeflateTask *d_tasks, uint32_t n, DeflateResult *d_results, int level,
+                   uint32_t *d_blk_lens) {
   if (n == 0) return ZIPC_OK;
   if (level == ZIPC_LEVEL_NONE) {
     stored_kernel<<<n, 256, 0, ctx->stream>>>(d_tasks, n, d_results);
@@ -725,7 +735,7 @@ int deflate_launch(zipc_b200_ctx *ctx, const DeflateTask *d_tasks, uint32_t n, D
   ZB_CUDA(ctx, cudaMemsetAsync(queue, 0, sizeof(unsigned int), ctx->stream));
   {
     KernelTimer kt(ctx);
-    deflate_kernel<<<grid, THREADS, kSmemBytes, ctx->stream>>>(d_tasks, n, d_results, queue, ctx->d_scratch.as<uint32_t>(), level);
+    deflate_kernel<<<grid, THREADS, kSmemBytes, ctx->stream>>>(d_tasks, n, d_results, queue, ctx->d_scratch.as<uint32_t>(), level, d_blk_lens);
   }
   ctx->launches++;
   ZB_CUDA(ctx, cudaGetLastError());

@@ -18,7 +18,8 @@ namespace {
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) & ~(a - 1); }
 
-// one CTA per copy; 16-byte vectors when both ends allow it
+// one CTA per copy; 16-byte vectors when both ends allow it, otherwise aligned 32-bit stores fed by funnel-shifted
+// aligned loads (payloads land at arbitrary archive offsets: LFH + name bytes in front of each)
 __global__ void __launch_bounds__(256) gather_kernel(const CopyDesc *__restrict__ descs, uint32_t n) {
   for (uint32_t k = blockIdx.x; k < n; k += gridDim.x) {
     const CopyDesc d = descs[k];
@@ -29,24 +30,31 @@ __global__ void __launch_bounds__(256) gather_kernel(const CopyDesc *__restrict_
       uint64_t nv = d.len >> 4;
       for (uint64_t i = threadIdx.x; i < nv; i += blockDim.x) t[i] = s[i];
       for (uint64_t i = (nv << 4) + threadIdx.x; i < d.len; i += blockDim.x) d.dst[i] = d.src[i];
-    } else if ((((uintptr_t)d.src ^ (uintptr_t)d.dst) & 3) == 0) {
-      // same misalignment: bytes up to a word boundary, then words
-      uint64_t head = (4 - ((uintptr_t)d.src & 3)) & 3;
+    } else {
+      // bytes up to a word boundary of the destination, then words
+      uint64_t head = (4 - ((uintptr_t)d.dst & 3)) & 3;
       if (head > d.len) head = d.len;
       for (uint64_t i = threadIdx.x; i < head; i += blockDim.x) d.dst[i] = d.src[i];
-      const uint32_t *s = reinterpret_cast<const uint32_t *>(d.src + head);
+      const uint8_t *sb = d.src + head;
+      const uint32_t sh = (uint32_t)((uintptr_t)sb & 3) * 8;
+      const uint32_t *s = reinterpret_cast<const uint32_t *>(sb - (sh >> 3));
       uint32_t *t = reinterpret_cast<uint32_t *>(d.dst + head);
-      uint64_t nw = (d.len - head) >> 2;
-      for (uint64_t i = threadIdx.x; i < nw; i += blockDim.x) t[i] = s[i];
+      const uint64_t nw = (d.len - head) >> 2;
+      if (sh == 0) {
+        for (uint64_t i = threadIdx.x; i < nw; i += blockDim.x) t[i] = s[i];
+      } else {
+        // word i of the destination = bytes [4i + sh/8, 4i + sh/8 + 4) of the aligned source words: s[i+1] holds at
+        // least one byte of the range, so it lies inside the source buffer's last touched word
+        for (uint64_t i = threadIdx.x; i < nw; i += blockDim.x) t[i] = __funnelshift_r(s[i], s[i + 1], sh);
+      }
       for (uint64_t i = head + (nw << 2) + threadIdx.x; i < d.len; i += blockDim.x) d.dst[i] = d.src[i];
-    } else {
-      for (uint64_t i = threadIdx.x; i < d.len; i += blockDim.x) d.dst[i] = d.src[i];
     }
   }
 }
 
 // Runs the encoder over n device-resident inputs.  Output of member i lands in a private slot
-// (d_slot[i], capacity slot_cap[i]); the caller compacts.  Checksums are of the INPUT (crc_op).
+// (d_slot[i], capacity slot_cap[i]); the caller compacts.  Checksums are of the INPUT (crc_op); Adler-32 is folded
+// per emitted block, which is what the reference's own zlib_decompress recomputes from the stream.
 int deflate_run(zipc_b200_ctx *ctx, int level, int ck, int adler_mode, size_t n,
                 const std::vector<const uint8_t *> &d_src, const size_t *src_len,
                 const std::vector<uint8_t *> &d_slot, const std::vector<size_t> &slot_cap,
@@ -62,22 +70,41 @@ int deflate_run(zipc_b200_ctx *ctx, int level, int ck, int adler_mode, size_t n,
   if (int st = ctx->d_res.reserve(n * (sizeof(DeflateResult) + sizeof(uint32_t)))) return st;
   if (int st = ctx->h_res.reserve(n * (sizeof(DeflateResult) + sizeof(uint32_t)))) return st;
   DeflateTask *ht = ctx->h_desc.as<DeflateTask>();
+  // Adler-32 is folded block by block over the encoder's own blocks (reference :1081-1086): the kernel reports
+  // the source length of every block it emits
+  const bool want_adler = checksum && ck == ZIPC_CK_ADLER32;
+  const bool blocks_from_kernel = want_adler && level != ZIPC_LEVEL_NONE;
+  std::vector<uint32_t> blk_off(n, 0);
+  size_t blk_total = 0;
+  if (blocks_from_kernel) {
+    for (size_t i = 0; i < n; i++) { blk_off[i] = (uint32_t)blk_total; blk_total += deflate_max_blocks(src_len[i]); }
+    if (blk_total > 0xFFFFFFF0ull) return ZIPC_ERR_INVALID_ARG;
+    if (int st = ctx->d_blk.reserve(blk_total * sizeof(uint32_t) + 64)) return st;
+  }
+  uint32_t *d_blk = blocks_from_kernel ? ctx->d_blk.as<uint32_t>() : nullptr;
   for (size_t k = 0; k < n; k++) {
     uint32_t i = order[k];
     ht[k].src = d_src[i]; ht[k].src_len = src_len[i]; ht[k].dst = d_slot[i]; ht[k].dst_cap = slot_cap[i];
-    ht[k].flags = flags ? (*flags)[i] : 0u; ht[k]._pad = 0;
+    ht[k].flags = flags ? (*flags)[i] : 0u; ht[k].blk_off = blk_off[i];
   }
   DeflateTask *dt = ctx->d_desc.as<DeflateTask>();
   DeflateResult *dr = ctx->d_res.as<DeflateResult>();
   ZB_CUDA(ctx, cudaMemcpyAsync(dt, ht, n * sizeof(DeflateTask), cudaMemcpyHostToDevice, ctx->stream));
-  if (int st = deflate_launch(ctx, dt, (uint32_t)n, dr, level)) return st;
+  if (int st = deflate_launch(ctx, dt, (uint32_t)n, dr, level, d_blk)) return st;
   DeflateResult *hr = ctx->h_res.as<DeflateResult>();
   ZB_CUDA(ctx, cudaMemcpyAsync(hr, dr, n * sizeof(DeflateResult), cudaMemcpyDeviceToHost, ctx->stream));
+  std::vector<uint32_t> h_blk;
+  if (blocks_from_kernel) {
+    h_blk.resize(blk_total);
+    ZB_CUDA(ctx, cudaMemcpyAsync(h_blk.data(), d_blk, blk_total * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  }
   ZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  std::vector<uint32_t> nblk(n, 0);
   for (size_t k = 0; k < n; k++) {
     uint32_t i = order[k];
     status[i] = (int)hr[k].status;
     out_len[i] = (size_t)hr[k].out_len;
+    nblk[i] = hr[k].status == ZIPC_OK ? hr[k].blocks : 0;
   }
   if (checksum) {
     if (ck == ZIPC_CK_CRC32) {
@@ -92,8 +119,17 @@ int deflate_run(zipc_b200_ctx *ctx, int level, int ck, int adler_mode, size_t n,
       ZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
       for (size_t i = 0; i < n; i++) checksum[i] ^= 0xFFFFFFFFu;
     } else if (ck == ZIPC_CK_ADLER32) {
-      std::vector<uint64_t> l(src_len, src_len + n);
-      if (int st = adler32_ranges(ctx, d_src.data(), l.data(), n, adler_mode, checksum)) return st;
+      // block lists per member, in member order
+      std::vector<uint32_t> lens;
+      if (blocks_from_kernel) {
+        for (size_t i = 0; i < n; i++) lens.insert(lens.end(), h_blk.begin() + blk_off[i], h_blk.begin() + blk_off[i] + nblk[i]);
+      } else {  // level `None: stored blocks of kStoredBlock source bytes (reference :1106-1116)
+        for (size_t i = 0; i < n; i++) {
+          nblk[i] = 0;
+          for (uint64_t o = 0; o < src_len[i]; o += kStoredBlock, nblk[i]++) lens.push_back((uint32_t)std::min<uint64_t>(kStoredBlock, src_len[i] - o));
+        }
+      }
+      if (int st = adler32_blocked(ctx, d_src.data(), nblk.data(), lens.data(), n, adler_mode, checksum)) return st;
     } else {
       for (size_t i = 0; i < n; i++) checksum[i] = 0;
     }
@@ -204,36 +240,35 @@ int zipc_b200_zlib_compress_batch(zipc_b200_ctx *ctx, int level, int adler_mode,
   if (int st = make_slots(ctx, n, src_len, d_slot, cap)) return st;
   std::vector<uint32_t> ad(n);
   if (int st = deflate_run(ctx, level, ZIPC_CK_ADLER32, adler_mode, n, d_src, src_len, d_slot, cap, dst_len, ad.data(), status)) return st;
-  // framing: 2 header bytes, body, big-endian Adler-32 (reference :1264-1277)
-  std::vector<size_t> off(n), body_off(n);
+  // framing: 2 header bytes, body, big-endian Adler-32 (reference :1264-1277).  Header and trailer bytes are placed
+  // by the same device gather as the bodies (one descriptor table, one launch), so fetch() sees complete streams.
+  std::vector<size_t> off(n), flen(n);
   size_t total = 0;
-  for (size_t i = 0; i < n; i++) { off[i] = total; body_off[i] = total + 2; total += align_up(dst_len[i] + 6, 16); }
-  if (int st = compact(ctx, n, d_slot, dst_len, body_off, total)) return st;
-  std::vector<size_t> flen(n);
-  for (size_t i = 0; i < n; i++) { flen[i] = dst_len[i] + 6; dst_off[i] = off[i]; }
-  ctx->last_off = off; ctx->last_len = flen; ctx->last_total = total;
-  // header and trailer bytes are written on the device copy so that fetch() sees complete streams
+  for (size_t i = 0; i < n; i++) { off[i] = total; flen[i] = dst_len[i] + 6; total += align_up(flen[i], 16); }
+  if (int st = ctx->d_out.reserve(total + 64)) return st;
   {
     const unsigned cmf = 0x78, hdr = (cmf << 8) | ((unsigned)level << 6), flg = (hdr + 31 - hdr % 31) & 0xFF;
     if (int st = ctx->h_res.reserve(n * 8)) return st;
+    if (int st = ctx->d_res.reserve(n * 8)) return st;
+    if (int st = ctx->h_desc.reserve(3 * n * sizeof(CopyDesc))) return st;
+    if (int st = ctx->d_desc2.reserve(3 * n * sizeof(CopyDesc))) return st;
     uint8_t *hb = ctx->h_res.as<uint8_t>();
+    uint8_t *db = ctx->d_res.as<uint8_t>(), *dout = ctx->d_out.as<uint8_t>();
+    CopyDesc *h = ctx->h_desc.as<CopyDesc>();
     for (size_t i = 0; i < n; i++) {
       hb[8 * i] = (uint8_t)cmf; hb[8 * i + 1] = (uint8_t)flg;
       hb[8 * i + 2] = (uint8_t)(ad[i] >> 24); hb[8 * i + 3] = (uint8_t)(ad[i] >> 16);
       hb[8 * i + 4] = (uint8_t)(ad[i] >> 8); hb[8 * i + 5] = (uint8_t)ad[i];
+      h[3 * i] = CopyDesc{db + 8 * i, dout + off[i], 2};
+      h[3 * i + 1] = CopyDesc{d_slot[i], dout + off[i] + 2, dst_len[i]};
+      h[3 * i + 2] = CopyDesc{db + 8 * i + 2, dout + off[i] + 2 + dst_len[i], 4};
     }
-    if (int st = ctx->d_res.reserve(n * 8)) return st;
-    ZB_CUDA(ctx, cudaMemcpyAsync(ctx->d_res.p, hb, n * 8, cudaMemcpyHostToDevice, ctx->stream));
-    if (int st = ctx->h_desc.reserve(2 * n * sizeof(CopyDesc))) return st;
-    if (int st = ctx->d_desc.reserve(2 * n * sizeof(CopyDesc))) return st;
-    CopyDesc *h = ctx->h_desc.as<CopyDesc>();
-    for (size_t i = 0; i < n; i++) {
-      h[2 * i] = CopyDesc{ctx->d_res.as<uint8_t>() + 8 * i, ctx->d_out.as<uint8_t>() + off[i], 2};
-      h[2 * i + 1] = CopyDesc{ctx->d_res.as<uint8_t>() + 8 * i + 2, ctx->d_out.as<uint8_t>() + off[i] + 2 + dst_len[i], 4};
-    }
-    ZB_CUDA(ctx, cudaMemcpyAsync(ctx->d_desc.p, h, 2 * n * sizeof(CopyDesc), cudaMemcpyHostToDevice, ctx->stream));
-    if (int st = gather_launch(ctx, ctx->d_desc.as<CopyDesc>(), (uint32_t)(2 * n))) return st;
+    ZB_CUDA(ctx, cudaMemcpyAsync(db, hb, n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    ZB_CUDA(ctx, cudaMemcpyAsync(ctx->d_desc2.p, h, 3 * n * sizeof(CopyDesc), cudaMemcpyHostToDevice, ctx->stream));
+    if (int st = gather_launch(ctx, ctx->d_desc2.as<CopyDesc>(), (uint32_t)(3 * n))) return st;
   }
+  for (size_t i = 0; i < n; i++) dst_off[i] = off[i];
+  ctx->last_off = off; ctx->last_len = flen; ctx->last_total = total;
   for (size_t i = 0; i < n; i++) { dst_len[i] = flen[i]; if (adler) adler[i] = ad[i]; }
   if (dst_need) *dst_need = total;
   if (!dst || dst_cap < total) { ZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); return ZIPC_ERR_DST_TOO_SMALL; }
@@ -345,6 +380,7 @@ int zipc_b200_zip_extract_batch(zipc_b200_ctx *ctx, const zipc_b200_member *ms, 
     if (m.is_dir) continue;
     if (m.gp_flags & 1) { status[i] = ZIPC_ERR_ZIP_ENCRYPTED; continue; }
     if (m.compression != 0 && m.compression != 8) { status[i] = ZIPC_ERR_ZIP_FORMAT; continue; }
+    if (m.compressed_size && !m.compressed_bytes) return ZIPC_ERR_INVALID_ARG;
     kind[i] = m.compression == 0 ? 1 : 2;
     src[i] = m.compressed_bytes + m.start;
     slen[i] = (size_t)m.compressed_size;

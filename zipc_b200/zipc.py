@@ -65,6 +65,10 @@ class File:
             compressed_size = len(compressed_bytes) - start
         if compressed_size < 0 or decompressed_size < 0:
             raise ValueError("size is negative")  # Invalid_argument
+        if start < 0 or start + compressed_size > len(compressed_bytes):
+            # the reference fails later, in String.sub / the codec's bounds checks (Invalid_argument); the C side
+            # trusts (start, compressed_size), so the range is checked where the record is made
+            raise ValueError("index out of bounds")
         if compressed_size > MAX_SIZE or decompressed_size > MAX_SIZE:
             return Error("Maximum ZIP byte size 4294967295 exceeded by compressed (%d) or decompressed (%d) file size"
                          % (compressed_size, decompressed_size), 30)
@@ -170,6 +174,8 @@ def _to_c(members: list[Member]):
             arr[i] = _lib.Member(C.cast(pb, C.c_void_p), len(p), 1, m.mode, m.mtime, 0, 0, 0, 0, None, 0, 0, 0, 0, 0)
         else:
             v = zd._as_view(f.compressed_bytes)
+            if f.start < 0 or f.compressed_size < 0 or f.start + f.compressed_size > v.size:
+                raise ValueError("index out of bounds")  # a hand-made FileT must not send the C side out of range
             keep.append(v)
             arr[i] = _lib.Member(C.cast(pb, C.c_void_p), len(p), 0, m.mode, m.mtime, f.version_made_by,
                                  f.version_needed_to_extract, f.gp_flags, f.compression, v.ctypes.data if v.size else None,
