@@ -250,6 +250,35 @@ int zipc_b200_zip_deflate_archive(zipc_b200_ctx *ctx, int level, size_t n,
                                   const int32_t *mode, const int64_t *mtime, const char *first,
                                   void *out, size_t out_cap, size_t *out_len);
 
+/* ---- box-wide entry points (SURVEY.md 8b "device_mask", 8e) -------------------------------------------------------- */
+/* One call drives every selected GPU of the node: a multi-context owns one zipc_b200_ctx (stream, arenas) and one
+ * host thread per device.  Batches are partitioned over the devices longest-first by member size (members are
+ * independent: no collective on the data path); one buffer is cut into contiguous slices whose checksums are
+ * merged on the host.  device_mask: bit d selects CUDA device d; 0 = every visible device.
+ * These replace the same reference functions as their single-device forms: a loop of
+ * Zipc.File.deflate_of_binary_string / File.to_binary_string over the members of an archive (zipc.ml:179-185,
+ * 205-225) and Crc_32.string of one string (zipc_deflate.ml:161-163). */
+typedef struct zipc_b200_mctx zipc_b200_mctx;
+int zipc_b200_mctx_create(uint64_t device_mask, zipc_b200_mctx **mctx);
+void zipc_b200_mctx_destroy(zipc_b200_mctx *mctx);
+int zipc_b200_mctx_device_count(const zipc_b200_mctx *mctx);
+/* The k-th device's context (owned by the mctx), e.g. for zipc_b200_ctx_launches. */
+zipc_b200_ctx *zipc_b200_mctx_ctx(zipc_b200_mctx *mctx, int k);
+const char *zipc_b200_mctx_last_error(const zipc_b200_mctx *mctx);
+/* Crc_32.string of one host buffer: G contiguous slices, G-1 zipc_b200_crc32_combine steps. */
+int zipc_b200_multi_crc32(zipc_b200_mctx *mctx, const void *src, size_t len, uint32_t *crc);
+/* zipc_b200_inflate_batch / zipc_b200_deflate_batch over all devices; same arguments and arena conventions
+ * (dst_off are offsets into ONE arena; after ZIPC_ERR_DST_TOO_SMALL use zipc_b200_multi_fetch). */
+int zipc_b200_multi_inflate_batch(zipc_b200_mctx *mctx, int checksum_kind, int adler_mode, size_t n,
+                                  const void *const *src, const size_t *src_len, const size_t *max_out,
+                                  void *dst, size_t dst_cap, size_t *dst_need,
+                                  size_t *dst_off, size_t *dst_len, uint32_t *checksum, int *status);
+int zipc_b200_multi_deflate_batch(zipc_b200_mctx *mctx, int level, int checksum_kind, int adler_mode,
+                                  size_t n, const void *const *src, const size_t *src_len,
+                                  void *dst, size_t dst_cap, size_t *dst_need,
+                                  size_t *dst_off, size_t *dst_len, uint32_t *checksum, int *status);
+int zipc_b200_multi_fetch(zipc_b200_mctx *mctx, void *dst, size_t dst_cap);
+
 void zipc_b200_free(void *p);
 
 /* ---- synthetic workloads (integer-only, host side) -------------------- */

@@ -14,6 +14,7 @@ let ok = 0 and err_checksum = 6 and err_zlib_method = 3 and err_invalid_arg = 8
 
 external strerror : int -> string = "zipc_cuda_strerror"
 external set_device : int -> unit = "zipc_cuda_set_device"
+external set_devices : int -> unit = "zipc_cuda_set_devices"
 
 (* Each stub copies its inputs into pinned staging memory BEFORE releasing the
    runtime lock (the GC may move strings while it is released) and allocates the
@@ -31,6 +32,14 @@ external zlib_decompress_stub :
   string -> int -> int -> int -> int * string * int32 * int32 = "zipc_cuda_zlib_decompress"
 external zlib_compress_stub :
   int -> string -> int -> int -> int * string * int32 = "zipc_cuda_zlib_compress"
+external deflate_segmented_stub :
+  int (* level *) -> string -> int (* segment_size *) -> int * string * int array * int32
+  = "zipc_cuda_deflate_segmented"
+external inflate_segmented_stub :
+  string -> int array (* flat index *) -> int * string * int32 = "zipc_cuda_inflate_segmented"
+external archive_stub :
+  int (* level *) -> string array (* paths *) -> string array (* payloads *) -> string (* first, "" = default *) ->
+  int * string = "zipc_cuda_archive"
 
 let range ?(start = 0) ?len s =
   let len = match len with None -> String.length s - start | Some l -> l in
@@ -117,3 +126,73 @@ let zlib_compress ?(level = `Default) ?start ?len s =
   match zlib_compress_stub (int_of_level level) s start len with
   | st, zs, adler when st = ok -> Ok (adler, zs)
   | st, _, _ -> Error (strerror st)
+
+(* ---- one large stream as independent segments ---- *)
+
+let deflate_segmented ?(level = `Default) ?(segment_size = 256 * 1024) s =
+  match deflate_segmented_stub (int_of_level level) s segment_size with
+  | st, cs, flat, crc when st = ok ->
+      Ok (cs, Array.init (Array.length flat / 2) (fun i -> (flat.(2 * i), flat.(2 * i + 1))), crc)
+  | st, _, _, _ -> Error (strerror st)
+
+let inflate_segmented ~index s =
+  let flat = Array.make (2 * Array.length index) 0 in
+  Array.iteri (fun i (c, u) -> flat.(2 * i) <- c; flat.(2 * i + 1) <- u) index;
+  match inflate_segmented_stub s flat with
+  | st, out, crc when st = ok -> Ok (out, crc)
+  | st, _, _ -> Error (strerror st)
+
+(* ---- ZIP layer ---- *)
+
+module File = struct
+  let deflate_of_binary_strings ?level ss =
+    Array.map2 (fun s -> function
+      | Error _ as e -> e
+      | Ok (crc, cs) ->
+          Zipc.File.make ~compression:Zipc.Deflate cs
+            ~decompressed_size:(String.length s) ~decompressed_crc_32:crc)
+      ss (deflate_batch ?level ~crc_op:Crc_32_op ss)
+
+  (* zipc.ml:205-225: encrypted -> error; Stored / Deflate handled; anything else -> error; then the CRC check *)
+  let to_binary_strings fs =
+    let job f =
+      if Zipc.File.is_encrypted f then `Err "Encrypted files are not supported" else
+      match Zipc.File.compression f with
+      | Zipc.Stored | Zipc.Deflate -> `Gpu
+      | c -> `Err (Format.asprintf "Compression %a not supported" Zipc.pp_compression c)
+    in
+    let jobs = Array.map job fs in
+    let idx = List.filter (fun i -> jobs.(i) = `Gpu) (List.init (Array.length fs) Fun.id) in
+    let deflated = List.filter (fun i -> Zipc.File.compression fs.(i) = Zipc.Deflate) idx in
+    let stored = List.filter (fun i -> Zipc.File.compression fs.(i) = Zipc.Stored) idx in
+    let arg i =
+      let f = fs.(i) in
+      (Zipc.File.compressed_bytes f, Zipc.File.start f, Zipc.File.compressed_size f,
+       Some (Zipc.File.decompressed_size f))
+    in
+    let inflated = inflate_batch ~crc_op:Crc_32_op (Array.of_list (List.map arg deflated)) in
+    let stored_crcs =
+      let a = Array.of_list stored in
+      crc32_batch_stub (Array.map (fun i -> Zipc.File.compressed_bytes fs.(i)) a)
+        (Array.map (fun i -> Zipc.File.start fs.(i)) a)
+        (Array.map (fun i -> Zipc.File.compressed_size fs.(i)) a)
+    in
+    let out = Array.map (function `Err m -> Error m | `Gpu -> Error "") jobs in
+    let check i s found =
+      let expect = Zipc.File.decompressed_crc_32 fs.(i) in
+      out.(i) <- (match Crc_32.check ~expect ~found with Ok () -> Ok s | Error _ as e -> e)
+    in
+    List.iteri (fun k i -> match inflated.(k) with
+      | Ok (s, crc) -> check i s crc
+      | Error m -> out.(i) <- Error ("deflate: " ^ m)) deflated;
+    List.iteri (fun k i ->
+      let f = fs.(i) in
+      check i (String.sub (Zipc.File.compressed_bytes f) (Zipc.File.start f) (Zipc.File.compressed_size f))
+        stored_crcs.(k)) stored;
+    out
+end
+
+let archive_to_binary_string ?(level = `Default) ?(first = "") members =
+  match archive_stub (int_of_level level) (Array.map fst members) (Array.map snd members) first with
+  | st, archive when st = ok -> Ok archive
+  | st, _ -> Error (strerror st)

@@ -35,6 +35,9 @@ EXPORTS = [
     "zipc_b200_zlib_compress_batch", "zipc_b200_deflate_segmented", "zipc_b200_inflate_segmented", "zipc_b200_ptime_to_dos", "zipc_b200_ptime_of_dos", "zipc_b200_zip_parse",
     "zipc_b200_zip_encoding_size", "zipc_b200_zip_assemble", "zipc_b200_zip_extract_batch",
     "zipc_b200_zip_deflate_archive", "zipc_b200_free", "zipc_b200_synth_text", "zipc_b200_synth_rand",
+    "zipc_b200_mctx_create", "zipc_b200_mctx_destroy", "zipc_b200_mctx_device_count", "zipc_b200_mctx_ctx",
+    "zipc_b200_mctx_last_error", "zipc_b200_multi_crc32", "zipc_b200_multi_inflate_batch",
+    "zipc_b200_multi_deflate_batch", "zipc_b200_multi_fetch",
 ]
 
 
@@ -98,6 +101,15 @@ def _declare(L):
         "zipc_b200_free": (None, [vp]),
         "zipc_b200_synth_text": (None, [u64, vp, sz]),
         "zipc_b200_synth_rand": (None, [u64, vp, sz]),
+        "zipc_b200_mctx_create": (i32, [u64, vpp]),
+        "zipc_b200_mctx_destroy": (None, [vp]),
+        "zipc_b200_mctx_device_count": (i32, [vp]),
+        "zipc_b200_mctx_ctx": (vp, [vp, i32]),
+        "zipc_b200_mctx_last_error": (C.c_char_p, [vp]),
+        "zipc_b200_multi_crc32": (i32, [vp, vp, sz, u32p]),
+        "zipc_b200_multi_inflate_batch": (i32, [vp, i32, i32, sz, vpp, szp, szp, vp, sz, szp, szp, szp, u32p, ip]),
+        "zipc_b200_multi_deflate_batch": (i32, [vp, i32, i32, i32, sz, vpp, szp, vp, sz, szp, szp, szp, u32p, ip]),
+        "zipc_b200_multi_fetch": (i32, [vp, vp, sz]),
     }
     assert set(sig) == set(EXPORTS)
     for name, (res, args) in sig.items():

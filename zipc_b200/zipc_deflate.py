@@ -269,6 +269,84 @@ class Context:
         return st.value, out[:n.value], crc.value
 
 
+class MultiContext:
+    """zipc_b200_mctx: one call drives every selected GPU of the node (device_mask bit d = CUDA device d; 0 = all).
+    Members of a batch are partitioned over the devices inside the library; results come back in input order."""
+
+    def __init__(self, device_mask: int = 0):
+        self.L = _lib.lib()
+        h = C.c_void_p()
+        st = self.L.zipc_b200_mctx_create(device_mask, C.byref(h))
+        if st:
+            raise ZipcB200Error(f"zipc_b200_mctx_create(mask={device_mask:#x}): {strerror(st)} -- libzipc_b200 has no CPU fallback")
+        self.h = h
+        self.devices = self.L.zipc_b200_mctx_device_count(h)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.zipc_b200_mctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, st, what):
+        if st:
+            raise ZipcB200Error(f"{what}: {strerror(st)} [{self.L.zipc_b200_mctx_last_error(self.h).decode()}]")
+
+    @property
+    def launches(self) -> int:
+        return sum(self.L.zipc_b200_ctx_launches(self.L.zipc_b200_mctx_ctx(self.h, k)) for k in range(self.devices))
+
+    def crc32(self, s) -> int:
+        v = _as_view(s)
+        out = C.c_uint32()
+        self._check(self.L.zipc_b200_multi_crc32(self.h, v.ctypes.data if v.size else None, v.size, C.byref(out)), "multi_crc32")
+        return out.value
+
+    def _arena_call(self, call, n):
+        need = C.c_size_t()
+        off = (C.c_size_t * max(n, 1))()
+        ln = (C.c_size_t * max(n, 1))()
+        st = call(None, 0, C.byref(need), off, ln)
+        if st not in (_lib.OK, _lib.ERR_DST_TOO_SMALL):
+            self._check(st, "multi batch call")
+        arena = np.empty(max(need.value, 1), dtype=np.uint8)
+        if st == _lib.ERR_DST_TOO_SMALL:
+            self._check(self.L.zipc_b200_multi_fetch(self.h, arena.ctypes.data, arena.size), "multi_fetch")
+        return arena, off, ln
+
+    def inflate_batch(self, items: Sequence, decompressed_sizes=None, crc_op: int = CK_NONE, adler_mode: int = ADLER_REF_COMPAT):
+        vs = [_as_view(x) for x in items]
+        n = len(vs)
+        ptrs, lens = Context._ptr_arrays(vs)
+        mo = (C.c_size_t * max(n, 1))()
+        for i in range(n):
+            d = None if decompressed_sizes is None else decompressed_sizes[i]
+            mo[i] = SIZE_UNKNOWN if d is None else d
+        ck = (C.c_uint32 * max(n, 1))()
+        stt = (C.c_int * max(n, 1))()
+        arena, off, ln = self._arena_call(
+            lambda dst, cap, need, o, l: self.L.zipc_b200_multi_inflate_batch(self.h, crc_op, adler_mode, n, ptrs, lens, mo,
+                                                                              dst, cap, need, o, l, ck, stt), n)
+        return [(stt[i], arena[off[i]:off[i] + ln[i]], ck[i]) for i in range(n)]
+
+    def deflate_batch(self, items: Sequence, level: str = "default", crc_op: int = CK_NONE, adler_mode: int = ADLER_REF_COMPAT):
+        vs = [_as_view(x) for x in items]
+        n = len(vs)
+        ptrs, lens = Context._ptr_arrays(vs)
+        ck = (C.c_uint32 * max(n, 1))()
+        stt = (C.c_int * max(n, 1))()
+        lv = LEVELS[level]
+        arena, off, ln = self._arena_call(
+            lambda dst, cap, need, o, l: self.L.zipc_b200_multi_deflate_batch(self.h, lv, crc_op, adler_mode, n, ptrs, lens, dst,
+                                                                              cap, need, o, l, ck, stt), n)
+        return [(stt[i], arena[off[i]:off[i] + ln[i]], ck[i]) for i in range(n)]
+
+
 _default: Context | None = None
 
 
