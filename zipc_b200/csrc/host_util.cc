@@ -1,5 +1,5 @@
 // host_util.cc -- host-only parts of libzipc_b200: messages, checksum combines, DOS time,
-// ZIP central-directory parsing / archive layout, synthetic workload generators.
+// ZIP central-directory parsing / archive layout.  (The synthetic workload generators live in synth.cc.)
 //
 // The archive code restates the *layout rules* of the reference's src/zipc.ml (cited per function);
 // payload bytes are produced elsewhere (GPU codecs) and only placed here.
@@ -320,62 +320,6 @@ int zipc_b200_zip_assemble(const zipc_b200_member *ms, size_t n, const char *fir
                            size_t *out_len) {
   if (!out_v) return ZIPC_ERR_INVALID_ARG;
   return zb::zip_assemble_impl(ms, n, first, out_v, out_cap, out_len, true, nullptr);
-}
-
-// ---- synthetic workloads -------------------------------------------------------------
-static inline uint64_t splitmix64(uint64_t &st) {
-  uint64_t z = (st += 0x9E3779B97F4A7C15ull);
-  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-  return z ^ (z >> 31);
-}
-
-void zipc_b200_synth_rand(uint64_t seed, void *out, size_t n) {  // rand-v1: raw splitmix64, little endian
-  uint8_t *o = static_cast<uint8_t *>(out);
-  uint64_t st = seed;
-  size_t i = 0;
-  for (; i + 8 <= n; i += 8) { uint64_t v = splitmix64(st); std::memcpy(o + i, &v, 8); }
-  if (i < n) { uint64_t v = splitmix64(st); std::memcpy(o + i, &v, n - i); }
-}
-
-// text-v1: Zipf-distributed words from a fixed 4096-word vocabulary, sentence punctuation, lines
-// wrapped once the column passes 72.  The vocabulary does not depend on `seed` (all members share
-// a language); the word sequence does.
-void zipc_b200_synth_text(uint64_t seed, void *out, size_t n) {
-  static std::vector<std::string> vocab;
-  static std::vector<uint64_t> cum;
-  if (vocab.empty()) {
-    static const char letters[] = "etaoinshrdlcumwfgypbvkjxqz";
-    uint64_t vs = 0x7a6970635f623230ull;
-    std::vector<std::string> v(4096);
-    for (auto &w : v) {
-      size_t len = 2 + splitmix64(vs) % 9;
-      for (size_t i = 0; i < len; i++) {
-        uint64_t r1 = splitmix64(vs), r2 = splitmix64(vs);
-        w.push_back(letters[(r1 % 26) * (r2 % 26) / 26]);
-      }
-    }
-    std::vector<uint64_t> c(4096);
-    uint64_t acc = 0;
-    for (size_t k = 0; k < 4096; k++) { acc += 0x100000000ull / (k + 1); c[k] = acc; }
-    cum.swap(c);
-    vocab.swap(v);
-  }
-  uint8_t *o = static_cast<uint8_t *>(out);
-  uint64_t st = seed * 0x9E3779B97F4A7C15ull + 0x632BE59BD9B4E019ull;
-  size_t pos = 0, col = 0;
-  while (pos < n) {
-    uint64_t r = splitmix64(st) % cum.back();
-    size_t k = (size_t)(std::upper_bound(cum.begin(), cum.end(), r) - cum.begin());
-    const std::string &w = vocab[k];
-    for (size_t i = 0; i < w.size() && pos < n; i++) o[pos++] = (uint8_t)w[i];
-    col += w.size();
-    uint64_t p = splitmix64(st) % 100;
-    if (p < 6) { if (pos < n) o[pos++] = '.'; col++; }
-    else if (p < 12) { if (pos < n) o[pos++] = ','; col++; }
-    if (col > 72) { if (pos < n) o[pos++] = '\n'; col = 0; }
-    else { if (pos < n) o[pos++] = ' '; col++; }
-  }
 }
 
 }  // extern "C"
