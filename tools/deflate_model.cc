@@ -131,54 +131,112 @@ void finalize_block(Block &b, const uint8_t *src, bool final, BitSink &out) {
 }  // namespace
 
 extern "C" {
-// returns 0; *out is malloc'ed.  stats[0..2] = stored/fixed/dynamic... (optional, may be null)
+// returns 0; *out is malloc'ed.
+// Order of the phases per tile t, as in the kernel (it matters: chain links of positions 32 KiB back are overwritten
+// by the insertion of the next tile, so that happens after the deep walks of this one): rounds of { P0(t) parse,
+// D(t) deep walks }, P1(t) final parse, I(t+1) insertion, S(t+1) shallow walks.
 int zipc_model_deflate(int level, const uint8_t *src, uint64_t n64, uint8_t **out_p, uint64_t *out_len) {
   const uint32_t n = (uint32_t)n64;
   LevelParams lp = level_params(level);
   Ring ring;
   Prev prev;
-  std::vector<uint16_t> head(1u << kHashBits, 0), first(kTile, 0), mlen(kTile + 1, 0), mdist(kTile + 1, 0);
+  std::vector<uint16_t> head(1u << kHashBits, 0);
+  // per tile (two generations: t and t + 1): first candidate / resume token, match length and distance
+  std::vector<uint16_t> tok[2], mlen[2], mdist[2];
+  for (int g = 0; g < 2; g++) { tok[g].assign(kTile, 0); mlen[g].assign(kTile + 1, 0); mdist[g].assign(kTile + 1, 0); }
   std::vector<uint8_t> obuf((size_t)n + n / 8 + 1024);
   BitSink sink{obuf.data(), 0, 0, 0};
   Block blk;
   blk.reset(0);
-  uint32_t pos = 0, kind = 0, carry_len = 0, carry_dist = 0, loaded = 0;
+  uint32_t pos = 0, kind = 0, loaded = 0;
   int tiles_in_block = 0;
-  for (uint32_t ts = 0; ts < n; ts += kTile) {
-    uint32_t te = std::min(ts + (uint32_t)kTile, n);
-    uint32_t want = std::min(n, te + (uint32_t)kTile);
+
+  auto insert = [&](uint32_t ts, int g) {
+    uint32_t te = std::min(ts + (uint32_t)kTile, n), want = std::min(n, te + (uint32_t)kTile);
     for (; loaded < want; loaded++) ring.put(loaded, src[loaded]);
     for (uint32_t p = ts; p < te; p++) {
-      if (p + 4 > n) { first[p - ts] = 0; continue; }
+      if (p + 4 > n) { tok[g][p - ts] = 0; continue; }
       uint32_t h = hash4(ring_load32(ring, p));
-      first[p - ts] = head[h];
+      tok[g][p - ts] = head[h];
       prev.l[p & (kWindow - 1)] = head[h];
       head[h] = (uint16_t)p;
     }
-    // slot 0 of mlen/mdist holds position ts-1 (carry), slot 1+i holds ts+i
-    mlen[0] = (uint16_t)carry_len; mdist[0] = (uint16_t)carry_dist;
+  };
+  auto shallow = [&](uint32_t ts, int g, uint32_t carry_len, uint32_t carry_dist) {
+    uint32_t te = std::min(ts + (uint32_t)kTile, n);
+    mlen[g][0] = (uint16_t)carry_len; mdist[g][0] = (uint16_t)carry_dist;  // slot 0 holds position ts-1, slot 1+i holds ts+i
     for (uint32_t p = ts; p < te; p++) {
-      uint32_t d = 0, l = 0;
-      if (p + 4 <= n) l = find_match(ring, prev, p, n, first[p - ts], lp.depth, lp.nice, d);
-      mlen[1 + p - ts] = (uint16_t)l; mdist[1 + p - ts] = (uint16_t)(d & 0xFFFF);
+      uint32_t i = p - ts, l = 0, d = 0, rt = p & 0xFFFFu;
+      if (p + 4 <= n) {
+        MatchState m;
+        match_begin(m, ring, p, n, tok[g][i], lp.shallow);
+        while (!m.done) match_step(m, ring, prev, lp.shallow_nice);
+        l = m.best >= (uint32_t)kMinMatch ? m.best : 0; d = m.best_dist; rt = match_resume_token(m);
+      }
+      mlen[g][1 + i] = (uint16_t)l; mdist[g][1 + i] = (uint16_t)d; tok[g][i] = (uint16_t)rt;
     }
+  };
+
+  if (n) { insert(0, 0); shallow(0, 0, 0, 0); }
+  int g = 0;
+  for (uint32_t ts = 0; ts < n; ts += kTile, g ^= 1) {
+    const uint32_t te = std::min(ts + (uint32_t)kTile, n);
+    std::vector<uint16_t> &ML = mlen[g], &MD = mdist[g], &TK = tok[g];
+    // D: visited positions continue their chain walk to the full depth; so do the positions a match taken there would land on
+    // and their lazy look-ahead (inside this tile), up to lp.hops landings away (breadth first).  A position is deepened at
+    // most once.
+    std::vector<uint8_t> claimed(kTile, 0);
+    // links of candidates that the insertion of tile t + 1 overwrites are not followed (the kernel inserts concurrently)
+    const uint32_t te1 = std::min(te + (uint32_t)kTile, n);
+    const uint32_t trim = (te < n && te1 > (uint32_t)kWindow) ? te1 - (uint32_t)kWindow : 0u;
+    for (int round = 0; round < lp.rounds; round++) {
+      // P0: which positions would a lazy parse over the current lengths visit?  Guessed paths, not stitched together: from
+      // the start of every 64-position sub-range (nothing pending), each followed to the end of its own sub-range.  Paths
+      // through the node graph merge after a few tokens, and the landings below cover the stretch before they do.  (The
+      // guess does not depend on where the real parse enters the tile, so it can be made before the previous tile is done.)
+      std::vector<uint32_t> todo;
+      std::vector<int> hop;  // how many landings away from a visited position
+      auto walk = [&](uint32_t q, uint32_t k, uint32_t end) {
+        while (q < end) {
+          uint32_t nk, em;
+          if (q + 4 <= n && !claimed[q - ts]) { todo.push_back(q); hop.push_back(0); }
+          q = lazy_next(q, k, ML[1 + q - ts], ML[q - ts], nk, em);
+          k = nk;
+        }
+      };
+      for (uint32_t r = ts; r < te; r += 64) {
+        walk(r, 0, std::min(te, r + 64));
+      }
+      for (size_t ti = 0; ti < todo.size(); ti++) {
+        const uint32_t p = todo[ti], i = p - ts;
+        if (claimed[i]) continue;
+        claimed[i] = 1;
+        MatchState m;
+        if (match_resume(m, ring, prev, p, n, ML[1 + i], MD[1 + i], TK[i], lp.depth - lp.shallow, trim)) {
+          while (!m.done) { match_step(m, ring, prev, lp.nice); match_trim(m, trim); }
+          if (m.best >= (uint32_t)kMinMatch) { ML[1 + i] = (uint16_t)m.best; MD[1 + i] = (uint16_t)m.best_dist; }
+        }
+        if (ML[1 + i] >= (uint32_t)kMinMatch && hop[ti] < lp.hops)
+          for (uint32_t q = p + ML[1 + i], k = 0; k < 2; k++, q++)
+            if (q < te && q + 4 <= n && !claimed[q - ts]) { todo.push_back(q); hop.push_back(hop[ti] + 1); }
+      }
+    }
+    // P1: the final parse
     while (pos < te) {
       uint32_t nk, em;
-      uint32_t ml = mlen[1 + pos - ts], mp = mlen[pos - ts];
+      uint32_t ml = ML[1 + pos - ts], mp = ML[pos - ts];
       uint32_t np = lazy_next(pos, kind, ml, mp, nk, em);
       if (em == 1) { uint8_t b = src[pos]; blk.toks.push_back(tok_lit(b)); blk.fl[b]++; blk.src_len += 1; }
       else if (em == 2) { uint8_t b = src[pos - 1]; blk.toks.push_back(tok_lit(b)); blk.fl[b]++; blk.src_len += 1; }
       else if (em == 3) {
-        uint32_t d = mdist[pos - ts] ? mdist[pos - ts] : 65536u;
-        if (d == 65536u) d = 32768;  // 32768 is stored as 0x8000, never 0; kept for clarity
-        uint32_t eb, ev;
+        uint32_t d = MD[pos - ts], eb, ev;
         blk.toks.push_back(tok_match(mp, d));
         blk.fl[len_sym_of(mp, eb, ev)]++; blk.fd[dist_sym_of(d, eb, ev)]++;
         blk.src_len += mp;
       }
       pos = np; kind = nk;
     }
-    carry_len = mlen[te - ts]; carry_dist = mdist[te - ts];  // position te-1
+    if (te < n) { insert(te, g ^ 1); shallow(te, g ^ 1, ML[te - ts], MD[te - ts]); }  // slot 0 carries position te-1
     tiles_in_block++;
     bool last = te == n;
     if (tiles_in_block == kTilesPerBlock || last) {

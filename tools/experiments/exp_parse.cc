@@ -66,7 +66,7 @@ static uint64_t block_bits(uint32_t *fl, uint32_t *fd, uint64_t src_len) {
   return std::min(st, std::min(dyn, fix));
 }
 
-struct Cfg { int S, D, R, nice, niceS; bool thresh; };
+struct Cfg { int S, D, R, nice, niceS; bool thresh; int closure = 0; };
 
 static uint64_t encode(const uint8_t *src, uint32_t n, const Cfg &c) {
   Ring ring; Prev prev;
@@ -102,7 +102,9 @@ static uint64_t encode(const uint8_t *src, uint32_t n, const Cfg &c) {
         q = np; k = nk;
       }
       if (todo.empty()) break;
-      for (uint32_t p : todo) {
+      for (size_t ti = 0; ti < todo.size(); ti++) {
+        uint32_t p = todo[ti];
+        if (deep[1 + p - ts]) continue;
         uint32_t d = 0;
         // optionally only look for something longer than what the previous position already offers (the reference's prev_match_len)
         uint32_t mb = kMinMatch - 1;
@@ -110,6 +112,11 @@ static uint64_t encode(const uint8_t *src, uint32_t n, const Cfg &c) {
         uint32_t l = fm(ring, prev, p, n, first[p - ts], c.D, c.nice, d, mb);
         if (l > mlen[1 + p - ts]) { mlen[1 + p - ts] = l; mdist[1 + p - ts] = d; }
         deep[1 + p - ts] = 1;
+        if (c.closure && mlen[1 + p - ts] >= 4) {  // where a match taken at p lands, and its lazy lookahead
+          uint32_t q = p + mlen[1 + p - ts];
+          for (uint32_t k = 0; k < (uint32_t)c.closure; k++)
+            if (q + k < te && q + k + 4 <= n && !deep[1 + q + k - ts]) todo.push_back(q + k);
+        }
       }
     }
     while (pos < te) {
@@ -144,20 +151,19 @@ int main(int argc, char **argv) {
     U += sz;
   }
   std::vector<Cfg> cfgs = {
-      {4, 0, 0, 32, 32, false},    // current fast
-      {12, 0, 0, 128, 128, false}, // current default
-      {48, 0, 0, 258, 258, false}, // current best
-      {1, 4, 1, 32, 32, false}, {2, 4, 1, 32, 32, false}, {2, 8, 2, 64, 32, false},
-      {2, 12, 1, 128, 32, false}, {2, 12, 2, 128, 32, false}, {2, 24, 2, 128, 32, false}, {2, 32, 2, 258, 32, false}, {2, 48, 2, 258, 32, false},
-      {2, 64, 2, 258, 32, false}, {2, 128, 2, 258, 32, false}, {2, 128, 3, 258, 32, false}, {4, 128, 2, 258, 32, false},
-      {2, 32, 2, 258, 32, true}, {2, 128, 2, 258, 32, true}, {1, 32, 2, 258, 32, false}, {1, 128, 2, 258, 32, false},
-      {2, 256, 2, 258, 32, false}, {2, 1024, 2, 258, 32, false},
+      {2, 16, 1, 128, 32, false, 0}, {2, 16, 1, 128, 32, false, 1}, {2, 16, 1, 128, 32, false, 2}, {2, 16, 2, 128, 32, false, 0},
+      {2, 48, 1, 258, 32, false, 2}, {2, 48, 2, 258, 32, false, 0},
+      {2, 128, 1, 258, 32, false, 1}, {2, 128, 1, 258, 32, false, 2}, {2, 128, 2, 258, 32, false, 0}, {2, 128, 2, 258, 32, false, 2},
+      {2, 1024, 1, 258, 32, false, 2}, {2, 1024, 2, 258, 32, false, 2},
+      {1, 4, 1, 32, 32, false, 2}, {1, 128, 1, 258, 32, false, 2},
   };
+
+
   for (const Cfg &c : cfgs) {
     g_steps = 0;
     uint64_t C = 0;
     for (auto &d : data) C += encode(d.data(), (uint32_t)d.size(), c);
-    printf("S=%-3d D=%-4d R=%d nice=%-3d niceS=%-3d thr=%d  ratio %.4f  steps/byte %.2f\n", c.S, c.D, c.R, c.nice, c.niceS, (int)c.thresh, (double)C / U,
+    printf("S=%-3d D=%-4d R=%d nice=%-3d niceS=%-3d clo=%d  ratio %.4f  steps/byte %.2f\n", c.S, c.D, c.R, c.nice, c.niceS, c.closure, (double)C / U,
            (double)g_steps / U);
   }
   return 0;

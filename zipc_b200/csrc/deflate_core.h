@@ -6,10 +6,14 @@
 //   * same hash (4 bytes * 0x9E3779B1, :1145-1148), same minimum match 4 / maximum 258 / window 32768
 //     (:1141-1143), same one-step lazy rule (:1224-1241), same exact bit costs for the stored / fixed /
 //     dynamic choice (:1045-1104) -- without the reference's never-cleared codelen_sym_freqs.
-//   * different on purpose: matches are searched at EVERY position in parallel against exact hash
-//     chains (the reference searches only where its serial parse lands), Huffman lengths come from the
-//     in-place minimum-redundancy algorithm on sorted frequencies plus a Kraft repair (the reference
-//     rebuilds with halved frequency caps, :404-473), blocks are cut every 30 tiles of 2048 bytes.
+//   * different on purpose: the search is two-phase.  EVERY position gets a shallow walk of its exact hash
+//     chain (1-2 candidates, all positions in parallel); a first lazy parse over those lengths tells which
+//     positions a parse visits at all (about 30 % of them), and only these -- plus the positions a match taken
+//     there would land on, transitively -- continue their walk to the level's full depth, which is where the
+//     reference spends its chain budget too (it searches only where its serial parse lands, :1219-1241).  The
+//     final parse then runs over the improved lengths.  Huffman lengths come from the in-place
+//     minimum-redundancy algorithm on sorted frequencies plus a Kraft repair (the reference rebuilds with
+//     halved frequency caps, :404-473), blocks are cut every 30 tiles of 2048 bytes.
 //     The streams are valid RFC 1951 and round-trip through the reference's inflate; they are not
 //     byte-identical to the reference's.
 #pragma once
@@ -33,13 +37,24 @@ constexpr int kHashBits = 14;
 constexpr int kRing = 65536;           // input ring in shared memory (power of two)
 constexpr int kNumLit = 286, kNumDist = 30, kNumClen = 19;
 
-struct LevelParams { int depth; int nice; };
+struct LevelParams {
+  int shallow;      // chain steps every position gets
+  int shallow_nice; // ... and the length at which that walk stops early
+  int depth;        // total chain steps of a position the parse visits (the reference: max_chain 4 / 128 / 4096, :754-764)
+  int nice;         // length at which the deep walk stops early
+  int rounds;       // parse -> deepen rounds before the final parse
+  int hops;         // the deep walks also cover the positions matches would land on, this many landings away
+};
 ZHD LevelParams level_params(int level) {
-  // chain steps per position and the length at which the walk stops early
   LevelParams p;
-  if (level <= 1) { p.depth = 4; p.nice = 32; }
-  else if (level == 2) { p.depth = 12; p.nice = 128; }
-  else { p.depth = 48; p.nice = 258; }
+  // fast, default: the whole chain budget at every position, no deep walks (the walks of ALL positions run in lock step,
+  // which is what a SIMT machine is good at; measured).  best: shallow everywhere, deep where a parse goes.
+  if (level <= 1) { p.shallow = 4; p.shallow_nice = 32; p.depth = 4; p.nice = 32; p.rounds = 0; p.hops = 0; }
+  else if (level == 2) { p.shallow = 12; p.shallow_nice = 128; p.depth = 12; p.nice = 128; p.rounds = 0; p.hops = 0; }
+  else { p.shallow = 2; p.shallow_nice = 32; p.depth = 1024; p.nice = 258; p.rounds = 2; p.hops = 2; }
+#ifdef ZB_FORCE_HOPS
+  p.hops = ZB_FORCE_HOPS;
+#endif
   return p;
 }
 
@@ -130,6 +145,7 @@ struct MatchState {
   uint32_t chk;        // the byte at p + best: a candidate can only beat `best` if it matches there
   int steps;
   bool done;
+  bool more;           // the walk stopped only because its step budget ran out: it can be resumed
 };
 
 template <class Ring>
@@ -143,6 +159,79 @@ ZHD void match_begin(MatchState &m, const Ring &ring, uint32_t p, uint32_t n, ui
   m.chk = (m.pw0 >> 24) & 0xFFu;  // byte at p + 3
   m.steps = depth;
   m.done = depth <= 0;
+  m.more = false;
+}
+
+// What a walk leaves behind for a later continuation, in 16 bits: the last candidate it evaluated (the chain goes on
+// from that candidate's link), or the position itself when there is nothing to continue.
+ZHD uint32_t match_resume_token(const MatchState &m) { return (m.more ? m.p - m.last_dist : m.p) & 0xFFFFu; }
+
+// Continues the walk of position p from (len, dist, token) as left by an earlier walk; false if there is nothing to do.
+// `trim`: chain links of candidates below this absolute position are not followed.  The deep walks of a tile run
+// while the next tile is being inserted into the chains, which overwrites the links of the positions 32 KiB
+// before it; stopping there keeps every walk independent of that timing (the candidates themselves are still
+// compared: the input ring holds them).
+template <class Ring, class Prev>
+ZHD bool match_resume(MatchState &m, const Ring &ring, const Prev &prev, uint32_t p, uint32_t n, uint32_t len, uint32_t dist,
+                      uint32_t token, int steps, uint32_t trim) {
+  const uint32_t last = (p - token) & 0xFFFFu;
+  if (last == 0 || steps <= 0 || p - last < trim) return false;
+  m.p = p;
+  m.max_len = n - p < (uint32_t)kMaxMatch ? n - p : (uint32_t)kMaxMatch;
+  m.best = len >= (uint32_t)kMinMatch ? len : kMinMatch - 1;
+  m.best_dist = len >= (uint32_t)kMinMatch ? dist : 0;
+  if (m.best >= m.max_len) return false;
+  m.last_dist = last;
+  m.reach = p < (uint32_t)kWindow ? p : (uint32_t)kWindow;
+  m.c = prev.link(p - last);
+  ring_load64(ring, p, m.pw0, m.pw1);
+  m.chk = ring_load8(ring, p + m.best);
+  m.steps = steps;
+  m.done = false;
+  m.more = false;
+  return true;
+}
+
+// Length of the match between position p (whose first 8 bytes are pw0, pw1) and the candidate position cp, at most max_len.
+template <class Ring>
+ZHD uint32_t match_compare(const Ring &ring, uint32_t p, uint32_t cp, uint32_t pw0, uint32_t pw1, uint32_t max_len) {
+  uint32_t len;
+  // candidates of one chain nearly always share the first 4 bytes (same hash), so both words are fetched at
+  // once: 3 aligned loads for 8 bytes instead of 2 + 2
+  uint32_t w0, w1;
+  ring_load64(ring, cp, w0, w1);
+  uint32_t x = w0 ^ pw0;
+  if (x) len = (uint32_t)
+#if defined(__CUDA_ARCH__)
+      (__ffs((int)x) - 1) >> 3;
+#else
+      __builtin_ctz(x) >> 3;
+#endif
+  else {
+    x = w1 ^ pw1;
+    if (x) len = 4 + ((uint32_t)
+#if defined(__CUDA_ARCH__)
+        (__ffs((int)x) - 1) >> 3);
+#else
+        __builtin_ctz(x) >> 3);
+#endif
+    else {
+      len = 8;
+      while (len < max_len) {
+        x = ring_load32(ring, cp + len) ^ ring_load32(ring, p + len);
+        if (x) {
+#if defined(__CUDA_ARCH__)
+          len += (uint32_t)(__ffs((int)x) - 1) >> 3;
+#else
+          len += (uint32_t)__builtin_ctz(x) >> 3;
+#endif
+          break;
+        }
+        len += 4;
+      }
+    }
+  }
+  return len > max_len ? max_len : len;
 }
 
 // Evaluates one candidate of the chain.
@@ -153,43 +242,7 @@ ZHD void match_step(MatchState &m, const Ring &ring, const Prev &prev, int nice)
   m.last_dist = dist;
   uint32_t cp = m.p - dist;
   if (m.best < m.max_len && ring_load8(ring, cp + m.best) == m.chk) {
-    uint32_t len;
-    // candidates of one chain nearly always share the first 4 bytes (same hash), so both words are fetched at
-    // once: 3 aligned loads for 8 bytes instead of 2 + 2
-    uint32_t w0, w1;
-    ring_load64(ring, cp, w0, w1);
-    uint32_t x = w0 ^ m.pw0;
-    if (x) len = (uint32_t)
-#if defined(__CUDA_ARCH__)
-        (__ffs((int)x) - 1) >> 3;
-#else
-        __builtin_ctz(x) >> 3;
-#endif
-    else {
-      x = w1 ^ m.pw1;
-      if (x) len = 4 + ((uint32_t)
-#if defined(__CUDA_ARCH__)
-          (__ffs((int)x) - 1) >> 3);
-#else
-          __builtin_ctz(x) >> 3);
-#endif
-      else {
-        len = 8;
-        while (len < m.max_len) {
-          x = ring_load32(ring, cp + len) ^ ring_load32(ring, m.p + len);
-          if (x) {
-#if defined(__CUDA_ARCH__)
-            len += (uint32_t)(__ffs((int)x) - 1) >> 3;
-#else
-            len += (uint32_t)__builtin_ctz(x) >> 3;
-#endif
-            break;
-          }
-          len += 4;
-        }
-      }
-    }
-    if (len > m.max_len) len = m.max_len;
+    const uint32_t len = match_compare(ring, m.p, cp, m.pw0, m.pw1, m.max_len);
     if (len > m.best) {
       m.best = len; m.best_dist = dist;
       if (len >= (uint32_t)nice || len == m.max_len) { m.done = true; return; }
@@ -197,7 +250,12 @@ ZHD void match_step(MatchState &m, const Ring &ring, const Prev &prev, int nice)
     }
   }
   m.c = prev.link(cp);
-  if (--m.steps <= 0) m.done = true;
+  if (--m.steps <= 0) { m.done = true; m.more = true; }
+}
+
+// after a step of a deep walk: do not follow the link of a candidate below `trim` (see match_resume)
+ZHD void match_trim(MatchState &m, uint32_t trim) {
+  if (!m.done && m.p - m.last_dist < trim) { m.done = true; m.more = false; }
 }
 
 // Longest match for absolute position p (p + 4 <= n).  Returns len (0 if < 4) and sets dist.
