@@ -88,6 +88,9 @@ const char *zipc_b200_last_error(const zipc_b200_ctx *ctx);
 void *zipc_b200_ctx_stream(zipc_b200_ctx *ctx);
 /* Number of kernels this ctx has launched so far (bench.py's gpu_launches). */
 uint64_t zipc_b200_ctx_launches(const zipc_b200_ctx *ctx);
+/* Diagnostics counters: 0 = kernels launched, 1 = large streams inflated in parallel inside the stream, 2 = large streams
+ * whose parallel decoding did not check out and that were decoded by the serial path instead. */
+uint64_t zipc_b200_ctx_counter(const zipc_b200_ctx *ctx, int which);
 /* Diagnostics: when enabled, every call brackets its dominant kernel (CRC tiles / Adler chunks / inflate /
  * deflate) with CUDA events on the ctx stream; zipc_b200_ctx_kernel_ms returns the duration of the last
  * bracketed kernel in milliseconds (it waits for that kernel), or a negative value if none. */
@@ -134,6 +137,11 @@ uint32_t zipc_b200_adler32_combine(uint32_t adler_a, uint32_t adler_b, uint64_t 
  *                   the ctx until the next call and can be fetched with zipc_b200_fetch().
  *   checksum[i]     checksum of output i (0 for ZIPC_CK_NONE)
  *   status[i]       ZIPC_OK / ZIPC_ERR_CORRUPTED / ZIPC_ERR_SIZE_EXCEEDED
+ * A stream is decoded by one warp; a LARGE stream (256 KiB of compressed data or more, no index needed) is decoded by many:
+ * block starts are found by scanning for valid dynamic-block headers, the chunks between them are decoded speculatively
+ * with the preceding 32 KiB unknown, and resolved once the chunks are seen to chain up exactly; any doubt (and any error
+ * inside the stream) sends the stream back to the one-warp decoder, so results and statuses are those of the serial
+ * reference loop (zipc_deflate.ml:593-616, 692-709) either way.
  */
 int zipc_b200_inflate_batch(zipc_b200_ctx *ctx, int checksum_kind, int adler_mode, size_t n,
                             const void *const *src, const size_t *src_len, const size_t *max_out,

@@ -24,7 +24,7 @@ SIZE_UNKNOWN = C.c_size_t(-1).value
 
 EXPORTS = [
     "zipc_b200_version", "zipc_b200_strerror", "zipc_b200_device_count", "zipc_b200_ctx_create",
-    "zipc_b200_ctx_destroy", "zipc_b200_last_error", "zipc_b200_ctx_stream", "zipc_b200_ctx_launches",
+    "zipc_b200_ctx_destroy", "zipc_b200_last_error", "zipc_b200_ctx_stream", "zipc_b200_ctx_launches", "zipc_b200_ctx_counter",
     "zipc_b200_ctx_profile", "zipc_b200_ctx_kernel_ms",
     "zipc_b200_host_alloc", "zipc_b200_host_free", "zipc_b200_dev_alloc", "zipc_b200_dev_free",
     "zipc_b200_memcpy_h2d", "zipc_b200_memcpy_d2h", "zipc_b200_sync",
@@ -63,6 +63,7 @@ def _declare(L):
         "zipc_b200_last_error": (C.c_char_p, [vp]),
         "zipc_b200_ctx_stream": (vp, [vp]),
         "zipc_b200_ctx_launches": (u64, [vp]),
+        "zipc_b200_ctx_counter": (u64, [vp, i32]),
         "zipc_b200_ctx_profile": (None, [vp, i32]),
         "zipc_b200_ctx_kernel_ms": (C.c_float, [vp]),
         "zipc_b200_host_alloc": (i32, [sz, vpp]),

@@ -60,7 +60,7 @@ adler_ranges_kernel(const AdlerSeg *__restrict__ segs, uint32_t nseg, uint2 *__r
 //   anything else       : depends on the exact s2 -> resolved serially, in order ("U"; ~4e-4 of chunks on random data)
 // RFC 1950 mode is the same scan with every chunk treated as "L" and exact arithmetic.
 constexpr int kFoldThreads = 1024;
-constexpr int kFoldItems = 8;                         // consecutive chunks per thread -> 64-byte coalesced loads
+constexpr int kFoldItems = 16;                        // consecutive chunks per thread -> 128-byte coalesced loads; fewer, larger tiles
 constexpr int kFoldTile = kFoldThreads * kFoldItems;  // chunks per pass of the CTA
 constexpr uint32_t kM = 65521u;
 constexpr int kFoldSmem = kFoldTile * 7;
@@ -262,6 +262,70 @@ adler_fold_kernel(const uint2 *__restrict__ ab, uint32_t first, uint32_t nchunks
     *out = (s2 << 16) + s1_carry;
   }
 }
+// ---- RFC 1950 mode: the chunk recurrence is a plain reduction ------------------------------------------------------------
+// With exact arithmetic a run of chunks acts on (s1, s2) as s1' = s1 + A, s2' = s2 + N s1 + B  (N = bytes, A = byte sum,
+// B = weighted sum), and two runs compose associatively: (N1, A1, B1) then (N2, A2, B2) = (N1 + N2, A1 + A2, B1 + B2 + N2 A1),
+// all modulo 65521.  So the per-chunk pairs are reduced in order by a tree: thread (8 chunks) -> warp -> CTA -> the last CTA
+// to finish combines the CTA results.  (The reference's signed remainder makes the same recurrence order dependent; that
+// flavour keeps the scan of adler_fold_kernel.)
+struct Seg { uint32_t n, a, b; };
+__device__ __forceinline__ Seg seg_join(Seg l, Seg r) {
+  Seg o;
+  o.n = (l.n + r.n) % kM;
+  o.a = (l.a + r.a) % kM;
+  o.b = (uint32_t)(((uint64_t)l.b + r.b + (uint64_t)r.n * l.a) % kM);
+  return o;
+}
+constexpr int kRedThreads = 1024, kRedItems = 8;
+__global__ void __launch_bounds__(kRedThreads)
+adler_reduce_rfc_kernel(const uint2 *__restrict__ ab, uint32_t first, uint32_t nchunks, Seg *__restrict__ cta_seg,
+                        unsigned int *__restrict__ ticket, uint32_t *__restrict__ out) {
+  __shared__ Seg warp_seg[32];
+  __shared__ bool last;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t base = (blockIdx.x * kRedThreads + tid) * kRedItems;
+  Seg s{0, 0, 0};
+#pragma unroll
+  for (int i = 0; i < kRedItems; i++) {
+    const uint32_t c = base + i;
+    if (c < nchunks) {
+      const uint2 e = ab[c];
+      s = seg_join(s, Seg{(c == 0 ? first : kChunk) % kM, e.x % kM, e.y % kM});
+    }
+  }
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {  // ordered tree: lane l joins with lane l + o on its right
+    Seg r;
+    r.n = __shfl_down_sync(0xffffffffu, s.n, o); r.a = __shfl_down_sync(0xffffffffu, s.a, o); r.b = __shfl_down_sync(0xffffffffu, s.b, o);
+    if ((lane & (2 * o - 1)) == 0) s = seg_join(s, r);
+  }
+  if (lane == 0) warp_seg[warp] = s;
+  __syncthreads();
+  if (warp == 0) {
+    s = warp_seg[lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      Seg r;
+      r.n = __shfl_down_sync(0xffffffffu, s.n, o); r.a = __shfl_down_sync(0xffffffffu, s.a, o); r.b = __shfl_down_sync(0xffffffffu, s.b, o);
+      if ((lane & (2 * o - 1)) == 0) s = seg_join(s, r);
+    }
+    if (lane == 0) {
+      cta_seg[blockIdx.x] = s;
+      __threadfence();
+      last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    }
+  }
+  __syncthreads();
+  if (last && tid == 0) {  // a few dozen CTA results, in order
+    __threadfence();
+    Seg t{0, 0, 0};
+    for (uint32_t i = 0; i < gridDim.x; i++) t = seg_join(t, *(volatile Seg *)&cta_seg[i]);
+    const uint32_t s1 = (1u + t.a) % kM, s2 = (t.n + t.b) % kM;  // from (s1, s2) = (1, 0)
+    *out = (s2 << 16) + s1;
+    *ticket = 0;
+  }
+}
+
 }  // namespace
 
 int adler32_launch_buffer(zipc_b200_ctx *ctx, const uint8_t *d_src, uint64_t len, int mode, uint32_t *h_out) {
@@ -282,10 +346,20 @@ int adler32_launch_buffer(zipc_b200_ctx *ctx, const uint8_t *d_src, uint64_t len
   }
   ctx->launches++;
   ZB_CUDA(ctx, cudaGetLastError());
-  // fold on the device: one CTA, no host round trip of the partials
   uint32_t *d_out = reinterpret_cast<uint32_t *>(d_ab + nchunks);
-  ZB_CUDA(ctx, cudaFuncSetAttribute(adler_fold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFoldSmem));  // per device
-  adler_fold_kernel<<<1, kFoldThreads, kFoldSmem, ctx->stream>>>(d_ab, first, nchunks, mode, d_out);
+  if (mode == ZIPC_ADLER_RFC1950) {
+    // exact arithmetic: an ordered reduction over all SMs' worth of threads
+    const uint32_t rgrid = (nchunks + kRedThreads * kRedItems - 1) / (kRedThreads * kRedItems);
+    if (int st = ctx->d_adler.reserve(64 + (size_t)rgrid * sizeof(Seg))) return st;
+    unsigned int *ticket = ctx->d_adler.as<unsigned int>();
+    if (ctx->adler_ticket_at != (void *)ticket) { ZB_CUDA(ctx, cudaMemsetAsync(ticket, 0, sizeof(unsigned int), ctx->stream)); ctx->adler_ticket_at = ticket; }
+    Seg *cta_seg = reinterpret_cast<Seg *>(ctx->d_adler.as<uint8_t>() + 64);
+    adler_reduce_rfc_kernel<<<rgrid, kRedThreads, 0, ctx->stream>>>(d_ab, first, nchunks, cta_seg, ticket, d_out);
+  } else {
+    // the reference's flavour: one CTA scans the partials (no host round trip)
+    ZB_CUDA(ctx, cudaFuncSetAttribute(adler_fold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFoldSmem));  // per device
+    adler_fold_kernel<<<1, kFoldThreads, kFoldSmem, ctx->stream>>>(d_ab, first, nchunks, mode, d_out);
+  }
   ctx->launches++;
   ZB_CUDA(ctx, cudaGetLastError());
   ZB_CUDA(ctx, cudaMemcpyAsync(h_out, d_out, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));

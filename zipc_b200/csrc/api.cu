@@ -5,6 +5,7 @@
 // returning per-member results.  There is no CPU implementation of any codec step in this file.
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 
@@ -137,6 +138,7 @@ static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) & ~(a - 1
 int upload_ranges(zipc_b200_ctx *ctx, size_t n, const void *const *src, const size_t *len,
                   std::vector<const uint8_t *> &d_ptr) {
   d_ptr.assign(n, nullptr);
+  ctx->epoch++;  // new input bytes: plans made over the old ones are void
   if (!n) return ZIPC_OK;
   uintptr_t lo = ~(uintptr_t)0, hi = 0;
   size_t sum = 0, live = 0;
@@ -246,11 +248,10 @@ static __global__ void xor_ffffffff_kernel(uint32_t *v, uint32_t n) {
   if (i < n) v[i] ^= 0xFFFFFFFFu;
 }
 
-// Core of every inflate entry point.  All pointers in d_src / d_dst are device addresses.
-// cap[i] == ZIPC_SIZE_UNKNOWN is not accepted here (the callers resolve sizes first).
-int inflate_core(zipc_b200_ctx *ctx, int ck, int adler_mode, size_t n, const std::vector<const uint8_t *> &d_src,
-                 const size_t *src_len, const std::vector<uint8_t *> &d_dst, const std::vector<size_t> &cap,
-                 bool count_only, size_t *out_len, uint32_t *checksum, int *status, uint32_t flags) {
+// One warp per stream (inflate.cu).  All pointers in d_src / d_dst are device addresses.
+static int inflate_serial_core(zipc_b200_ctx *ctx, int ck, int adler_mode, size_t n, const std::vector<const uint8_t *> &d_src,
+                               const size_t *src_len, const std::vector<uint8_t *> &d_dst, const std::vector<size_t> &cap,
+                               bool count_only, size_t *out_len, uint32_t *checksum, int *status, uint32_t flags) {
   if (!n) return ZIPC_OK;
   if (n > 0xFFFFFFF0ull) return ZIPC_ERR_INVALID_ARG;
   // longest streams first: the tail of the dynamic queue is made of short ones
@@ -267,7 +268,7 @@ int inflate_core(zipc_b200_ctx *ctx, int ck, int adler_mode, size_t n, const std
     ht[k].src = d_src[i]; ht[k].src_len = src_len[i];
     ht[k].dst = count_only ? nullptr : d_dst[i];
     ht[k].dst_cap = cap[i] == ZIPC_SIZE_UNKNOWN ? ~0ull : (uint64_t)cap[i];
-    ht[k].flags = flags; ht[k]._pad = 0;
+    ht[k].flags = flags; ht[k]._pad = 0; ht[k].start_bit = 0; ht[k].stop_bit = ~0ull;
   }
   InflateTask *dt = ctx->d_desc.as<InflateTask>();
   CrcSeg *dsegs = reinterpret_cast<CrcSeg *>(dt + n);
@@ -297,6 +298,154 @@ int inflate_core(zipc_b200_ctx *ctx, int ck, int adler_mode, size_t n, const std
   }
   if (adler && checksum)  // folded block by block inside the kernel (reference :682-690)
     for (size_t k = 0; k < n; k++) checksum[order[k]] = hr[k].status == ZIPC_OK ? hr[k]._pad : 0u;
+  return ZIPC_OK;
+}
+
+// ---- intra-stream parallel inflate of one large stream (no index): find block starts, decode the chunks speculatively into
+// 16-bit symbols, check that the chunks chain up exactly, resolve.  *ok = false means "decode it serially": nothing found,
+// a wrong guess, an error inside the stream (the serial decoder then reports the reference's exact status), or a chunk that
+// expands more than its symbol buffer allows.  Reference: the serial core zipc_deflate.ml:593-616, 692-709.
+static uint64_t env_u64(const char *name, uint64_t dflt) {
+  const char *v = std::getenv(name);
+  return (v && *v) ? std::strtoull(v, nullptr, 10) : dflt;
+}
+// tuning knobs (read on every call, so that tests can vary them): compressed bytes per chunk; smallest stream that is tried
+static uint64_t par_chunk_bytes() { return std::max<uint64_t>(4096, env_u64("ZIPC_B200_PAR_CHUNK", 32768)); }
+static uint64_t par_min_bytes() { return env_u64("ZIPC_B200_PAR_MIN", 262144); }
+
+static int par_speculate(zipc_b200_ctx *ctx, const uint8_t *d_src, size_t src_len, bool *ok) {
+  *ok = false;
+  zipc_b200_ctx::ParPlan &plan = ctx->par_plan;
+  if (plan.src == d_src && plan.src_len == src_len && plan.epoch == ctx->epoch && !plan.len.empty()) { *ok = true; return ZIPC_OK; }
+  plan.len.clear(); plan.spec_off.clear(); plan.total = 0;
+  const uint64_t cb = par_chunk_bytes();
+  const uint32_t nch = (uint32_t)((src_len + cb - 1) / cb);
+  if (nch < 4 || src_len > (1ull << 40)) return ZIPC_OK;
+  // 1. block starts
+  const size_t tab = (size_t)nch * (sizeof(uint64_t) * 4 + sizeof(InflateTask) + sizeof(InflateResult)) + 256;
+  if (int st = ctx->d_par.reserve(tab)) return st;
+  if (int st = ctx->h_res.reserve(tab)) return st;
+  uint64_t *d_found = ctx->d_par.as<uint64_t>();
+  if (int st = inflate_find_starts(ctx, d_src, src_len, cb, nch, d_found)) return st;
+  uint64_t *h_found = ctx->h_res.as<uint64_t>();
+  ZB_CUDA(ctx, cudaMemcpyAsync(h_found, d_found, (size_t)nch * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+  ZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  std::vector<uint64_t> start;
+  start.push_back(0);
+  for (uint32_t k = 1; k < nch; k++) if (h_found[k] != ~0ull && h_found[k] > start.back()) start.push_back(h_found[k]);
+  const uint32_t m = (uint32_t)start.size();
+  if (m < 2) return ZIPC_OK;
+  // 2. speculative decode: symbol buffers sized for a 24-fold expansion of every chunk
+  std::vector<uint64_t> spec_off(m), capv(m);
+  uint64_t spec_total = 0;
+  for (uint32_t k = 0; k < m; k++) {
+    const uint64_t stop = k + 1 < m ? start[k + 1] : 8ull * src_len;
+    const uint64_t bytes = (stop - start[k] + 7) / 8;
+    capv[k] = (24 * bytes + 65536 + 7) & ~7ull;
+    spec_off[k] = spec_total;
+    spec_total += capv[k];
+  }
+  if (spec_total > (6ull << 30)) return ZIPC_OK;  // 12 GiB of symbols: leave such streams to the serial path
+  if (int st = ctx->d_spec.reserve(spec_total * 2 + 64)) return st;
+  std::vector<InflateTask> tasks(m);
+  for (uint32_t k = 0; k < m; k++) {
+    InflateTask &t = tasks[k];
+    t.src = d_src; t.src_len = src_len;
+    t.dst = reinterpret_cast<uint8_t *>(ctx->d_spec.as<uint16_t>() + spec_off[k]);
+    t.dst_cap = capv[k]; t.flags = 0; t._pad = 0;
+    t.start_bit = start[k]; t.stop_bit = k + 1 < m ? start[k + 1] : ~0ull;
+  }
+  InflateTask *d_tasks = reinterpret_cast<InflateTask *>(ctx->d_par.as<uint64_t>() + 4 * (size_t)nch);
+  InflateResult *d_results = reinterpret_cast<InflateResult *>(d_tasks + nch);
+  ZB_CUDA(ctx, cudaMemcpyAsync(d_tasks, tasks.data(), m * sizeof(InflateTask), cudaMemcpyHostToDevice, ctx->stream));
+  if (int st = inflate_launch_spec(ctx, d_tasks, m, d_results)) return st;
+  InflateResult *h_results = reinterpret_cast<InflateResult *>(ctx->h_res.as<uint64_t>() + 4 * (size_t)nch);
+  ZB_CUDA(ctx, cudaMemcpyAsync(h_results, d_results, m * sizeof(InflateResult), cudaMemcpyDeviceToHost, ctx->stream));
+  ZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  // 3. the chunks must chain up exactly: each one ends, at a block boundary, where the next one was found to start
+  uint32_t used = 0;
+  for (uint32_t k = 0; k < m; k++) {
+    const InflateResult &r = h_results[k];
+    if (r.status != ZIPC_OK) return ZIPC_OK;
+    used = k + 1;
+    if (r.final_seen) break;  // the stream ends here (bytes after the final block are ignored, as in the reference)
+    if (k + 1 == m || r.end_bit != start[k + 1]) return ZIPC_OK;
+  }
+  if (!h_results[used - 1].final_seen) return ZIPC_OK;
+  plan.src = d_src; plan.src_len = src_len; plan.epoch = ctx->epoch;
+  plan.spec_off.assign(spec_off.begin(), spec_off.begin() + used);
+  plan.len.resize(used);
+  plan.total = 0;
+  for (uint32_t k = 0; k < used; k++) { plan.len[k] = h_results[k].out_len; plan.total += plan.len[k]; }
+  *ok = true;
+  return ZIPC_OK;
+}
+
+static int par_resolve(zipc_b200_ctx *ctx, uint8_t *d_dst, bool *ok) {
+  const zipc_b200_ctx::ParPlan &plan = ctx->par_plan;
+  const uint32_t m = (uint32_t)plan.len.size();
+  *ok = false;
+  std::vector<uint64_t> tab(3 * (size_t)m);
+  uint64_t off = 0;
+  for (uint32_t k = 0; k < m; k++) { tab[k] = plan.spec_off[k]; tab[m + k] = off; tab[2 * m + k] = plan.len[k]; off += plan.len[k]; }
+  if (int st = ctx->d_win.reserve((size_t)m * 32768 + 64)) return st;
+  uint64_t *d_tab = ctx->d_par.as<uint64_t>();  // (the chunk tables of the speculation are dead)
+  if (int st = ctx->d_small.reserve(256)) return st;
+  uint32_t *d_bad = ctx->d_small.as<uint32_t>() + 48;
+  ZB_CUDA(ctx, cudaMemcpyAsync(d_tab, tab.data(), tab.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+  ZB_CUDA(ctx, cudaMemsetAsync(d_bad, 0, sizeof(uint32_t), ctx->stream));
+  if (int st = inflate_resolve(ctx, ctx->d_spec.as<uint16_t>(), d_tab, d_tab + m, d_tab + 2 * m, m, ctx->d_win.as<uint8_t>(), d_dst, d_bad)) return st;
+  uint32_t bad = 1;
+  ZB_CUDA(ctx, cudaMemcpyAsync(&bad, d_bad, sizeof bad, cudaMemcpyDeviceToHost, ctx->stream));
+  ZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  *ok = bad == 0;
+  return ZIPC_OK;
+}
+
+// Core of every inflate entry point.  All pointers in d_src / d_dst are device addresses.
+// cap[i] == ZIPC_SIZE_UNKNOWN is only accepted in a count-only pass (the callers resolve sizes first).
+// Large streams are decoded in parallel inside the stream where that works out; everything else (and every stream whose
+// parallel decoding does not check out) goes to the warp-per-stream decoder.
+int inflate_core(zipc_b200_ctx *ctx, int ck, int adler_mode, size_t n, const std::vector<const uint8_t *> &d_src,
+                 const size_t *src_len, const std::vector<uint8_t *> &d_dst, const std::vector<size_t> &cap,
+                 bool count_only, size_t *out_len, uint32_t *checksum, int *status, uint32_t flags) {
+  std::vector<char> done(n, 0);
+  size_t ndone = 0;
+  if (flags == 0 && ck != ZIPC_CK_ADLER32 && par_min_bytes() != 0) {  // (Adler-32 is folded block by block: serial path)
+    for (size_t i = 0; i < n; i++) {
+      if (src_len[i] < par_min_bytes()) continue;
+      bool ok = false;
+      if (int st = par_speculate(ctx, d_src[i], src_len[i], &ok)) return st;
+      const uint64_t total = ctx->par_plan.total;
+      if (ok && cap[i] != ZIPC_SIZE_UNKNOWN && total > cap[i]) ok = false;  // the serial decoder reports the exact error
+      if (ok && !count_only) {
+        if (int st = par_resolve(ctx, d_dst[i], &ok)) return st;
+        if (ok && checksum) {
+          checksum[i] = 0;
+          if (ck == ZIPC_CK_CRC32) {
+            uint32_t *d_crc = ctx->d_small.as<uint32_t>() + 32;
+            if (int st = crc32_launch_buffer(ctx, d_dst[i], total, d_crc)) return st;
+            ZB_CUDA(ctx, cudaMemcpyAsync(&checksum[i], d_crc, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+            ZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+          }
+        }
+      }
+      if (ok) { done[i] = 1; ndone++; status[i] = ZIPC_OK; out_len[i] = (size_t)total; ctx->par_streams++; }
+      else ctx->par_fallbacks++;
+    }
+  }
+  if (ndone == 0) return inflate_serial_core(ctx, ck, adler_mode, n, d_src, src_len, d_dst, cap, count_only, out_len, checksum, status, flags);
+  if (ndone == n) return ZIPC_OK;
+  // the rest through the warp-per-stream decoder
+  const size_t r = n - ndone;
+  std::vector<const uint8_t *> s2(r);
+  std::vector<uint8_t *> d2(r);
+  std::vector<size_t> l2(r), c2(r), ol(r);
+  std::vector<uint32_t> ck2(r), idx(r);
+  std::vector<int> st2(r);
+  for (size_t i = 0, j = 0; i < n; i++) if (!done[i]) { idx[j] = (uint32_t)i; s2[j] = d_src[i]; d2[j] = d_dst[i]; l2[j] = src_len[i]; c2[j] = cap[i]; j++; }
+  if (int st = inflate_serial_core(ctx, ck, adler_mode, r, s2, l2.data(), d2, c2, count_only, ol.data(), checksum ? ck2.data() : nullptr, st2.data(), flags)) return st;
+  for (size_t j = 0; j < r; j++) { out_len[idx[j]] = ol[j]; status[idx[j]] = st2[j]; if (checksum) checksum[idx[j]] = ck2[j]; }
   return ZIPC_OK;
 }
 
@@ -350,6 +499,7 @@ void zipc_b200_ctx_destroy(zipc_b200_ctx *ctx) {
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   ctx->d_in.release(); ctx->d_out.release(); ctx->d_desc.release(); ctx->d_res.release();
   ctx->d_scratch.release(); ctx->d_scratch2.release(); ctx->d_small.release(); ctx->d_slots.release(); ctx->d_desc2.release(); ctx->d_blk.release();
+  ctx->d_par.release(); ctx->d_spec.release(); ctx->d_win.release(); ctx->d_adler.release();
   ctx->h_stage.release(); ctx->h_res.release(); ctx->h_desc.release();
   if (ctx->d_crc_tabs) cudaFree(ctx->d_crc_tabs);
   if (ctx->ev0) { cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); }
@@ -360,6 +510,10 @@ void zipc_b200_ctx_destroy(zipc_b200_ctx *ctx) {
 const char *zipc_b200_last_error(const zipc_b200_ctx *ctx) { return ctx ? ctx->last_error.c_str() : ""; }
 void *zipc_b200_ctx_stream(zipc_b200_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
 uint64_t zipc_b200_ctx_launches(const zipc_b200_ctx *ctx) { return ctx ? ctx->launches : 0; }
+uint64_t zipc_b200_ctx_counter(const zipc_b200_ctx *ctx, int which) {
+  if (!ctx) return 0;
+  return which == 0 ? ctx->launches : which == 1 ? ctx->par_streams : which == 2 ? ctx->par_fallbacks : 0;
+}
 void zipc_b200_ctx_profile(zipc_b200_ctx *ctx, int enable) {
   if (!ctx) return;
   DeviceGuard g(ctx->device);

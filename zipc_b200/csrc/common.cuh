@@ -69,12 +69,19 @@ struct InflateTask {  // one deflate stream to inflate
   uint64_t dst_cap;   // ?decompressed_size, or ~0ull when unknown (count-only pass)
   uint32_t flags;     // kInflateSegment: a piece of a segmented stream, ends where its input ends
   uint32_t _pad;
+  // speculative decoding of one chunk of a large stream (inflate_kernel<.., SPEC>): decoding starts at the block header at
+  // bit start_bit of the stream and stops at the first block boundary at or after stop_bit; dst holds 16-bit symbols
+  // (dst_cap counts symbols): a byte, or 0x8000 | w for "byte w of the 32 KiB that precede this chunk's output"
+  uint64_t start_bit, stop_bit;
 };
 constexpr uint32_t kInflateSegment = 1u;
 struct InflateResult {
   uint64_t out_len;
   uint32_t status;
   uint32_t _pad;      // fused Adler-32 of the output when the kernel was asked for it
+  uint64_t end_bit;   // (speculative chunks) stream bit position after the last block decoded
+  uint32_t final_seen; // (speculative chunks) that block had BFINAL set
+  uint32_t _pad2;
 };
 
 struct DeflateTask {  // one input to deflate (a ZIP member or an independent segment)
@@ -115,7 +122,22 @@ struct zipc_b200_ctx {
   uint32_t *d_crc_tabs = nullptr;   // see crc32.cu: strided[4][256] | std[4][256] | xp16[32]
   // work buffers (grow-only)
   zb::DevBuf d_in, d_out, d_desc, d_res, d_scratch, d_scratch2, d_small, d_slots, d_desc2, d_blk;
+  zb::DevBuf d_par, d_spec, d_win;   // intra-stream parallel inflate: chunk tables, speculative symbols, windows
   zb::PinBuf h_stage, h_res, h_desc;
+
+  // intra-stream parallel inflate: the plan of the last large stream decoded speculatively (a count-only pass is followed by
+  // the real pass over the same device bytes; `epoch` changes whenever new input is uploaded)
+  struct ParPlan {
+    const uint8_t *src = nullptr;
+    size_t src_len = 0;
+    uint64_t epoch = 0;
+    std::vector<uint64_t> spec_off, len;
+    uint64_t total = 0;
+  } par_plan;
+  uint64_t epoch = 1;
+  zb::DevBuf d_adler;                // adler32.cu: CTA partials + arrival counter of the RFC 1950 reduction
+  void *adler_ticket_at = nullptr;   // where the counter was last zeroed (the kernel resets it itself afterwards)
+  uint64_t par_streams = 0, par_fallbacks = 0;   // diagnostics: large streams decoded in parallel / handed back to the serial path
 
   // results of the last batch call kept for zipc_b200_fetch()
   std::vector<size_t> last_off, last_len;
@@ -186,5 +208,16 @@ int zip_assemble_impl(const zipc_b200_member *ms, size_t n, const char *first, v
 // inflate.cu
 int inflate_launch(zipc_b200_ctx *ctx, const InflateTask *d_tasks, uint32_t n, InflateResult *d_results,
                    bool count_only, int adler_mode /* -1: none */);
+// intra-stream parallel inflate (a large stream without an index): the three device steps; api.cu orchestrates
+// 1. for every chunk k >= 1 of `chunk_bytes` compressed bytes, the first bit position >= 8 * k * chunk_bytes at which a valid
+//    dynamic-Huffman block header starts (d_found[k], ~0 if none before the next chunk's own search range ends)
+int inflate_find_starts(zipc_b200_ctx *ctx, const uint8_t *d_src, uint64_t src_len, uint64_t chunk_bytes, uint32_t nchunks,
+                        uint64_t *d_found);
+// 2. speculative decode of the chunks (tasks carry start_bit / stop_bit, dst = 16-bit symbols)
+int inflate_launch_spec(zipc_b200_ctx *ctx, const InflateTask *d_tasks, uint32_t n, InflateResult *d_results);
+// 3. resolve: windows chunk by chunk, then every symbol to its byte.  d_spec_off / d_out_off / d_len: per chunk (device).
+//    *d_bad is set if chunk 0 refers to bytes before the stream
+int inflate_resolve(zipc_b200_ctx *ctx, const uint16_t *d_spec, const uint64_t *d_spec_off, const uint64_t *d_out_off,
+                    const uint64_t *d_len, uint32_t nchunks, uint8_t *d_windows, uint8_t *d_dst, uint32_t *d_bad);
 
 }  // namespace zb

@@ -35,6 +35,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
+#include <type_traits>
 
 #include "common.cuh"
 #include "adler_core.cuh"
@@ -340,8 +341,104 @@ __device__ __noinline__ uint32_t slow_token(const WarpWork &wk, const WarpTabs &
   return 0;
 }
 
+// ---- dynamic block header (reference :623-669): HLIT / HDIST / HCLEN, the code length code, the run-length coded lengths,
+// then both decoders.  Called right after the three block-type bits; every lane parses the header redundantly (uniform
+// control flow, broadcast reads of the ring).  Returns true if the header is not acceptable to the reference's decoder.
+__device__ bool read_dynamic_header(Input &in, WarpWork &wk, WarpTabs &mine, uint16_t *my_syms, const uint16_t *s_len_tab,
+                                    const uint32_t *s_dist_tab, int lane) {
+  WarpScratch &ws = wk.build;
+  // every lane parses the header redundantly (uniform control flow, broadcast reads of the ring)
+  uint32_t hlit = 257 + in.get(wk, 5, lane);
+  uint32_t hdist = 1 + in.get(wk, 5, lane);
+  uint32_t hclen = 4 + in.get(wk, 4, lane);
+  bool bad = hlit > 286 || hdist > 30;
+  // code length code lengths, 3 bits per symbol, packed by symbol
+  uint64_t clc = 0;
+  for (uint32_t i = 0; i < hclen; i++) clc |= (uint64_t)in.get(wk, 3, lane) << (3 * c_clen_order[i]);
+  if (in.overrun(wk)) bad = true;
+  // code-length decoder (7-bit table in the distance area, 8-bit entries: len << 5 | sym)
+  uint8_t *cl_lut = reinterpret_cast<uint8_t *>(mine.dist);
+  uint64_t next = 0;  // next code per length, 8 bits each
+  if (!bad) {
+    uint64_t cnt5 = 0;  // codes per length, 5 bits each (max 19)
+    int max_sym = -1;
+    for (int s = 0; s < 19; s++) {
+      uint32_t l = (uint32_t)(clc >> (3 * s)) & 7u;
+      if (l) { cnt5 += 1ull << (5 * l); max_sym = s; }
+    }
+    int available = 1, num_codes = 0, code = 0;
+    for (int l = 0; l < 8; l++) {
+      int used = l ? (int)((cnt5 >> (5 * l)) & 31u) : 0;
+      if (used > available) bad = true;
+      available = 2 * (available - used);
+      num_codes += used;
+      int prev_used = l > 1 ? (int)((cnt5 >> (5 * (l - 1))) & 31u) : 0;
+      code = l ? (code + prev_used) << 1 : 0;
+      next |= (uint64_t)(code & 0xff) << (8 * l);
+    }
+    if ((num_codes > 1 && available > 0) || (num_codes == 1 && ((cnt5 >> 5) & 31u) != 1) || max_sym == -1)
+      bad = true;
+  }
+  if (!bad) {
+    __syncwarp();
+    reinterpret_cast<uint32_t *>(cl_lut)[lane] = 0;
+    __syncwarp();
+    if (lane == 0) {
+      for (int s = 0; s < 19; s++) {
+        uint32_t l = (uint32_t)(clc >> (3 * s)) & 7u;
+        if (!l) continue;
+        uint32_t code = (uint32_t)(next >> (8 * l)) & 0xffu;
+        next += 1ull << (8 * l);
+        uint32_t rev = __brev(code) >> (32 - l);
+        for (uint32_t k = rev; k < 128; k += (1u << l)) cl_lut[k] = (uint8_t)((l << 5) | s);
+      }
+    }
+    __syncwarp();
+    // decode hlit + hdist code lengths straight into the build scratch
+    uint32_t num = 0, total = hlit + hdist, prev = 0;
+    while (num < total && !bad) {
+      in.ensure(wk, lane);
+      uint32_t w = in.peek32(wk);
+      uint32_t e = cl_lut[w & 127u];
+      if (!e) { bad = true; break; }
+      uint32_t used = e >> 5;
+      uint32_t sym = e & 31u, rep = 1, val = sym;
+      if (sym == 16) {
+        if (num == 0) { bad = true; break; }
+        rep = 3 + ((w >> used) & 3u); used += 2; val = prev;
+      } else if (sym == 17) { rep = 3 + ((w >> used) & 7u); used += 3; val = 0; }
+      else if (sym == 18) { rep = 11 + ((w >> used) & 127u); used += 7; val = 0; }
+      in.P += used;
+      if (rep > total - num) { bad = true; break; }
+      if (lane == 0)
+        for (uint32_t r = 0; r < rep; r++) ws.len[num + r] = (uint8_t)val;
+      num += rep;
+      prev = val;
+    }
+    if (in.overrun(wk)) bad = true;
+    __syncwarp();
+    if (!bad) {
+      for (uint32_t i = total + lane; i < 320; i += 32) ws.len[i] = 0;
+      if (lane == 0) ws.err = 0;
+      __syncwarp();
+      if (ws.len[256] == 0) bad = true;  // no end-of-block code (:662)
+      __syncwarp();
+      if (!bad) build_decoder_warp<false>(ws, 0, (int)hlit, LB, mine.lit, mine.lit_cnt, my_syms, s_len_tab, s_dist_tab, lane);
+      __syncwarp();
+      if (!bad && !ws.err) build_decoder_warp<true>(ws, (int)hlit, (int)hdist, DB, mine.dist, mine.dist_cnt, my_syms + 288, s_len_tab, s_dist_tab, lane);
+      __syncwarp();
+      if (ws.err) bad = true;
+    }
+  }
+  return bad;
+}
+
 // ---- the kernel ------------------------------------------------------------------------------------------
-template <bool COUNT_ONLY>
+// SPEC: speculative decoding of one chunk of a large stream (intra-stream parallel inflate).  The chunk starts at a block
+// header somewhere inside the stream, so the 32 KiB of output that precede it are unknown: the output is 16-bit symbols, a
+// byte or 0x8000 | w = "byte w of that unknown window" (copies of such symbols simply carry them along), resolved later by
+// resolve_kernel.  Decoding stops at the first block boundary at or after the task's stop_bit.
+template <bool COUNT_ONLY, bool SPEC>
 __global__ void __launch_bounds__(THREADS, 1)
 inflate_kernel(const InflateTask *__restrict__ tasks, uint32_t ntasks, InflateResult *__restrict__ results,
                unsigned int *__restrict__ queue, uint16_t *__restrict__ g_syms, int adler_mode) {
@@ -388,6 +485,8 @@ inflate_kernel(const InflateTask *__restrict__ tasks, uint32_t ntasks, InflateRe
   uint64_t stored_at = 0;     // stream offset of the stored block's bytes
   uint32_t ad_state = 1;      // running Adler-32 (reference :558, :682-690)
   bool ad_pending = false;    // a block just ended: fold [st.ad_from, out_pos)
+  uint64_t stop_bit = ~0ull;  // SPEC: finish at the first block boundary at or after this stream bit
+  typedef typename std::conditional<SPEC, uint16_t, uint8_t>::type elem_t;  // what one output symbol is
 
   for (;;) {
     // ---- A: pull work -----------------------------------------------------------------------------------
@@ -407,6 +506,7 @@ inflate_kernel(const InflateTask *__restrict__ tasks, uint32_t ntasks, InflateRe
       out_pos = 0; status = ZIPC_OK; final_blk = false;
       ad_state = 1; ad_pending = false;
       in.open(wk, lane);
+      if (SPEC) { in.seek_bits(wk, (uint64_t)st.skew + t.start_bit, lane); stop_bit = t.stop_bit; }
       state = S_HDR;
     }
 
@@ -437,89 +537,7 @@ inflate_kernel(const InflateTask *__restrict__ tasks, uint32_t ntasks, InflateRe
         use_fixed = true;
         state = S_DATA;
       } else if (type == 2) {
-        // every lane parses the header redundantly (uniform control flow, broadcast reads of the ring)
-        uint32_t hlit = 257 + in.get(wk, 5, lane);
-        uint32_t hdist = 1 + in.get(wk, 5, lane);
-        uint32_t hclen = 4 + in.get(wk, 4, lane);
-        bool bad = hlit > 286 || hdist > 30;
-        // code length code lengths, 3 bits per symbol, packed by symbol
-        uint64_t clc = 0;
-        for (uint32_t i = 0; i < hclen; i++) clc |= (uint64_t)in.get(wk, 3, lane) << (3 * c_clen_order[i]);
-        if (in.overrun(wk)) bad = true;
-        // code-length decoder (7-bit table in the distance area, 8-bit entries: len << 5 | sym)
-        uint8_t *cl_lut = reinterpret_cast<uint8_t *>(mine.dist);
-        uint64_t next = 0;  // next code per length, 8 bits each
-        if (!bad) {
-          uint64_t cnt5 = 0;  // codes per length, 5 bits each (max 19)
-          int max_sym = -1;
-          for (int s = 0; s < 19; s++) {
-            uint32_t l = (uint32_t)(clc >> (3 * s)) & 7u;
-            if (l) { cnt5 += 1ull << (5 * l); max_sym = s; }
-          }
-          int available = 1, num_codes = 0, code = 0;
-          for (int l = 0; l < 8; l++) {
-            int used = l ? (int)((cnt5 >> (5 * l)) & 31u) : 0;
-            if (used > available) bad = true;
-            available = 2 * (available - used);
-            num_codes += used;
-            int prev_used = l > 1 ? (int)((cnt5 >> (5 * (l - 1))) & 31u) : 0;
-            code = l ? (code + prev_used) << 1 : 0;
-            next |= (uint64_t)(code & 0xff) << (8 * l);
-          }
-          if ((num_codes > 1 && available > 0) || (num_codes == 1 && ((cnt5 >> 5) & 31u) != 1) || max_sym == -1)
-            bad = true;
-        }
-        if (!bad) {
-          __syncwarp();
-          reinterpret_cast<uint32_t *>(cl_lut)[lane] = 0;
-          __syncwarp();
-          if (lane == 0) {
-            for (int s = 0; s < 19; s++) {
-              uint32_t l = (uint32_t)(clc >> (3 * s)) & 7u;
-              if (!l) continue;
-              uint32_t code = (uint32_t)(next >> (8 * l)) & 0xffu;
-              next += 1ull << (8 * l);
-              uint32_t rev = __brev(code) >> (32 - l);
-              for (uint32_t k = rev; k < 128; k += (1u << l)) cl_lut[k] = (uint8_t)((l << 5) | s);
-            }
-          }
-          __syncwarp();
-          // decode hlit + hdist code lengths straight into the build scratch
-          uint32_t num = 0, total = hlit + hdist, prev = 0;
-          while (num < total && !bad) {
-            in.ensure(wk, lane);
-            uint32_t w = in.peek32(wk);
-            uint32_t e = cl_lut[w & 127u];
-            if (!e) { bad = true; break; }
-            uint32_t used = e >> 5;
-            uint32_t sym = e & 31u, rep = 1, val = sym;
-            if (sym == 16) {
-              if (num == 0) { bad = true; break; }
-              rep = 3 + ((w >> used) & 3u); used += 2; val = prev;
-            } else if (sym == 17) { rep = 3 + ((w >> used) & 7u); used += 3; val = 0; }
-            else if (sym == 18) { rep = 11 + ((w >> used) & 127u); used += 7; val = 0; }
-            in.P += used;
-            if (rep > total - num) { bad = true; break; }
-            if (lane == 0)
-              for (uint32_t r = 0; r < rep; r++) ws.len[num + r] = (uint8_t)val;
-            num += rep;
-            prev = val;
-          }
-          if (in.overrun(wk)) bad = true;
-          __syncwarp();
-          if (!bad) {
-            for (uint32_t i = total + lane; i < 320; i += 32) ws.len[i] = 0;
-            if (lane == 0) ws.err = 0;
-            __syncwarp();
-            if (ws.len[256] == 0) bad = true;  // no end-of-block code (:662)
-            __syncwarp();
-            if (!bad) build_decoder_warp<false>(ws, 0, (int)hlit, LB, mine.lit, mine.lit_cnt, my_syms, s_len_tab, s_dist_tab, lane);
-            __syncwarp();
-            if (!bad && !ws.err) build_decoder_warp<true>(ws, (int)hlit, (int)hdist, DB, mine.dist, mine.dist_cnt, my_syms + 288, s_len_tab, s_dist_tab, lane);
-            __syncwarp();
-            if (ws.err) bad = true;
-          }
-        }
+        const bool bad = read_dynamic_header(in, wk, mine, my_syms, s_len_tab, s_dist_tab, lane);
         if (bad) { status = ZIPC_ERR_CORRUPTED; state = S_FINISH; }
         else {
           use_fixed = false;
@@ -672,7 +690,8 @@ inflate_kernel(const InflateTask *__restrict__ tasks, uint32_t ntasks, InflateRe
         const uint32_t hist0 = out_pos < 32768 ? (uint32_t)out_pos : 32768u;
         const uint64_t room64 = st.out_cap - out_pos;
         const uint32_t room0 = room64 > 0x7FFFFFFFull ? 0x7FFFFFFFu : (uint32_t)room64;
-        const bool corrupt = have && ((mlen && mdist > min(hist0 + trel, 32768u)) || P0 + tend > st.limit);
+        // (SPEC: a distance may reach into the unknown window before the chunk; the format caps it at 32768)
+        const bool corrupt = have && ((!SPEC && mlen && mdist > min(hist0 + trel, 32768u)) || P0 + tend > st.limit);
         const bool exceed = have && trel + tlen > room0;
         const uint32_t fm = __ballot_sync(0xffffffffu, corrupt || exceed);
         if (fm) {
@@ -688,7 +707,10 @@ inflate_kernel(const InflateTask *__restrict__ tasks, uint32_t ntasks, InflateRe
       if (stop == 1 && state == S_DATA) {  // end of block
         in.P += eob_bits;
         if (in.overrun(wk)) { status = ZIPC_ERR_CORRUPTED; state = S_FINISH; }
-        else { state = final_blk ? S_FINISH : S_HDR; ad_pending = true; }
+        else {
+          state = final_blk ? S_FINISH : S_HDR; ad_pending = true;
+          if (SPEC && in.consumed(wk) >= stop_bit) state = S_FINISH;
+        }
       }
 
       // ---- E: execute the round's tokens -------------------------------------------------------------------
@@ -698,9 +720,23 @@ inflate_kernel(const InflateTask *__restrict__ tasks, uint32_t ntasks, InflateRe
         const uint32_t tlen = have ? (mlen ? mlen : 1u) : 0u;
         // a match is independent of this round when all of its source bytes precede the round
         const bool dep = mlen && mdist < trel + min(mdist, mlen);
-        uint8_t *const obase = dst + out_pos;
+        elem_t *const obase = reinterpret_cast<elem_t *>(dst) + out_pos;
+        // element q of a match whose output starts at round offset orel: from the output `odist` elements back (overlapping
+        // matches repeat their first odist elements), or -- SPEC only -- from the unknown window before the chunk
+        auto fetch = [&](uint32_t orel, uint32_t olen, uint32_t odist, uint32_t q) -> uint32_t {
+          const uint32_t qq = odist < olen ? q % odist : q;
+          unsigned int v;
+          if (SPEC) {
+            const int64_t sidx = (int64_t)(out_pos + orel + qq) - (int64_t)odist;
+            if (sidx < 0) return 0x8000u | (uint32_t)(32768 + sidx);
+            asm volatile("ld.global.cg.u16 %0, [%1];" : "=r"(v) : "l"(reinterpret_cast<const uint16_t *>(dst) + sidx) : "memory");
+          } else {
+            asm volatile("ld.global.cg.u8 %0, [%1];" : "=r"(v) : "l"(dst + out_pos + orel + qq - odist) : "memory");
+          }
+          return v;
+        };
         // E1: literals go straight out, one lane each (no loads involved)
-        if (have && !mlen) obase[trel] = (uint8_t)tx;
+        if (have && !mlen) obase[trel] = (elem_t)tx;
         // independent matches: their bytes flattened over the lanes
         const uint32_t li = (dep || !mlen) ? 0u : tlen;
         uint32_t incI = li;
@@ -717,8 +753,8 @@ inflate_kernel(const InflateTask *__restrict__ tasks, uint32_t ntasks, InflateRe
         uint32_t rbase = 0;  // independent tokens that end before the current window
         constexpr int kPasses = 4;  // loads of up to 128 bytes are in flight before the first store
         for (uint32_t base = 0; base < totalI; base += 32 * kPasses) {
-          uint8_t val[kPasses];
-          uint8_t *dq[kPasses];
+          uint32_t val[kPasses];
+          elem_t *dq[kPasses];
 #pragma unroll
           for (int u = 0; u < kPasses; u++) {
             const uint32_t wb = base + 32 * u;
@@ -733,20 +769,14 @@ inflate_kernel(const InflateTask *__restrict__ tasks, uint32_t ntasks, InflateRe
             const uint32_t ox = __shfl_sync(0xffffffffu, tx, own);
             const uint32_t orel = __shfl_sync(0xffffffffu, trel, own);
             const uint32_t q = b - __shfl_sync(0xffffffffu, istart, own);
-            uint8_t *dp = obase + orel;
             const uint32_t olen = ox >> 16, odist = ox & 0xFFFFu;
-            dq[u] = act ? dp + q : nullptr;
-            val[u] = (uint8_t)ox;
-            if (act && olen) {
-              const uint8_t *sp = dp - odist + (odist < olen ? q % odist : q);
-              unsigned int v;
-              asm volatile("ld.global.cg.u8 %0, [%1];" : "=r"(v) : "l"(sp) : "memory");
-              val[u] = (uint8_t)v;
-            }
+            dq[u] = act ? obase + orel + q : nullptr;
+            val[u] = ox & 0xFFu;
+            if (act && olen) val[u] = fetch(orel, olen, odist, q);
           }
 #pragma unroll
           for (int u = 0; u < kPasses; u++)
-            if (dq[u]) *dq[u] = val[u];
+            if (dq[u]) *dq[u] = (elem_t)val[u];
         }
         __syncwarp();
         // E2: matches that read bytes produced in this round, in token order
@@ -757,13 +787,7 @@ inflate_kernel(const InflateTask *__restrict__ tasks, uint32_t ntasks, InflateRe
           const uint32_t ox = __shfl_sync(0xffffffffu, tx, t);
           const uint32_t orel = __shfl_sync(0xffffffffu, trel, t);
           const uint32_t olen = ox >> 16, odist = ox & 0xFFFFu;
-          uint8_t *dp = obase + orel;
-          for (uint32_t q = lane; q < olen; q += 32) {
-            const uint8_t *sp = dp - odist + (odist < olen ? q % odist : q);
-            unsigned int v;
-            asm volatile("ld.global.cg.u8 %0, [%1];" : "=r"(v) : "l"(sp) : "memory");
-            dp[q] = (uint8_t)v;
-          }
+          for (uint32_t q = lane; q < olen; q += 32) obase[orel + q] = (elem_t)fetch(orel, olen, odist, q);
           __syncwarp();
         }
       }
@@ -773,13 +797,14 @@ inflate_kernel(const InflateTask *__restrict__ tasks, uint32_t ntasks, InflateRe
     // ---- stored block: one coalesced copy from the input (reference :678-680) ------------------------------------
     if (state == S_STORED) {
       if (!COUNT_ONLY) {
-        uint8_t *dp = dst + out_pos;
+        elem_t *dp = reinterpret_cast<elem_t *>(dst) + out_pos;
         const uint8_t *sp = st.src + stored_at;
         for (uint32_t i = lane; i < stored_len; i += 32) dp[i] = sp[i];
         __syncwarp();
       }
       out_pos += stored_len;
       state = final_blk ? S_FINISH : S_HDR;
+      if (SPEC && in.consumed(wk) >= stop_bit) state = S_FINISH;
       ad_pending = true;
     }
 
@@ -787,7 +812,7 @@ inflate_kernel(const InflateTask *__restrict__ tasks, uint32_t ntasks, InflateRe
     // Adler-32 restarts its 5552-byte chunk grid at every block and, as written in the reference, reduces
     // with a signed remainder, so it has to be folded block by block to stay bit-exact.
     if (ad_pending) {
-      if (!COUNT_ONLY && adler_mode >= 0) {
+      if (!COUNT_ONLY && !SPEC && adler_mode >= 0) {
         __syncwarp();
         ad_state = adler_update_warp<true>(ad_state, dst + st.ad_from, out_pos - st.ad_from, adler_mode, lane);
         ad_state = __shfl_sync(0xffffffffu, ad_state, 0);
@@ -805,10 +830,128 @@ inflate_kernel(const InflateTask *__restrict__ tasks, uint32_t ntasks, InflateRe
         r.out_len = status == ZIPC_OK ? out_pos : 0;
         r.status = status;
         r._pad = status == ZIPC_OK ? ad_state : 0;  // fused Adler-32 of the output (when requested)
+        r.end_bit = in.consumed(wk);
+        r.final_seen = final_blk ? 1u : 0u;
+        r._pad2 = 0;
         results[task] = r;
       }
       state = S_IDLE;
     }
+  }
+}
+
+// ---- intra-stream parallel inflate: where do blocks start? -----------------------------------------------------------------
+// A deflate stream has no index, but a dynamic-Huffman block header is so constrained (HLIT / HDIST ranges, a complete
+// code-length code, run-length coded lengths that fit exactly, an end-of-block code, complete literal/length and distance
+// codes) that scanning for a bit position where a valid one starts finds real block starts with next to no false positives
+// (the approach of pugz / rapidgzip).  One warp per chunk k >= 1 scans [8 k chunk_bytes, 8 (k + 1) chunk_bytes): the lanes
+// test 32 consecutive bit offsets with a cheap filter (block type, HLIT, HDIST, Kraft sum of the code-length code); offsets
+// that pass are validated by the decoder's own header reader, in order, and the first valid one is reported.  A wrong
+// guess is caught later: the chunk before it must END exactly there, or the caller falls back to serial decoding.
+// Stored and fixed blocks are not looked for (their headers say too little); the previous chunk just runs through them.
+__global__ void __launch_bounds__(THREADS, 1)
+find_starts_kernel(const uint8_t *__restrict__ src, uint64_t src_len, uint64_t chunk_bytes, uint32_t nchunks,
+                   uint64_t *__restrict__ found, uint16_t *__restrict__ g_syms) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  WarpTabs *tabs = reinterpret_cast<WarpTabs *>(smem_raw);
+  WarpWork *works = reinterpret_cast<WarpWork *>(tabs + WARPS + 1);
+  uint16_t *s_len_tab = reinterpret_cast<uint16_t *>(works + WARPS);
+  uint32_t *s_dist_tab = reinterpret_cast<uint32_t *>(s_len_tab + 32);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x < 29) s_len_tab[threadIdx.x] = c_len_tab[threadIdx.x];
+  if (threadIdx.x < 30) s_dist_tab[threadIdx.x] = c_dist_tab[threadIdx.x];
+  __syncthreads();
+  WarpTabs &mine = tabs[warp];
+  WarpWork &wk = works[warp];
+  uint16_t *my_syms = g_syms + (size_t)(blockIdx.x * WARPS + warp) * SYMS_PER_SLOT;
+  for (uint32_t k = 1 + blockIdx.x * WARPS + warp; k < nchunks; k += gridDim.x * WARPS) {
+    __syncwarp();
+    if (lane == 0) { wk.st.src = src; wk.st.src_len = src_len; wk.st.out_cap = 0; wk.st.ad_from = 0; }
+    Input in{};
+    in.open(wk, lane);
+    const uint64_t skew = wk.st.skew, limit = wk.st.limit;
+    const uint64_t beg = skew + 8 * (uint64_t)k * chunk_bytes;
+    uint64_t end = beg + 8 * chunk_bytes;
+    if (end > limit) end = limit;
+    uint64_t hit = ~0ull;
+    in.seek_bits(wk, beg, lane);
+    for (uint64_t base = beg; base < end && hit == ~0ull; base += 32) {
+      if ((uint32_t)(base >> 5) < in.w0) in.seek_bits(wk, base, lane);  // a header parse moved the ring on
+      in.P = base;
+      in.ensure(wk, lane);
+      // cheap filter at offset base + lane: 17 bits of block header + up to 19 three-bit code-length code lengths
+      const uint64_t pos = base + lane;
+      bool ok = pos < end && pos + 17 + 57 <= limit;
+      const uint32_t w0 = Input::peek32_at(wk, pos), w1 = Input::peek32_at(wk, pos + 32), w2 = Input::peek32_at(wk, pos + 64);
+      ok = ok && (w0 & 7u) == 4u;                                        // BFINAL 0, BTYPE 2
+      ok = ok && ((w0 >> 3) & 31u) <= 29u && ((w0 >> 8) & 31u) <= 29u;   // HLIT <= 286, HDIST <= 30
+      if (ok) {
+        const uint32_t hclen = 4 + ((w0 >> 13) & 15u);
+        const unsigned long long cl = (unsigned long long)(w0 >> 17) | ((unsigned long long)w1 << 15) | ((unsigned long long)w2 << 47);
+        uint32_t kraft = 0;
+        for (uint32_t i = 0; i < hclen; i++) {
+          const uint32_t l = (uint32_t)(cl >> (3 * i)) & 7u;
+          kraft += l ? 128u >> l : 0u;
+        }
+        ok = kraft == 128u;                                              // a complete code over the code lengths
+      }
+      uint32_t surv = __ballot_sync(0xffffffffu, ok);
+      while (surv) {  // full validation by the decoder's own header reader, in stream order
+        const int l = __ffs((int)surv) - 1;
+        surv &= surv - 1;
+        const uint64_t cand = base + l;
+        if ((uint32_t)(cand >> 5) < in.w0) in.seek_bits(wk, cand, lane);
+        in.P = cand + 3;
+        if (!read_dynamic_header(in, wk, mine, my_syms, s_len_tab, s_dist_tab, lane)) { hit = cand; break; }
+      }
+    }
+    if (lane == 0) found[k] = hit == ~0ull ? ~0ull : hit - skew;
+  }
+}
+
+// ---- resolve the speculative symbols ------------------------------------------------------------------------------------------
+// windows[k] = the 32 KiB of output before chunk k.  One CTA walks the chunks in order: window k + 1 is the last 32 KiB of
+// (window k followed by chunk k's symbols resolved against window k).
+__global__ void __launch_bounds__(1024, 1)
+window_chain_kernel(const uint16_t *__restrict__ spec, const uint64_t *__restrict__ spec_off, const uint64_t *__restrict__ len,
+                    uint32_t nchunks, uint8_t *__restrict__ windows, uint32_t *__restrict__ bad) {
+  for (uint32_t i = threadIdx.x; i < 32768; i += 1024) windows[i] = 0;  // nothing precedes the stream
+  __syncthreads();
+  for (uint32_t k = 0; k + 1 < nchunks; k++) {
+    const uint8_t *W = windows + (size_t)k * 32768;
+    uint8_t *N = windows + (size_t)(k + 1) * 32768;
+    const uint64_t n = len[k];
+    const uint16_t *s = spec + spec_off[k];
+    for (uint32_t j = threadIdx.x; j < 32768; j += 1024) {
+      uint8_t b;
+      if (n >= 32768) {
+        const uint32_t e = s[n - 32768 + j];
+        if (e & 0x8000u) { b = W[e & 0x7FFFu]; if (k == 0) *bad = 1; } else b = (uint8_t)e;
+      } else if (j < 32768 - n) {
+        b = W[j + n];
+      } else {
+        const uint32_t e = s[j - (32768 - n)];
+        if (e & 0x8000u) { b = W[e & 0x7FFFu]; if (k == 0) *bad = 1; } else b = (uint8_t)e;
+      }
+      N[j] = b;
+    }
+    __threadfence_block();
+    __syncthreads();
+  }
+}
+
+// every symbol of every chunk to its byte (blockIdx.y = chunk)
+__global__ void __launch_bounds__(256)
+resolve_kernel(const uint16_t *__restrict__ spec, const uint64_t *__restrict__ spec_off, const uint64_t *__restrict__ out_off,
+               const uint64_t *__restrict__ len, const uint8_t *__restrict__ windows, uint8_t *__restrict__ dst, uint32_t *__restrict__ bad) {
+  const uint32_t k = blockIdx.y;
+  const uint64_t n = len[k];
+  const uint16_t *s = spec + spec_off[k];
+  const uint8_t *W = windows + (size_t)k * 32768;
+  uint8_t *o = dst + out_off[k];
+  for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t v = s[e];
+    if (v & 0x8000u) { o[e] = W[v & 0x7FFFu]; if (k == 0) *bad = 1; } else o[e] = (uint8_t)v;
   }
 }
 
@@ -820,8 +963,10 @@ int inflate_launch(zipc_b200_ctx *ctx, const InflateTask *d_tasks, uint32_t n, I
                    bool count_only, int adler_mode) {
   if (n == 0) return ZIPC_OK;
   if (!(g_attr_devs >> (ctx->device & 63) & 1ull)) {
-    ZB_CUDA(ctx, cudaFuncSetAttribute(inflate_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-    ZB_CUDA(ctx, cudaFuncSetAttribute(inflate_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+    ZB_CUDA(ctx, cudaFuncSetAttribute(inflate_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+    ZB_CUDA(ctx, cudaFuncSetAttribute(inflate_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+    ZB_CUDA(ctx, cudaFuncSetAttribute(inflate_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+    ZB_CUDA(ctx, cudaFuncSetAttribute(find_starts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
     g_attr_devs |= 1ull << (ctx->device & 63);
   }
   // one warp per stream; spread the streams over all SMs first
@@ -836,9 +981,57 @@ int inflate_launch(zipc_b200_ctx *ctx, const InflateTask *d_tasks, uint32_t n, I
   }
   KernelTimer kt(ctx);
   if (count_only)
-    inflate_kernel<true><<<grid, THREADS, kSmemBytes, ctx->stream>>>(d_tasks, n, d_results, queue, ctx->d_scratch.as<uint16_t>(), -1);
+    inflate_kernel<true, false><<<grid, THREADS, kSmemBytes, ctx->stream>>>(d_tasks, n, d_results, queue, ctx->d_scratch.as<uint16_t>(), -1);
   else
-    inflate_kernel<false><<<grid, THREADS, kSmemBytes, ctx->stream>>>(d_tasks, n, d_results, queue, ctx->d_scratch.as<uint16_t>(), adler_mode);
+    inflate_kernel<false, false><<<grid, THREADS, kSmemBytes, ctx->stream>>>(d_tasks, n, d_results, queue, ctx->d_scratch.as<uint16_t>(), adler_mode);
+  ctx->launches++;
+  ZB_CUDA(ctx, cudaGetLastError());
+  return ZIPC_OK;
+}
+
+int inflate_find_starts(zipc_b200_ctx *ctx, const uint8_t *d_src, uint64_t src_len, uint64_t chunk_bytes, uint32_t nchunks,
+                        uint64_t *d_found) {
+  if (!(g_attr_devs >> (ctx->device & 63) & 1ull)) {
+    ZB_CUDA(ctx, cudaFuncSetAttribute(inflate_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+    ZB_CUDA(ctx, cudaFuncSetAttribute(inflate_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+    ZB_CUDA(ctx, cudaFuncSetAttribute(inflate_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+    ZB_CUDA(ctx, cudaFuncSetAttribute(find_starts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+    g_attr_devs |= 1ull << (ctx->device & 63);
+  }
+  uint32_t grid = (nchunks + WARPS - 1) / WARPS;
+  if (grid > (uint32_t)ctx->sm_count) grid = (uint32_t)ctx->sm_count;
+  if (grid == 0) grid = 1;
+  size_t sym_bytes = (size_t)(grid * WARPS + grid) * SYMS_PER_SLOT * sizeof(uint16_t);
+  if (int st = ctx->d_scratch.reserve(sym_bytes + 256 + 4096)) return st;
+  find_starts_kernel<<<grid, THREADS, kSmemBytes, ctx->stream>>>(d_src, src_len, chunk_bytes, nchunks, d_found, ctx->d_scratch.as<uint16_t>());
+  ctx->launches++;
+  ZB_CUDA(ctx, cudaGetLastError());
+  return ZIPC_OK;
+}
+
+int inflate_launch_spec(zipc_b200_ctx *ctx, const InflateTask *d_tasks, uint32_t n, InflateResult *d_results) {
+  if (n == 0) return ZIPC_OK;
+  uint32_t grid = (n + WARPS - 1) / WARPS;   // spread the chunks: one warp each
+  if (grid > (uint32_t)ctx->sm_count) grid = (uint32_t)ctx->sm_count;
+  size_t sym_bytes = (size_t)(grid * WARPS + grid) * SYMS_PER_SLOT * sizeof(uint16_t);
+  if (int st = ctx->d_scratch.reserve(sym_bytes + 256 + 4096)) return st;
+  unsigned int *queue = reinterpret_cast<unsigned int *>(ctx->d_scratch.as<uint8_t>() + sym_bytes);
+  unsigned int start = grid * WARPS;  // tasks [0, start) are assigned statically
+  ZB_CUDA(ctx, cudaMemcpyAsync(queue, &start, sizeof start, cudaMemcpyHostToDevice, ctx->stream));
+  KernelTimer kt(ctx);
+  inflate_kernel<false, true><<<grid, THREADS, kSmemBytes, ctx->stream>>>(d_tasks, n, d_results, queue, ctx->d_scratch.as<uint16_t>(), -1);
+  ctx->launches++;
+  ZB_CUDA(ctx, cudaGetLastError());
+  return ZIPC_OK;
+}
+
+int inflate_resolve(zipc_b200_ctx *ctx, const uint16_t *d_spec, const uint64_t *d_spec_off, const uint64_t *d_out_off,
+                    const uint64_t *d_len, uint32_t nchunks, uint8_t *d_windows, uint8_t *d_dst, uint32_t *d_bad) {
+  if (!nchunks) return ZIPC_OK;
+  window_chain_kernel<<<1, 1024, 0, ctx->stream>>>(d_spec, d_spec_off, d_len, nchunks, d_windows, d_bad);
+  ctx->launches++;
+  dim3 grid((unsigned)std::max(1, ctx->sm_count * 8 / (int)std::min<uint32_t>(nchunks, 64u)), nchunks);
+  resolve_kernel<<<grid, 256, 0, ctx->stream>>>(d_spec, d_spec_off, d_out_off, d_len, d_windows, d_dst, d_bad);
   ctx->launches++;
   ZB_CUDA(ctx, cudaGetLastError());
   return ZIPC_OK;

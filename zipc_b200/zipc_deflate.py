@@ -135,6 +135,11 @@ class Context:
     def stream(self) -> int:
         return self.L.zipc_b200_ctx_stream(self.h) or 0
 
+    @property
+    def parallel_streams(self) -> tuple[int, int]:
+        """(large streams inflated in parallel inside the stream, large streams handed back to the one-warp decoder)"""
+        return self.L.zipc_b200_ctx_counter(self.h, 1), self.L.zipc_b200_ctx_counter(self.h, 2)
+
     @staticmethod
     def _ptr_arrays(items: Sequence[np.ndarray]):
         n = len(items)
