@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <numeric>
 
 #include "common.cuh"
@@ -310,11 +311,15 @@ static uint64_t env_u64(const char *name, uint64_t dflt) {
   return (v && *v) ? std::strtoull(v, nullptr, 10) : dflt;
 }
 // tuning knobs (read on every call, so that tests can vary them): compressed bytes per chunk; smallest stream that is tried
-static uint64_t par_chunk_bytes() { return std::max<uint64_t>(4096, env_u64("ZIPC_B200_PAR_CHUNK", 32768)); }
+static uint64_t par_chunk_bytes() { return std::max<uint64_t>(4096, env_u64("ZIPC_B200_PAR_CHUNK", 8192)); }
 static uint64_t par_min_bytes() { return env_u64("ZIPC_B200_PAR_MIN", 262144); }
+
+static bool par_debug() { static const bool v = env_u64("ZIPC_B200_PAR_DEBUG", 0) != 0; return v; }
+static double now_ms() { timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec * 1e3 + t.tv_nsec / 1e6; }
 
 static int par_speculate(zipc_b200_ctx *ctx, const uint8_t *d_src, size_t src_len, bool *ok) {
   *ok = false;
+  const double t_begin = par_debug() ? (cudaStreamSynchronize(ctx->stream), now_ms()) : 0;
   zipc_b200_ctx::ParPlan &plan = ctx->par_plan;
   if (plan.src == d_src && plan.src_len == src_len && plan.epoch == ctx->epoch && !plan.len.empty()) { *ok = true; return ZIPC_OK; }
   plan.len.clear(); plan.spec_off.clear(); plan.total = 0;
@@ -330,6 +335,7 @@ static int par_speculate(zipc_b200_ctx *ctx, const uint8_t *d_src, size_t src_le
   uint64_t *h_found = ctx->h_res.as<uint64_t>();
   ZB_CUDA(ctx, cudaMemcpyAsync(h_found, d_found, (size_t)nch * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
   ZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  const double t_found = par_debug() ? now_ms() : 0;
   std::vector<uint64_t> start;
   start.push_back(0);
   for (uint32_t k = 1; k < nch; k++) if (h_found[k] != ~0ull && h_found[k] > start.back()) start.push_back(h_found[k]);
@@ -362,6 +368,9 @@ static int par_speculate(zipc_b200_ctx *ctx, const uint8_t *d_src, size_t src_le
   InflateResult *h_results = reinterpret_cast<InflateResult *>(ctx->h_res.as<uint64_t>() + 4 * (size_t)nch);
   ZB_CUDA(ctx, cudaMemcpyAsync(h_results, d_results, m * sizeof(InflateResult), cudaMemcpyDeviceToHost, ctx->stream));
   ZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (par_debug())
+    std::fprintf(stderr, "[par] %zu bytes, %u nominal chunks, %u block starts: find %.2f ms, speculative decode %.2f ms\n", src_len, nch, m,
+                 t_found - t_begin, now_ms() - t_found);
   // 3. the chunks must chain up exactly: each one ends, at a block boundary, where the next one was found to start
   uint32_t used = 0;
   for (uint32_t k = 0; k < m; k++) {
@@ -385,10 +394,11 @@ static int par_resolve(zipc_b200_ctx *ctx, uint8_t *d_dst, bool *ok) {
   const zipc_b200_ctx::ParPlan &plan = ctx->par_plan;
   const uint32_t m = (uint32_t)plan.len.size();
   *ok = false;
+  const double t_begin = par_debug() ? (cudaStreamSynchronize(ctx->stream), now_ms()) : 0;
   std::vector<uint64_t> tab(3 * (size_t)m);
   uint64_t off = 0;
   for (uint32_t k = 0; k < m; k++) { tab[k] = plan.spec_off[k]; tab[m + k] = off; tab[2 * m + k] = plan.len[k]; off += plan.len[k]; }
-  if (int st = ctx->d_win.reserve((size_t)m * 32768 + 64)) return st;
+  if (int st = ctx->d_win.reserve((size_t)m * 32768 * 2 * 2 + 64)) return st;  // two arrays of 16-bit window maps
   uint64_t *d_tab = ctx->d_par.as<uint64_t>();  // (the chunk tables of the speculation are dead)
   if (int st = ctx->d_small.reserve(256)) return st;
   uint32_t *d_bad = ctx->d_small.as<uint32_t>() + 48;
@@ -399,6 +409,7 @@ static int par_resolve(zipc_b200_ctx *ctx, uint8_t *d_dst, bool *ok) {
   ZB_CUDA(ctx, cudaMemcpyAsync(&bad, d_bad, sizeof bad, cudaMemcpyDeviceToHost, ctx->stream));
   ZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   *ok = bad == 0;
+  if (par_debug()) std::fprintf(stderr, "[par] resolve of %u chunks (%llu bytes): %.2f ms\n", m, (unsigned long long)plan.total, now_ms() - t_begin);
   return ZIPC_OK;
 }
 
@@ -685,6 +696,7 @@ int zipc_b200_inflate_batch_dev(zipc_b200_ctx *ctx, int ck, int adler_mode, size
     return ZIPC_ERR_INVALID_ARG;
   if (!n) return ZIPC_OK;
   DeviceGuard g(ctx->device);
+  ctx->epoch++;  // the caller's device bytes may have changed since the last call
   std::vector<const uint8_t *> d_src(n);
   std::vector<uint8_t *> d_dst(n);
   std::vector<size_t> cap(n);

@@ -216,7 +216,7 @@ int inflate_find_starts(zipc_b200_ctx *ctx, const uint8_t *d_src, uint64_t src_l
 // 2. speculative decode of the chunks (tasks carry start_bit / stop_bit, dst = 16-bit symbols)
 int inflate_launch_spec(zipc_b200_ctx *ctx, const InflateTask *d_tasks, uint32_t n, InflateResult *d_results);
 // 3. resolve: windows chunk by chunk, then every symbol to its byte.  d_spec_off / d_out_off / d_len: per chunk (device).
-//    *d_bad is set if chunk 0 refers to bytes before the stream
+//    d_windows: 4 * 32768 bytes per chunk of scratch.  *d_bad is set if anything refers to bytes before the stream
 int inflate_resolve(zipc_b200_ctx *ctx, const uint16_t *d_spec, const uint64_t *d_spec_off, const uint64_t *d_out_off,
                     const uint64_t *d_len, uint32_t nchunks, uint8_t *d_windows, uint8_t *d_dst, uint32_t *d_bad);
 

@@ -858,8 +858,15 @@ find_starts_kernel(const uint8_t *__restrict__ src, uint64_t src_len, uint64_t c
   uint16_t *s_len_tab = reinterpret_cast<uint16_t *>(works + WARPS);
   uint32_t *s_dist_tab = reinterpret_cast<uint32_t *>(s_len_tab + 32);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // Kraft weight (in 1/128) of three 3-bit code lengths at once: the fixed-Huffman slot of the table area is unused here
+  uint8_t *kraft3 = reinterpret_cast<uint8_t *>(&tabs[WARPS]);
   if (threadIdx.x < 29) s_len_tab[threadIdx.x] = c_len_tab[threadIdx.x];
   if (threadIdx.x < 30) s_dist_tab[threadIdx.x] = c_dist_tab[threadIdx.x];
+  if (threadIdx.x < 512) {
+    uint32_t w = 0;
+    for (int f = 0; f < 3; f++) { const uint32_t l = (threadIdx.x >> (3 * f)) & 7u; w += l ? 128u >> l : 0u; }
+    kraft3[threadIdx.x] = (uint8_t)w;   // <= 3 * 64
+  }
   __syncthreads();
   WarpTabs &mine = tabs[warp];
   WarpWork &wk = works[warp];
@@ -887,12 +894,11 @@ find_starts_kernel(const uint8_t *__restrict__ src, uint64_t src_len, uint64_t c
       ok = ok && ((w0 >> 3) & 31u) <= 29u && ((w0 >> 8) & 31u) <= 29u;   // HLIT <= 286, HDIST <= 30
       if (ok) {
         const uint32_t hclen = 4 + ((w0 >> 13) & 15u);
-        const unsigned long long cl = (unsigned long long)(w0 >> 17) | ((unsigned long long)w1 << 15) | ((unsigned long long)w2 << 47);
+        unsigned long long cl = (unsigned long long)(w0 >> 17) | ((unsigned long long)w1 << 15) | ((unsigned long long)w2 << 47);
+        cl &= ~0ull >> (64 - 3 * hclen);                                 // the lengths that are there (12 .. 57 bits)
         uint32_t kraft = 0;
-        for (uint32_t i = 0; i < hclen; i++) {
-          const uint32_t l = (uint32_t)(cl >> (3 * i)) & 7u;
-          kraft += l ? 128u >> l : 0u;
-        }
+#pragma unroll
+        for (int g = 0; g < 7; g++) kraft += kraft3[(uint32_t)(cl >> (9 * g)) & 511u];
         ok = kraft == 128u;                                              // a complete code over the code lengths
       }
       uint32_t surv = __ballot_sync(0xffffffffu, ok);
@@ -910,48 +916,50 @@ find_starts_kernel(const uint8_t *__restrict__ src, uint64_t src_len, uint64_t c
 }
 
 // ---- resolve the speculative symbols ------------------------------------------------------------------------------------------
-// windows[k] = the 32 KiB of output before chunk k.  One CTA walks the chunks in order: window k + 1 is the last 32 KiB of
-// (window k followed by chunk k's symbols resolved against window k).
-__global__ void __launch_bounds__(1024, 1)
-window_chain_kernel(const uint16_t *__restrict__ spec, const uint64_t *__restrict__ spec_off, const uint64_t *__restrict__ len,
-                    uint32_t nchunks, uint8_t *__restrict__ windows, uint32_t *__restrict__ bad) {
-  for (uint32_t i = threadIdx.x; i < 32768; i += 1024) windows[i] = 0;  // nothing precedes the stream
-  __syncthreads();
-  for (uint32_t k = 0; k + 1 < nchunks; k++) {
-    const uint8_t *W = windows + (size_t)k * 32768;
-    uint8_t *N = windows + (size_t)(k + 1) * 32768;
-    const uint64_t n = len[k];
-    const uint16_t *s = spec + spec_off[k];
-    for (uint32_t j = threadIdx.x; j < 32768; j += 1024) {
-      uint8_t b;
-      if (n >= 32768) {
-        const uint32_t e = s[n - 32768 + j];
-        if (e & 0x8000u) { b = W[e & 0x7FFFu]; if (k == 0) *bad = 1; } else b = (uint8_t)e;
-      } else if (j < 32768 - n) {
-        b = W[j + n];
-      } else {
-        const uint32_t e = s[j - (32768 - n)];
-        if (e & 0x8000u) { b = W[e & 0x7FFFu]; if (k == 0) *bad = 1; } else b = (uint8_t)e;
-      }
-      N[j] = b;
-    }
-    __threadfence_block();
-    __syncthreads();
-  }
-}
-
-// every symbol of every chunk to its byte (blockIdx.y = chunk)
+// Chunk k turns the 32 KiB before it (window k) into the 32 KiB after it (window k + 1): entry j of that map is a byte, or
+// "entry w of window k".  Such maps compose associatively, so the windows of all chunks come out of a parallel prefix over
+// the chunks (log2(chunks) rounds of pointer doubling, every round all chunks at once) instead of a walk chunk by chunk.
+// map[k][j], 16 bits each; after the last round map[k] IS window k + 1 (a marker left over would refer to bytes before the
+// stream: corrupt).
 __global__ void __launch_bounds__(256)
-resolve_kernel(const uint16_t *__restrict__ spec, const uint64_t *__restrict__ spec_off, const uint64_t *__restrict__ out_off,
-               const uint64_t *__restrict__ len, const uint8_t *__restrict__ windows, uint8_t *__restrict__ dst, uint32_t *__restrict__ bad) {
+win_init_kernel(const uint16_t *__restrict__ spec, const uint64_t *__restrict__ spec_off, const uint64_t *__restrict__ len,
+                uint16_t *__restrict__ map) {
   const uint32_t k = blockIdx.y;
   const uint64_t n = len[k];
   const uint16_t *s = spec + spec_off[k];
-  const uint8_t *W = windows + (size_t)k * 32768;
+  uint16_t *m = map + (size_t)k * 32768;
+  for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < 32768; j += gridDim.x * blockDim.x)
+    m[j] = n >= 32768 ? s[n - 32768 + j] : (j < 32768 - n ? (uint16_t)(0x8000u | (j + (uint32_t)n)) : s[j - (32768 - (uint32_t)n)]);
+}
+__global__ void __launch_bounds__(256)
+win_round_kernel(const uint16_t *__restrict__ in, uint16_t *__restrict__ out, uint32_t stride) {
+  const uint32_t k = blockIdx.y;
+  const uint16_t *m = in + (size_t)k * 32768;
+  const uint16_t *prev = k >= stride ? in + (size_t)(k - stride) * 32768 : nullptr;
+  uint16_t *o = out + (size_t)k * 32768;
+  for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < 32768; j += gridDim.x * blockDim.x) {
+    uint16_t v = m[j];
+    if ((v & 0x8000u) && prev) v = prev[v & 0x7FFFu];
+    o[j] = v;
+  }
+}
+
+// every symbol of every chunk to its byte (blockIdx.y = chunk); window k = map[k - 1]
+__global__ void __launch_bounds__(256)
+resolve_kernel(const uint16_t *__restrict__ spec, const uint64_t *__restrict__ spec_off, const uint64_t *__restrict__ out_off,
+               const uint64_t *__restrict__ len, const uint16_t *__restrict__ map, uint8_t *__restrict__ dst, uint32_t *__restrict__ bad) {
+  const uint32_t k = blockIdx.y;
+  const uint64_t n = len[k];
+  const uint16_t *s = spec + spec_off[k];
+  const uint16_t *W = k ? map + (size_t)(k - 1) * 32768 : nullptr;
   uint8_t *o = dst + out_off[k];
   for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (uint64_t)gridDim.x * blockDim.x) {
-    const uint32_t v = s[e];
-    if (v & 0x8000u) { o[e] = W[v & 0x7FFFu]; if (k == 0) *bad = 1; } else o[e] = (uint8_t)v;
+    uint32_t v = s[e];
+    if (v & 0x8000u) {
+      v = W ? W[v & 0x7FFFu] : 0x8000u;
+      if (v & 0x8000u) { *bad = 1; v = 0; }   // a reference to bytes before the stream
+    }
+    o[e] = (uint8_t)v;
   }
 }
 
@@ -1028,10 +1036,18 @@ int inflate_launch_spec(zipc_b200_ctx *ctx, const InflateTask *d_tasks, uint32_t
 int inflate_resolve(zipc_b200_ctx *ctx, const uint16_t *d_spec, const uint64_t *d_spec_off, const uint64_t *d_out_off,
                     const uint64_t *d_len, uint32_t nchunks, uint8_t *d_windows, uint8_t *d_dst, uint32_t *d_bad) {
   if (!nchunks) return ZIPC_OK;
-  window_chain_kernel<<<1, 1024, 0, ctx->stream>>>(d_spec, d_spec_off, d_len, nchunks, d_windows, d_bad);
+  // d_windows: two map arrays of nchunks * 32768 16-bit entries (ping-pong of the doubling rounds)
+  uint16_t *a = reinterpret_cast<uint16_t *>(d_windows), *b = a + (size_t)nchunks * 32768;
+  const dim3 wgrid(8, nchunks);
+  win_init_kernel<<<wgrid, 256, 0, ctx->stream>>>(d_spec, d_spec_off, d_len, a);
   ctx->launches++;
+  for (uint32_t stride = 1; stride < nchunks; stride <<= 1) {
+    win_round_kernel<<<wgrid, 256, 0, ctx->stream>>>(a, b, stride);
+    ctx->launches++;
+    std::swap(a, b);
+  }
   dim3 grid((unsigned)std::max(1, ctx->sm_count * 8 / (int)std::min<uint32_t>(nchunks, 64u)), nchunks);
-  resolve_kernel<<<grid, 256, 0, ctx->stream>>>(d_spec, d_spec_off, d_out_off, d_len, d_windows, d_dst, d_bad);
+  resolve_kernel<<<grid, 256, 0, ctx->stream>>>(d_spec, d_spec_off, d_out_off, d_len, a, d_dst, d_bad);
   ctx->launches++;
   ZB_CUDA(ctx, cudaGetLastError());
   return ZIPC_OK;
