@@ -140,6 +140,23 @@ int upload_ranges(zipc_b200_ctx *ctx, size_t n, const void *const *src, const si
                   std::vector<const uint8_t *> &d_ptr) {
   d_ptr.assign(n, nullptr);
   ctx->epoch++;  // new input bytes: plans made over the old ones are void
+  // pipelined batches: wait for this group's turn on the bus; the next group may go once these bytes have arrived
+  struct GatePass {
+    zipc_b200_ctx *c;
+    bool held = false;
+    explicit GatePass(zipc_b200_ctx *ctx) : c(ctx) {
+      if (!c->gate || c->gate_passed) return;
+      std::unique_lock<std::mutex> lk(c->gate->m);
+      c->gate->cv.wait(lk, [&] { return c->gate->turn == c->gate_ticket; });
+      held = true;
+    }
+    ~GatePass() {
+      if (!held) return;
+      cudaStreamSynchronize(c->stream);
+      { std::lock_guard<std::mutex> lk(c->gate->m); c->gate->turn++; c->gate_passed = true; }
+      c->gate->cv.notify_all();
+    }
+  } gate_pass(ctx);
   if (!n) return ZIPC_OK;
   uintptr_t lo = ~(uintptr_t)0, hi = 0;
   size_t sum = 0, live = 0;
@@ -472,6 +489,19 @@ static int finish_to_host(zipc_b200_ctx *ctx, size_t n, const std::vector<size_t
   return d2h(ctx, dst, ctx->d_out.p, total);
 }
 
+// The pipelined sub-contexts of ctx, or null if this batch should run as one piece: it is small, there is no caller arena
+// to copy into while kernels run, or ctx is a sub-context itself.  ZIPC_B200_PIPE = groups (default 8, 0 or 1 = off).
+zipc_b200_mctx *pipeline_for(zipc_b200_ctx *ctx, size_t n, const size_t *len, const void *dst) {
+  if (ctx->is_sub || !dst || n < 1024) return nullptr;
+  static const uint64_t depth = env_u64("ZIPC_B200_PIPE", 8);
+  if (depth < 2) return nullptr;
+  uint64_t total = 0;
+  for (size_t i = 0; i < n; i++) total += len[i];
+  if (total < (64ull << 20)) return nullptr;
+  if (!ctx->pipe && pipeline_create(ctx->device, (int)depth, &ctx->pipe) != ZIPC_OK) { ctx->pipe = nullptr; return nullptr; }
+  return ctx->pipe;
+}
+
 }  // namespace zb
 
 using namespace zb;
@@ -506,6 +536,7 @@ int zipc_b200_ctx_create(int device, zipc_b200_ctx **out) {
 
 void zipc_b200_ctx_destroy(zipc_b200_ctx *ctx) {
   if (!ctx) return;
+  if (ctx->pipe) { zipc_b200_mctx_destroy(ctx->pipe); ctx->pipe = nullptr; }
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   ctx->d_in.release(); ctx->d_out.release(); ctx->d_desc.release(); ctx->d_res.release();
@@ -653,6 +684,9 @@ int zipc_b200_inflate_batch(zipc_b200_ctx *ctx, int ck, int adler_mode, size_t n
   if (dst_need) *dst_need = 0;
   if (!n) return ZIPC_OK;
   DeviceGuard g(ctx->device);
+  // (Not pipelined like zipc_b200_deflate_batch: a group's kernel lasts as long as its largest member takes on one warp
+  // (~14 ms for 256 KiB), whatever the group's size, so no download can start earlier than that and groups gain nothing:
+  // measured 26.5 GB/s in 6 groups against 28.0 GB/s in one piece, DESIGN.md.)
   std::vector<const uint8_t *> d_src;
   if (int st = upload_ranges(ctx, n, src, src_len, d_src)) return st;
   // resolve unknown output sizes with a count-only pass (no bytes are written)

@@ -5,6 +5,8 @@
 #include <stdint.h>
 #include <stddef.h>
 
+#include <condition_variable>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -46,6 +48,17 @@ struct PinBuf {
   int reserve(size_t bytes);
   void release();
   template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+// ---- copy / compute pipelining of one large batch --------------------------------------------
+// A large host-pointer batch is cut into groups that run on sub-contexts of the same device (own stream, own arenas), one
+// host thread each: the upload of group k + 1 and the download of group k - 1 then run under the kernel of group k.  The
+// uploads take turns in group order (a ticket), so that group 0's kernel can start after 1/G of the input has arrived
+// instead of all groups' copies sharing the bus and finishing together.
+struct UploadGate {
+  std::mutex m;
+  std::condition_variable cv;
+  size_t turn = 0;
 };
 
 // ---- device descriptors ---------------------------------------------------------------------
@@ -139,6 +152,13 @@ struct zipc_b200_ctx {
   void *adler_ticket_at = nullptr;   // where the counter was last zeroed (the kernel resets it itself afterwards)
   uint64_t par_streams = 0, par_fallbacks = 0;   // diagnostics: large streams decoded in parallel / handed back to the serial path
 
+  // pipelining (multi.cc): a sub-context waits for its turn to upload; the parent owns the sub-contexts
+  zb::UploadGate *gate = nullptr;
+  size_t gate_ticket = 0;
+  bool gate_passed = false;
+  bool is_sub = false;
+  struct zipc_b200_mctx *pipe = nullptr;
+
   // results of the last batch call kept for zipc_b200_fetch()
   std::vector<size_t> last_off, last_len;
   size_t last_total = 0;
@@ -202,6 +222,10 @@ int upload_ranges(zipc_b200_ctx *ctx, size_t n, const void *const *src, const si
 int inflate_core(zipc_b200_ctx *ctx, int ck, int adler_mode, size_t n, const std::vector<const uint8_t *> &d_src,
                  const size_t *src_len, const std::vector<uint8_t *> &d_dst, const std::vector<size_t> &cap,
                  bool count_only, size_t *out_len, uint32_t *checksum, int *status, uint32_t flags = 0);
+// api.cu / multi.cc: copy / compute pipelining of large host-pointer batches on one device
+zipc_b200_mctx *pipeline_for(zipc_b200_ctx *ctx, size_t n, const size_t *len, const void *dst);
+int pipeline_create(int device, int depth, zipc_b200_mctx **out);
+uint64_t pipeline_launches(const zipc_b200_mctx *m);
 // host_util.cc
 int zip_assemble_impl(const zipc_b200_member *ms, size_t n, const char *first, void *out_v, size_t out_cap,
                       size_t *out_len, bool copy_payload, uint64_t *payload_off);

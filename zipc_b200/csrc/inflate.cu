@@ -977,9 +977,11 @@ int inflate_launch(zipc_b200_ctx *ctx, const InflateTask *d_tasks, uint32_t n, I
     ZB_CUDA(ctx, cudaFuncSetAttribute(find_starts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
     g_attr_devs |= 1ull << (ctx->device & 63);
   }
-  // one warp per stream; spread the streams over all SMs first
+  // one warp per stream.  A small batch takes only as many CTAs as it fills with streams (32 per CTA), so that the kernels of
+  // other groups of a pipelined batch -- other streams of the same device -- find free SMs next to it
   uint32_t grid = (uint32_t)ctx->sm_count;
-  if (grid > n) grid = n;
+  if (n < 8u * grid) { if (grid > n) grid = n; }                        // few streams: spread them, a stream alone on an SM runs faster
+  else if (grid > (n + WARPS - 1) / WARPS) grid = (n + WARPS - 1) / WARPS;
   size_t sym_bytes = (size_t)(grid * WARPS + grid) * SYMS_PER_SLOT * sizeof(uint16_t);
   if (int st = ctx->d_scratch.reserve(sym_bytes + 256 + 4096)) return st;
   unsigned int *queue = reinterpret_cast<unsigned int *>(ctx->d_scratch.as<uint8_t>() + sym_bytes);

@@ -3,8 +3,8 @@
 // The reference is single-threaded and in-memory (src/zipc.mli:415-416); its unit of work on this path is a
 // ZIP member (Zipc.File.deflate_of_binary_string / to_binary_string, src/zipc.ml:179-185, 205-225) or one
 // string (Crc_32.string, src/zipc_deflate.ml:161-163).  Members are independent, so a batch is partitioned over
-// the GPUs with no data-path collective: longest-processing-time-first on the bytes that
-// dominate the work, one host thread + one zipc_b200_ctx (stream, arenas) per device, results gathered into
+// the GPUs with no data-path collective: contiguous runs of equal byte sums (or longest-first when
+// there are only a few members), one host thread + one zipc_b200_ctx (stream, arenas) per device, results gathered into
 // the caller's arena; a single buffer is cut into contiguous slices whose CRC-32s are merged with
 // x^(8 len) mod P on the host.  Pure orchestration over the single-device C ABI: no kernels here.
 #include <algorithm>
@@ -14,11 +14,13 @@
 #include <thread>
 #include <vector>
 
-#include "../../include/zipc_b200.h"
+#include "common.cuh"
 
 struct zipc_b200_mctx {
   std::vector<int> devices;
   std::vector<zipc_b200_ctx *> ctxs;
+  bool pipelined = false;   // sub-contexts of ONE device: uploads take turns (zb::UploadGate)
+  zb::UploadGate gate;
   // layout of the last batch call, for zipc_b200_multi_fetch
   std::vector<size_t> base, need;
   size_t total = 0;
@@ -29,18 +31,32 @@ namespace {
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) & ~(a - 1); }
 
-// LPT: heaviest first onto the least loaded device.  Returns the member indices per device (input order kept
-// inside a device, so outputs of one device stay in caller order).
-std::vector<std::vector<uint32_t>> partition_lpt(const size_t *weight, size_t n, size_t g) {
+// Members onto devices.  Many members: contiguous runs of the caller's order with equal byte sums -- members that lie
+// next to each other in host memory (an in-memory archive) then travel to their device as ONE span; a device balances
+// its own members over its SMs anyway.  Few members: longest-processing-time first (heaviest onto the least loaded
+// device), because one large member can outweigh a whole run.  Returns the member indices per device, ascending.
+std::vector<std::vector<uint32_t>> partition_members(const size_t *weight, size_t n, size_t g) {
+  std::vector<std::vector<uint32_t>> parts(g);
+  if (n >= 64 * g) {
+    uint64_t total = 0;
+    for (size_t i = 0; i < n; i++) total += (uint64_t)weight[i] + 4096;  // a member costs a little even when it is tiny
+    uint64_t run = 0;
+    size_t d = 0;
+    for (size_t i = 0; i < n; i++) {
+      while (d + 1 < g && run >= total * (d + 1) / g) d++;
+      parts[d].push_back((uint32_t)i);
+      run += (uint64_t)weight[i] + 4096;
+    }
+    return parts;
+  }
   std::vector<uint32_t> order(n);
   std::iota(order.begin(), order.end(), 0u);
   std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return weight[a] > weight[b]; });
   std::vector<uint64_t> load(g, 0);
-  std::vector<std::vector<uint32_t>> parts(g);
   for (uint32_t i : order) {
     size_t d = (size_t)(std::min_element(load.begin(), load.end()) - load.begin());
     parts[d].push_back(i);
-    load[d] += (uint64_t)weight[i] + 4096;  // a member costs a little even when it is tiny
+    load[d] += (uint64_t)weight[i] + 4096;
   }
   for (auto &p : parts) std::sort(p.begin(), p.end());
   return parts;
@@ -56,29 +72,57 @@ void for_each_device(size_t g, F f) {
 }
 
 // Shared driver of the two codec batch calls.  run(d, idx, need, off, len, ck, st) executes the single-device call
-// for the members idx on device d WITHOUT an arena (results stay in that device's ctx).
+// for the members idx on context d WITHOUT an arena (results stay in that context); each thread then waits until the
+// contexts before it know how much they produced, which fixes its place in the caller's arena, and fetches its part --
+// while later contexts are still computing.
 template <class Run>
 int batch_multi(zipc_b200_mctx *m, size_t n, const size_t *weight, void *dst, size_t dst_cap, size_t *dst_need,
                 size_t *dst_off, size_t *dst_len, uint32_t *checksum, int *status, Run run) {
-  const size_t g = m->ctxs.size();
-  auto parts = partition_lpt(weight, n, g);
+  size_t g = m->ctxs.size();
+  if (m->pipelined) g = std::max<size_t>(1, std::min(g, n / 256));  // every group gets members (the upload tickets need that)
+  auto parts = partition_members(weight, n, g);
   std::vector<int> rc(g, ZIPC_OK);
-  m->need.assign(g, 0);
+  m->need.assign(m->ctxs.size(), 0);
+  m->base.assign(m->ctxs.size(), 0);
   std::vector<std::vector<size_t>> off(g), len(g);
   std::vector<std::vector<uint32_t>> ck(g);
   std::vector<std::vector<int>> st(g);
+  std::mutex mu;
+  std::condition_variable cv;
+  std::vector<char> known(g, 0);
+  if (m->pipelined) { std::lock_guard<std::mutex> lk(m->gate.m); m->gate.turn = 0; }
   for_each_device(g, [&](size_t d) {
     const size_t k = parts[d].size();
     off[d].assign(k, 0); len[d].assign(k, 0); ck[d].assign(k, 0); st[d].assign(k, 0);
-    if (!k) return;
-    int r = run(d, parts[d], &m->need[d], off[d].data(), len[d].data(), ck[d].data(), st[d].data());
+    zipc_b200_ctx *c = m->ctxs[d];
+    if (m->pipelined) { c->gate = &m->gate; c->gate_ticket = d; c->gate_passed = false; }
+    int r = ZIPC_OK;
+    if (k) r = run(d, parts[d], &m->need[d], off[d].data(), len[d].data(), ck[d].data(), st[d].data());
+    if (m->pipelined && !c->gate_passed) {  // the call never got to its upload: do not hold up the groups behind it
+      std::unique_lock<std::mutex> lk(m->gate.m);
+      m->gate.cv.wait(lk, [&] { return m->gate.turn == d; });
+      m->gate.turn++;
+      lk.unlock();
+      m->gate.cv.notify_all();
+    }
+    c->gate = nullptr;
     rc[d] = r == ZIPC_ERR_DST_TOO_SMALL ? ZIPC_OK : r;
+    size_t base = 0;
+    {
+      std::unique_lock<std::mutex> lk(mu);
+      known[d] = 1;
+      cv.notify_all();
+      cv.wait(lk, [&] { for (size_t j = 0; j < d; j++) if (!known[j]) return false; return true; });
+      for (size_t j = 0; j < d; j++) base += align_up(m->need[j], 16);
+    }
+    m->base[d] = base;
+    if (rc[d] == ZIPC_OK && dst && m->need[d] && base + m->need[d] <= dst_cap)
+      rc[d] = zipc_b200_fetch(c, static_cast<uint8_t *>(dst) + base, m->need[d]);
   });
   for (size_t d = 0; d < g; d++)
-    if (rc[d]) { m->last_error = std::string("device ") + std::to_string(m->devices[d]) + ": " + zipc_b200_last_error(m->ctxs[d]); return rc[d]; }
-  m->base.assign(g, 0);
+    if (rc[d]) { m->last_error = std::string("context ") + std::to_string(d) + ": " + zipc_b200_last_error(m->ctxs[d]); return rc[d]; }
   size_t total = 0;
-  for (size_t d = 0; d < g; d++) { m->base[d] = total; total += align_up(m->need[d], 16); }
+  for (size_t d = 0; d < g; d++) total += align_up(m->need[d], 16);
   m->total = total;
   for (size_t d = 0; d < g; d++)
     for (size_t j = 0; j < parts[d].size(); j++) {
@@ -88,7 +132,7 @@ int batch_multi(zipc_b200_mctx *m, size_t n, const size_t *weight, void *dst, si
     }
   if (dst_need) *dst_need = total;
   if (!dst || dst_cap < total) return ZIPC_ERR_DST_TOO_SMALL;
-  return zipc_b200_multi_fetch(m, dst, dst_cap);
+  return ZIPC_OK;
 }
 
 }  // namespace
@@ -190,3 +234,29 @@ int zipc_b200_multi_fetch(zipc_b200_mctx *m, void *dst, size_t dst_cap) {
 }
 
 }  // extern "C"
+
+namespace zb {
+
+int pipeline_create(int device, int depth, zipc_b200_mctx **out) {
+  *out = nullptr;
+  zipc_b200_mctx *m = new (std::nothrow) zipc_b200_mctx();
+  if (!m) return ZIPC_ERR_NOMEM;
+  m->pipelined = true;
+  for (int k = 0; k < depth; k++) {
+    zipc_b200_ctx *c = nullptr;
+    if (int st = zipc_b200_ctx_create(device, &c)) { zipc_b200_mctx_destroy(m); return st; }
+    c->is_sub = true;
+    m->devices.push_back(device);
+    m->ctxs.push_back(c);
+  }
+  *out = m;
+  return ZIPC_OK;
+}
+
+uint64_t pipeline_launches(const zipc_b200_mctx *m) {
+  uint64_t n = 0;
+  for (const zipc_b200_ctx *c : m->ctxs) n += c->launches;
+  return n;
+}
+
+}  // namespace zb

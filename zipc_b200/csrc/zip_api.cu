@@ -188,6 +188,12 @@ int zipc_b200_deflate_batch(zipc_b200_ctx *ctx, int level, int ck, int adler_mod
   if (dst_need) *dst_need = 0;
   if (!n) return ZIPC_OK;
   DeviceGuard g(ctx->device);
+  if (zipc_b200_mctx *pipe = pipeline_for(ctx, n, src_len, dst)) {  // large batch: copies under the kernels
+    const uint64_t l0 = pipeline_launches(pipe);
+    const int rc = zipc_b200_multi_deflate_batch(pipe, level, ck, adler_mode, n, src, src_len, dst, dst_cap, dst_need, dst_off, dst_len, checksum, status);
+    ctx->launches += pipeline_launches(pipe) - l0;
+    if (rc != ZIPC_ERR_DST_TOO_SMALL) return rc;
+  }
   std::vector<const uint8_t *> d_src;
   if (int st = upload_ranges(ctx, n, src, src_len, d_src)) return st;
   std::vector<uint8_t *> d_slot;
