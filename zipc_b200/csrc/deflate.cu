@@ -88,6 +88,33 @@ constexpr uint32_t kExit = 2 * kTile; // jump codes >= kExit leave the tile
 template <int BW> __device__ __forceinline__ void bar_front() { asm volatile("bar.sync 1, %0;" ::"n"((NWARPS - BW) * 32) : "memory"); }
 template <int BW> __device__ __forceinline__ void bar_back() { asm volatile("bar.sync 2, %0;" ::"n"(BW * 32) : "memory"); }
 
+// ---- input staging by the copy engine: cp.async.bulk (global -> shared, 1-D) completing on an mbarrier ---------------------
+// One elected thread asks for the next tile's bytes a whole tile ahead; nobody spends instructions on staging, the front
+// group only waits on the barrier's phase when it gets to the tile (by then the bytes have long arrived).
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t arrivals) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%1], %0;" ::"r"(arrivals), "r"(smem_u32(bar)) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%1], %0;" ::"r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+               : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  GUARD_DECL(g_w)
+  while (!mbar_try_wait(bar, parity)) { GUARD(g_w, 20000u, 600 + parity); }
+}
+
 // ---- shared memory map ------------------------------------------------------------------------------------
 constexpr int GEN_TOK = 0;                                   // u16[kTile]: first candidate, then the resume token
 constexpr int GEN_MLEN = GEN_TOK + kTile * 2;                // u16[kTile + 8]: slot 0 = the position before the tile
@@ -138,11 +165,12 @@ struct Shared {
   uint32_t *scan;    // [NWARPS + 1]
   uint32_t *sc;      // scalars
   uint32_t *pslot;   // [32] parse: entry hand-over between lanes
+  uint64_t *ldbar;   // mbarrier of the input staging
 };
 
 // scalar slots in sh.sc
 enum { SC_TASK = 0, SC_OUTW, SC_CARRY, SC_CBITS, SC_OVERFLOW, SC_M_L, SC_M_D, SC_NHDR, SC_BTYPE, SC_HLIT, SC_HDIST,
-       SC_SUMDYN, SC_SUMFIX, SC_BLK_SRCLEN, SC_NRSYM, SC_HCLEN, SC_HDRBITS, SC_BATCH, SC_QHEAD, SC_OQN, SC_EXIT, SC_VQN /* [2] */ };
+       SC_SUMDYN, SC_SUMFIX, SC_BLK_SRCLEN, SC_NRSYM, SC_HCLEN, SC_HDRBITS, SC_BATCH, SC_QHEAD, SC_OQN, SC_EXIT, SC_VQN /* [2] */, SC_VQN1, SC_LD_PHASES /* bulk copies issued so far */ };
 
 __device__ __forceinline__ Gen gen_of(uint8_t *base, int g) {  // plain arithmetic on the shared base: the address space stays known
   uint8_t *b = base + OFF_GEN + g * GEN_BYTES;
@@ -194,9 +222,10 @@ __device__ __forceinline__ Shared carve(uint8_t *base) {
   s.scan = reinterpret_cast<uint32_t *>(m + 4096 + 128);         // 40 words
   s.sc = s.scan + 40;                                            // 32 words
   s.pslot = s.sc + 32;                                           // 32 words
+  s.ldbar = reinterpret_cast<uint64_t *>(s.pslot + 32);          // 8 bytes, 8-byte aligned
   return s;
 }
-static_assert(kChunk32 * kMaxClasses * 2 <= 4096 && 4096 + 128 + (40 + 32 + 32) * 4 <= MISC_BYTES, "misc area");
+static_assert(kChunk32 * kMaxClasses * 2 <= 4096 && 4096 + 128 + (40 + 32 + 32) * 4 + 8 <= MISC_BYTES, "misc area");
 
 // lanes of the warp whose key equals mine, from one ballot per key bit (match.any takes a hardware loop over
 // the distinct values: ~400 clk for 32 different hashes; this is BITS ballots + logic ops)
@@ -627,8 +656,9 @@ __device__ __forceinline__ void guess_visits(const uint16_t *mlen, const uint32_
 
 // ---- front end: stage, hash, partition, insert, shallow walks of one tile (FRONT_THREADS threads) -----------------
 // ft: thread index inside the front group; fw: warp index inside the group.  Uses bar_front() only.
+// `state`: bits 0..31 = input bytes resident in the ring or on their way, bit 32 = a bulk copy is in flight.  Returns the new state.
 template <int BW>
-__device__ __noinline__ uint32_t front_end(int gen, const uint8_t *src, uint32_t n, uint32_t ts, uint32_t loaded,
+__device__ __noinline__ uint64_t front_end(int gen, const uint8_t *src, uint32_t n, uint32_t ts, uint64_t state,
                                            int level, int ft, int fw, int lane) {
   constexpr int FRONT_WARPS = NWARPS - BW, FRONT_THREADS = FRONT_WARPS * 32, BACK_THREADS = BW * 32;
   constexpr int kClasses = FRONT_WARPS, kRankRounds = (kChunk32 + FRONT_WARPS - 1) / FRONT_WARPS;
@@ -642,17 +672,43 @@ __device__ __noinline__ uint32_t front_end(int gen, const uint8_t *src, uint32_t
   const uint32_t te = min(ts + (uint32_t)kTile, n), want = min(n, te + (uint32_t)kTile);
   const uint32_t lt_mask = (1u << lane) - 1u;
   PH_DECL
-  // 1. stage input [loaded, want)
-  if ((((uintptr_t)src) & 15) == 0 && (loaded & 15) == 0) {  // 16-byte vectors (slots of the packed arena are aligned)
-    const uint32_t nv = (want - loaded) >> 4;
-    const uint4 *sv = reinterpret_cast<const uint4 *>(src + loaded);
-    for (uint32_t i = ft; i < nv; i += FRONT_THREADS)
-      *reinterpret_cast<uint4 *>(sh.ringb + ((loaded + 16 * i) & (kRing - 1))) = __ldg(sv + i);
-    for (uint32_t i = loaded + 16 * nv + ft; i < want; i += FRONT_THREADS) sh.ringb[i & (kRing - 1)] = src[i];
+  // 1. stage input: this tile needs [.., want); the copy engine was asked for it one tile ago, and is now asked for the next
+  uint32_t loaded = (uint32_t)state;
+  bool in_flight = (state >> 32) & 1u;
+  if ((((uintptr_t)src) & 15) == 0) {  // 16-byte aligned source (slots of the packed arena are): bulk copies
+    uint32_t phases = sh.sc[SC_LD_PHASES];
+    // issue [a, b) as one mbarrier phase (two copies when the ring wraps); the ragged tail of the member by plain stores
+    auto issue = [&](uint32_t a, uint32_t b) -> bool {
+      const uint32_t b16 = b == n ? (b & ~15u) : b;
+      if (ft == 0) for (uint32_t i = max(a, b16); i < b; i++) sh.ringb[i & (kRing - 1)] = src[i];
+      if (b16 <= a) return false;
+      if (ft == 0) {
+        const uint32_t len = b16 - a, ro = a & (kRing - 1), first = min(len, (uint32_t)kRing - ro);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_expect_tx(sh.ldbar, len);
+        bulk_g2s(sh.ringb + ro, src + a, first, sh.ldbar);
+        if (first < len) bulk_g2s(sh.ringb, src + a + first, len - first, sh.ldbar);
+      }
+      return true;
+    };
+    if (in_flight) { mbar_wait(sh.ldbar, (phases - 1) & 1u); in_flight = false; }
+    if (loaded < want) {  // (first tile of a member: nothing was asked for yet)
+      if (issue(loaded, want)) { phases++; mbar_wait(sh.ldbar, (phases - 1) & 1u); }
+      loaded = want;
+    }
+    // A waiter tests the PARITY of a phase, so the next phase may only be opened once every thread has seen this one
+    // complete: two completions behind a slow waiter's back look like none.  Hence the barrier before the prefetch.
+    bar_front<BW>();
+    const uint32_t next_want = min(n, want + (uint32_t)kTile);
+    if (next_want > loaded) {
+      if (issue(loaded, next_want)) { phases++; in_flight = true; }
+      loaded = next_want;
+    }
+    if (ft == 0) sh.sc[SC_LD_PHASES] = phases;
   } else {
     for (uint32_t i = loaded + ft; i < want; i += FRONT_THREADS) sh.ringb[i & (kRing - 1)] = src[i];
+    loaded = want;
   }
-  loaded = want;
   for (int i = ft; i < kChunk32 * kClasses / 2; i += FRONT_THREADS) reinterpret_cast<uint32_t *>(sh.cnt)[i] = 0;
   if (ft == 0) sh.sc[SC_BATCH] = 0;
   bar_front<BW>();
@@ -778,7 +834,7 @@ __device__ __noinline__ uint32_t front_end(int gen, const uint8_t *src, uint32_t
   PH_AT(PH_F_SHALLOW, BACK_THREADS);
   // 4. the positions a parse of this tile is guessed to visit: the deep walks' first queue
   if (fw == 0 && lp.rounds > 0) guess_visits(G.mlen, nullptr, ts, te, n, sh.vq + gen * kTile, &sh.sc[SC_VQN + gen], lane);
-  return loaded;
+  return (uint64_t)loaded | ((uint64_t)in_flight << 32);
 }
 
 // ---- jump codes of the lazy parse: node v = 2 * (p - ts) + kind; codes >= kExit leave the tile -------------------
@@ -967,7 +1023,8 @@ __device__ void encode_member(const DeflateTask t, int level, uint32_t *toks, De
   }
   __syncthreads();
 
-  uint32_t pos = 0, kind = 0, loaded = 0, ntok = 0, nblocks = 0;
+  uint32_t pos = 0, kind = 0, ntok = 0, nblocks = 0;
+  uint64_t loaded = 0;  // staging state of the front end (front threads only)
   uint64_t blk_src_start = 0;
   int tiles_in_block = 0, g = 0;
   PH_DECL
@@ -1018,7 +1075,6 @@ __device__ void encode_member(const DeflateTask t, int level, uint32_t *toks, De
       // ---- front end: tile t + 1 -------------------------------------------------------------------------------------
       loaded = front_end<BW>(g ^ 1, src, n, te, loaded, level, ft, fw, lane);
     }
-    if (back && more) loaded = min(n, min(te + (uint32_t)kTile, n) + (uint32_t)kTile);  // keep the uniform copy in step
     __syncthreads();
     PH(PH_BACK_WAIT);
     // ---- all warps: tokens of tile t -------------------------------------------------------------------------------------
@@ -1123,6 +1179,7 @@ deflate_kernel(const DeflateTask *__restrict__ tasks, uint32_t ntasks, DeflateRe
   ZB_SMEM;
   const Shared sh = carve(smem_raw);
   uint32_t *toks = tok_scratch + (size_t)blockIdx.x * kTokCap;
+  if (threadIdx.x == 0) { mbar_init(sh.ldbar, 1); sh.sc[SC_LD_PHASES] = 0; }
   for (;;) {
     __syncthreads();
     if (threadIdx.x == 0) sh.sc[SC_TASK] = atomicAdd(queue, 1u);
