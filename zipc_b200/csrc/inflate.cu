@@ -104,10 +104,10 @@ struct WarpState {
 struct __align__(16) WarpWork {
   WarpState st;
   union {
-    uint8_t cand[WBITS];  // by bit offset from the round's start
+    uint8_t cand[WBITS + 64];  // by bit offset from the round's start; the 64 bytes behind the window say "stop"
     WarpScratch build;    // table construction never overlaps a decoding round
   };
-  uint16_t tokq[ROUND_TOKENS];  // bit offsets of the round's tokens, in order (bit 15: decoded by the slow path)
+  uint16_t tokq[ROUND_TOKENS + 2];  // candidate addresses of the round's tokens, in order, then where the walk ended
   uint32_t slow_tx[ROUND_TOKENS];   // slow path tokens: the token ...
   uint16_t slow_end[ROUND_TOKENS];  // ... and the bit offset where it ends
   uint32_t ring[64];      // compressed input, words [w0, w0 + 64) of the stream
@@ -584,57 +584,81 @@ inflate_kernel(const InflateTask *__restrict__ tasks, uint32_t ntasks, InflateRe
           const uint32_t c = (e & 0xC0u) == kCbIsLen ? p + (e2 & 0xFFu) : e;
           wk.cand[j * 32 + lane] = (uint8_t)c;
         }
+        if (lane < 16) reinterpret_cast<uint32_t *>(wk.cand + WBITS)[lane] = 0xFEFEFEFEu;  // (table building reuses the area)
       }
       __syncwarp();
-      // D2: follow the chain of real tokens through the candidates.  All lanes walk alike; the only per-token
-      // work is the chain itself (load, add) and one store of the token's offset.
+      // D2: follow the chain of real tokens through the candidates.  All lanes walk alike, 32 steps, straight line:
+      // load the candidate, note its address as token k, add the bits it occupies.  A candidate with bit 7 set (end
+      // of block, a code the tables do not hold, the padding behind the window) counts as zero bits, so the walk
+      // stays where it stopped and the tokens from there on repeat one address: token k is real iff entry k + 1
+      // differs from entry k.  4 instructions per step, no branch (the loop with its exit tests carried 10).
       {
-        // The loop body is the per-token cost of the whole decoder, so it is kept to: load, test, store, two adds,
-        // two compares.  Everything else (end of block, long codes) happens outside of it.
-        // Written in PTX: the compiler's version of this loop carried 15 instructions per token.
         const uint32_t cand_sa = (uint32_t)__cvta_generic_to_shared(wk.cand);
         const uint32_t tokq_sa = (uint32_t)__cvta_generic_to_shared(wk.tokq);
-        uint32_t ca = cand_sa, qa = tokq_sa;  // shared addresses of the current candidate / the next queue slot
+        uint32_t ca = cand_sa;
         // the queue keeps the low 16 bits of a token's candidate address: offset = (entry - cand_sa) mod 2^16
-        const uint32_t ca_end = cand_sa + WBITS, qa_end = tokq_sa + 2 * ROUND_TOKENS;
-        for (;;) {
-          uint32_t c;
-          asm volatile(
-              "{\n"
-              ".reg .pred p;\n"
-              "WALK:\n"
-              "  ld.shared.u8 %0, [%1];\n"
-              "  setp.ge.u32 p, %0, 0x80;\n"
-              "  @p bra WALK_DONE;\n"
-              "  st.shared.u16 [%2], %1;\n"
-              "  add.u32 %1, %1, %0;\n"
-              "  add.u32 %2, %2, 2;\n"
-              "  setp.lt.u32 p, %1, %3;\n"
-              "  setp.lt.and.u32 p, %2, %4, p;\n"
-              "  @p bra WALK;\n"
-              "  mov.u32 %0, 0;\n"
-              "WALK_DONE:\n"
-              "}\n"
-              : "=&r"(c), "+r"(ca), "+r"(qa)
-              : "r"(ca_end), "r"(qa_end)
-              : "memory");
-          if (c == 0) break;
-          if (c < kCbSlow) { stop = 1; eob_bits = c & 31u; break; }
-          // long or invalid code: decode this one token serially and go on
-          uint32_t stx = 0, sbits = 0;
-          const uint32_t o = ca - cand_sa, k = (qa - tokq_sa) >> 1;
-          const uint32_t r = slow_token(wk, T, g_syms + (size_t)(use_fixed ? gridDim.x * WARPS + blockIdx.x : slot) * SYMS_PER_SLOT, s_len_tab, s_dist_tab, P0 + o, stx, sbits);
-          if (r) { stop = r == 1 ? 1u : 3u; eob_bits = sbits; break; }
-          wk.slow_tx[k] = stx;
-          wk.slow_end[k] = (uint16_t)(o + sbits);
-          wk.tokq[k] = (uint16_t)ca;
-          slowmask |= 1u << k;
-          ca += sbits;
-          qa += 2;
-          if (ca >= ca_end || qa >= qa_end) break;
+        asm volatile(
+            "{\n"
+            ".reg .s32 c;\n"
+              "  ld.shared.s8 c, [%0];\n  st.shared.u16 [%1+0], %0;\n  max.s32 c, c, 0;\n  add.u32 %0, %0, c;\n"
+              "  ld.shared.s8 c, [%0];\n  st.shared.u16 [%1+2], %0;\n  max.s32 c, c, 0;\n  add.u32 %0, %0, c;\n"
+              "  ld.shared.s8 c, [%0];\n  st.shared.u16 [%1+4], %0;\n  max.s32 c, c, 0;\n  add.u32 %0, %0, c;\n"
+              "  ld.shared.s8 c, [%0];\n  st.shared.u16 [%1+6], %0;\n  max.s32 c, c, 0;\n  add.u32 %0, %0, c;\n"
+              "  ld.shared.s8 c, [%0];\n  st.shared.u16 [%1+8], %0;\n  max.s32 c, c, 0;\n  add.u32 %0, %0, c;\n"
+              "  ld.shared.s8 c, [%0];\n  st.shared.u16 [%1+10], %0;\n  max.s32 c, c, 0;\n  add.u32 %0, %0, c;\n"
+              "  ld.shared.s8 c, [%0];\n  st.shared.u16 [%1+12], %0;\n  max.s32 c, c, 0;\n  add.u32 %0, %0, c;\n"
+              "  ld.shared.s8 c, [%0];\n  st.shared.u16 [%1+14], %0;\n  max.s32 c, c, 0;\n  add.u32 %0, %0, c;\n"
+              "  ld.shared.s8 c, [%0];\n  st.shared.u16 [%1+16], %0;\n  max.s32 c, c, 0;\n  add.u32 %0, %0, c;\n"
+              "  ld.shared.s8 c, [%0];\n  st.shared.u16 [%1+18], %0;\n  max.s32 c, c, 0;\n  add.u32 %0, %0, c;\n"
+              "  ld.shared.s8 c, [%0];\n  st.shared.u16 [%1+20], %0;\n  max.s32 c, c, 0;\n  add.u32 %0, %0, c;\n"
+              "  ld.shared.s8 c, [%0];\n  st.shared.u16 [%1+22], %0;\n  max.s32 c, c, 0;\n  add.u32 %0, %0, c;\n"
+              "  ld.shared.s8 c, [%0];\n  st.shared.u16 [%1+24], %0;\n  max.s32 c, c, 0;\n  add.u32 %0, %0, c;\n"
+              "  ld.shared.s8 c, [%0];\n  st.shared.u16 [%1+26], %0;\n  max.s32 c, c, 0;\n  add.u32 %0, %0, c;\n"
+              "  ld.shared.s8 c, [%0];\n  st.shared.u16 [%1+28], %0;\n  max.s32 c, c, 0;\n  add.u32 %0, %0, c;\n"
+              "  ld.shared.s8 c, [%0];\n  st.shared.u16 [%1+30], %0;\n  max.s32 c, c, 0;\n  add.u32 %0, %0, c;\n"
+              "  ld.shared.s8 c, [%0];\n  st.shared.u16 [%1+32], %0;\n  max.s32 c, c, 0;\n  add.u32 %0, %0, c;\n"
+              "  ld.shared.s8 c, [%0];\n  st.shared.u16 [%1+34], %0;\n  max.s32 c, c, 0;\n  add.u32 %0, %0, c;\n"
+              "  ld.shared.s8 c, [%0];\n  st.shared.u16 [%1+36], %0;\n  max.s32 c, c, 0;\n  add.u32 %0, %0, c;\n"
+              "  ld.shared.s8 c, [%0];\n  st.shared.u16 [%1+38], %0;\n  max.s32 c, c, 0;\n  add.u32 %0, %0, c;\n"
+              "  ld.shared.s8 c, [%0];\n  st.shared.u16 [%1+40], %0;\n  max.s32 c, c, 0;\n  add.u32 %0, %0, c;\n"
+              "  ld.shared.s8 c, [%0];\n  st.shared.u16 [%1+42], %0;\n  max.s32 c, c, 0;\n  add.u32 %0, %0, c;\n"
+              "  ld.shared.s8 c, [%0];\n  st.shared.u16 [%1+44], %0;\n  max.s32 c, c, 0;\n  add.u32 %0, %0, c;\n"
+              "  ld.shared.s8 c, [%0];\n  st.shared.u16 [%1+46], %0;\n  max.s32 c, c, 0;\n  add.u32 %0, %0, c;\n"
+              "  ld.shared.s8 c, [%0];\n  st.shared.u16 [%1+48], %0;\n  max.s32 c, c, 0;\n  add.u32 %0, %0, c;\n"
+              "  ld.shared.s8 c, [%0];\n  st.shared.u16 [%1+50], %0;\n  max.s32 c, c, 0;\n  add.u32 %0, %0, c;\n"
+              "  ld.shared.s8 c, [%0];\n  st.shared.u16 [%1+52], %0;\n  max.s32 c, c, 0;\n  add.u32 %0, %0, c;\n"
+              "  ld.shared.s8 c, [%0];\n  st.shared.u16 [%1+54], %0;\n  max.s32 c, c, 0;\n  add.u32 %0, %0, c;\n"
+              "  ld.shared.s8 c, [%0];\n  st.shared.u16 [%1+56], %0;\n  max.s32 c, c, 0;\n  add.u32 %0, %0, c;\n"
+              "  ld.shared.s8 c, [%0];\n  st.shared.u16 [%1+58], %0;\n  max.s32 c, c, 0;\n  add.u32 %0, %0, c;\n"
+              "  ld.shared.s8 c, [%0];\n  st.shared.u16 [%1+60], %0;\n  max.s32 c, c, 0;\n  add.u32 %0, %0, c;\n"
+              "  ld.shared.s8 c, [%0];\n  st.shared.u16 [%1+62], %0;\n  max.s32 c, c, 0;\n  add.u32 %0, %0, c;\n"
+            "  st.shared.u16 [%1+64], %0;\n"
+            "}\n"
+            : "+r"(ca)
+            : "r"(tokq_sa)
+            : "memory");
+        __syncwarp();
+        const uint32_t q0 = wk.tokq[lane], q1 = wk.tokq[lane + 1];
+        const uint32_t stuck = __ballot_sync(0xffffffffu, q0 == q1);
+        n = stuck ? (uint32_t)(__ffs((int)stuck) - 1) : (uint32_t)ROUND_TOKENS;
+        uint32_t o = (ca - cand_sa) & 0xFFFFu;   // where the walk stands: behind the last real token
+        if (n < (uint32_t)ROUND_TOKENS && o < (uint32_t)WBITS) {
+          const uint32_t c = wk.cand[o];
+          if (c < kCbSlow) { stop = 1; eob_bits = c & 31u; }
+          else {
+            // long or invalid code: this one token goes through the canonical walk and ends the round
+            uint32_t stx = 0, sbits = 0;
+            const uint32_t r = slow_token(wk, T, g_syms + (size_t)(use_fixed ? gridDim.x * WARPS + blockIdx.x : slot) * SYMS_PER_SLOT, s_len_tab, s_dist_tab, P0 + o, stx, sbits);
+            if (r) { stop = r == 1 ? 1u : 3u; eob_bits = sbits; }
+            else {
+              wk.slow_tx[n] = stx;
+              wk.slow_end[n] = (uint16_t)(o + sbits);
+              slowmask = 1u << n;
+              o += sbits;
+              n++;
+            }
+          }
         }
-        n = (qa - tokq_sa) >> 1;
-        const uint32_t o = ca - cand_sa;
         in.P += o;
       }
       __syncwarp();
