@@ -108,158 +108,188 @@ __device__ __forceinline__ uint32_t block_scan(uint32_t v, uint32_t *scratch, ui
   return warp ? op(scratch[32 + warp - 1], x) : x;
 }
 
+// One CTA per tile of kFoldTile chunks.  Everything that does not need the state before the tile runs in parallel over the
+// tiles; what does is passed down a chain of tagged 64-bit words in global memory (tag = this launch's epoch, so nothing has
+// to be cleared between calls):
+//   chain_a[t] = byte-sum of tile t (mod M): every later tile adds up its predecessors' entries to know s1 at its start;
+//   chain_s[t] = s2 after tile t (residue, sign): tile t + 1 waits for it only at the very end, for the handful of chunks
+//                whose outcome depends on the exact s2 ("U"), which one thread walks through a dense list.
+// Tiles are numbered in the order the CTAs start (a counter), so a tile only ever waits for tiles that are already running.
+__device__ __forceinline__ uint64_t chain_wait(const uint64_t *p, uint32_t epoch) {
+  uint64_t v;
+  do { asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); } while ((uint32_t)(v >> 32) != epoch);
+  return v;
+}
+__device__ __forceinline__ void chain_post(uint64_t *p, uint32_t epoch, uint32_t payload) {
+  const uint64_t v = ((uint64_t)epoch << 32) | payload;
+  asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
 __global__ void __launch_bounds__(kFoldThreads, 1)
-adler_fold_kernel(const uint2 *__restrict__ ab, uint32_t first, uint32_t nchunks, int mode, uint32_t *__restrict__ out) {
+adler_fold_kernel(const uint2 *__restrict__ ab, uint32_t first, uint32_t nchunks, uint32_t epoch, unsigned int *__restrict__ counter,
+                  uint64_t *__restrict__ chain_a, uint64_t *__restrict__ chain_s, uint32_t *__restrict__ out) {
   __shared__ uint32_t scratch[64];
-  extern __shared__ __align__(16) uint8_t fold_smem[];  // kFoldSmem bytes: per-chunk W, residue, class for the serial walk
-  uint32_t *smW = reinterpret_cast<uint32_t *>(fold_smem);
-  uint16_t *smR = reinterpret_cast<uint16_t *>(fold_smem + kFoldTile * 4);
-  uint8_t *smK = fold_smem + kFoldTile * 6;
-  __shared__ uint32_t smU[kFoldItems][32];
-  __shared__ uint32_t s_corr, s_neg;
+  extern __shared__ __align__(16) uint8_t fold_smem[];  // kFoldSmem bytes: the tile's U chunks, in order: W, residue before, where the sign comes from
+  uint32_t *uW = reinterpret_cast<uint32_t *>(fold_smem);
+  uint16_t *uR = reinterpret_cast<uint16_t *>(fold_smem + kFoldTile * 4);
+  uint8_t *uF = fold_smem + kFoldTile * 6;
+  __shared__ uint8_t lastk[kFoldThreads];
+  __shared__ uint32_t s_tile, s_nn, s_klast;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t K = (uint32_t)((1ull << 32) % kM);
-  const bool quirk = mode == ZIPC_ADLER_REF_COMPAT;
-  uint32_t s1_carry = 1u;   // s1 before the tile
-  uint32_t r_carry = 0u;    // residue of s2 before the tile
-  uint32_t nn_carry = 1u;   // s2 known non-negative before the tile
-  if (tid == 0) s_neg = 0;  // sign of s2 before the tile (exact; used by the serial walk only)
-  for (uint32_t t0 = 0; t0 < nchunks; t0 += kFoldTile) {
-    const uint32_t base = t0 + tid * kFoldItems;
-    uint32_t A[kFoldItems], B[kFoldItems];
-    if (base + kFoldItems <= nchunks) {
-      const uint4 *p = reinterpret_cast<const uint4 *>(ab + base);  // 64-byte aligned: base is a multiple of 8
+  if (tid == 0) s_tile = atomicAdd(counter, 1u);
+  __syncthreads();
+  const uint32_t tile = s_tile, ntiles = gridDim.x;
+  const uint32_t t0 = tile * kFoldTile, base = t0 + tid * kFoldItems;
+  const int last = (int)min((uint32_t)kFoldTile, nchunks - t0) - 1;  // index of the tile's last chunk
+
+  uint32_t A[kFoldItems], B[kFoldItems];
+  if (base + kFoldItems <= nchunks) {
+    const uint4 *p = reinterpret_cast<const uint4 *>(ab + base);  // 64-byte aligned: base is a multiple of 8
 #pragma unroll
-      for (int i = 0; i < kFoldItems / 2; i++) {
-        uint4 u = p[i];
-        A[2 * i] = u.x; B[2 * i] = u.y; A[2 * i + 1] = u.z; B[2 * i + 1] = u.w;
-      }
-    } else {
+    for (int i = 0; i < kFoldItems / 2; i++) {
+      uint4 u = p[i];
+      A[2 * i] = u.x; B[2 * i] = u.y; A[2 * i + 1] = u.z; B[2 * i + 1] = u.w;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < kFoldItems; i++) {
+      uint2 e = base + i < nchunks ? ab[base + i] : make_uint2(0u, 0u);
+      A[i] = e.x; B[i] = e.y;
+    }
+  }
+  // s1 before every chunk: the tile's own prefix sums, then the sums of the tiles before it
+  uint32_t pa[kFoldItems], asum = 0;
+#pragma unroll
+  for (int i = 0; i < kFoldItems; i++) { pa[i] = asum; asum += A[i] % kM; }
+  asum %= kM;
+  uint32_t atot;
+  const uint32_t ainc = block_scan<OpAddMod>(asum, scratch, &atot);
+  if (tid == 0) chain_post(chain_a + tile, epoch, atot);
+  uint32_t before = 0;
+  for (uint32_t j = tid; j < tile; j += kFoldThreads) before = (before + (uint32_t)chain_wait(chain_a + j, epoch)) % kM;
+  uint32_t s1_carry;
+  block_scan<OpAddMod>(before, scratch, &s1_carry);
+  s1_carry = (s1_carry + 1u) % kM;
+  const uint32_t s1_thread = (s1_carry + ainc + kM - asum) % kM;
+  // W, class
+  uint32_t W[kFoldItems], k[kFoldItems], gp = OpCarry::identity;
+#pragma unroll
+  for (int i = 0; i < kFoldItems; i++) {
+    uint32_t s1 = (s1_thread + pa[i]) % kM;
+    uint32_t n = base + i == 0 ? first : 5552u;
+    W[i] = n * s1 + B[i];  // < 2^32: 5552*65520 + 255*5552*5553/2
+    uint32_t c;
+    if (base + i >= nchunks) c = 4;                                    // past the end: identity
+    else if (W[i] >= kM && W[i] < 0x80000000u - kM) c = 0;             // L
+    else if (W[i] >= 0x80000000u + kM) c = 1;                          // H
+    else if (W[i] < kM) c = 2;                                         // low W
+    else c = 3;                                                        // U
+    k[i] = c;
+    if (c == 0) gp = 2u; else if (c == 1 || c == 3) gp = 0u;
+  }
+  uint32_t gtot;
+  const uint32_t ginc = block_scan<OpCarry>(gp, scratch, &gtot);
+  uint32_t gexc = __shfl_up_sync(0xffffffffu, ginc, 1);
+  if (lane == 0) gexc = warp ? scratch[32 + warp - 1] : OpCarry::identity;
+  // low-W chunks at the head of the tile (nothing before them fixes the sign) need the sign before the tile: the only
+  // case in which the whole CTA waits for its predecessor (zero-filled data behind a negative state)
+  bool open_head = (gexc & 3u) == 1u, needs = false;
+#pragma unroll
+  for (int i = 0; i < kFoldItems; i++) {
+    if (k[i] == 2 && open_head) needs = true;
+    if (k[i] != 2 && k[i] != 4) open_head = false;
+  }
+  uint32_t neg_in = 0, r_carry = 0;
+  bool have_pred = tile == 0;
+  if (__syncthreads_or(needs) && tile) {
+    if (tid == 0) s_nn = (uint32_t)chain_wait(chain_s + tile - 1, epoch);
+    __syncthreads();
+    neg_in = s_nn >> 17; r_carry = s_nn & 0x1FFFFu; have_pred = true;
+  }
+  uint32_t nn_in = (gexc >> 1) | (gexc & (neg_in ^ 1u) & 1u);
+  // resolve low-W chunks, deltas
+  uint32_t pd[kFoldItems], dsum = 0, nu = 0;
+#pragma unroll
+  for (int i = 0; i < kFoldItems; i++) {
+    if (k[i] == 2) k[i] = nn_in ? 0u : 3u;
+    if (k[i] != 4) nn_in = k[i] == 0;
+    nu += k[i] == 3;
+    pd[i] = dsum;
+    uint32_t w = W[i] % kM;
+    dsum += k[i] == 0 ? w : k[i] == 1 ? (w + kM - K) % kM : 0u;
+  }
+  dsum %= kM;
+  uint32_t dtot;
+  const uint32_t dinc = block_scan<OpAddMod>(dsum, scratch, &dtot);
+  const uint32_t r_thread = (dinc + kM - dsum) % kM;   // residue before the thread's chunks, without the tile's carry-in
+  // the U chunks, in order
+  lastk[tid] = (uint8_t)k[kFoldItems - 1];
+  if (tid == last / kFoldItems) {
+#pragma unroll
+    for (int i = 0; i < kFoldItems; i++)
+      if (i == last % kFoldItems) s_klast = k[i];
+  }
+  uint32_t nutot;
+  {
+    // (plain sums: at most kFoldTile)
+    uint32_t x = nu;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += t; }
+    __syncthreads();
+    if (lane == 31) scratch[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+      uint32_t w = scratch[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += t; }
+      scratch[32 + lane] = w;
+    }
+    __syncthreads();
+    nutot = scratch[63];
+    uint32_t at = (warp ? scratch[32 + warp - 1] : 0u) + x - nu;
+    if (nu) {
 #pragma unroll
       for (int i = 0; i < kFoldItems; i++) {
-        uint2 e = base + i < nchunks ? ab[base + i] : make_uint2(0u, 0u);
-        A[i] = e.x; B[i] = e.y;
+        if (k[i] != 3) continue;
+        const uint32_t kp = i ? k[i - 1] : tid ? (uint32_t)lastk[tid - 1] : 5u;
+        uW[at] = W[i];
+        uR[at] = (uint16_t)((r_thread + pd[i]) % kM);
+        uF[at] = (uint8_t)(kp == 0 ? 0 : kp == 1 ? 1 : kp == 3 ? 2 : 3);   // sign before: +, -, the walk's own, the tile's carry-in
+        at++;
       }
     }
-    // s1 before every chunk
-    uint32_t pa[kFoldItems], asum = 0;
-#pragma unroll
-    for (int i = 0; i < kFoldItems; i++) { pa[i] = asum; asum += A[i] % kM; }
-    asum %= kM;
-    uint32_t atot;
-    uint32_t ainc = block_scan<OpAddMod>(asum, scratch, &atot);
-    const uint32_t s1_thread = (s1_carry + ainc + kM - asum) % kM;
-    // W, class
-    uint32_t W[kFoldItems], k[kFoldItems], gp = OpCarry::identity;
-#pragma unroll
-    for (int i = 0; i < kFoldItems; i++) {
-      uint32_t s1 = (s1_thread + pa[i]) % kM;
-      uint32_t n = base + i == 0 ? first : 5552u;
-      W[i] = n * s1 + B[i];  // < 2^32: 5552*65520 + 255*5552*5553/2
-      uint32_t c;
-      if (base + i >= nchunks) c = 4;                                    // past the end: identity
-      else if (!quirk) c = 0;                                            // exact arithmetic: every chunk is "L"
-      else if (W[i] >= kM && W[i] < 0x80000000u - kM) c = 0;             // L
-      else if (W[i] >= 0x80000000u + kM) c = 1;                          // H
-      else if (W[i] < kM) c = 2;                                         // low W
-      else c = 3;                                                        // U
-      k[i] = c;
-      if (c == 0) gp = 2u; else if (c == 1 || c == 3) gp = 0u;
-    }
-    uint32_t nn_in = nn_carry;
-    if (quirk) {
-      uint32_t gtot;
-      uint32_t ginc = block_scan<OpCarry>(gp, scratch, &gtot);
-      uint32_t gexc = __shfl_up_sync(0xffffffffu, ginc, 1);
-      if (lane == 0) gexc = warp ? scratch[32 + warp - 1] : OpCarry::identity;
-      nn_in = (gexc >> 1) | (gexc & nn_carry & 1u);
-      nn_carry = (gtot >> 1) | (gtot & nn_carry & 1u);
-    }
-    // resolve low-W chunks, deltas
-    uint32_t pd[kFoldItems], dsum = 0, has_u = 0;
-#pragma unroll
-    for (int i = 0; i < kFoldItems; i++) {
-      if (k[i] == 2) k[i] = nn_in ? 0u : 3u;
-      if (k[i] != 4) nn_in = k[i] == 0;
-      has_u |= k[i] == 3;
-      pd[i] = dsum;
-      uint32_t w = W[i] % kM;
-      dsum += k[i] == 0 ? w : k[i] == 1 ? (w + kM - K) % kM : 0u;
-    }
-    dsum %= kM;
-    uint32_t dtot;
-    uint32_t dinc = block_scan<OpAddMod>(dsum, scratch, &dtot);
-    const uint32_t r_thread = (r_carry + dinc + kM - dsum) % kM;
-    uint32_t corr = 0;
-    if (quirk) {
-      const uint32_t any_u = __syncthreads_or(has_u);
-      // sign after the last chunk of the tile, unless the walk below overrides it
-      {
-        int last = (int)min((uint32_t)kFoldTile, nchunks - t0) - 1;
-        if (last / kFoldItems == tid && !any_u) s_neg = k[last % kFoldItems] == 1;
-      }
-      if (any_u) {
-#pragma unroll
-        for (int i = 0; i < kFoldItems; i++) {
-          smW[i * kFoldThreads + tid] = W[i];  // [item][thread]: conflict-free
-          smR[i * kFoldThreads + tid] = (uint16_t)((r_thread + pd[i]) % kM);
-          smK[i * kFoldThreads + tid] = (uint8_t)k[i];
-          uint32_t bal = __ballot_sync(0xffffffffu, k[i] == 3);
-          if (lane == 0) smU[i][warp] = bal;
-        }
-        __syncthreads();
-        // warp 0 finds the warps that own uncertain chunks (one lane per warp), lane 0 walks only those
-        uint32_t warps_u = 0;
-        if (warp == 0) {
-          uint32_t mine = 0;
-          for (int i = 0; i < kFoldItems; i++) mine |= smU[i][lane];
-          warps_u = __ballot_sync(0xffffffffu, mine != 0);
-        }
-        if (tid == 0) {
-          bool neg = s_neg != 0;   // sign before the tile
-          int last_idx = -1;       // last chunk whose sign `neg` describes (-1: the tile's predecessor)
-          uint32_t c = 0;
-          while (warps_u) {
-            const int w = __ffs(warps_u) - 1;
-            warps_u &= warps_u - 1;
-            uint32_t any = 0;
-            for (int i = 0; i < kFoldItems; i++) any |= smU[i][w];
-            while (any) {
-              int l = __ffs(any) - 1;
-              any &= any - 1;
-              for (int i = 0; i < kFoldItems; i++) {
-                if (!((smU[i][w] >> l) & 1u)) continue;
-                const int th = w * 32 + l, j = th * kFoldItems + i, at = i * kFoldThreads + th;
-                if (last_idx != j - 1)  // j >= 1 here: last_idx == -1 covers j == 0
-                  neg = (i ? smK[at - kFoldThreads] : smK[(kFoldItems - 1) * kFoldThreads + th - 1]) == 1;
-                uint32_t r = (smR[at] + c) % kM;
-                long long v = (neg && r) ? (long long)r - kM : (long long)r;
-                long long X = v + (long long)smW[at];
-                long long Y = X >= (1ll << 31) ? X - (1ll << 32) : X;
-                uint32_t m = (uint32_t)(Y < 0 ? -Y : Y) % kM;  // |Y| < 2^31 + M
-                neg = Y < 0;
-                uint32_t r2 = neg && m ? kM - m : m;
-                c = (r2 + kM - smR[at]) % kM;
-                last_idx = j;
-              }
-            }
-          }
-          int last = (int)min((uint32_t)kFoldTile, nchunks - t0) - 1;
-          s_neg = last_idx == last ? (uint32_t)neg : (uint32_t)(smK[(last % kFoldItems) * kFoldThreads + last / kFoldItems] == 1);
-          s_corr = c;
-        }
-        __syncthreads();
-        corr = s_corr;
-      }
-    }
-    s1_carry = (s1_carry + atot) % kM;
-    r_carry = (r_carry + dtot + corr) % kM;
-    __syncthreads();
   }
+  __syncthreads();
   if (tid == 0) {
-    bool neg = quirk && s_neg;
-    uint32_t s2 = (neg && r_carry) ? r_carry - kM : r_carry;
-    *out = (s2 << 16) + s1_carry;
+    if (!have_pred) {
+      const uint32_t v = (uint32_t)chain_wait(chain_s + tile - 1, epoch);
+      neg_in = v >> 17; r_carry = v & 0x1FFFFu;
+    }
+    bool neg = neg_in != 0;
+    uint32_t c = 0;
+    for (uint32_t e = 0; e < nutot; e++) {
+      const uint32_t f = uF[e];
+      if (f == 0) neg = false; else if (f == 1) neg = true; else if (f == 3) neg = neg_in != 0;
+      const uint32_t rf = (uR[e] + r_carry) % kM, r = (rf + c) % kM;
+      const long long v = (neg && r) ? (long long)r - kM : (long long)r;
+      const long long X = v + (long long)uW[e];
+      const long long Y = X >= (1ll << 31) ? X - (1ll << 32) : X;
+      const uint32_t m = (uint32_t)(Y < 0 ? -Y : Y) % kM;  // |Y| < 2^31 + M
+      neg = Y < 0;
+      const uint32_t r2 = neg && m ? kM - m : m;
+      c = (r2 + kM - rf) % kM;
+    }
+    // sign after the tile: the walk's if the last chunk was a U chunk, else what the last chunk's class says
+    const uint32_t neg_out = s_klast == 3 ? (uint32_t)neg : (uint32_t)(s_klast == 1);
+    const uint32_t r_out = (r_carry + dtot + c) % kM;
+    if (tile + 1 < ntiles) chain_post(chain_s + tile, epoch, (neg_out << 17) | r_out);
+    else {
+      const uint32_t s1 = (s1_carry + atot) % kM;
+      const uint32_t s2 = (neg_out && r_out) ? r_out - kM : r_out;
+      *out = (s2 << 16) + s1;
+      *counter = 0;
+    }
   }
 }
 // ---- RFC 1950 mode: the chunk recurrence is a plain reduction ------------------------------------------------------------
@@ -356,9 +386,22 @@ int adler32_launch_buffer(zipc_b200_ctx *ctx, const uint8_t *d_src, uint64_t len
     Seg *cta_seg = reinterpret_cast<Seg *>(ctx->d_adler.as<uint8_t>() + 64);
     adler_reduce_rfc_kernel<<<rgrid, kRedThreads, 0, ctx->stream>>>(d_ab, first, nchunks, cta_seg, ticket, d_out);
   } else {
-    // the reference's flavour: one CTA scans the partials (no host round trip)
+    // the reference's flavour: one CTA per tile of chunks, the order-dependent part handed down a chain (no host round trip)
+    const uint32_t ntiles = (nchunks + kFoldTile - 1) / kFoldTile;
+    const size_t need = 64 + 2 * (size_t)ntiles * sizeof(uint64_t);
+    if (need > ctx->d_adler_chain.cap) {  // tags of earlier launches must survive, fresh memory must read as "no tag"
+      if (int st = ctx->d_adler_chain.reserve(2 * need)) return st;
+      ZB_CUDA(ctx, cudaMemsetAsync(ctx->d_adler_chain.p, 0, ctx->d_adler_chain.cap, ctx->stream));
+      ctx->adler_epoch = 0;
+    }
+    if (++ctx->adler_epoch == 0) {  // 2^32 launches later: start over
+      ZB_CUDA(ctx, cudaMemsetAsync(ctx->d_adler_chain.p, 0, ctx->d_adler_chain.cap, ctx->stream));
+      ctx->adler_epoch = 1;
+    }
+    unsigned int *counter = ctx->d_adler_chain.as<unsigned int>();
+    uint64_t *chain_a = reinterpret_cast<uint64_t *>(ctx->d_adler_chain.as<uint8_t>() + 64), *chain_s = chain_a + ntiles;
     ZB_CUDA(ctx, cudaFuncSetAttribute(adler_fold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFoldSmem));  // per device
-    adler_fold_kernel<<<1, kFoldThreads, kFoldSmem, ctx->stream>>>(d_ab, first, nchunks, mode, d_out);
+    adler_fold_kernel<<<ntiles, kFoldThreads, kFoldSmem, ctx->stream>>>(d_ab, first, nchunks, ctx->adler_epoch, counter, chain_a, chain_s, d_out);
   }
   ctx->launches++;
   ZB_CUDA(ctx, cudaGetLastError());

@@ -541,7 +541,7 @@ void zipc_b200_ctx_destroy(zipc_b200_ctx *ctx) {
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   ctx->d_in.release(); ctx->d_out.release(); ctx->d_desc.release(); ctx->d_res.release();
   ctx->d_scratch.release(); ctx->d_scratch2.release(); ctx->d_small.release(); ctx->d_slots.release(); ctx->d_desc2.release(); ctx->d_blk.release();
-  ctx->d_par.release(); ctx->d_spec.release(); ctx->d_win.release(); ctx->d_adler.release();
+  ctx->d_par.release(); ctx->d_spec.release(); ctx->d_win.release(); ctx->d_adler.release(); ctx->d_adler_chain.release();
   ctx->h_stage.release(); ctx->h_res.release(); ctx->h_desc.release();
   if (ctx->d_crc_tabs) cudaFree(ctx->d_crc_tabs);
   if (ctx->ev0) { cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); }

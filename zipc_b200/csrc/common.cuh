@@ -149,6 +149,8 @@ struct zipc_b200_ctx {
   } par_plan;
   uint64_t epoch = 1;
   zb::DevBuf d_adler;                // adler32.cu: CTA partials + arrival counter of the RFC 1950 reduction
+  zb::DevBuf d_adler_chain;          // adler32.cu: tile counter + the two chains of the REF_COMPAT fold (tagged by adler_epoch)
+  uint32_t adler_epoch = 0;
   void *adler_ticket_at = nullptr;   // where the counter was last zeroed (the kernel resets it itself afterwards)
   uint64_t par_streams = 0, par_fallbacks = 0;   // diagnostics: large streams decoded in parallel / handed back to the serial path
 
