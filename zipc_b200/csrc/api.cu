@@ -269,16 +269,23 @@ static __global__ void xor_ffffffff_kernel(uint32_t *v, uint32_t n) {
 // One warp per stream (inflate.cu).  All pointers in d_src / d_dst are device addresses.
 static int inflate_serial_core(zipc_b200_ctx *ctx, int ck, int adler_mode, size_t n, const std::vector<const uint8_t *> &d_src,
                                const size_t *src_len, const std::vector<uint8_t *> &d_dst, const std::vector<size_t> &cap,
-                               bool count_only, size_t *out_len, uint32_t *checksum, int *status, uint32_t flags) {
+                               bool count_only, size_t *out_len, uint32_t *checksum, int *status, uint32_t flags,
+                               const DownloadPlan *plan) {
   if (!n) return ZIPC_OK;
   if (n > 0xFFFFFFF0ull) return ZIPC_ERR_INVALID_ARG;
-  // longest streams first: the tail of the dynamic queue is made of short ones
+  const bool grouped = plan && plan->ngroups && !count_only;
+  // longest streams first: the tail of the dynamic queue is made of short ones.  With a progressive download the groups
+  // go in download order instead (smallest outputs first), so that the copies start early and never run dry.
   std::vector<uint32_t> order(n);
   std::iota(order.begin(), order.end(), 0u);
-  std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return src_len[a] > src_len[b]; });
+  if (grouped)
+    std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
+      return plan->group_of[a] != plan->group_of[b] ? plan->group_of[a] < plan->group_of[b] : src_len[a] < src_len[b]; });
+  else
+    std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return src_len[a] > src_len[b]; });
   if (int st = ctx->h_desc.reserve(n * sizeof(InflateTask))) return st;
   if (int st = ctx->d_desc.reserve(n * (sizeof(InflateTask) + sizeof(CrcSeg)))) return st;
-  if (int st = ctx->d_res.reserve(n * (sizeof(InflateResult) + sizeof(uint32_t)))) return st;
+  if (int st = ctx->d_res.reserve(n * (sizeof(InflateResult) + sizeof(uint32_t)) + 1024)) return st;
   if (int st = ctx->h_res.reserve(n * (sizeof(InflateResult) + sizeof(uint32_t)))) return st;
   InflateTask *ht = ctx->h_desc.as<InflateTask>();
   for (size_t k = 0; k < n; k++) {
@@ -286,7 +293,7 @@ static int inflate_serial_core(zipc_b200_ctx *ctx, int ck, int adler_mode, size_
     ht[k].src = d_src[i]; ht[k].src_len = src_len[i];
     ht[k].dst = count_only ? nullptr : d_dst[i];
     ht[k].dst_cap = cap[i] == ZIPC_SIZE_UNKNOWN ? ~0ull : (uint64_t)cap[i];
-    ht[k].flags = flags; ht[k]._pad = 0; ht[k].start_bit = 0; ht[k].stop_bit = ~0ull;
+    ht[k].flags = flags; ht[k].group = grouped ? plan->group_of[i] : 0u; ht[k].start_bit = 0; ht[k].stop_bit = ~0ull;
   }
   InflateTask *dt = ctx->d_desc.as<InflateTask>();
   CrcSeg *dsegs = reinterpret_cast<CrcSeg *>(dt + n);
@@ -294,7 +301,18 @@ static int inflate_serial_core(zipc_b200_ctx *ctx, int ck, int adler_mode, size_
   uint32_t *dck = reinterpret_cast<uint32_t *>(dr + n);
   ZB_CUDA(ctx, cudaMemcpyAsync(dt, ht, n * sizeof(InflateTask), cudaMemcpyHostToDevice, ctx->stream));
   const bool adler = !count_only && ck == ZIPC_CK_ADLER32;
-  if (int st = inflate_launch(ctx, dt, (uint32_t)n, dr, count_only, adler ? adler_mode : -1)) return st;
+  unsigned int *d_gcount = nullptr;
+  if (grouped) {
+    std::vector<unsigned int> cnt(plan->ngroups, 0u);
+    for (size_t i = 0; i < n; i++) cnt[plan->group_of[i]]++;
+    d_gcount = reinterpret_cast<unsigned int *>(dck + n);  // behind the checksums (the buffer has 1 KiB to spare)
+    if (!ctx->h_gflag) ZB_CUDA(ctx, cudaHostAlloc(reinterpret_cast<void **>(&ctx->h_gflag), 256 * sizeof(uint32_t), cudaHostAllocMapped));
+    if (!ctx->copy_stream) ZB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    for (uint32_t g = 0; g < plan->ngroups; g++) reinterpret_cast<volatile uint32_t *>(ctx->h_gflag)[g] = cnt[g] ? 0u : 1u;
+    ZB_CUDA(ctx, cudaMemcpyAsync(d_gcount, cnt.data(), plan->ngroups * sizeof(unsigned int), cudaMemcpyHostToDevice, ctx->stream));
+    ZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // (cnt is pageable: the copy must be over before it goes away)
+  }
+  if (int st = inflate_launch(ctx, dt, (uint32_t)n, dr, count_only, adler ? adler_mode : -1, d_gcount, grouped ? ctx->h_gflag : nullptr)) return st;
   bool crc = !count_only && ck == ZIPC_CK_CRC32;
   if (crc) {
     make_crc_segs_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(dt, dr, (uint32_t)n, dsegs);
@@ -307,6 +325,20 @@ static int inflate_serial_core(zipc_b200_ctx *ctx, int ck, int adler_mode, size_
   uint32_t *hck = reinterpret_cast<uint32_t *>(hr + n);
   ZB_CUDA(ctx, cudaMemcpyAsync(hr, dr, n * sizeof(InflateResult) + (crc ? n * sizeof(uint32_t) : 0),
                                cudaMemcpyDeviceToHost, ctx->stream));
+  if (grouped) {
+    // copy every group's range out as soon as the kernel says the group is complete (or the stream is through: then all are)
+    const volatile uint32_t *flag = reinterpret_cast<volatile uint32_t *>(ctx->h_gflag);
+    bool through = false;
+    for (uint32_t g = 0; g < plan->ngroups; g++) {
+      while (!through && !flag[g]) {
+        for (int spin = 0; spin < 2000 && !flag[g]; spin++) { }
+        if (!flag[g] && cudaStreamQuery(ctx->stream) != cudaErrorNotReady) through = true;
+      }
+      if (plan->gbytes[g])
+        ZB_CUDA(ctx, cudaMemcpyAsync(plan->dst + plan->goff[g], ctx->d_out.as<uint8_t>() + plan->goff[g], plan->gbytes[g],
+                                     cudaMemcpyDeviceToHost, ctx->copy_stream));
+    }
+  }
   ZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   for (size_t k = 0; k < n; k++) {
     uint32_t i = order[k];
@@ -375,7 +407,7 @@ static int par_speculate(zipc_b200_ctx *ctx, const uint8_t *d_src, size_t src_le
     InflateTask &t = tasks[k];
     t.src = d_src; t.src_len = src_len;
     t.dst = reinterpret_cast<uint8_t *>(ctx->d_spec.as<uint16_t>() + spec_off[k]);
-    t.dst_cap = capv[k]; t.flags = 0; t._pad = 0;
+    t.dst_cap = capv[k]; t.flags = 0; t.group = 0;
     t.start_bit = start[k]; t.stop_bit = k + 1 < m ? start[k + 1] : ~0ull;
   }
   InflateTask *d_tasks = reinterpret_cast<InflateTask *>(ctx->d_par.as<uint64_t>() + 4 * (size_t)nch);
@@ -436,10 +468,10 @@ static int par_resolve(zipc_b200_ctx *ctx, uint8_t *d_dst, bool *ok) {
 // parallel decoding does not check out) goes to the warp-per-stream decoder.
 int inflate_core(zipc_b200_ctx *ctx, int ck, int adler_mode, size_t n, const std::vector<const uint8_t *> &d_src,
                  const size_t *src_len, const std::vector<uint8_t *> &d_dst, const std::vector<size_t> &cap,
-                 bool count_only, size_t *out_len, uint32_t *checksum, int *status, uint32_t flags) {
+                 bool count_only, size_t *out_len, uint32_t *checksum, int *status, uint32_t flags, const DownloadPlan *plan) {
   std::vector<char> done(n, 0);
   size_t ndone = 0;
-  if (flags == 0 && ck != ZIPC_CK_ADLER32 && par_min_bytes() != 0) {  // (Adler-32 is folded block by block: serial path)
+  if (flags == 0 && ck != ZIPC_CK_ADLER32 && par_min_bytes() != 0 && !(plan && plan->ngroups)) {  // (Adler-32 is folded block by block: serial path)
     for (size_t i = 0; i < n; i++) {
       if (src_len[i] < par_min_bytes()) continue;
       bool ok = false;
@@ -462,7 +494,7 @@ int inflate_core(zipc_b200_ctx *ctx, int ck, int adler_mode, size_t n, const std
       else ctx->par_fallbacks++;
     }
   }
-  if (ndone == 0) return inflate_serial_core(ctx, ck, adler_mode, n, d_src, src_len, d_dst, cap, count_only, out_len, checksum, status, flags);
+  if (ndone == 0) return inflate_serial_core(ctx, ck, adler_mode, n, d_src, src_len, d_dst, cap, count_only, out_len, checksum, status, flags, plan);
   if (ndone == n) return ZIPC_OK;
   // the rest through the warp-per-stream decoder
   const size_t r = n - ndone;
@@ -472,8 +504,58 @@ int inflate_core(zipc_b200_ctx *ctx, int ck, int adler_mode, size_t n, const std
   std::vector<uint32_t> ck2(r), idx(r);
   std::vector<int> st2(r);
   for (size_t i = 0, j = 0; i < n; i++) if (!done[i]) { idx[j] = (uint32_t)i; s2[j] = d_src[i]; d2[j] = d_dst[i]; l2[j] = src_len[i]; c2[j] = cap[i]; j++; }
-  if (int st = inflate_serial_core(ctx, ck, adler_mode, r, s2, l2.data(), d2, c2, count_only, ol.data(), checksum ? ck2.data() : nullptr, st2.data(), flags)) return st;
+  if (int st = inflate_serial_core(ctx, ck, adler_mode, r, s2, l2.data(), d2, c2, count_only, ol.data(), checksum ? ck2.data() : nullptr, st2.data(), flags, nullptr)) return st;
   for (size_t j = 0; j < r; j++) { out_len[idx[j]] = ol[j]; status[idx[j]] = st2[j]; if (checksum) checksum[idx[j]] = ck2[j]; }
+  return ZIPC_OK;
+}
+
+// ---- progressive download ---------------------------------------------------------------------------------------------------
+// ZIPC_B200_DOWNLOAD_GROUPS: groups of a progressive download (default 16; 0 or 1 = one copy after the kernel).
+int plan_arena(zipc_b200_ctx *ctx, size_t n, const size_t *cap, const size_t *src_len, const char *grouped, void *dst,
+               size_t dst_cap, std::vector<size_t> &off, size_t &total, DownloadPlan &plan) {
+  static const uint64_t want = std::min<uint64_t>(env_u64("ZIPC_B200_DOWNLOAD_GROUPS", 16), 200);
+  off.assign(n, 0);
+  plan = DownloadPlan{};
+  size_t sum = 0, ng = 0;
+  bool ok = want >= 2 && dst && !ctx->is_sub;
+  for (size_t i = 0; i < n; i++) {
+    sum += align_up(cap[i], 16);
+    if (grouped[i]) { ng++; if (src_len[i] >= par_min_bytes() && par_min_bytes()) ok = false; }  // (large streams: decoded in parallel)
+  }
+  total = sum;
+  if (!ok || ng < 1024 || sum < (64ull << 20) || dst_cap < sum || !is_pinned(dst)) {
+    size_t t = 0;
+    for (size_t i = 0; i < n; i++) { off[i] = t; t += align_up(cap[i], 16); }
+    return ZIPC_OK;
+  }
+  // grouped streams by ascending output size, equal counts per group; then everything else
+  std::vector<uint32_t> idx;
+  idx.reserve(ng);
+  for (size_t i = 0; i < n; i++) if (grouped[i]) idx.push_back((uint32_t)i);
+  std::sort(idx.begin(), idx.end(), [&](uint32_t a, uint32_t b) { return cap[a] != cap[b] ? cap[a] < cap[b] : a < b; });
+  const uint32_t G = (uint32_t)want;
+  plan.ngroups = G; plan.group_of.assign(n, 0); plan.goff.assign(G, 0); plan.gbytes.assign(G, 0); plan.dst = static_cast<uint8_t *>(dst);
+  size_t t = 0;
+  for (size_t r = 0; r < idx.size(); r++) {
+    const uint32_t i = idx[r], g = (uint32_t)(r * G / idx.size());
+    if (plan.gbytes[g] == 0) plan.goff[g] = t;
+    plan.group_of[i] = g;
+    off[i] = t;
+    t += align_up(cap[i], 16);
+    plan.gbytes[g] = t - plan.goff[g];
+  }
+  plan.tail_off = t;
+  for (size_t i = 0; i < n; i++) if (!grouped[i]) { off[i] = t; t += align_up(cap[i], 16); }
+  plan.tail_bytes = t - plan.tail_off;
+  return ZIPC_OK;
+}
+
+// the grouped ranges are on their way (inflate_core); copy the rest and wait for all of it
+int finish_download(zipc_b200_ctx *ctx, const DownloadPlan &plan) {
+  if (plan.tail_bytes)
+    ZB_CUDA(ctx, cudaMemcpyAsync(plan.dst + plan.tail_off, ctx->d_out.as<uint8_t>() + plan.tail_off, plan.tail_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  ZB_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
+  ZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return ZIPC_OK;
 }
 
@@ -545,6 +627,8 @@ void zipc_b200_ctx_destroy(zipc_b200_ctx *ctx) {
   ctx->h_stage.release(); ctx->h_res.release(); ctx->h_desc.release();
   if (ctx->d_crc_tabs) cudaFree(ctx->d_crc_tabs);
   if (ctx->ev0) { cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); }
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  if (ctx->h_gflag) cudaFreeHost(ctx->h_gflag);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -684,9 +768,9 @@ int zipc_b200_inflate_batch(zipc_b200_ctx *ctx, int ck, int adler_mode, size_t n
   if (dst_need) *dst_need = 0;
   if (!n) return ZIPC_OK;
   DeviceGuard g(ctx->device);
-  // (Not pipelined like zipc_b200_deflate_batch: a group's kernel lasts as long as its largest member takes on one warp
+  // (Not cut into groups on sub-contexts like zipc_b200_deflate_batch: a group's kernel lasts as long as its largest member takes on one warp
   // (~14 ms for 256 KiB), whatever the group's size, so no download can start earlier than that and groups gain nothing:
-  // measured 26.5 GB/s in 6 groups against 28.0 GB/s in one piece, DESIGN.md.)
+  // measured 26.5 GB/s in 6 groups against 28.0 GB/s in one piece.  What overlaps instead is the download: plan_arena.)
   std::vector<const uint8_t *> d_src;
   if (int st = upload_ranges(ctx, n, src, src_len, d_src)) return st;
   // resolve unknown output sizes with a count-only pass (no bytes are written)
@@ -704,15 +788,25 @@ int zipc_b200_inflate_batch(zipc_b200_ctx *ctx, int ck, int adler_mode, size_t n
     for (size_t i = 0; i < n; i++)
       if (cap[i] == ZIPC_SIZE_UNKNOWN) { was_unknown[i] = 1; cap[i] = cs[i] == ZIPC_OK ? cl[i] : 0; }
   }
-  std::vector<size_t> off(n);
+  std::vector<size_t> off;
   size_t total = 0;
-  for (size_t i = 0; i < n; i++) { off[i] = total; total += align_up(cap[i], 16); }
+  DownloadPlan plan;
+  {
+    const std::vector<char> all(n, 1);
+    if (int st = plan_arena(ctx, n, cap.data(), src_len, all.data(), dst, dst_cap, off, total, plan)) return st;
+  }
   if (int st = ctx->d_out.reserve(total + 64)) return st;
   for (size_t i = 0; i < n; i++) d_dst[i] = ctx->d_out.as<uint8_t>() + off[i];
-  if (int st = inflate_core(ctx, ck, adler_mode, n, d_src, src_len, d_dst, cap, false, dst_len, checksum, status)) return st;
+  if (int st = inflate_core(ctx, ck, adler_mode, n, d_src, src_len, d_dst, cap, false, dst_len, checksum, status, 0, &plan)) return st;
   // a stream of unknown size that failed while being sized keeps that (uncapped) verdict
   for (size_t i = 0; i < n; i++)
     if (was_unknown[i] && cs[i] != ZIPC_OK) { status[i] = cs[i]; dst_len[i] = 0; if (checksum) checksum[i] = 0; }
+  if (plan.ngroups) {
+    ctx->last_off = off; ctx->last_len.assign(dst_len, dst_len + n); ctx->last_total = total;
+    for (size_t i = 0; i < n; i++) dst_off[i] = off[i];
+    if (dst_need) *dst_need = total;
+    return finish_download(ctx, plan);
+  }
   return finish_to_host(ctx, n, off, dst_len, total, dst, dst_cap, dst_need, dst_off);
 }
 

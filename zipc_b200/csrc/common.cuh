@@ -81,7 +81,7 @@ struct InflateTask {  // one deflate stream to inflate
   uint8_t *dst;       // may be null in count-only mode
   uint64_t dst_cap;   // ?decompressed_size, or ~0ull when unknown (count-only pass)
   uint32_t flags;     // kInflateSegment: a piece of a segmented stream, ends where its input ends
-  uint32_t _pad;
+  uint32_t group;     // progressive download: the group whose counter this stream decrements when it is done
   // speculative decoding of one chunk of a large stream (inflate_kernel<.., SPEC>): decoding starts at the block header at
   // bit start_bit of the stream and stops at the first block boundary at or after stop_bit; dst holds 16-bit symbols
   // (dst_cap counts symbols): a byte, or 0x8000 | w for "byte w of the 32 KiB that precede this chunk's output"
@@ -137,6 +137,8 @@ struct zipc_b200_ctx {
   zb::DevBuf d_in, d_out, d_desc, d_res, d_scratch, d_scratch2, d_small, d_slots, d_desc2, d_blk;
   zb::DevBuf d_par, d_spec, d_win;   // intra-stream parallel inflate: chunk tables, speculative symbols, windows
   zb::PinBuf h_stage, h_res, h_desc;
+  cudaStream_t copy_stream = nullptr;  // progressive downloads (api.cu)
+  uint32_t *h_gflag = nullptr;         // mapped host memory: group-complete flags written by inflate_kernel
 
   // intra-stream parallel inflate: the plan of the last large stream decoded speculatively (a count-only pass is followed by
   // the real pass over the same device bytes; `epoch` changes whenever new input is uploaded)
@@ -221,9 +223,25 @@ int h2d(zipc_b200_ctx *ctx, void *d, const void *h, size_t bytes);
 int d2h(zipc_b200_ctx *ctx, void *h, const void *d, size_t bytes);
 int upload_ranges(zipc_b200_ctx *ctx, size_t n, const void *const *src, const size_t *len,
                   std::vector<const uint8_t *> &d_ptr);
+// Progressive download of an inflate batch (api.cu): the streams are sorted by output size into groups that own contiguous
+// ranges of the output arena; the decoder counts every group down and raises a flag in mapped host memory when a group is
+// complete, and the host starts that range's copy while the kernel works on the larger streams.
+struct DownloadPlan {
+  uint32_t ngroups = 0;                 // 0: not used, the arena is in member order and comes back with one copy
+  std::vector<uint32_t> group_of;       // per stream handed to inflate_core
+  std::vector<size_t> goff, gbytes;     // arena range of each group
+  uint8_t *dst = nullptr;               // the caller's (pinned) arena
+  size_t tail_off = 0, tail_bytes = 0;  // arena range of everything that is not a grouped stream (copied at the end)
+};
 int inflate_core(zipc_b200_ctx *ctx, int ck, int adler_mode, size_t n, const std::vector<const uint8_t *> &d_src,
                  const size_t *src_len, const std::vector<uint8_t *> &d_dst, const std::vector<size_t> &cap,
-                 bool count_only, size_t *out_len, uint32_t *checksum, int *status, uint32_t flags = 0);
+                 bool count_only, size_t *out_len, uint32_t *checksum, int *status, uint32_t flags = 0,
+                 const DownloadPlan *plan = nullptr);
+// Lay out the output arena of n members (cap[i] bytes each, 16-byte aligned slots).  grouped[i] != 0 marks the streams that
+// go through the inflate kernel.  Fills off / total, and plan when the batch qualifies for a progressive download.
+int plan_arena(zipc_b200_ctx *ctx, size_t n, const size_t *cap, const size_t *src_len, const char *grouped, void *dst,
+               size_t dst_cap, std::vector<size_t> &off, size_t &total, DownloadPlan &plan);
+int finish_download(zipc_b200_ctx *ctx, const DownloadPlan &plan);
 // api.cu / multi.cc: copy / compute pipelining of large host-pointer batches on one device
 zipc_b200_mctx *pipeline_for(zipc_b200_ctx *ctx, size_t n, const size_t *len, const void *dst);
 int pipeline_create(int device, int depth, zipc_b200_mctx **out);
@@ -233,7 +251,8 @@ int zip_assemble_impl(const zipc_b200_member *ms, size_t n, const char *first, v
                       size_t *out_len, bool copy_payload, uint64_t *payload_off);
 // inflate.cu
 int inflate_launch(zipc_b200_ctx *ctx, const InflateTask *d_tasks, uint32_t n, InflateResult *d_results,
-                   bool count_only, int adler_mode /* -1: none */);
+                   bool count_only, int adler_mode /* -1: none */, unsigned int *d_group_count = nullptr,
+                   uint32_t *group_flag = nullptr);
 // intra-stream parallel inflate (a large stream without an index): the three device steps; api.cu orchestrates
 // 1. for every chunk k >= 1 of `chunk_bytes` compressed bytes, the first bit position >= 8 * k * chunk_bytes at which a valid
 //    dynamic-Huffman block header starts (d_found[k], ~0 if none before the next chunk's own search range ends)

@@ -441,8 +441,11 @@ __device__ bool read_dynamic_header(Input &in, WarpWork &wk, WarpTabs &mine, uin
 template <bool COUNT_ONLY, bool SPEC>
 __global__ void __launch_bounds__(THREADS, 1)
 inflate_kernel(const InflateTask *__restrict__ tasks, uint32_t ntasks, InflateResult *__restrict__ results,
-               unsigned int *__restrict__ queue, uint16_t *__restrict__ g_syms, int adler_mode) {
+               unsigned int *__restrict__ queue, uint16_t *__restrict__ g_syms, int adler_mode,
+               unsigned int *__restrict__ group_count, uint32_t *__restrict__ group_flag) {
   // adler_mode: -1 = no checksum in this kernel, else ZIPC_ADLER_* (fused per-block Adler-32 of the output)
+  // group_count / group_flag (may be null): streams left in each download group; the warp that finishes a group's last
+  // stream raises the group's flag (mapped host memory), and the host starts copying that range of the arena
   extern __shared__ __align__(16) uint8_t smem_raw[];
   WarpTabs *tabs = reinterpret_cast<WarpTabs *>(smem_raw);                  // [WARPS] + fixed
   WarpTabs &fixed = tabs[WARPS];
@@ -859,6 +862,14 @@ inflate_kernel(const InflateTask *__restrict__ tasks, uint32_t ntasks, InflateRe
         r._pad2 = 0;
         results[task] = r;
       }
+      if (!COUNT_ONLY && !SPEC && group_count) {
+        __threadfence();   // every lane: my bytes of this stream are out
+        __syncwarp();
+        if (lane == 0 && atomicSub(&group_count[tasks[task].group], 1u) == 1u) {
+          __threadfence_system();
+          *reinterpret_cast<volatile uint32_t *>(&group_flag[tasks[task].group]) = 1u;
+        }
+      }
       state = S_IDLE;
     }
   }
@@ -992,7 +1003,7 @@ unsigned long long g_attr_devs = 0;  // bit d: attributes set on device d (funct
 }  // namespace
 
 int inflate_launch(zipc_b200_ctx *ctx, const InflateTask *d_tasks, uint32_t n, InflateResult *d_results,
-                   bool count_only, int adler_mode) {
+                   bool count_only, int adler_mode, unsigned int *d_group_count, uint32_t *group_flag) {
   if (n == 0) return ZIPC_OK;
   if (!(g_attr_devs >> (ctx->device & 63) & 1ull)) {
     ZB_CUDA(ctx, cudaFuncSetAttribute(inflate_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
@@ -1015,9 +1026,10 @@ int inflate_launch(zipc_b200_ctx *ctx, const InflateTask *d_tasks, uint32_t n, I
   }
   KernelTimer kt(ctx);
   if (count_only)
-    inflate_kernel<true, false><<<grid, THREADS, kSmemBytes, ctx->stream>>>(d_tasks, n, d_results, queue, ctx->d_scratch.as<uint16_t>(), -1);
+    inflate_kernel<true, false><<<grid, THREADS, kSmemBytes, ctx->stream>>>(d_tasks, n, d_results, queue, ctx->d_scratch.as<uint16_t>(), -1, nullptr, nullptr);
   else
-    inflate_kernel<false, false><<<grid, THREADS, kSmemBytes, ctx->stream>>>(d_tasks, n, d_results, queue, ctx->d_scratch.as<uint16_t>(), adler_mode);
+    inflate_kernel<false, false><<<grid, THREADS, kSmemBytes, ctx->stream>>>(d_tasks, n, d_results, queue, ctx->d_scratch.as<uint16_t>(), adler_mode,
+                                                                            d_group_count, group_flag);
   ctx->launches++;
   ZB_CUDA(ctx, cudaGetLastError());
   return ZIPC_OK;
@@ -1053,7 +1065,7 @@ int inflate_launch_spec(zipc_b200_ctx *ctx, const InflateTask *d_tasks, uint32_t
   unsigned int start = grid * WARPS;  // tasks [0, start) are assigned statically
   ZB_CUDA(ctx, cudaMemcpyAsync(queue, &start, sizeof start, cudaMemcpyHostToDevice, ctx->stream));
   KernelTimer kt(ctx);
-  inflate_kernel<false, true><<<grid, THREADS, kSmemBytes, ctx->stream>>>(d_tasks, n, d_results, queue, ctx->d_scratch.as<uint16_t>(), -1);
+  inflate_kernel<false, true><<<grid, THREADS, kSmemBytes, ctx->stream>>>(d_tasks, n, d_results, queue, ctx->d_scratch.as<uint16_t>(), -1, nullptr, nullptr);
   ctx->launches++;
   ZB_CUDA(ctx, cudaGetLastError());
   return ZIPC_OK;

@@ -394,9 +394,14 @@ int zipc_b200_zip_extract_batch(zipc_b200_ctx *ctx, const zipc_b200_member *ms, 
   }
   std::vector<const uint8_t *> d_src;
   if (int st = upload_ranges(ctx, n, src.data(), slen.data(), d_src)) return st;
-  std::vector<size_t> off(n);
+  std::vector<size_t> off;
   size_t total = 0;
-  for (size_t i = 0; i < n; i++) { off[i] = total; total += align_up(cap[i], 16); }
+  DownloadPlan plan;
+  {
+    std::vector<char> grouped(n);
+    for (size_t i = 0; i < n; i++) grouped[i] = kind[i] == 2;
+    if (int st = plan_arena(ctx, n, cap.data(), slen.data(), grouped.data(), dst, dst_cap, off, total, plan)) return st;
+  }
   if (int st = ctx->d_out.reserve(total + 64)) return st;
   // deflate members through the inflate kernel (with CRC-32 of the output)
   std::vector<uint32_t> idx;
@@ -409,7 +414,9 @@ int zipc_b200_zip_extract_batch(zipc_b200_ctx *ctx, const zipc_b200_member *ms, 
     std::vector<uint32_t> ck(k);
     std::vector<int> st2(k);
     for (size_t j = 0; j < k; j++) { s2[j] = d_src[idx[j]]; d2[j] = ctx->d_out.as<uint8_t>() + off[idx[j]]; l2[j] = slen[idx[j]]; c2[j] = cap[idx[j]]; }
-    if (int st = inflate_core(ctx, ZIPC_CK_CRC32, 0, k, s2, l2.data(), d2, c2, false, ol.data(), ck.data(), st2.data())) return st;
+    DownloadPlan plan2 = plan;  // the same groups, indexed like the arrays handed to inflate_core
+    if (plan.ngroups) { plan2.group_of.resize(k); for (size_t j = 0; j < k; j++) plan2.group_of[j] = plan.group_of[idx[j]]; }
+    if (int st = inflate_core(ctx, ZIPC_CK_CRC32, 0, k, s2, l2.data(), d2, c2, false, ol.data(), ck.data(), st2.data(), 0, &plan2)) return st;
     for (size_t j = 0; j < k; j++) {
       size_t i = idx[j];
       status[i] = st2[j]; dst_len[i] = ol[j];
@@ -452,6 +459,7 @@ int zipc_b200_zip_extract_batch(zipc_b200_ctx *ctx, const zipc_b200_member *ms, 
   for (size_t i = 0; i < n; i++) dst_off[i] = off[i];
   if (dst_need) *dst_need = total;
   if (!dst || dst_cap < total) return ZIPC_ERR_DST_TOO_SMALL;
+  if (plan.ngroups) return finish_download(ctx, plan);
   return d2h(ctx, dst, ctx->d_out.p, total);
 }
 
