@@ -137,8 +137,9 @@ static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) & ~(a - 1
 // span have the same kind of memory (pinned or pageable).  Otherwise every range is copied on its own: pinned ranges
 // by DMA, pageable ones packed through the staging buffer.
 int upload_ranges(zipc_b200_ctx *ctx, size_t n, const void *const *src, const size_t *len,
-                  std::vector<const uint8_t *> &d_ptr) {
+                  std::vector<const uint8_t *> &d_ptr, UploadSplit *split) {
   d_ptr.assign(n, nullptr);
+  if (split) split->done = false;
   ctx->epoch++;  // new input bytes: plans made over the old ones are void
   // pipelined batches: wait for this group's turn on the bus; the next group may go once these bytes have arrived
   struct GatePass {
@@ -193,8 +194,33 @@ int upload_ranges(zipc_b200_ctx *ctx, size_t n, const void *const *src, const si
     size_t pre = lo & 15;  // keep the host alignment so 16-byte paths stay aligned
     if (int st = ctx->d_in.reserve(pre + span + 64)) return st;
     uint8_t *base = ctx->d_in.as<uint8_t>() + pre;
-    if (int st = h2d(ctx, base, (const void *)lo, span)) return st;
     for (size_t i = 0; i < n; i++) d_ptr[i] = len[i] ? base + ((uintptr_t)src[i] - lo) : base;
+    if (split && split->want && span >= (128u << 20) && !ctx->gate && is_pinned((const void *)lo)) {
+      // two halves, cut at the start of a range: the first on the context's stream (what follows on that stream may use it),
+      // the second on its own stream, its arrival announced through d_upflag
+      uintptr_t cut = hi;
+      for (size_t i = 0; i < n; i++) { const uintptr_t a = (uintptr_t)src[i]; if (len[i] && a >= lo + span / 2 && a < cut) cut = a; }
+      if (cut > lo && cut < hi) {
+        if (!ctx->upload_stream) ZB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->upload_stream, cudaStreamNonBlocking));
+        if (!ctx->h_gflag) ZB_CUDA(ctx, cudaHostAlloc(reinterpret_cast<void **>(&ctx->h_gflag), 256 * sizeof(uint32_t), cudaHostAllocMapped));
+        if (!ctx->d_upflag) {
+          ZB_CUDA(ctx, cudaMalloc(reinterpret_cast<void **>(&ctx->d_upflag), 64));
+          ZB_CUDA(ctx, cudaMemset(ctx->d_upflag, 0, 64));
+        }
+        if (++ctx->upload_serial == 0) ctx->upload_serial = 1;
+        ctx->h_gflag[255] = ctx->upload_serial;
+        ZB_CUDA(ctx, cudaMemcpyAsync(base, (const void *)lo, cut - lo, cudaMemcpyHostToDevice, ctx->stream));
+        if (!ctx->ev_half) ZB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_half, cudaEventDisableTiming));
+        ZB_CUDA(ctx, cudaEventRecord(ctx->ev_half, ctx->stream));
+        ZB_CUDA(ctx, cudaStreamWaitEvent(ctx->upload_stream, ctx->ev_half, 0));  // one half after the other: the first gets the whole bus
+        ZB_CUDA(ctx, cudaMemcpyAsync(base + (cut - lo), (const void *)cut, hi - cut, cudaMemcpyHostToDevice, ctx->upload_stream));
+        ZB_CUDA(ctx, cudaMemcpyAsync(ctx->d_upflag, &ctx->h_gflag[255], sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->upload_stream));
+        ctx->upload_split_live = true;
+        split->done = true; split->cut = cut;
+        return ZIPC_OK;
+      }
+    }
+    if (int st = h2d(ctx, base, (const void *)lo, span)) return st;
     return ZIPC_OK;
   }
   size_t total = 0, pageable = 0;
@@ -293,7 +319,8 @@ static int inflate_serial_core(zipc_b200_ctx *ctx, int ck, int adler_mode, size_
     ht[k].src = d_src[i]; ht[k].src_len = src_len[i];
     ht[k].dst = count_only ? nullptr : d_dst[i];
     ht[k].dst_cap = cap[i] == ZIPC_SIZE_UNKNOWN ? ~0ull : (uint64_t)cap[i];
-    ht[k].flags = flags; ht[k].group = grouped ? plan->group_of[i] : 0u; ht[k].start_bit = 0; ht[k].stop_bit = ~0ull;
+    ht[k].flags = flags | (grouped && !plan->late.empty() && plan->late[i] ? kInflateLateInput : 0u);
+    ht[k].group = grouped ? plan->group_of[i] : 0u; ht[k].start_bit = 0; ht[k].stop_bit = ~0ull;
   }
   InflateTask *dt = ctx->d_desc.as<InflateTask>();
   CrcSeg *dsegs = reinterpret_cast<CrcSeg *>(dt + n);
@@ -312,7 +339,13 @@ static int inflate_serial_core(zipc_b200_ctx *ctx, int ck, int adler_mode, size_
     ZB_CUDA(ctx, cudaMemcpyAsync(d_gcount, cnt.data(), plan->ngroups * sizeof(unsigned int), cudaMemcpyHostToDevice, ctx->stream));
     ZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // (cnt is pageable: the copy must be over before it goes away)
   }
-  if (int st = inflate_launch(ctx, dt, (uint32_t)n, dr, count_only, adler ? adler_mode : -1, d_gcount, grouped ? ctx->h_gflag : nullptr)) return st;
+  const bool late = grouped && !plan->late.empty() && ctx->upload_split_live;
+  if (ctx->upload_split_live && !late) {  // nobody will wait for the late half inside the kernel: wait for it here
+    ZB_CUDA(ctx, cudaStreamSynchronize(ctx->upload_stream));
+    ctx->upload_split_live = false;
+  }
+  if (int st = inflate_launch(ctx, dt, (uint32_t)n, dr, count_only, adler ? adler_mode : -1, d_gcount, grouped ? ctx->h_gflag : nullptr,
+                              late ? ctx->d_upflag : nullptr, ctx->upload_serial)) return st;
   bool crc = !count_only && ck == ZIPC_CK_CRC32;
   if (crc) {
     make_crc_segs_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(dt, dr, (uint32_t)n, dsegs);
@@ -340,6 +373,7 @@ static int inflate_serial_core(zipc_b200_ctx *ctx, int ck, int adler_mode, size_
     }
   }
   ZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (late) { ZB_CUDA(ctx, cudaStreamSynchronize(ctx->upload_stream)); ctx->upload_split_live = false; }
   for (size_t k = 0; k < n; k++) {
     uint32_t i = order[k];
     status[i] = (int)hr[k].status;
@@ -510,31 +544,39 @@ int inflate_core(zipc_b200_ctx *ctx, int ck, int adler_mode, size_t n, const std
 }
 
 // ---- progressive download ---------------------------------------------------------------------------------------------------
-// ZIPC_B200_DOWNLOAD_GROUPS: groups of a progressive download (default 16; 0 or 1 = one copy after the kernel).
-int plan_arena(zipc_b200_ctx *ctx, size_t n, const size_t *cap, const size_t *src_len, const char *grouped, void *dst,
+// ZIPC_B200_DOWNLOAD_GROUPS: groups of a progressive download (default 32; 0 or 1 = one copy after the kernel).
+static uint64_t download_groups() { static const uint64_t v = std::min<uint64_t>(env_u64("ZIPC_B200_DOWNLOAD_GROUPS", 32), 200); return v; }
+
+bool progressive_ok(zipc_b200_ctx *ctx, size_t n, const size_t *cap, const size_t *src_len, const char *grouped, void *dst, size_t dst_cap) {
+  if (download_groups() < 2 || !dst || ctx->is_sub) return false;
+  size_t sum = 0, ng = 0;
+  for (size_t i = 0; i < n; i++) {
+    if (cap[i] == ZIPC_SIZE_UNKNOWN) return false;
+    sum += align_up(cap[i], 16);
+    if (grouped[i]) { ng++; if (par_min_bytes() && src_len[i] >= par_min_bytes()) return false; }  // (large streams: decoded in parallel)
+  }
+  return ng >= 1024 && sum >= (64ull << 20) && dst_cap >= sum && is_pinned(dst);
+}
+
+int plan_arena(zipc_b200_ctx *ctx, size_t n, const size_t *cap, const size_t *src_len, const char *grouped, const char *late, void *dst,
                size_t dst_cap, std::vector<size_t> &off, size_t &total, DownloadPlan &plan) {
-  static const uint64_t want = std::min<uint64_t>(env_u64("ZIPC_B200_DOWNLOAD_GROUPS", 16), 200);
   off.assign(n, 0);
   plan = DownloadPlan{};
-  size_t sum = 0, ng = 0;
-  bool ok = want >= 2 && dst && !ctx->is_sub;
-  for (size_t i = 0; i < n; i++) {
-    sum += align_up(cap[i], 16);
-    if (grouped[i]) { ng++; if (src_len[i] >= par_min_bytes() && par_min_bytes()) ok = false; }  // (large streams: decoded in parallel)
-  }
-  total = sum;
-  if (!ok || ng < 1024 || sum < (64ull << 20) || dst_cap < sum || !is_pinned(dst)) {
+  if (!progressive_ok(ctx, n, cap, src_len, grouped, dst, dst_cap)) {
     size_t t = 0;
     for (size_t i = 0; i < n; i++) { off[i] = t; t += align_up(cap[i], 16); }
+    total = t;
     return ZIPC_OK;
   }
-  // grouped streams by ascending output size, equal counts per group; then everything else
+  // grouped streams: those of the early half of the upload first, then by ascending output size; equal counts per group
   std::vector<uint32_t> idx;
-  idx.reserve(ng);
   for (size_t i = 0; i < n; i++) if (grouped[i]) idx.push_back((uint32_t)i);
-  std::sort(idx.begin(), idx.end(), [&](uint32_t a, uint32_t b) { return cap[a] != cap[b] ? cap[a] < cap[b] : a < b; });
-  const uint32_t G = (uint32_t)want;
+  std::sort(idx.begin(), idx.end(), [&](uint32_t a, uint32_t b) {
+    const int la = late ? late[a] != 0 : 0, lb = late ? late[b] != 0 : 0;
+    return la != lb ? la < lb : cap[a] != cap[b] ? cap[a] < cap[b] : a < b; });
+  const uint32_t G = (uint32_t)download_groups();
   plan.ngroups = G; plan.group_of.assign(n, 0); plan.goff.assign(G, 0); plan.gbytes.assign(G, 0); plan.dst = static_cast<uint8_t *>(dst);
+  if (late) plan.late.assign(late, late + n);
   size_t t = 0;
   for (size_t r = 0; r < idx.size(); r++) {
     const uint32_t i = idx[r], g = (uint32_t)(r * G / idx.size());
@@ -547,6 +589,7 @@ int plan_arena(zipc_b200_ctx *ctx, size_t n, const size_t *cap, const size_t *sr
   plan.tail_off = t;
   for (size_t i = 0; i < n; i++) if (!grouped[i]) { off[i] = t; t += align_up(cap[i], 16); }
   plan.tail_bytes = t - plan.tail_off;
+  total = t;
   return ZIPC_OK;
 }
 
@@ -628,6 +671,9 @@ void zipc_b200_ctx_destroy(zipc_b200_ctx *ctx) {
   if (ctx->d_crc_tabs) cudaFree(ctx->d_crc_tabs);
   if (ctx->ev0) { cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); }
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  if (ctx->upload_stream) cudaStreamDestroy(ctx->upload_stream);
+  if (ctx->d_upflag) cudaFree(ctx->d_upflag);
+  if (ctx->ev_half) cudaEventDestroy(ctx->ev_half);
   if (ctx->h_gflag) cudaFreeHost(ctx->h_gflag);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -771,12 +817,15 @@ int zipc_b200_inflate_batch(zipc_b200_ctx *ctx, int ck, int adler_mode, size_t n
   // (Not cut into groups on sub-contexts like zipc_b200_deflate_batch: a group's kernel lasts as long as its largest member takes on one warp
   // (~14 ms for 256 KiB), whatever the group's size, so no download can start earlier than that and groups gain nothing:
   // measured 26.5 GB/s in 6 groups against 28.0 GB/s in one piece.  What overlaps instead is the download: plan_arena.)
-  std::vector<const uint8_t *> d_src;
-  if (int st = upload_ranges(ctx, n, src, src_len, d_src)) return st;
-  // resolve unknown output sizes with a count-only pass (no bytes are written)
   std::vector<size_t> cap(n);
   bool any_unknown = false;
   for (size_t i = 0; i < n; i++) { cap[i] = max_out ? max_out[i] : ZIPC_SIZE_UNKNOWN; any_unknown |= cap[i] == ZIPC_SIZE_UNKNOWN; }
+  const std::vector<char> all(n, 1);
+  UploadSplit split;
+  split.want = !any_unknown && progressive_ok(ctx, n, cap.data(), src_len, all.data(), dst, dst_cap);
+  std::vector<const uint8_t *> d_src;
+  if (int st = upload_ranges(ctx, n, src, src_len, d_src, &split)) return st;
+  // resolve unknown output sizes with a count-only pass (no bytes are written)
   std::vector<uint8_t *> d_dst(n, nullptr);
   std::vector<int> cs;
   std::vector<char> was_unknown(n, 0);
@@ -792,8 +841,9 @@ int zipc_b200_inflate_batch(zipc_b200_ctx *ctx, int ck, int adler_mode, size_t n
   size_t total = 0;
   DownloadPlan plan;
   {
-    const std::vector<char> all(n, 1);
-    if (int st = plan_arena(ctx, n, cap.data(), src_len, all.data(), dst, dst_cap, off, total, plan)) return st;
+    std::vector<char> late;
+    if (split.done) { late.resize(n); for (size_t i = 0; i < n; i++) late[i] = src_len[i] && (uintptr_t)src[i] >= split.cut; }
+    if (int st = plan_arena(ctx, n, cap.data(), src_len, all.data(), split.done ? late.data() : nullptr, dst, dst_cap, off, total, plan)) return st;
   }
   if (int st = ctx->d_out.reserve(total + 64)) return st;
   for (size_t i = 0; i < n; i++) d_dst[i] = ctx->d_out.as<uint8_t>() + off[i];

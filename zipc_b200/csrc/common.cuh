@@ -88,6 +88,7 @@ struct InflateTask {  // one deflate stream to inflate
   uint64_t start_bit, stop_bit;
 };
 constexpr uint32_t kInflateSegment = 1u;
+constexpr uint32_t kInflateLateInput = 2u;  // the stream's bytes arrive with the second half of a split upload: wait for it
 struct InflateResult {
   uint64_t out_len;
   uint32_t status;
@@ -138,6 +139,11 @@ struct zipc_b200_ctx {
   zb::DevBuf d_par, d_spec, d_win;   // intra-stream parallel inflate: chunk tables, speculative symbols, windows
   zb::PinBuf h_stage, h_res, h_desc;
   cudaStream_t copy_stream = nullptr;  // progressive downloads (api.cu)
+  cudaStream_t upload_stream = nullptr;  // late half of a split upload
+  uint32_t *d_upflag = nullptr;        // device word: serial number of the last completed late half
+  uint32_t upload_serial = 0;
+  cudaEvent_t ev_half = nullptr;       // first half of a split upload is through
+  bool upload_split_live = false;      // the late half of the current upload is still on its way
   uint32_t *h_gflag = nullptr;         // mapped host memory: group-complete flags written by inflate_kernel
 
   // intra-stream parallel inflate: the plan of the last large stream decoded speculatively (a count-only pass is followed by
@@ -221,8 +227,16 @@ int gather_launch(zipc_b200_ctx *ctx, const CopyDesc *d_descs, uint32_t n);
 // api.cu helpers shared with zip_api.cu
 int h2d(zipc_b200_ctx *ctx, void *d, const void *h, size_t bytes);
 int d2h(zipc_b200_ctx *ctx, void *h, const void *d, size_t bytes);
+// A split upload (api.cu upload_ranges): the first half of a large pinned span goes out on the context's stream, the second
+// on upload_stream, followed by the serial number of the upload into ctx->d_upflag; streams whose bytes lie at or above
+// `cut` are decoded only after the kernel has seen that number.
+struct UploadSplit {
+  bool want = false;        // in: the caller can deal with a split
+  bool done = false;        // out: the upload was split
+  uintptr_t cut = 0;        // out: host address where the late half begins
+};
 int upload_ranges(zipc_b200_ctx *ctx, size_t n, const void *const *src, const size_t *len,
-                  std::vector<const uint8_t *> &d_ptr);
+                  std::vector<const uint8_t *> &d_ptr, UploadSplit *split = nullptr);
 // Progressive download of an inflate batch (api.cu): the streams are sorted by output size into groups that own contiguous
 // ranges of the output arena; the decoder counts every group down and raises a flag in mapped host memory when a group is
 // complete, and the host starts that range's copy while the kernel works on the larger streams.
@@ -232,6 +246,7 @@ struct DownloadPlan {
   std::vector<size_t> goff, gbytes;     // arena range of each group
   uint8_t *dst = nullptr;               // the caller's (pinned) arena
   size_t tail_off = 0, tail_bytes = 0;  // arena range of everything that is not a grouped stream (copied at the end)
+  std::vector<char> late;               // per stream handed to inflate_core: its input comes with the late half of the upload
 };
 int inflate_core(zipc_b200_ctx *ctx, int ck, int adler_mode, size_t n, const std::vector<const uint8_t *> &d_src,
                  const size_t *src_len, const std::vector<uint8_t *> &d_dst, const std::vector<size_t> &cap,
@@ -239,7 +254,9 @@ int inflate_core(zipc_b200_ctx *ctx, int ck, int adler_mode, size_t n, const std
                  const DownloadPlan *plan = nullptr);
 // Lay out the output arena of n members (cap[i] bytes each, 16-byte aligned slots).  grouped[i] != 0 marks the streams that
 // go through the inflate kernel.  Fills off / total, and plan when the batch qualifies for a progressive download.
-int plan_arena(zipc_b200_ctx *ctx, size_t n, const size_t *cap, const size_t *src_len, const char *grouped, void *dst,
+// late[i] != 0 (may be null): the stream's input arrives with the late half of a split upload; such streams form the later groups.
+bool progressive_ok(zipc_b200_ctx *ctx, size_t n, const size_t *cap, const size_t *src_len, const char *grouped, void *dst, size_t dst_cap);
+int plan_arena(zipc_b200_ctx *ctx, size_t n, const size_t *cap, const size_t *src_len, const char *grouped, const char *late, void *dst,
                size_t dst_cap, std::vector<size_t> &off, size_t &total, DownloadPlan &plan);
 int finish_download(zipc_b200_ctx *ctx, const DownloadPlan &plan);
 // api.cu / multi.cc: copy / compute pipelining of large host-pointer batches on one device
@@ -252,7 +269,7 @@ int zip_assemble_impl(const zipc_b200_member *ms, size_t n, const char *first, v
 // inflate.cu
 int inflate_launch(zipc_b200_ctx *ctx, const InflateTask *d_tasks, uint32_t n, InflateResult *d_results,
                    bool count_only, int adler_mode /* -1: none */, unsigned int *d_group_count = nullptr,
-                   uint32_t *group_flag = nullptr);
+                   uint32_t *group_flag = nullptr, const uint32_t *d_upflag = nullptr, uint32_t upload_serial = 0);
 // intra-stream parallel inflate (a large stream without an index): the three device steps; api.cu orchestrates
 // 1. for every chunk k >= 1 of `chunk_bytes` compressed bytes, the first bit position >= 8 * k * chunk_bytes at which a valid
 //    dynamic-Huffman block header starts (d_found[k], ~0 if none before the next chunk's own search range ends)

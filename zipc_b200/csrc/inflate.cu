@@ -442,10 +442,13 @@ template <bool COUNT_ONLY, bool SPEC>
 __global__ void __launch_bounds__(THREADS, 1)
 inflate_kernel(const InflateTask *__restrict__ tasks, uint32_t ntasks, InflateResult *__restrict__ results,
                unsigned int *__restrict__ queue, uint16_t *__restrict__ g_syms, int adler_mode,
-               unsigned int *__restrict__ group_count, uint32_t *__restrict__ group_flag) {
+               unsigned int *__restrict__ group_count, uint32_t *__restrict__ group_flag,
+               const uint32_t *__restrict__ upload_flag, uint32_t upload_serial) {
   // adler_mode: -1 = no checksum in this kernel, else ZIPC_ADLER_* (fused per-block Adler-32 of the output)
   // group_count / group_flag (may be null): streams left in each download group; the warp that finishes a group's last
   // stream raises the group's flag (mapped host memory), and the host starts copying that range of the arena
+  // upload_flag / upload_serial: a stream flagged kInflateLateInput is opened only once *upload_flag == upload_serial (its
+  // bytes travel with the second half of a split upload, on another stream, while this kernel already works on the first)
   extern __shared__ __align__(16) uint8_t smem_raw[];
   WarpTabs *tabs = reinterpret_cast<WarpTabs *>(smem_raw);                  // [WARPS] + fixed
   WarpTabs &fixed = tabs[WARPS];
@@ -503,6 +506,15 @@ inflate_kernel(const InflateTask *__restrict__ tasks, uint32_t ntasks, InflateRe
       }
       if (task >= ntasks) break;
       const InflateTask t = tasks[task];
+      if (!COUNT_ONLY && !SPEC && (t.flags & kInflateLateInput) && upload_flag) {
+        // (bounded: if that copy failed the host reports it; the warp then decodes whatever is there and the call fails anyway)
+        uint32_t seen = 0;
+        for (uint32_t spins = 0; spins < (1u << 24); spins++) {
+          asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(upload_flag) : "memory");
+          if (seen == upload_serial) break;
+          __nanosleep(256);
+        }
+      }
       __syncwarp();
       if (lane == 0) { st.src = t.src; st.src_len = t.src_len; st.out_cap = t.dst_cap; st.ad_from = 0; }
       dst = t.dst; segment = (t.flags & kInflateSegment) != 0;
@@ -1003,7 +1015,8 @@ unsigned long long g_attr_devs = 0;  // bit d: attributes set on device d (funct
 }  // namespace
 
 int inflate_launch(zipc_b200_ctx *ctx, const InflateTask *d_tasks, uint32_t n, InflateResult *d_results,
-                   bool count_only, int adler_mode, unsigned int *d_group_count, uint32_t *group_flag) {
+                   bool count_only, int adler_mode, unsigned int *d_group_count, uint32_t *group_flag, const uint32_t *d_upflag,
+                   uint32_t upload_serial) {
   if (n == 0) return ZIPC_OK;
   if (!(g_attr_devs >> (ctx->device & 63) & 1ull)) {
     ZB_CUDA(ctx, cudaFuncSetAttribute(inflate_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
@@ -1026,10 +1039,10 @@ int inflate_launch(zipc_b200_ctx *ctx, const InflateTask *d_tasks, uint32_t n, I
   }
   KernelTimer kt(ctx);
   if (count_only)
-    inflate_kernel<true, false><<<grid, THREADS, kSmemBytes, ctx->stream>>>(d_tasks, n, d_results, queue, ctx->d_scratch.as<uint16_t>(), -1, nullptr, nullptr);
+    inflate_kernel<true, false><<<grid, THREADS, kSmemBytes, ctx->stream>>>(d_tasks, n, d_results, queue, ctx->d_scratch.as<uint16_t>(), -1, nullptr, nullptr, nullptr, 0);
   else
     inflate_kernel<false, false><<<grid, THREADS, kSmemBytes, ctx->stream>>>(d_tasks, n, d_results, queue, ctx->d_scratch.as<uint16_t>(), adler_mode,
-                                                                            d_group_count, group_flag);
+                                                                            d_group_count, group_flag, d_upflag, upload_serial);
   ctx->launches++;
   ZB_CUDA(ctx, cudaGetLastError());
   return ZIPC_OK;
@@ -1065,7 +1078,7 @@ int inflate_launch_spec(zipc_b200_ctx *ctx, const InflateTask *d_tasks, uint32_t
   unsigned int start = grid * WARPS;  // tasks [0, start) are assigned statically
   ZB_CUDA(ctx, cudaMemcpyAsync(queue, &start, sizeof start, cudaMemcpyHostToDevice, ctx->stream));
   KernelTimer kt(ctx);
-  inflate_kernel<false, true><<<grid, THREADS, kSmemBytes, ctx->stream>>>(d_tasks, n, d_results, queue, ctx->d_scratch.as<uint16_t>(), -1, nullptr, nullptr);
+  inflate_kernel<false, true><<<grid, THREADS, kSmemBytes, ctx->stream>>>(d_tasks, n, d_results, queue, ctx->d_scratch.as<uint16_t>(), -1, nullptr, nullptr, nullptr, 0);
   ctx->launches++;
   ZB_CUDA(ctx, cudaGetLastError());
   return ZIPC_OK;

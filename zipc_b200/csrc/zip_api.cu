@@ -392,15 +392,20 @@ int zipc_b200_zip_extract_batch(zipc_b200_ctx *ctx, const zipc_b200_member *ms, 
     slen[i] = (size_t)m.compressed_size;
     cap[i] = kind[i] == 1 ? (size_t)m.compressed_size : (size_t)m.decompressed_size;
   }
+  std::vector<char> grouped(n);
+  bool all_deflate = true;   // (stored members are copied by a kernel that does not wait for a late half)
+  for (size_t i = 0; i < n; i++) { grouped[i] = kind[i] == 2; all_deflate &= kind[i] != 1; }
+  UploadSplit split;
+  split.want = all_deflate && progressive_ok(ctx, n, cap.data(), slen.data(), grouped.data(), dst, dst_cap);
   std::vector<const uint8_t *> d_src;
-  if (int st = upload_ranges(ctx, n, src.data(), slen.data(), d_src)) return st;
+  if (int st = upload_ranges(ctx, n, src.data(), slen.data(), d_src, &split)) return st;
   std::vector<size_t> off;
   size_t total = 0;
   DownloadPlan plan;
   {
-    std::vector<char> grouped(n);
-    for (size_t i = 0; i < n; i++) grouped[i] = kind[i] == 2;
-    if (int st = plan_arena(ctx, n, cap.data(), slen.data(), grouped.data(), dst, dst_cap, off, total, plan)) return st;
+    std::vector<char> late;
+    if (split.done) { late.resize(n); for (size_t i = 0; i < n; i++) late[i] = slen[i] && (uintptr_t)src[i] >= split.cut; }
+    if (int st = plan_arena(ctx, n, cap.data(), slen.data(), grouped.data(), split.done ? late.data() : nullptr, dst, dst_cap, off, total, plan)) return st;
   }
   if (int st = ctx->d_out.reserve(total + 64)) return st;
   // deflate members through the inflate kernel (with CRC-32 of the output)
@@ -415,7 +420,11 @@ int zipc_b200_zip_extract_batch(zipc_b200_ctx *ctx, const zipc_b200_member *ms, 
     std::vector<int> st2(k);
     for (size_t j = 0; j < k; j++) { s2[j] = d_src[idx[j]]; d2[j] = ctx->d_out.as<uint8_t>() + off[idx[j]]; l2[j] = slen[idx[j]]; c2[j] = cap[idx[j]]; }
     DownloadPlan plan2 = plan;  // the same groups, indexed like the arrays handed to inflate_core
-    if (plan.ngroups) { plan2.group_of.resize(k); for (size_t j = 0; j < k; j++) plan2.group_of[j] = plan.group_of[idx[j]]; }
+    if (plan.ngroups) {
+      plan2.group_of.resize(k);
+      for (size_t j = 0; j < k; j++) plan2.group_of[j] = plan.group_of[idx[j]];
+      if (!plan.late.empty()) { plan2.late.resize(k); for (size_t j = 0; j < k; j++) plan2.late[j] = plan.late[idx[j]]; }
+    }
     if (int st = inflate_core(ctx, ZIPC_CK_CRC32, 0, k, s2, l2.data(), d2, c2, false, ol.data(), ck.data(), st2.data(), 0, &plan2)) return st;
     for (size_t j = 0; j < k; j++) {
       size_t i = idx[j];
