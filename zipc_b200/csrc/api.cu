@@ -129,6 +129,10 @@ int d2h(zipc_b200_ctx *ctx, void *h, const void *d, size_t bytes) {
 }
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) & ~(a - 1); }
+static uint64_t env_u64(const char *name, uint64_t dflt) {
+  const char *v = std::getenv(name);
+  return (v && *v) ? std::strtoull(v, nullptr, 10) : dflt;
+}
 
 // Uploads n host ranges into ctx->d_in and returns their device addresses.  Never reads a byte of host memory that
 // lies in a page none of the ranges touches: the ranges are sent as ONE span only when, in address order, every gap
@@ -139,7 +143,7 @@ static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) & ~(a - 1
 int upload_ranges(zipc_b200_ctx *ctx, size_t n, const void *const *src, const size_t *len,
                   std::vector<const uint8_t *> &d_ptr, UploadSplit *split) {
   d_ptr.assign(n, nullptr);
-  if (split) split->done = false;
+  if (split) split->parts = 0;
   ctx->epoch++;  // new input bytes: plans made over the old ones are void
   // pipelined batches: wait for this group's turn on the bus; the next group may go once these bytes have arrived
   struct GatePass {
@@ -196,27 +200,37 @@ int upload_ranges(zipc_b200_ctx *ctx, size_t n, const void *const *src, const si
     uint8_t *base = ctx->d_in.as<uint8_t>() + pre;
     for (size_t i = 0; i < n; i++) d_ptr[i] = len[i] ? base + ((uintptr_t)src[i] - lo) : base;
     if (split && split->want && span >= (128u << 20) && !ctx->gate && is_pinned((const void *)lo)) {
-      // two halves, cut at the start of a range: the first on the context's stream (what follows on that stream may use it),
-      // the second on its own stream, its arrival announced through d_upflag
-      uintptr_t cut = hi;
-      for (size_t i = 0; i < n; i++) { const uintptr_t a = (uintptr_t)src[i]; if (len[i] && a >= lo + span / 2 && a < cut) cut = a; }
-      if (cut > lo && cut < hi) {
+      // K parts (ZIPC_B200_UPLOAD_PARTS, default 2: measured 40.3 GB/s end to end on C3, 36-37 with 3 to 6 parts, whose
+      // size-ordered queues each end in a tail of large streams), cut at starts of ranges: the first on the context's stream (what follows on that stream may use it), the
+      // others one after the other on their own stream, each arrival announced through d_upflag
+      static const uint64_t want_parts = std::min<uint64_t>(env_u64("ZIPC_B200_UPLOAD_PARTS", 2), 8);
+      uint32_t K = 1;
+      for (uint32_t p = 1; p < want_parts; p++) {
+        const uintptr_t target = lo + span / want_parts * p;
+        uintptr_t cut = hi;
+        for (size_t i = 0; i < n; i++) { const uintptr_t a = (uintptr_t)src[i]; if (len[i] && a >= target && a < cut) cut = a; }
+        if (cut < hi && cut > (K > 1 ? split->cut[K - 1] : lo)) split->cut[K++] = cut;
+      }
+      if (K >= 2) {
         if (!ctx->upload_stream) ZB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->upload_stream, cudaStreamNonBlocking));
         if (!ctx->h_gflag) ZB_CUDA(ctx, cudaHostAlloc(reinterpret_cast<void **>(&ctx->h_gflag), 256 * sizeof(uint32_t), cudaHostAllocMapped));
         if (!ctx->d_upflag) {
           ZB_CUDA(ctx, cudaMalloc(reinterpret_cast<void **>(&ctx->d_upflag), 64));
           ZB_CUDA(ctx, cudaMemset(ctx->d_upflag, 0, 64));
         }
-        if (++ctx->upload_serial == 0) ctx->upload_serial = 1;
-        ctx->h_gflag[255] = ctx->upload_serial;
-        ZB_CUDA(ctx, cudaMemcpyAsync(base, (const void *)lo, cut - lo, cudaMemcpyHostToDevice, ctx->stream));
+        ctx->upload_serial += 16;  // counts of this upload: serial + 1 .. serial + K - 1
+        ZB_CUDA(ctx, cudaMemcpyAsync(base, (const void *)lo, split->cut[1] - lo, cudaMemcpyHostToDevice, ctx->stream));
         if (!ctx->ev_half) ZB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_half, cudaEventDisableTiming));
         ZB_CUDA(ctx, cudaEventRecord(ctx->ev_half, ctx->stream));
-        ZB_CUDA(ctx, cudaStreamWaitEvent(ctx->upload_stream, ctx->ev_half, 0));  // one half after the other: the first gets the whole bus
-        ZB_CUDA(ctx, cudaMemcpyAsync(base + (cut - lo), (const void *)cut, hi - cut, cudaMemcpyHostToDevice, ctx->upload_stream));
-        ZB_CUDA(ctx, cudaMemcpyAsync(ctx->d_upflag, &ctx->h_gflag[255], sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->upload_stream));
+        ZB_CUDA(ctx, cudaStreamWaitEvent(ctx->upload_stream, ctx->ev_half, 0));  // one part after the other: each gets the whole bus
+        for (uint32_t p = 1; p < K; p++) {
+          const uintptr_t a = split->cut[p], b = p + 1 < K ? split->cut[p + 1] : hi;
+          ctx->h_gflag[240 + p] = ctx->upload_serial + p;
+          ZB_CUDA(ctx, cudaMemcpyAsync(base + (a - lo), (const void *)a, b - a, cudaMemcpyHostToDevice, ctx->upload_stream));
+          ZB_CUDA(ctx, cudaMemcpyAsync(ctx->d_upflag, &ctx->h_gflag[240 + p], sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->upload_stream));
+        }
         ctx->upload_split_live = true;
-        split->done = true; split->cut = cut;
+        split->parts = K;
         return ZIPC_OK;
       }
     }
@@ -319,7 +333,7 @@ static int inflate_serial_core(zipc_b200_ctx *ctx, int ck, int adler_mode, size_
     ht[k].src = d_src[i]; ht[k].src_len = src_len[i];
     ht[k].dst = count_only ? nullptr : d_dst[i];
     ht[k].dst_cap = cap[i] == ZIPC_SIZE_UNKNOWN ? ~0ull : (uint64_t)cap[i];
-    ht[k].flags = flags | (grouped && !plan->late.empty() && plan->late[i] ? kInflateLateInput : 0u);
+    ht[k].flags = flags | (grouped && !plan->late.empty() ? (uint32_t)plan->late[i] << kInflatePartShift : 0u);
     ht[k].group = grouped ? plan->group_of[i] : 0u; ht[k].start_bit = 0; ht[k].stop_bit = ~0ull;
   }
   InflateTask *dt = ctx->d_desc.as<InflateTask>();
@@ -389,10 +403,6 @@ static int inflate_serial_core(zipc_b200_ctx *ctx, int ck, int adler_mode, size_
 // 16-bit symbols, check that the chunks chain up exactly, resolve.  *ok = false means "decode it serially": nothing found,
 // a wrong guess, an error inside the stream (the serial decoder then reports the reference's exact status), or a chunk that
 // expands more than its symbol buffer allows.  Reference: the serial core zipc_deflate.ml:593-616, 692-709.
-static uint64_t env_u64(const char *name, uint64_t dflt) {
-  const char *v = std::getenv(name);
-  return (v && *v) ? std::strtoull(v, nullptr, 10) : dflt;
-}
 // tuning knobs (read on every call, so that tests can vary them): compressed bytes per chunk; smallest stream that is tried
 static uint64_t par_chunk_bytes() { return std::max<uint64_t>(4096, env_u64("ZIPC_B200_PAR_CHUNK", 8192)); }
 static uint64_t par_min_bytes() { return env_u64("ZIPC_B200_PAR_MIN", 262144); }
@@ -568,11 +578,11 @@ int plan_arena(zipc_b200_ctx *ctx, size_t n, const size_t *cap, const size_t *sr
     total = t;
     return ZIPC_OK;
   }
-  // grouped streams: those of the early half of the upload first, then by ascending output size; equal counts per group
+  // grouped streams: in the order in which the parts of the upload arrive, then by ascending output size; equal counts per group
   std::vector<uint32_t> idx;
   for (size_t i = 0; i < n; i++) if (grouped[i]) idx.push_back((uint32_t)i);
   std::sort(idx.begin(), idx.end(), [&](uint32_t a, uint32_t b) {
-    const int la = late ? late[a] != 0 : 0, lb = late ? late[b] != 0 : 0;
+    const int la = late ? late[a] : 0, lb = late ? late[b] : 0;
     return la != lb ? la < lb : cap[a] != cap[b] ? cap[a] < cap[b] : a < b; });
   const uint32_t G = (uint32_t)download_groups();
   plan.ngroups = G; plan.group_of.assign(n, 0); plan.goff.assign(G, 0); plan.gbytes.assign(G, 0); plan.dst = static_cast<uint8_t *>(dst);
@@ -842,8 +852,8 @@ int zipc_b200_inflate_batch(zipc_b200_ctx *ctx, int ck, int adler_mode, size_t n
   DownloadPlan plan;
   {
     std::vector<char> late;
-    if (split.done) { late.resize(n); for (size_t i = 0; i < n; i++) late[i] = src_len[i] && (uintptr_t)src[i] >= split.cut; }
-    if (int st = plan_arena(ctx, n, cap.data(), src_len, all.data(), split.done ? late.data() : nullptr, dst, dst_cap, off, total, plan)) return st;
+    if (split.parts) { late.resize(n); for (size_t i = 0; i < n; i++) late[i] = src_len[i] ? (char)split.part_of(src[i]) : 0; }
+    if (int st = plan_arena(ctx, n, cap.data(), src_len, all.data(), split.parts ? late.data() : nullptr, dst, dst_cap, off, total, plan)) return st;
   }
   if (int st = ctx->d_out.reserve(total + 64)) return st;
   for (size_t i = 0; i < n; i++) d_dst[i] = ctx->d_out.as<uint8_t>() + off[i];

@@ -88,7 +88,7 @@ struct InflateTask {  // one deflate stream to inflate
   uint64_t start_bit, stop_bit;
 };
 constexpr uint32_t kInflateSegment = 1u;
-constexpr uint32_t kInflateLateInput = 2u;  // the stream's bytes arrive with the second half of a split upload: wait for it
+constexpr uint32_t kInflatePartShift = 1, kInflatePartMask = 7u;  // flags bits 1..3: the part of a split upload that carries the stream's bytes (0: no wait)
 struct InflateResult {
   uint64_t out_len;
   uint32_t status;
@@ -227,13 +227,14 @@ int gather_launch(zipc_b200_ctx *ctx, const CopyDesc *d_descs, uint32_t n);
 // api.cu helpers shared with zip_api.cu
 int h2d(zipc_b200_ctx *ctx, void *d, const void *h, size_t bytes);
 int d2h(zipc_b200_ctx *ctx, void *h, const void *d, size_t bytes);
-// A split upload (api.cu upload_ranges): the first half of a large pinned span goes out on the context's stream, the second
-// on upload_stream, followed by the serial number of the upload into ctx->d_upflag; streams whose bytes lie at or above
-// `cut` are decoded only after the kernel has seen that number.
+// A split upload (api.cu upload_ranges): the first part of a large pinned span goes out on the context's stream, the others
+// one after the other on upload_stream, each followed by a count (ctx->upload_serial + part) into ctx->d_upflag; a stream
+// whose bytes lie in part p >= 1 is decoded only after the kernel has seen that count.
 struct UploadSplit {
   bool want = false;        // in: the caller can deal with a split
-  bool done = false;        // out: the upload was split
-  uintptr_t cut = 0;        // out: host address where the late half begins
+  uint32_t parts = 0;       // out: number of parts (0: the upload was not split)
+  uintptr_t cut[8] = {0};   // out: host address where part p begins (p = 1 .. parts - 1)
+  uint32_t part_of(const void *p) const { uint32_t k = 0; for (uint32_t j = 1; j < parts; j++) if ((uintptr_t)p >= cut[j]) k = j; return k; }
 };
 int upload_ranges(zipc_b200_ctx *ctx, size_t n, const void *const *src, const size_t *len,
                   std::vector<const uint8_t *> &d_ptr, UploadSplit *split = nullptr);
@@ -246,7 +247,7 @@ struct DownloadPlan {
   std::vector<size_t> goff, gbytes;     // arena range of each group
   uint8_t *dst = nullptr;               // the caller's (pinned) arena
   size_t tail_off = 0, tail_bytes = 0;  // arena range of everything that is not a grouped stream (copied at the end)
-  std::vector<char> late;               // per stream handed to inflate_core: its input comes with the late half of the upload
+  std::vector<char> late;               // per stream handed to inflate_core: the part of a split upload that carries its input (0: the first)
 };
 int inflate_core(zipc_b200_ctx *ctx, int ck, int adler_mode, size_t n, const std::vector<const uint8_t *> &d_src,
                  const size_t *src_len, const std::vector<uint8_t *> &d_dst, const std::vector<size_t> &cap,
@@ -254,7 +255,7 @@ int inflate_core(zipc_b200_ctx *ctx, int ck, int adler_mode, size_t n, const std
                  const DownloadPlan *plan = nullptr);
 // Lay out the output arena of n members (cap[i] bytes each, 16-byte aligned slots).  grouped[i] != 0 marks the streams that
 // go through the inflate kernel.  Fills off / total, and plan when the batch qualifies for a progressive download.
-// late[i] != 0 (may be null): the stream's input arrives with the late half of a split upload; such streams form the later groups.
+// late[i] (may be null): the part of a split upload that carries the stream's input; later parts form later groups.
 bool progressive_ok(zipc_b200_ctx *ctx, size_t n, const size_t *cap, const size_t *src_len, const char *grouped, void *dst, size_t dst_cap);
 int plan_arena(zipc_b200_ctx *ctx, size_t n, const size_t *cap, const size_t *src_len, const char *grouped, const char *late, void *dst,
                size_t dst_cap, std::vector<size_t> &off, size_t &total, DownloadPlan &plan);

@@ -447,8 +447,8 @@ inflate_kernel(const InflateTask *__restrict__ tasks, uint32_t ntasks, InflateRe
   // adler_mode: -1 = no checksum in this kernel, else ZIPC_ADLER_* (fused per-block Adler-32 of the output)
   // group_count / group_flag (may be null): streams left in each download group; the warp that finishes a group's last
   // stream raises the group's flag (mapped host memory), and the host starts copying that range of the arena
-  // upload_flag / upload_serial: a stream flagged kInflateLateInput is opened only once *upload_flag == upload_serial (its
-  // bytes travel with the second half of a split upload, on another stream, while this kernel already works on the first)
+  // upload_flag / upload_serial: a stream whose flags name part p >= 1 of a split upload is opened only once *upload_flag has
+  // reached upload_serial + p (its bytes travel on another stream while this kernel already works on the first part)
   extern __shared__ __align__(16) uint8_t smem_raw[];
   WarpTabs *tabs = reinterpret_cast<WarpTabs *>(smem_raw);                  // [WARPS] + fixed
   WarpTabs &fixed = tabs[WARPS];
@@ -506,12 +506,13 @@ inflate_kernel(const InflateTask *__restrict__ tasks, uint32_t ntasks, InflateRe
       }
       if (task >= ntasks) break;
       const InflateTask t = tasks[task];
-      if (!COUNT_ONLY && !SPEC && (t.flags & kInflateLateInput) && upload_flag) {
+      if (!COUNT_ONLY && !SPEC && ((t.flags >> kInflatePartShift) & kInflatePartMask) && upload_flag) {
+        const uint32_t need = upload_serial + ((t.flags >> kInflatePartShift) & kInflatePartMask);
         // (bounded: if that copy failed the host reports it; the warp then decodes whatever is there and the call fails anyway)
         uint32_t seen = 0;
         for (uint32_t spins = 0; spins < (1u << 24); spins++) {
           asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(upload_flag) : "memory");
-          if (seen == upload_serial) break;
+          if ((int32_t)(seen - need) >= 0) break;
           __nanosleep(256);
         }
       }

@@ -404,8 +404,8 @@ int zipc_b200_zip_extract_batch(zipc_b200_ctx *ctx, const zipc_b200_member *ms, 
   DownloadPlan plan;
   {
     std::vector<char> late;
-    if (split.done) { late.resize(n); for (size_t i = 0; i < n; i++) late[i] = slen[i] && (uintptr_t)src[i] >= split.cut; }
-    if (int st = plan_arena(ctx, n, cap.data(), slen.data(), grouped.data(), split.done ? late.data() : nullptr, dst, dst_cap, off, total, plan)) return st;
+    if (split.parts) { late.resize(n); for (size_t i = 0; i < n; i++) late[i] = slen[i] ? (char)split.part_of(src[i]) : 0; }
+    if (int st = plan_arena(ctx, n, cap.data(), slen.data(), grouped.data(), split.parts ? late.data() : nullptr, dst, dst_cap, off, total, plan)) return st;
   }
   if (int st = ctx->d_out.reserve(total + 64)) return st;
   // deflate members through the inflate kernel (with CRC-32 of the output)
