@@ -1,8 +1,16 @@
+#!/bin/bash
+# Round-2 evidence pass (run on the GPU box through gpurun): tests, both bench arms, launch list, ncu captures of the
+# dominant kernels ON THE BENCH COMMAND.  Outputs under gpurun_out/r02/; the summaries are made from them with
+# tools/ncu_summary.py and kept under profiles/.
 set -x
-mkdir -p gpurun_out/r02
-timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/r02/pytest_gpu.txt 2>&1; tail -3 gpurun_out/r02/pytest_gpu.txt
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:deflate_kernel -s 1 -c 1 -f -o gpurun_out/r02/deflate_default python tools/prof_codec.py deflate 1200 default > gpurun_out/r02/ncu_deflate.log 2>&1
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:deflate_kernel -s 1 -c 1 -f -o gpurun_out/r02/deflate_fast python tools/prof_codec.py deflate 1200 fast > gpurun_out/r02/ncu_deflate_fast.log 2>&1
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:inflate_kernel -s 1 -c 1 -f -o gpurun_out/r02/inflate python tools/prof_codec.py inflate 1200 default > gpurun_out/r02/ncu_inflate.log 2>&1
-timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/r02/launches_bench.csv python bench.py --steps 2 --warmup 1 > gpurun_out/r02/bench_under_ncu.log 2>&1
-ls -la gpurun_out/r02
+O=gpurun_out/r02
+mkdir -p $O
+timeout 900 python -m pytest tests -m gpu -x -q > $O/pytest_gpu.txt 2>&1; tail -3 $O/pytest_gpu.txt
+timeout 600 python bench.py > $O/bench_default.json 2> $O/bench_default.err; tail -c 600 $O/bench_default.json
+timeout 600 python bench.py --impl reference > $O/bench_reference_arm.json 2> $O/bench_reference.err; tail -c 400 $O/bench_reference_arm.json
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv --log-file $O/launches_bench.csv python bench.py --steps 2 --warmup 1 > $O/bench_under_ncu.log 2>&1
+for w in deflate inflate crc32; do
+  case $w in deflate) k=deflate_kernel;; inflate) k=inflate_kernel;; crc32) k=crc32_tiles_kernel;; esac
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:$k -s 2 -c 1 -f -o $O/bench_$w python bench.py --workload $w --no-also --steps 1 --warmup 2 > $O/ncu_bench_$w.log 2>&1
+done
+ls -la $O
