@@ -458,6 +458,61 @@ def run_stream_c1(h: Harness):
     return {"workload": "C1: 64 MiB text-v1(seed=1) as one RFC 1951 stream; CRC-32 fused both ways; pinned host buffers in and out", **res}
 
 
+def run_stream_c5(h: Harness, synth, rank, world, dist, torch, local, slice_bytes=512 << 20, seg=256 << 10):
+    """C5: ONE RFC 1951 stream spread over the GPUs of the box (4 GiB at N = 8): every rank compresses its contiguous
+    512 MiB slice as a piece of the stream (segment-independent, only the last rank's piece carries BFINAL), the pieces are
+    byte aligned so their concatenation in rank order is the stream; back through the per-piece index; the whole-stream
+    CRC-32 is the host combine of the slices'.  Pinned host buffers in and out on every rank (end to end); no collective on
+    the data path (NCCL only for the max over ranks and the gather of three scalars per rank)."""
+    L = h.L
+    # every collective below is reached by every rank whatever happens locally: a local failure is a flag, not an exception
+    err = None
+    try:
+        data = h.pinned(make_text(synth, 5 * 64 + rank, slice_bytes))   # (the stream's content: 32 MiB pieces of text-v1, seeds by position)
+        cbuf = h.pinned(np.zeros(data.size + (data.size >> 3) + 65536, dtype=np.uint8))
+        obuf = h.pinned(np.zeros(data.size, dtype=np.uint8))
+        nmax = -(-data.size // seg) + 1
+        index = np.zeros((nmax + 1, 2), dtype=np.uint64)
+        ip = index.ctypes.data_as(C.POINTER(C.c_uint64))
+        n, nseg, crc, crc2, st, olen = C.c_size_t(), C.c_size_t(), C.c_uint32(), C.c_uint32(), C.c_int(), C.c_size_t()
+        last_piece = 1 if rank == world - 1 else 0
+        dfn = lambda: L.zipc_b200_deflate_segmented(h.ctx.h, 2, data.ctypes.data, data.size, seg, last_piece, cbuf.ctypes.data, cbuf.size,
+                                                    C.byref(n), ip, nmax + 1, C.byref(nseg), C.byref(crc))
+        ifn = lambda: L.zipc_b200_inflate_segmented(h.ctx.h, cbuf.ctypes.data, n.value, ip, nseg.value, obuf.ctypes.data, obuf.size,
+                                                    C.byref(olen), C.byref(crc2), C.byref(st))
+        if dfn() != 0 or ifn() != 0:
+            err = "segmented call failed: " + L.zipc_b200_last_error(h.ctx.h).decode()
+    except Exception as e:
+        err = repr(e)
+    good = torch.tensor([0.0 if err else 1.0], dtype=torch.float64, device=f"cuda:{local}")
+    dist.all_reduce(good, op=dist.ReduceOp.MIN)
+    if float(good[0]) == 0.0:
+        return {"error": err or "another rank failed"}
+
+    def timed(fn, reps=3):
+        torch.cuda.synchronize(); dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps): fn()
+        t = torch.tensor([(time.perf_counter() - t0) / reps], dtype=torch.float64, device=f"cuda:{local}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0])
+    td = timed(dfn)
+    ti = timed(ifn)
+    ok = st.value == 0 and crc2.value == crc.value and olen.value == data.size and bytes(obuf[-4096:]) == bytes(data[-4096:])
+    mine = torch.tensor([float(crc.value), float(n.value), 1.0 if ok else 0.0], dtype=torch.float64, device=f"cuda:{local}")
+    allv = [torch.zeros_like(mine) for _ in range(world)]
+    dist.all_gather(allv, mine)
+    whole = int(allv[0][0])
+    for k in range(1, world):
+        whole = L.zipc_b200_crc32_combine(whole, int(allv[k][0]), data.size)
+    total = data.size * world
+    return {"workload": "C5: one RFC 1951 stream of %d x 512 MiB text-v1 slices (4 GiB at N = 8), %d KiB segments, default level; pinned host buffers "
+                        "in and out on every rank; time = max over ranks" % (world, seg >> 10),
+            "total_bytes": total, "deflate_e2e_GBps": round(total / td / 1e9, 2), "inflate_e2e_GBps": round(total / ti / 1e9, 2),
+            "ratio": round(sum(float(v[1]) for v in allv) / total, 4), "pieces_ok": int(sum(float(v[2]) for v in allv)), "pieces": world,
+            "stream_crc32": "%08x" % whole}
+
+
 def run_de_yardstick(h: Harness, datas, streams, reps=3):
     """the Blackwell decompression engine on the same members (cuMemBatchDecompressAsync): a yardstick, not a product path"""
     so = os.path.join(ROOT, "tools", "libde_yardstick.so")
@@ -890,6 +945,11 @@ def main():
             guard("stream_c1", lambda: run_stream_c1(h))
             guard("de_yardstick", lambda: run_de_yardstick(h, datas, get_streams()))
         else:
+            # C5: one stream over all GPUs of the box (every rank takes part)
+            def c5():
+                d = run_stream_c5(h, synth, rank, world, dist, torch, local)
+                return d
+            guard("stream_c5", c5)
             # strong scaling: rank 0 drives all GPUs through the box-wide entry points; the other ranks stay off their GPUs
             get_streams()
             torch.cuda.synchronize()

@@ -131,7 +131,9 @@ uint32_t zipc_b200_adler32_combine(uint32_t adler_a, uint32_t adler_b, uint64_t 
  *   src[i],src_len[i]  compressed stream i (host memory)
  *   max_out[i]      ?decompressed_size of stream i, or ZIPC_SIZE_UNKNOWN
  *   dst,dst_cap     caller's output arena (host).  Stream i's output is written at dst_off[i]
- *                   (assigned by the library, 16-byte aligned) with length dst_len[i].
+ *                   (assigned by the library, 16-byte aligned, NOT necessarily in input order: a large batch into a
+ *                   pinned arena is laid out in download order, smallest outputs first, so that finished ranges are
+ *                   copied out while the kernel still works on the larger streams) with length dst_len[i].
  *                   If dst is NULL or too small the call returns ZIPC_ERR_DST_TOO_SMALL and
  *                   *dst_need holds the arena size to provide; outputs then stay available in
  *                   the ctx until the next call and can be fetched with zipc_b200_fetch().

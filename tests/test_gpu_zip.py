@@ -214,3 +214,69 @@ def test_large_batches_are_pipelined_and_equal(ctx):
     assert rc == 0 and (st == 0).all() and (ol == slen).all() and (ck2 == ck).all()
     for i in range(0, n, 97):
         assert out[int(ooff[i]):int(ooff[i]) + int(ol[i])].tobytes() == datas[i].tobytes()
+
+
+def test_inflate_progressive_download_and_split_upload(ctx):
+    """A large inflate batch from pinned memory into a pinned arena: the upload goes in two halves, the streams are decoded in
+    download order (by output size, the late half's behind the others) and every group's arena range is copied out while the
+    kernel still runs.  Offsets are the library's choice: they must tile the arena without overlap; contents, lengths,
+    checksums and the statuses of damaged members must be those of the plain path."""
+    import ctypes as C
+    import zlib
+    from zipc_b200 import synth
+    L = ctx.L
+    n = 2400
+    datas = [synth.text_v1(9000 + i, 20_000 + (i * 7919) % 90_000).tobytes() for i in range(n)]
+    U = sum(len(d) for d in datas)
+    assert U > (128 << 20)
+    comp = []
+    for i, d in enumerate(datas):
+        co = zlib.compressobj(6, zlib.DEFLATED, -15)
+        comp.append(co.compress(d) + co.flush())
+    bad = {5: "flip", n // 2 + 3: "flip", n - 7: "cut"}
+    for i, how in bad.items():
+        c = bytearray(comp[i])
+        if how == "flip":
+            c[len(c) // 2] ^= 0x5A
+            c[len(c) // 2 + 1] ^= 0xC3
+        else:
+            c = c[: len(c) // 2]
+        comp[i] = bytes(c)
+    Ctot = sum(len(c) for c in comp)
+    assert Ctot > (40 << 20)
+    hsrc = C.c_void_p(); hdst = C.c_void_p()
+    cap = U + 16 * n + 4096
+    assert L.zipc_b200_host_alloc(Ctot + 64, C.byref(hsrc)) == 0 and L.zipc_b200_host_alloc(cap, C.byref(hdst)) == 0
+    try:
+        src = np.ctypeslib.as_array(C.cast(hsrc, C.POINTER(C.c_uint8)), shape=(Ctot + 64,))
+        dst = np.ctypeslib.as_array(C.cast(hdst, C.POINTER(C.c_uint8)), shape=(cap,))
+        dst[:] = 0xEE
+        offs = np.zeros(n, dtype=np.uint64); t = 0
+        for i, c in enumerate(comp):
+            offs[i] = t; src[t:t + len(c)] = np.frombuffer(c, dtype=np.uint8); t += len(c)
+        clen = np.array([len(c) for c in comp], dtype=np.uint64)
+        ulen = np.array([len(d) for d in datas], dtype=np.uint64)
+        ptrs = (C.c_void_p * n)(*[hsrc.value + int(o) for o in offs])
+        P = lambda a, ty: a.ctypes.data_as(C.POINTER(ty))
+        need = C.c_size_t(); ooff = np.zeros(n, dtype=np.uint64); ol = np.zeros(n, dtype=np.uint64)
+        ck = np.zeros(n, dtype=np.uint32); st = np.zeros(n, dtype=np.int32)
+        for rep in range(2):  # twice: the serial numbers and flags of the first call must not leak into the second
+            rc = L.zipc_b200_inflate_batch(ctx.h, 2, 0, n, ptrs, P(clen, C.c_size_t), P(ulen, C.c_size_t), hdst, cap, C.byref(need),
+                                           P(ooff, C.c_size_t), P(ol, C.c_size_t), P(ck, C.c_uint32), P(st, C.c_int))
+            assert rc == 0 and need.value <= cap
+            # the slots tile the arena: sorted by offset, each starts where the previous one's 16-byte aligned slot ends
+            order = np.argsort(ooff, kind="stable")
+            ends = ooff[order] + ((ulen[order] + 15) & ~np.uint64(15))
+            assert int(ooff[order][0]) == 0 and (ooff[order][1:] == ends[:-1]).all() and int(ends[-1]) == need.value
+            assert not (np.diff(ooff.astype(np.int64)) > 0).all()   # (download order, not input order: the progressive path ran)
+            for i in range(n):
+                if i in bad:  # (a flipped byte may still be a valid stream: then the checksum tells)
+                    assert (st[i] != 0 and ol[i] == 0) or int(ck[i]) != zlib.crc32(datas[i]), (i, st[i])
+                    continue
+                assert st[i] == 0 and ol[i] == ulen[i]
+                if i % 41 == 0 or i < 4 or i > n - 4:
+                    assert dst[int(ooff[i]):int(ooff[i]) + int(ol[i])].tobytes() == datas[i]
+                assert int(ck[i]) == zlib.crc32(datas[i])
+            dst[:] = 0x11
+    finally:
+        L.zipc_b200_host_free(hsrc); L.zipc_b200_host_free(hdst)

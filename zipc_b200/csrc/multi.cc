@@ -71,16 +71,29 @@ void for_each_device(size_t g, F f) {
   for (auto &t : th) t.join();
 }
 
-// Shared driver of the two codec batch calls.  run(d, idx, need, off, len, ck, st) executes the single-device call
-// for the members idx on context d WITHOUT an arena (results stay in that context); each thread then waits until the
-// contexts before it know how much they produced, which fixes its place in the caller's arena, and fetches its part --
-// while later contexts are still computing.
+// Shared driver of the two codec batch calls.  run(d, idx, part_dst, part_cap, need, off, len, ck, st) executes the
+// single-device call for the members idx on context d.  Output sizes unknown (deflate; inflate without sizes): the call
+// runs WITHOUT an arena (results stay in that context); each thread then waits until the contexts before it know how much
+// they produced, which fixes its place in the caller's arena, and fetches its part -- while later contexts are still
+// computing.  Output sizes known (`out_size`: inflate with ?decompressed_size): every part's place is known beforehand and
+// the single-device call writes there itself (and may download progressively, api.cu plan_arena).
 template <class Run>
 int batch_multi(zipc_b200_mctx *m, size_t n, const size_t *weight, void *dst, size_t dst_cap, size_t *dst_need,
-                size_t *dst_off, size_t *dst_len, uint32_t *checksum, int *status, Run run) {
+                size_t *dst_off, size_t *dst_len, uint32_t *checksum, int *status, Run run, const size_t *out_size = nullptr) {
   size_t g = m->ctxs.size();
   if (m->pipelined) g = std::max<size_t>(1, std::min(g, n / 256));  // every group gets members (the upload tickets need that)
   auto parts = partition_members(weight, n, g);
+  std::vector<size_t> part_base(g, 0), part_size(g, 0);
+  bool placed = false;
+  if (out_size && dst && !m->pipelined) {
+    size_t t = 0;
+    for (size_t d = 0; d < g; d++) {
+      part_base[d] = t;
+      for (uint32_t i : parts[d]) part_size[d] += align_up(out_size[i], 16);
+      t += part_size[d];
+    }
+    placed = t <= dst_cap;
+  }
   std::vector<int> rc(g, ZIPC_OK);
   m->need.assign(m->ctxs.size(), 0);
   m->base.assign(m->ctxs.size(), 0);
@@ -97,7 +110,8 @@ int batch_multi(zipc_b200_mctx *m, size_t n, const size_t *weight, void *dst, si
     zipc_b200_ctx *c = m->ctxs[d];
     if (m->pipelined) { c->gate = &m->gate; c->gate_ticket = d; c->gate_passed = false; }
     int r = ZIPC_OK;
-    if (k) r = run(d, parts[d], &m->need[d], off[d].data(), len[d].data(), ck[d].data(), st[d].data());
+    if (k) r = run(d, parts[d], placed ? static_cast<uint8_t *>(dst) + part_base[d] : nullptr, placed ? part_size[d] : 0, &m->need[d],
+                   off[d].data(), len[d].data(), ck[d].data(), st[d].data());
     if (m->pipelined && !c->gate_passed) {  // the call never got to its upload: do not hold up the groups behind it
       std::unique_lock<std::mutex> lk(m->gate.m);
       m->gate.cv.wait(lk, [&] { return m->gate.turn == d; });
@@ -107,6 +121,7 @@ int batch_multi(zipc_b200_mctx *m, size_t n, const size_t *weight, void *dst, si
     }
     c->gate = nullptr;
     rc[d] = r == ZIPC_ERR_DST_TOO_SMALL ? ZIPC_OK : r;
+    if (placed) { m->need[d] = part_size[d]; m->base[d] = part_base[d]; return; }
     size_t base = 0;
     {
       std::unique_lock<std::mutex> lk(mu);
@@ -195,14 +210,17 @@ int zipc_b200_multi_inflate_batch(zipc_b200_mctx *m, int ck, int adler_mode, siz
   if (!m || (n && (!src || !src_len || !dst_off || !dst_len || !status))) return ZIPC_ERR_INVALID_ARG;
   if (dst_need) *dst_need = 0;
   if (!n) return ZIPC_OK;
+  bool all_known = max_out != nullptr;
+  for (size_t i = 0; i < n && all_known; i++) all_known = max_out[i] != ZIPC_SIZE_UNKNOWN;
   return batch_multi(m, n, src_len, dst, dst_cap, dst_need, dst_off, dst_len, checksum, status,
-                     [&](size_t d, const std::vector<uint32_t> &idx, size_t *need, size_t *off, size_t *len, uint32_t *c, int *st) {
+                     [&](size_t d, const std::vector<uint32_t> &idx, void *pdst, size_t pcap, size_t *need, size_t *off, size_t *len, uint32_t *c, int *st) {
                        const size_t k = idx.size();
                        std::vector<const void *> p(k);
                        std::vector<size_t> l(k), mo(k);
                        for (size_t j = 0; j < k; j++) { p[j] = src[idx[j]]; l[j] = src_len[idx[j]]; mo[j] = max_out ? max_out[idx[j]] : ZIPC_SIZE_UNKNOWN; }
-                       return zipc_b200_inflate_batch(m->ctxs[d], ck, adler_mode, k, p.data(), l.data(), mo.data(), nullptr, 0, need, off, len, c, st);
-                     });
+                       return zipc_b200_inflate_batch(m->ctxs[d], ck, adler_mode, k, p.data(), l.data(), mo.data(), pdst, pcap, need, off, len, c, st);
+                     },
+                     all_known ? max_out : nullptr);
 }
 
 int zipc_b200_multi_deflate_batch(zipc_b200_mctx *m, int level, int ck, int adler_mode, size_t n, const void *const *src,
@@ -212,7 +230,7 @@ int zipc_b200_multi_deflate_batch(zipc_b200_mctx *m, int level, int ck, int adle
   if (dst_need) *dst_need = 0;
   if (!n) return ZIPC_OK;
   return batch_multi(m, n, src_len, dst, dst_cap, dst_need, dst_off, dst_len, checksum, status,
-                     [&](size_t d, const std::vector<uint32_t> &idx, size_t *need, size_t *off, size_t *len, uint32_t *c, int *st) {
+                     [&](size_t d, const std::vector<uint32_t> &idx, void *, size_t, size_t *need, size_t *off, size_t *len, uint32_t *c, int *st) {
                        const size_t k = idx.size();
                        std::vector<const void *> p(k);
                        std::vector<size_t> l(k);
