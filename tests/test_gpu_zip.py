@@ -280,3 +280,29 @@ def test_inflate_progressive_download_and_split_upload(ctx):
             dst[:] = 0x11
     finally:
         L.zipc_b200_host_free(hsrc); L.zipc_b200_host_free(hdst)
+
+
+def test_large_archive_pipelined_equals_plain(ctx):
+    """zipc_b200_zip_deflate_archive of a large member set given in path order goes through the pipeline (every group's
+    payloads copied to their archive offsets while later groups are compressed); given in reverse order it takes the plain
+    path.  Zipc.to_binary_string writes members in path order either way: the two archives are the same bytes."""
+    import io
+    import zipfile
+    from zipc_b200 import synth, zipc
+    from zipc_b200 import zipc_deflate as zd
+    zd.set_default_context(ctx)
+    n = 1500
+    datas = [synth.text_v1(5000 + i, 30_000 + (i * 6151) % 60_000) for i in range(n)]
+    assert sum(d.size for d in datas) > (64 << 20)
+    paths = ["big/%05d.txt" % i for i in range(n)]
+    l0 = ctx.launches
+    a = zipc.archive_of_binary_strings(paths, datas).get_ok()
+    l1 = ctx.launches
+    b = zipc.archive_of_binary_strings(paths[::-1], datas[::-1]).get_ok()
+    l2 = ctx.launches
+    assert bytes(a) == bytes(b)
+    assert (l1 - l0) > (l2 - l1)          # the pipelined call launched one set of kernels per group
+    zf = zipfile.ZipFile(io.BytesIO(bytes(a)))
+    assert zf.testzip() is None and len(zf.namelist()) == n
+    for i in (0, 1, n // 2, n - 1):
+        assert zf.read(paths[i]) == datas[i].tobytes()

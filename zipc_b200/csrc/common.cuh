@@ -59,6 +59,11 @@ struct UploadGate {
   std::mutex m;
   std::condition_variable cv;
   size_t turn = 0;
+  // The groups' deflate kernels run in group order, at most two at a time (the tail of one under the start of the next):
+  // group k's kernel waits for the event behind group k - 2's.  Left to itself the block scheduler interleaves the CTAs
+  // of all queued kernels, every group finishes at the end, and the downloads have nothing to overlap with (measured).
+  std::vector<cudaEvent_t> done;    // behind the deflate kernel of each group
+  std::vector<char> launched;       // ... which has been recorded (or will never be) in this batch
 };
 
 // ---- device descriptors ---------------------------------------------------------------------
@@ -140,6 +145,7 @@ struct zipc_b200_ctx {
   zb::PinBuf h_stage, h_res, h_desc;
   cudaStream_t copy_stream = nullptr;  // progressive downloads (api.cu)
   cudaStream_t upload_stream = nullptr;  // late half of a split upload
+  cudaStream_t hi_stream = nullptr;      // high priority: compaction of a pipelined group (zip_api.cu compact)
   uint32_t *d_upflag = nullptr;        // device word: serial number of the last completed late half
   uint32_t upload_serial = 0;
   cudaEvent_t ev_half = nullptr;       // first half of a split upload is through
@@ -223,7 +229,7 @@ int deflate_launch(zipc_b200_ctx *ctx, const DeflateTask *d_tasks, uint32_t n, D
 inline uint32_t deflate_max_blocks(uint64_t src_len) { return (uint32_t)(src_len / 61440) + 2; }
 constexpr uint32_t kStoredBlock = 65534;  // source bytes per block at level `None (reference :747-750, :1106-1116)
 // zip_api.cu: n independent copies on the device (compaction of per-member output slots)
-int gather_launch(zipc_b200_ctx *ctx, const CopyDesc *d_descs, uint32_t n);
+int gather_launch(zipc_b200_ctx *ctx, const CopyDesc *d_descs, uint32_t n, cudaStream_t stream = nullptr);
 // api.cu helpers shared with zip_api.cu
 int h2d(zipc_b200_ctx *ctx, void *d, const void *h, size_t bytes);
 int d2h(zipc_b200_ctx *ctx, void *h, const void *d, size_t bytes);
@@ -260,10 +266,18 @@ bool progressive_ok(zipc_b200_ctx *ctx, size_t n, const size_t *cap, const size_
 int plan_arena(zipc_b200_ctx *ctx, size_t n, const size_t *cap, const size_t *src_len, const char *grouped, const char *late, void *dst,
                size_t dst_cap, std::vector<size_t> &off, size_t &total, DownloadPlan &plan);
 int finish_download(zipc_b200_ctx *ctx, const DownloadPlan &plan);
+// ZIPC_B200_PIPE_DEBUG=1: time stamps of the stages of a pipelined batch on stderr (group ticket, stage, ms)
+void pipe_mark(const zipc_b200_ctx *ctx, const char *stage);
 // api.cu / multi.cc: copy / compute pipelining of large host-pointer batches on one device
 zipc_b200_mctx *pipeline_for(zipc_b200_ctx *ctx, size_t n, const size_t *len, const void *dst);
 int pipeline_create(int device, int depth, zipc_b200_mctx **out);
 uint64_t pipeline_launches(const zipc_b200_mctx *m);
+int pipeline_deflate_gapped(zipc_b200_mctx *m, int level, size_t n, const void *const *src, const size_t *src_len, const uint32_t *gap,
+                            void *dst, size_t dst_cap, size_t *dst_need, size_t *dst_off, size_t *dst_len, uint32_t *crc, int *status);
+// zip_api.cu: zipc_b200_deflate_batch on one context with a caller-defined output layout
+int deflate_batch_layout(zipc_b200_ctx *ctx, int level, int ck, int adler_mode, size_t n, const void *const *src, const size_t *src_len,
+                         void *dst, size_t dst_cap, size_t *dst_need, size_t *dst_off, size_t *dst_len, uint32_t *checksum, int *status,
+                         const uint32_t *gap, size_t align);
 // host_util.cc
 int zip_assemble_impl(const zipc_b200_member *ms, size_t n, const char *first, void *out_v, size_t out_cap,
                       size_t *out_len, bool copy_payload, uint64_t *payload_off);

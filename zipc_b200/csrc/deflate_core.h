@@ -55,6 +55,9 @@ ZHD LevelParams level_params(int level) {
 #ifdef ZB_FORCE_HOPS
   p.hops = ZB_FORCE_HOPS;
 #endif
+#ifdef ZB_DEFAULT_DEPTH  // tuning builds of the host model: chain budget / nice length of level default
+  if (level == 2) { p.shallow = p.depth = ZB_DEFAULT_DEPTH; p.shallow_nice = p.nice = ZB_DEFAULT_NICE; }
+#endif
   return p;
 }
 

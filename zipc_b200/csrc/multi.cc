@@ -79,9 +79,14 @@ void for_each_device(size_t g, F f) {
 // the single-device call writes there itself (and may download progressively, api.cu plan_arena).
 template <class Run>
 int batch_multi(zipc_b200_mctx *m, size_t n, const size_t *weight, void *dst, size_t dst_cap, size_t *dst_need,
-                size_t *dst_off, size_t *dst_len, uint32_t *checksum, int *status, Run run, const size_t *out_size = nullptr) {
+                size_t *dst_off, size_t *dst_len, uint32_t *checksum, int *status, Run run, const size_t *out_size = nullptr,
+                size_t align = 16) {
   size_t g = m->ctxs.size();
-  if (m->pipelined) g = std::max<size_t>(1, std::min(g, n / 256));  // every group gets members (the upload tickets need that)
+  if (m->pipelined) {  // every group gets members (the upload tickets need that) and enough bytes to be worth its fixed costs
+    uint64_t bytes = 0;
+    for (size_t i = 0; i < n; i++) bytes += weight[i];
+    g = std::max<size_t>(1, std::min({g, n / 256, (size_t)(bytes / (32u << 20))}));
+  }
   auto parts = partition_members(weight, n, g);
   std::vector<size_t> part_base(g, 0), part_size(g, 0);
   bool placed = false;
@@ -103,7 +108,7 @@ int batch_multi(zipc_b200_mctx *m, size_t n, const size_t *weight, void *dst, si
   std::mutex mu;
   std::condition_variable cv;
   std::vector<char> known(g, 0);
-  if (m->pipelined) { std::lock_guard<std::mutex> lk(m->gate.m); m->gate.turn = 0; }
+  if (m->pipelined) { std::lock_guard<std::mutex> lk(m->gate.m); m->gate.turn = 0; m->gate.launched.assign(m->gate.done.size(), 0); }
   for_each_device(g, [&](size_t d) {
     const size_t k = parts[d].size();
     off[d].assign(k, 0); len[d].assign(k, 0); ck[d].assign(k, 0); st[d].assign(k, 0);
@@ -119,6 +124,10 @@ int batch_multi(zipc_b200_mctx *m, size_t n, const size_t *weight, void *dst, si
       lk.unlock();
       m->gate.cv.notify_all();
     }
+    if (m->pipelined && d < m->gate.launched.size()) {  // a call that never launched must not hold up the groups behind it either
+      { std::lock_guard<std::mutex> lk(m->gate.m); m->gate.launched[d] = 1; }
+      m->gate.cv.notify_all();
+    }
     c->gate = nullptr;
     rc[d] = r == ZIPC_ERR_DST_TOO_SMALL ? ZIPC_OK : r;
     if (placed) { m->need[d] = part_size[d]; m->base[d] = part_base[d]; return; }
@@ -128,16 +137,17 @@ int batch_multi(zipc_b200_mctx *m, size_t n, const size_t *weight, void *dst, si
       known[d] = 1;
       cv.notify_all();
       cv.wait(lk, [&] { for (size_t j = 0; j < d; j++) if (!known[j]) return false; return true; });
-      for (size_t j = 0; j < d; j++) base += align_up(m->need[j], 16);
+      for (size_t j = 0; j < d; j++) base += align_up(m->need[j], align);
     }
     m->base[d] = base;
     if (rc[d] == ZIPC_OK && dst && m->need[d] && base + m->need[d] <= dst_cap)
       rc[d] = zipc_b200_fetch(c, static_cast<uint8_t *>(dst) + base, m->need[d]);
+    zb::pipe_mark(c, "fetched");
   });
   for (size_t d = 0; d < g; d++)
     if (rc[d]) { m->last_error = std::string("context ") + std::to_string(d) + ": " + zipc_b200_last_error(m->ctxs[d]); return rc[d]; }
   size_t total = 0;
-  for (size_t d = 0; d < g; d++) total += align_up(m->need[d], 16);
+  for (size_t d = 0; d < g; d++) total += align_up(m->need[d], align);
   m->total = total;
   for (size_t d = 0; d < g; d++)
     for (size_t j = 0; j < parts[d].size(); j++) {
@@ -175,6 +185,10 @@ int zipc_b200_mctx_create(uint64_t device_mask, zipc_b200_mctx **out) {
 
 void zipc_b200_mctx_destroy(zipc_b200_mctx *m) {
   if (!m) return;
+  if (!m->gate.done.empty() && !m->devices.empty()) {
+    cudaSetDevice(m->devices[0]);
+    for (cudaEvent_t e : m->gate.done) cudaEventDestroy(e);
+  }
   for (zipc_b200_ctx *c : m->ctxs) zipc_b200_ctx_destroy(c);
   delete m;
 }
@@ -267,8 +281,31 @@ int pipeline_create(int device, int depth, zipc_b200_mctx **out) {
     m->devices.push_back(device);
     m->ctxs.push_back(c);
   }
+  cudaSetDevice(device);
+  for (int k = 0; k < depth; k++) {
+    cudaEvent_t e = nullptr;
+    if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) { zipc_b200_mctx_destroy(m); return ZIPC_ERR_CUDA; }
+    m->gate.done.push_back(e);
+  }
+  m->gate.launched.assign(depth, 0);
   *out = m;
   return ZIPC_OK;
+}
+
+// Payloads of a ZIP archive through the pipeline: like zipc_b200_multi_deflate_batch, but every output is preceded by
+// gap[i] free bytes (its local file header) and nothing is padded, so dst_off[] are the payloads' offsets in the archive.
+int pipeline_deflate_gapped(zipc_b200_mctx *m, int level, size_t n, const void *const *src, const size_t *src_len, const uint32_t *gap,
+                            void *dst, size_t dst_cap, size_t *dst_need, size_t *dst_off, size_t *dst_len, uint32_t *crc, int *status) {
+  return batch_multi(m, n, src_len, dst, dst_cap, dst_need, dst_off, dst_len, crc, status,
+                     [&](size_t d, const std::vector<uint32_t> &idx, void *, size_t, size_t *need, size_t *off, size_t *len, uint32_t *c, int *st) {
+                       const size_t k = idx.size();
+                       std::vector<const void *> p(k);
+                       std::vector<size_t> l(k);
+                       std::vector<uint32_t> gp(k);
+                       for (size_t j = 0; j < k; j++) { p[j] = src[idx[j]]; l[j] = src_len[idx[j]]; gp[j] = gap[idx[j]]; }
+                       return deflate_batch_layout(m->ctxs[d], level, ZIPC_CK_CRC32, 0, k, p.data(), l.data(), nullptr, 0, need, off, len, c, st, gp.data(), 1);
+                     },
+                     nullptr, 1);
 }
 
 uint64_t pipeline_launches(const zipc_b200_mctx *m) {

@@ -65,7 +65,7 @@ int deflate_run(zipc_b200_ctx *ctx, int level, int ck, int adler_mode, size_t n,
   std::vector<uint32_t> order(n);
   std::iota(order.begin(), order.end(), 0u);
   std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return src_len[a] > src_len[b]; });
-  if (int st = ctx->h_desc.reserve(n * std::max(sizeof(DeflateTask), sizeof(CrcSeg)))) return st;
+  if (int st = ctx->h_desc.reserve(n * (sizeof(DeflateTask) + sizeof(CrcSeg)))) return st;
   if (int st = ctx->d_desc.reserve(n * sizeof(DeflateTask))) return st;
   if (int st = ctx->d_res.reserve(n * (sizeof(DeflateResult) + sizeof(uint32_t)))) return st;
   if (int st = ctx->h_res.reserve(n * (sizeof(DeflateResult) + sizeof(uint32_t)))) return st;
@@ -89,16 +89,48 @@ int deflate_run(zipc_b200_ctx *ctx, int level, int ck, int adler_mode, size_t n,
   }
   DeflateTask *dt = ctx->d_desc.as<DeflateTask>();
   DeflateResult *dr = ctx->d_res.as<DeflateResult>();
+  // CRC-32 of the inputs FIRST: in a pipelined batch the kernels of the next groups take every SM the moment this group's
+  // deflate kernel lets go of it, and a checksum kernel queued behind it would wait for all of them (measured: the
+  // checksums of 16 groups piled up behind the last group's kernel, 7 ms)
+  const bool want_crc = checksum && ck == ZIPC_CK_CRC32;
+  uint32_t *dc = nullptr;
+  if (want_crc) {
+    if (int st = ctx->d_desc2.reserve(n * (sizeof(CrcSeg) + sizeof(uint32_t)))) return st;
+    CrcSeg *hs = reinterpret_cast<CrcSeg *>(ht + n);
+    for (size_t i = 0; i < n; i++) { hs[i].ptr = d_src[i]; hs[i].len = src_len[i]; hs[i].init = 0xFFFFFFFFu; hs[i]._pad = 0; }
+    CrcSeg *ds = ctx->d_desc2.as<CrcSeg>();
+    dc = reinterpret_cast<uint32_t *>(ds + n);
+    ZB_CUDA(ctx, cudaMemcpyAsync(ds, hs, n * sizeof(CrcSeg), cudaMemcpyHostToDevice, ctx->stream));
+    if (int st = crc32_launch_segments(ctx, ds, (uint32_t)n, dc)) return st;
+  }
   ZB_CUDA(ctx, cudaMemcpyAsync(dt, ht, n * sizeof(DeflateTask), cudaMemcpyHostToDevice, ctx->stream));
-  if (int st = deflate_launch(ctx, dt, (uint32_t)n, dr, level, d_blk)) return st;
+  UploadGate *gate = ctx->gate;
+  const size_t ticket = ctx->gate_ticket;
+  const bool ordered = gate && ticket < gate->done.size();
+  if (ordered && ticket >= 2) {  // (see UploadGate)
+    std::unique_lock<std::mutex> lk(gate->m);
+    gate->cv.wait(lk, [&] { return gate->launched[ticket - 2] != 0; });
+    lk.unlock();
+    ZB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, gate->done[ticket - 2], 0));
+  }
+  const int launch_rc = deflate_launch(ctx, dt, (uint32_t)n, dr, level, d_blk);
+  if (ordered) {
+    if (launch_rc == ZIPC_OK) cudaEventRecord(gate->done[ticket], ctx->stream);
+    { std::lock_guard<std::mutex> lk(gate->m); gate->launched[ticket] = 1; }
+    gate->cv.notify_all();
+  }
+  if (launch_rc) return launch_rc;
   DeflateResult *hr = ctx->h_res.as<DeflateResult>();
   ZB_CUDA(ctx, cudaMemcpyAsync(hr, dr, n * sizeof(DeflateResult), cudaMemcpyDeviceToHost, ctx->stream));
+  uint32_t *hck = reinterpret_cast<uint32_t *>(hr + n);  // (pinned: a copy into the caller's pageable array would block every thread of a pipelined batch)
+  if (want_crc) ZB_CUDA(ctx, cudaMemcpyAsync(hck, dc, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
   std::vector<uint32_t> h_blk;
   if (blocks_from_kernel) {
     h_blk.resize(blk_total);
     ZB_CUDA(ctx, cudaMemcpyAsync(h_blk.data(), d_blk, blk_total * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
   }
   ZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  pipe_mark(ctx, "kernel done");
   std::vector<uint32_t> nblk(n, 0);
   for (size_t k = 0; k < n; k++) {
     uint32_t i = order[k];
@@ -108,16 +140,7 @@ int deflate_run(zipc_b200_ctx *ctx, int level, int ck, int adler_mode, size_t n,
   }
   if (checksum) {
     if (ck == ZIPC_CK_CRC32) {
-      if (int st = ctx->d_desc2.reserve(n * (sizeof(CrcSeg) + sizeof(uint32_t)))) return st;
-      CrcSeg *hs = ctx->h_desc.as<CrcSeg>();
-      for (size_t i = 0; i < n; i++) { hs[i].ptr = d_src[i]; hs[i].len = src_len[i]; hs[i].init = 0xFFFFFFFFu; hs[i]._pad = 0; }
-      CrcSeg *ds = ctx->d_desc2.as<CrcSeg>();
-      uint32_t *dc = reinterpret_cast<uint32_t *>(ds + n);
-      ZB_CUDA(ctx, cudaMemcpyAsync(ds, hs, n * sizeof(CrcSeg), cudaMemcpyHostToDevice, ctx->stream));
-      if (int st = crc32_launch_segments(ctx, ds, (uint32_t)n, dc)) return st;
-      ZB_CUDA(ctx, cudaMemcpyAsync(checksum, dc, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
-      ZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-      for (size_t i = 0; i < n; i++) checksum[i] ^= 0xFFFFFFFFu;
+      for (size_t i = 0; i < n; i++) checksum[i] = hck[i] ^ 0xFFFFFFFFu;
     } else if (ck == ZIPC_CK_ADLER32) {
       // block lists per member, in member order
       std::vector<uint32_t> lens;
@@ -157,19 +180,60 @@ int compact(zipc_b200_ctx *ctx, size_t n, const std::vector<uint8_t *> &d_slot, 
   if (int st = ctx->d_desc2.reserve(n * sizeof(CopyDesc))) return st;
   CopyDesc *h = ctx->h_desc.as<CopyDesc>();
   for (size_t i = 0; i < n; i++) { h[i].src = d_slot[i]; h[i].dst = ctx->d_out.as<uint8_t>() + off[i]; h[i].len = len[i]; }
-  ZB_CUDA(ctx, cudaMemcpyAsync(ctx->d_desc2.p, h, n * sizeof(CopyDesc), cudaMemcpyHostToDevice, ctx->stream));
-  return gather_launch(ctx, ctx->d_desc2.as<CopyDesc>(), (uint32_t)n);
+  // A group of a pipelined batch compacts on a high-priority stream: its few CTAs then get the first SMs the running deflate
+  // kernel (of a later group) gives up, ahead of the deflate kernels already queued behind that one.  (The host has seen
+  // this group's results, so nothing on the context's stream is pending.)
+  cudaStream_t s = ctx->stream;
+  if (ctx->is_sub) {
+    if (!ctx->hi_stream) {
+      int lo = 0, hi = 0;
+      ZB_CUDA(ctx, cudaDeviceGetStreamPriorityRange(&lo, &hi));
+      ZB_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->hi_stream, cudaStreamNonBlocking, hi));
+    }
+    s = ctx->hi_stream;
+  }
+  ZB_CUDA(ctx, cudaMemcpyAsync(ctx->d_desc2.p, h, n * sizeof(CopyDesc), cudaMemcpyHostToDevice, s));
+  if (int st = gather_launch(ctx, ctx->d_desc2.as<CopyDesc>(), (uint32_t)n, s)) return st;
+  if (s != ctx->stream) ZB_CUDA(ctx, cudaStreamSynchronize(s));
+  return ZIPC_OK;
 }
 
 }  // namespace
 
-int gather_launch(zipc_b200_ctx *ctx, const CopyDesc *d_descs, uint32_t n) {
+int gather_launch(zipc_b200_ctx *ctx, const CopyDesc *d_descs, uint32_t n, cudaStream_t stream) {
   if (!n) return ZIPC_OK;
   uint32_t grid = std::min<uint32_t>(n, (uint32_t)ctx->sm_count * 8);
-  gather_kernel<<<grid, 256, 0, ctx->stream>>>(d_descs, n);
+  gather_kernel<<<grid, 256, 0, stream ? stream : ctx->stream>>>(d_descs, n);
   ctx->launches++;
   ZB_CUDA(ctx, cudaGetLastError());
   return ZIPC_OK;
+}
+
+// One context's worth of zipc_b200_deflate_batch with a caller-defined layout of the outputs: `gap[i]` bytes (may be null)
+// are left free in front of output i and every output's length is rounded up to `align` -- (nullptr, 16) is the public
+// call's layout, (local file header sizes, 1) puts the payloads where they lie inside a ZIP archive.
+int deflate_batch_layout(zipc_b200_ctx *ctx, int level, int ck, int adler_mode, size_t n, const void *const *src, const size_t *src_len,
+                         void *dst, size_t dst_cap, size_t *dst_need, size_t *dst_off, size_t *dst_len, uint32_t *checksum, int *status,
+                         const uint32_t *gap, size_t align) {
+  DeviceGuard g(ctx->device);
+  pipe_mark(ctx, "begin");
+  std::vector<const uint8_t *> d_src;
+  if (int st = upload_ranges(ctx, n, src, src_len, d_src)) return st;
+  pipe_mark(ctx, "uploaded");
+  std::vector<uint8_t *> d_slot;
+  std::vector<size_t> cap;
+  if (int st = make_slots(ctx, n, src_len, d_slot, cap)) return st;
+  if (int st = deflate_run(ctx, level, ck, adler_mode, n, d_src, src_len, d_slot, cap, dst_len, checksum, status)) return st;
+  pipe_mark(ctx, "deflated");
+  std::vector<size_t> off(n);
+  size_t total = 0;
+  for (size_t i = 0; i < n; i++) { off[i] = total + (gap ? gap[i] : 0); total = off[i] + align_up(dst_len[i], align); }
+  if (int st = compact(ctx, n, d_slot, dst_len, off, total)) return st;
+  ctx->last_off = off; ctx->last_len.assign(dst_len, dst_len + n); ctx->last_total = total;
+  for (size_t i = 0; i < n; i++) dst_off[i] = off[i];
+  if (dst_need) *dst_need = total;
+  if (!dst || dst_cap < total) { ZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); pipe_mark(ctx, "compacted"); return ZIPC_ERR_DST_TOO_SMALL; }
+  return d2h(ctx, dst, ctx->d_out.p, total);
 }
 
 }  // namespace zb
@@ -194,21 +258,7 @@ int zipc_b200_deflate_batch(zipc_b200_ctx *ctx, int level, int ck, int adler_mod
     ctx->launches += pipeline_launches(pipe) - l0;
     if (rc != ZIPC_ERR_DST_TOO_SMALL) return rc;
   }
-  std::vector<const uint8_t *> d_src;
-  if (int st = upload_ranges(ctx, n, src, src_len, d_src)) return st;
-  std::vector<uint8_t *> d_slot;
-  std::vector<size_t> cap;
-  if (int st = make_slots(ctx, n, src_len, d_slot, cap)) return st;
-  if (int st = deflate_run(ctx, level, ck, adler_mode, n, d_src, src_len, d_slot, cap, dst_len, checksum, status)) return st;
-  std::vector<size_t> off(n);
-  size_t total = 0;
-  for (size_t i = 0; i < n; i++) { off[i] = total; total += align_up(dst_len[i], 16); }
-  if (int st = compact(ctx, n, d_slot, dst_len, off, total)) return st;
-  ctx->last_off = off; ctx->last_len.assign(dst_len, dst_len + n); ctx->last_total = total;
-  for (size_t i = 0; i < n; i++) dst_off[i] = off[i];
-  if (dst_need) *dst_need = total;
-  if (!dst || dst_cap < total) { ZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); return ZIPC_ERR_DST_TOO_SMALL; }
-  return d2h(ctx, dst, ctx->d_out.p, total);
+  return deflate_batch_layout(ctx, level, ck, adler_mode, n, src, src_len, dst, dst_cap, dst_need, dst_off, dst_len, checksum, status, nullptr, 16);
 }
 
 int zipc_b200_deflate_batch_dev(zipc_b200_ctx *ctx, int level, int ck, int adler_mode, size_t n, const void *d_src_v,
@@ -488,27 +538,66 @@ int zipc_b200_zip_deflate_archive(zipc_b200_ctx *ctx, int level, size_t n, const
     norm[i].assign(paths[i], path_len[i]);
     for (char &c : norm[i]) if (c == '\\') c = '/';
   }
+  std::vector<size_t> clen(n);
+  std::vector<uint32_t> crc(n);
+  std::vector<int> st_m(n);
+  auto fill_members = [&](std::vector<zipc_b200_member> &ms) {
+    for (size_t i = 0; i < n; i++) {
+      zipc_b200_member &m = ms[i];
+      std::memset(&m, 0, sizeof m);
+      m.path = norm[i].data(); m.path_len = (uint32_t)norm[i].size();
+      m.mode = mode ? mode[i] : 0644;
+      m.mtime = mtime ? std::max<int64_t>(mtime[i], 315532800) : 315532800;
+      m.version_made_by = 0x314; m.version_needed = 20; m.gp_flags = 0x800;  // File.make defaults (zipc.ml:138-143)
+      m.compression = 8;
+      m.compressed_size = clen[i]; m.decompressed_size = src_len[i]; m.crc32 = crc[i];
+    }
+  };
+  // A large archive whose members come in path order (the order Zipc.to_binary_string writes them in, none of them the
+  // `first` member unless it is the first anyway): through the pipeline, every group's payloads copied straight to their
+  // place in `out` while the later groups are compressed; the headers are written around them afterwards.
+  if (out) {
+    bool in_order = true;
+    const char *f = first ? first : "mimetype";
+    const size_t flen = std::strlen(f);
+    for (size_t i = 0; i < n && in_order; i++) {
+      if (i && !(norm[i - 1] < norm[i])) in_order = false;   // (bytewise, like String.compare; equal paths shadow each other)
+      if (i && norm[i].size() == flen && std::memcmp(norm[i].data(), f, flen) == 0) in_order = false;
+    }
+    zipc_b200_mctx *pipe = in_order ? pipeline_for(ctx, n, src_len, out) : nullptr;
+    if (pipe) {
+      std::vector<uint32_t> gap(n);
+      for (size_t i = 0; i < n; i++) gap[i] = 30u + (uint32_t)norm[i].size();
+      std::vector<size_t> poff(n);
+      size_t need = 0;
+      const uint64_t l0 = pipeline_launches(pipe);
+      const int rc = pipeline_deflate_gapped(pipe, level, n, src, src_len, gap.data(), out, out_cap, &need, poff.data(), clen.data(), crc.data(), st_m.data());
+      ctx->launches += pipeline_launches(pipe) - l0;
+      if (rc == ZIPC_OK) {
+        for (size_t i = 0; i < n; i++) if (st_m[i]) return st_m[i];
+        std::vector<zipc_b200_member> ms(n);
+        fill_members(ms);
+        std::vector<uint64_t> want(n, ~0ull);
+        size_t total = 0;
+        if (int st = zip_assemble_impl(ms.data(), n, first, nullptr, 0, &total, false, want.data())) return st;
+        bool placed = true;
+        for (size_t i = 0; i < n && placed; i++) placed = want[i] == poff[i];
+        if (placed) return zip_assemble_impl(ms.data(), n, first, out, out_cap, out_len, false, nullptr);
+      } else if (rc != ZIPC_ERR_DST_TOO_SMALL) {
+        return rc;
+      }
+      // (too small for the payloads, or not where the layout wants them: the plain path below reports / redoes it)
+    }
+  }
   std::vector<const uint8_t *> d_src;
   if (int st = upload_ranges(ctx, n, src, src_len, d_src)) return st;
   std::vector<uint8_t *> d_slot;
   std::vector<size_t> cap;
   if (int st = make_slots(ctx, n, src_len, d_slot, cap)) return st;
-  std::vector<size_t> clen(n);
-  std::vector<uint32_t> crc(n);
-  std::vector<int> st_m(n);
   if (int st = deflate_run(ctx, level, ZIPC_CK_CRC32, 0, n, d_src, src_len, d_slot, cap, clen.data(), crc.data(), st_m.data())) return st;
   for (size_t i = 0; i < n; i++) if (st_m[i]) return st_m[i];
   std::vector<zipc_b200_member> ms(n);
-  for (size_t i = 0; i < n; i++) {
-    zipc_b200_member &m = ms[i];
-    std::memset(&m, 0, sizeof m);
-    m.path = norm[i].data(); m.path_len = (uint32_t)norm[i].size();
-    m.mode = mode ? mode[i] : 0644;
-    m.mtime = mtime ? std::max<int64_t>(mtime[i], 315532800) : 315532800;
-    m.version_made_by = 0x314; m.version_needed = 20; m.gp_flags = 0x800;  // File.make defaults (zipc.ml:138-143)
-    m.compression = 8;
-    m.compressed_size = clen[i]; m.decompressed_size = src_len[i]; m.crc32 = crc[i];
-  }
+  fill_members(ms);
   // layout first, then the GPU gathers every payload to its archive offset, then headers on the host
   std::vector<uint64_t> poff(n, ~0ull);  // members shadowed by a later duplicate path keep ~0
   size_t total = 0;
