@@ -406,7 +406,7 @@ int adler32_launch_buffer(zipc_b200_ctx *ctx, const uint8_t *d_src, uint64_t len
   ctx->launches++;
   ZB_CUDA(ctx, cudaGetLastError());
   ZB_CUDA(ctx, cudaMemcpyAsync(h_out, d_out, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
-  ZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  ZB_CUDA(ctx, stream_sync(ctx, ctx->stream));
   return ZIPC_OK;
 }
 
@@ -439,7 +439,7 @@ int adler32_ranges(zipc_b200_ctx *ctx, const uint8_t *const *d_ptrs, const uint6
   ZB_CUDA(ctx, cudaGetLastError());
   uint2 *h_ab = ctx->h_res.as<uint2>();
   ZB_CUDA(ctx, cudaMemcpyAsync(h_ab, ctx->d_scratch2.p, total * sizeof(uint2), cudaMemcpyDeviceToHost, ctx->stream));
-  ZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  ZB_CUDA(ctx, stream_sync(ctx, ctx->stream));
   k = 0;
   for (size_t i = 0; i < n; i++) {
     uint32_t s1 = 1, s2 = 0;
@@ -490,7 +490,7 @@ int adler32_blocked(zipc_b200_ctx *ctx, const uint8_t *const *d_ptrs, const uint
   ZB_CUDA(ctx, cudaGetLastError());
   uint2 *h_ab = ctx->h_res.as<uint2>();
   ZB_CUDA(ctx, cudaMemcpyAsync(h_ab, ctx->d_scratch2.p, total * sizeof(uint2), cudaMemcpyDeviceToHost, ctx->stream));
-  ZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  ZB_CUDA(ctx, stream_sync(ctx, ctx->stream));
   k = 0;
   nb = 0;
   for (size_t i = 0; i < n; i++) {

@@ -26,6 +26,14 @@ int set_cuda_error(zipc_b200_ctx *ctx, cudaError_t e, const char *what) {
                                                                         : ZIPC_ERR_CUDA;
 }
 
+cudaError_t stream_sync(zipc_b200_ctx *ctx, cudaStream_t s) {
+  if (!ctx->is_sub) return cudaStreamSynchronize(s);
+  if (!ctx->ev_block)
+    if (cudaError_t e = cudaEventCreateWithFlags(&ctx->ev_block, cudaEventBlockingSync | cudaEventDisableTiming)) return e;
+  if (cudaError_t e = cudaEventRecord(ctx->ev_block, s)) return e;
+  return cudaEventSynchronize(ctx->ev_block);
+}
+
 int DevBuf::reserve(size_t bytes) {
   if (bytes <= cap) return ZIPC_OK;
   if (p) { cudaFree(p); p = nullptr; cap = 0; }
@@ -98,7 +106,7 @@ int d2h(zipc_b200_ctx *ctx, void *h, const void *d, size_t bytes) {
   if (!bytes) return ZIPC_OK;
   if (is_pinned(h) || bytes <= (1u << 16)) {
     ZB_CUDA(ctx, cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, ctx->stream));
-    ZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ZB_CUDA(ctx, stream_sync(ctx, ctx->stream));
     return ZIPC_OK;
   }
   if (int st = ctx->h_stage.reserve(2 * kStageChunk)) return st;
@@ -157,7 +165,7 @@ int upload_ranges(zipc_b200_ctx *ctx, size_t n, const void *const *src, const si
     }
     ~GatePass() {
       if (!held) return;
-      cudaStreamSynchronize(c->stream);
+      stream_sync(c, c->stream);
       { std::lock_guard<std::mutex> lk(c->gate->m); c->gate->turn++; c->gate_passed = true; }
       c->gate->cv.notify_all();
     }
@@ -351,7 +359,7 @@ static int inflate_serial_core(zipc_b200_ctx *ctx, int ck, int adler_mode, size_
     if (!ctx->copy_stream) ZB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
     for (uint32_t g = 0; g < plan->ngroups; g++) reinterpret_cast<volatile uint32_t *>(ctx->h_gflag)[g] = cnt[g] ? 0u : 1u;
     ZB_CUDA(ctx, cudaMemcpyAsync(d_gcount, cnt.data(), plan->ngroups * sizeof(unsigned int), cudaMemcpyHostToDevice, ctx->stream));
-    ZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // (cnt is pageable: the copy must be over before it goes away)
+    ZB_CUDA(ctx, stream_sync(ctx, ctx->stream));  // (cnt is pageable: the copy must be over before it goes away)
   }
   const bool late = grouped && !plan->late.empty() && ctx->upload_split_live;
   if (ctx->upload_split_live && !late) {  // nobody will wait for the late half inside the kernel: wait for it here
@@ -386,7 +394,7 @@ static int inflate_serial_core(zipc_b200_ctx *ctx, int ck, int adler_mode, size_
                                      cudaMemcpyDeviceToHost, ctx->copy_stream));
     }
   }
-  ZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  ZB_CUDA(ctx, stream_sync(ctx, ctx->stream));
   if (late) { ZB_CUDA(ctx, cudaStreamSynchronize(ctx->upload_stream)); ctx->upload_split_live = false; }
   for (size_t k = 0; k < n; k++) {
     uint32_t i = order[k];
@@ -427,7 +435,7 @@ static int par_speculate(zipc_b200_ctx *ctx, const uint8_t *d_src, size_t src_le
   if (int st = inflate_find_starts(ctx, d_src, src_len, cb, nch, d_found)) return st;
   uint64_t *h_found = ctx->h_res.as<uint64_t>();
   ZB_CUDA(ctx, cudaMemcpyAsync(h_found, d_found, (size_t)nch * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
-  ZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  ZB_CUDA(ctx, stream_sync(ctx, ctx->stream));
   const double t_found = par_debug() ? now_ms() : 0;
   std::vector<uint64_t> start;
   start.push_back(0);
@@ -460,7 +468,7 @@ static int par_speculate(zipc_b200_ctx *ctx, const uint8_t *d_src, size_t src_le
   if (int st = inflate_launch_spec(ctx, d_tasks, m, d_results)) return st;
   InflateResult *h_results = reinterpret_cast<InflateResult *>(ctx->h_res.as<uint64_t>() + 4 * (size_t)nch);
   ZB_CUDA(ctx, cudaMemcpyAsync(h_results, d_results, m * sizeof(InflateResult), cudaMemcpyDeviceToHost, ctx->stream));
-  ZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  ZB_CUDA(ctx, stream_sync(ctx, ctx->stream));
   if (par_debug())
     std::fprintf(stderr, "[par] %zu bytes, %u nominal chunks, %u block starts: find %.2f ms, speculative decode %.2f ms\n", src_len, nch, m,
                  t_found - t_begin, now_ms() - t_found);
@@ -500,7 +508,7 @@ static int par_resolve(zipc_b200_ctx *ctx, uint8_t *d_dst, bool *ok) {
   if (int st = inflate_resolve(ctx, ctx->d_spec.as<uint16_t>(), d_tab, d_tab + m, d_tab + 2 * m, m, ctx->d_win.as<uint8_t>(), d_dst, d_bad)) return st;
   uint32_t bad = 1;
   ZB_CUDA(ctx, cudaMemcpyAsync(&bad, d_bad, sizeof bad, cudaMemcpyDeviceToHost, ctx->stream));
-  ZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  ZB_CUDA(ctx, stream_sync(ctx, ctx->stream));
   *ok = bad == 0;
   if (par_debug()) std::fprintf(stderr, "[par] resolve of %u chunks (%llu bytes): %.2f ms\n", m, (unsigned long long)plan.total, now_ms() - t_begin);
   return ZIPC_OK;
@@ -530,7 +538,7 @@ int inflate_core(zipc_b200_ctx *ctx, int ck, int adler_mode, size_t n, const std
             uint32_t *d_crc = ctx->d_small.as<uint32_t>() + 32;
             if (int st = crc32_launch_buffer(ctx, d_dst[i], total, d_crc)) return st;
             ZB_CUDA(ctx, cudaMemcpyAsync(&checksum[i], d_crc, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
-            ZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            ZB_CUDA(ctx, stream_sync(ctx, ctx->stream));
           }
         }
       }
@@ -608,7 +616,7 @@ int finish_download(zipc_b200_ctx *ctx, const DownloadPlan &plan) {
   if (plan.tail_bytes)
     ZB_CUDA(ctx, cudaMemcpyAsync(plan.dst + plan.tail_off, ctx->d_out.as<uint8_t>() + plan.tail_off, plan.tail_bytes, cudaMemcpyDeviceToHost, ctx->stream));
   ZB_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
-  ZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  ZB_CUDA(ctx, stream_sync(ctx, ctx->stream));
   return ZIPC_OK;
 }
 
@@ -690,6 +698,7 @@ void zipc_b200_ctx_destroy(zipc_b200_ctx *ctx) {
   if (ctx->hi_stream) cudaStreamDestroy(ctx->hi_stream);
   if (ctx->d_upflag) cudaFree(ctx->d_upflag);
   if (ctx->ev_half) cudaEventDestroy(ctx->ev_half);
+  if (ctx->ev_block) cudaEventDestroy(ctx->ev_block);
   if (ctx->h_gflag) cudaFreeHost(ctx->h_gflag);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -742,7 +751,7 @@ int zipc_b200_memcpy_h2d(zipc_b200_ctx *ctx, void *dptr, const void *src, size_t
   if (!ctx) return ZIPC_ERR_INVALID_ARG;
   DeviceGuard g(ctx->device);
   if (int st = h2d(ctx, dptr, src, bytes)) return st;
-  ZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  ZB_CUDA(ctx, stream_sync(ctx, ctx->stream));
   return ZIPC_OK;
 }
 int zipc_b200_memcpy_d2h(zipc_b200_ctx *ctx, void *dst, const void *dptr, size_t bytes) {
@@ -753,7 +762,7 @@ int zipc_b200_memcpy_d2h(zipc_b200_ctx *ctx, void *dst, const void *dptr, size_t
 int zipc_b200_sync(zipc_b200_ctx *ctx) {
   if (!ctx) return ZIPC_ERR_INVALID_ARG;
   DeviceGuard g(ctx->device);
-  ZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  ZB_CUDA(ctx, stream_sync(ctx, ctx->stream));
   return ZIPC_OK;
 }
 
@@ -771,7 +780,7 @@ int zipc_b200_crc32_dev(zipc_b200_ctx *ctx, const void *d_src, size_t len, uint3
   uint32_t *d_crc = ctx->d_small.as<uint32_t>() + 32;
   if (int st = crc32_launch_buffer(ctx, static_cast<const uint8_t *>(d_src), len, d_crc)) return st;
   ZB_CUDA(ctx, cudaMemcpyAsync(crc, d_crc, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
-  ZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  ZB_CUDA(ctx, stream_sync(ctx, ctx->stream));
   return ZIPC_OK;
 }
 
@@ -816,7 +825,7 @@ int zipc_b200_crc32_batch(zipc_b200_ctx *ctx, size_t n, const void *const *src, 
   ZB_CUDA(ctx, cudaMemcpyAsync(ctx->d_desc.p, hs, n * sizeof(CrcSeg), cudaMemcpyHostToDevice, ctx->stream));
   if (int st = crc32_launch_segments(ctx, ctx->d_desc.as<CrcSeg>(), (uint32_t)n, ctx->d_res.as<uint32_t>())) return st;
   ZB_CUDA(ctx, cudaMemcpyAsync(crc, ctx->d_res.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
-  ZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  ZB_CUDA(ctx, stream_sync(ctx, ctx->stream));
   for (size_t i = 0; i < n; i++) crc[i] ^= 0xFFFFFFFFu;
   return ZIPC_OK;
 }

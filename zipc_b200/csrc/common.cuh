@@ -148,6 +148,7 @@ struct zipc_b200_ctx {
   cudaStream_t hi_stream = nullptr;      // high priority: compaction of a pipelined group (zip_api.cu compact)
   uint32_t *d_upflag = nullptr;        // device word: serial number of the last completed late half
   uint32_t upload_serial = 0;
+  cudaEvent_t ev_block = nullptr;      // stream_sync of a sub-context
   cudaEvent_t ev_half = nullptr;       // first half of a split upload is through
   bool upload_split_live = false;      // the late half of the current upload is still on its way
   uint32_t *h_gflag = nullptr;         // mapped host memory: group-complete flags written by inflate_kernel
@@ -233,6 +234,9 @@ int gather_launch(zipc_b200_ctx *ctx, const CopyDesc *d_descs, uint32_t n, cudaS
 // api.cu helpers shared with zip_api.cu
 int h2d(zipc_b200_ctx *ctx, void *d, const void *h, size_t bytes);
 int d2h(zipc_b200_ctx *ctx, void *h, const void *d, size_t bytes);
+// cudaStreamSynchronize; the threads of a pipelined batch (sub-contexts) sleep on a blocking event instead of spinning: there
+// are up to 24 of them per process, and a box runs one process per GPU
+cudaError_t stream_sync(zipc_b200_ctx *ctx, cudaStream_t s);
 // A split upload (api.cu upload_ranges): the first part of a large pinned span goes out on the context's stream, the others
 // one after the other on upload_stream, each followed by a count (ctx->upload_serial + part) into ctx->d_upflag; a stream
 // whose bytes lie in part p >= 1 is decoded only after the kernel has seen that count.

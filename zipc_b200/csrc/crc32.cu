@@ -74,7 +74,7 @@ int crc_tables_upload(zipc_b200_ctx *ctx) {
   ZB_CUDA(ctx, cudaMalloc(&ctx->d_crc_tabs, kTabWords * sizeof(uint32_t)));
   ZB_CUDA(ctx, cudaMemcpyAsync(ctx->d_crc_tabs, t.data(), kTabWords * sizeof(uint32_t),
                                cudaMemcpyHostToDevice, ctx->stream));
-  ZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  ZB_CUDA(ctx, stream_sync(ctx, ctx->stream));
   return ZIPC_OK;
 }
 

@@ -129,7 +129,7 @@ int deflate_run(zipc_b200_ctx *ctx, int level, int ck, int adler_mode, size_t n,
     h_blk.resize(blk_total);
     ZB_CUDA(ctx, cudaMemcpyAsync(h_blk.data(), d_blk, blk_total * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
   }
-  ZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  ZB_CUDA(ctx, stream_sync(ctx, ctx->stream));
   pipe_mark(ctx, "kernel done");
   std::vector<uint32_t> nblk(n, 0);
   for (size_t k = 0; k < n; k++) {
@@ -194,7 +194,7 @@ int compact(zipc_b200_ctx *ctx, size_t n, const std::vector<uint8_t *> &d_slot, 
   }
   ZB_CUDA(ctx, cudaMemcpyAsync(ctx->d_desc2.p, h, n * sizeof(CopyDesc), cudaMemcpyHostToDevice, s));
   if (int st = gather_launch(ctx, ctx->d_desc2.as<CopyDesc>(), (uint32_t)n, s)) return st;
-  if (s != ctx->stream) ZB_CUDA(ctx, cudaStreamSynchronize(s));
+  if (s != ctx->stream) ZB_CUDA(ctx, stream_sync(ctx, s));
   return ZIPC_OK;
 }
 
@@ -232,7 +232,7 @@ int deflate_batch_layout(zipc_b200_ctx *ctx, int level, int ck, int adler_mode, 
   ctx->last_off = off; ctx->last_len.assign(dst_len, dst_len + n); ctx->last_total = total;
   for (size_t i = 0; i < n; i++) dst_off[i] = off[i];
   if (dst_need) *dst_need = total;
-  if (!dst || dst_cap < total) { ZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); pipe_mark(ctx, "compacted"); return ZIPC_ERR_DST_TOO_SMALL; }
+  if (!dst || dst_cap < total) { ZB_CUDA(ctx, stream_sync(ctx, ctx->stream)); pipe_mark(ctx, "compacted"); return ZIPC_ERR_DST_TOO_SMALL; }
   return d2h(ctx, dst, ctx->d_out.p, total);
 }
 
@@ -327,7 +327,7 @@ int zipc_b200_zlib_compress_batch(zipc_b200_ctx *ctx, int level, int adler_mode,
   ctx->last_off = off; ctx->last_len = flen; ctx->last_total = total;
   for (size_t i = 0; i < n; i++) { dst_len[i] = flen[i]; if (adler) adler[i] = ad[i]; }
   if (dst_need) *dst_need = total;
-  if (!dst || dst_cap < total) { ZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); return ZIPC_ERR_DST_TOO_SMALL; }
+  if (!dst || dst_cap < total) { ZB_CUDA(ctx, stream_sync(ctx, ctx->stream)); return ZIPC_ERR_DST_TOO_SMALL; }
   return d2h(ctx, dst, ctx->d_out.p, total);
 }
 
@@ -375,7 +375,7 @@ int zipc_b200_deflate_segmented(zipc_b200_ctx *ctx, int level, const void *src, 
   if (int st = compact(ctx, nseg, d_slot, clen.data(), off, total)) return st;
   ctx->last_off = off; ctx->last_len = clen; ctx->last_total = total;
   *dst_len = total;
-  if (!dst || dst_cap < total) { ZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); return ZIPC_ERR_DST_TOO_SMALL; }
+  if (!dst || dst_cap < total) { ZB_CUDA(ctx, stream_sync(ctx, ctx->stream)); return ZIPC_ERR_DST_TOO_SMALL; }
   return d2h(ctx, dst, ctx->d_out.p, total);
 }
 
@@ -414,7 +414,7 @@ int zipc_b200_inflate_segmented(zipc_b200_ctx *ctx, const void *src, size_t len,
     ZB_CUDA(ctx, cudaMemcpyAsync(crc32, d_crc, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
   }
   ctx->last_off.assign(1, 0); ctx->last_len.assign(1, (size_t)utotal); ctx->last_total = utotal;
-  if (!dst || dst_cap < utotal) { ZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); return ZIPC_ERR_DST_TOO_SMALL; }
+  if (!dst || dst_cap < utotal) { ZB_CUDA(ctx, stream_sync(ctx, ctx->stream)); return ZIPC_ERR_DST_TOO_SMALL; }
   return d2h(ctx, dst, ctx->d_out.p, utotal);
 }
 
@@ -505,7 +505,7 @@ int zipc_b200_zip_extract_batch(zipc_b200_ctx *ctx, const zipc_b200_member *ms, 
     if (int st = crc32_launch_segments(ctx, ds, (uint32_t)k, dck)) return st;
     std::vector<uint32_t> ck(k);
     ZB_CUDA(ctx, cudaMemcpyAsync(ck.data(), dck, k * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
-    ZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ZB_CUDA(ctx, stream_sync(ctx, ctx->stream));
     for (size_t j = 0; j < k; j++) {
       size_t i = idx[j];
       uint32_t c = ck[j] ^ 0xFFFFFFFFu;
