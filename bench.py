@@ -60,15 +60,21 @@ def make_config(which, level, members):
     return c
 
 
-def ncu_traffic(which):
-    """DRAM bytes per launch of the dominant kernel, from the committed ncu capture of this command (profiles/)."""
+def ncu_capture(which):
+    """What the committed ncu capture of this command says about the dominant kernel (profiles/rNN_traffic.json)."""
     for name in ("r02_traffic.json", "r01_traffic.json"):
         try:
             with open(os.path.join(ROOT, "profiles", name)) as f:
-                return int(json.load(f)[which]["traffic_bytes"])
+                return json.load(f)[which]
         except Exception:
             continue
-    return None
+    return {}
+
+
+def ncu_traffic(which):
+    """DRAM bytes per launch of the dominant kernel"""
+    t = ncu_capture(which).get("traffic_bytes")
+    return int(t) if t is not None else None
 
 
 def measured_peak_gbs():
@@ -810,7 +816,8 @@ def main():
         ach = r["algo_bytes"] / (r["kernel_ms"] / 1e3) / 1e9
         which = {"crc32_tiles_kernel": "crc32", "inflate_kernel<false>": "inflate", "deflate_kernel": "deflate"}[r["kernel"]]
         return {"bound": "hbm", "achieved": round(ach, 1), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4), "traffic": ncu_traffic(which),
-                "kernel": r["kernel"], "kernel_ms": round(r["kernel_ms"], 4), "algorithmic_bytes": int(r["algo_bytes"]), "peak_source": peak_src}
+                "kernel": r["kernel"], "kernel_ms": round(r["kernel_ms"], 4), "algorithmic_bytes": int(r["algo_bytes"]), "peak_source": peak_src,
+                "ncu": {k: v for k, v in ncu_capture(which).items() if k not in ("traffic_bytes", "kernel")}}
 
     def brief(r, which, level=None):
         d = {"metric": METRIC[which], "value": round(r["value"], 2), "unit": "GB/s", "e2e": round(r["e2e"], 3) if r.get("e2e") else None,
