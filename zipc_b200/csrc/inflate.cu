@@ -62,6 +62,13 @@ constexpr int WBITS = 32 * NB;  // speculation window
 constexpr int WARPS = ZB_INFLATE_WARPS;    // warps per CTA (one CTA per SM)
 constexpr int THREADS = WARPS * 32;
 constexpr int ROUND_TOKENS = 32;  // one token per lane
+// Refills of the compressed-input ring: ZB_INFLATE_BULK = 1 asks the copy engine (cp.async.bulk, 128 bytes per refill, completion
+// on a per-warp mbarrier) instead of one coalesced load per lane kept in a register until it is needed.
+#ifndef ZB_INFLATE_BULK
+#define ZB_INFLATE_BULK 0
+#endif
+constexpr int kRingWords = ZB_INFLATE_BULK ? 128 : 64;
+constexpr uint32_t kRingMask = kRingWords - 1;
 constexpr int SYMS_PER_SLOT = 320;     // sorted symbols: 288 litlen + 32 dist
 
 // Table entries are laid out for the speculative pass (D1), whose only question is "how many bits, or stop":
@@ -110,11 +117,13 @@ struct __align__(16) WarpWork {
   uint16_t tokq[ROUND_TOKENS + 2];  // candidate addresses of the round's tokens, in order, then where the walk ended
   uint32_t slow_tx[ROUND_TOKENS];   // slow path tokens: the token ...
   uint16_t slow_end[ROUND_TOKENS];  // ... and the bit offset where it ends
-  uint32_t ring[64];      // compressed input, words [w0, w0 + 64) of the stream
+  alignas(16) uint32_t ring[kRingWords];  // compressed input: words [w0, w0 + 64) of the stream (+ the segment on its way, bulk variant)
+  alignas(8) uint64_t ldbar;              // bulk variant: mbarrier of the warp's refills
   uint8_t cidx[32];       // E1: lane holding the r-th independent token
 };
 
 constexpr size_t kSmemBytes = sizeof(WarpTabs) * (WARPS + 1) + sizeof(WarpWork) * WARPS + 64 + 128 + 64;
+static_assert(kSmemBytes <= 227 * 1024, "one CTA of 32 warps per SM: tables + work areas must fit the opt-in shared memory");
 
 enum : uint32_t { S_IDLE = 0, S_HDR = 1, S_DATA = 2, S_STORED = 3, S_FINISH = 4, S_EXIT = 5 };
 
@@ -134,13 +143,57 @@ __constant__ uint8_t c_clen_order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4
 // ---- compressed input: a 64-word ring per warp, all state warp-uniform -----------------------------------------
 struct Input {
   uint32_t w0;             // ring holds words [w0, w0 + 64), w0 % 32 == 0
+#if ZB_INFLATE_BULK
+  uint32_t ph;             // bit 0: parity of the mbarrier phase the next refill completes; bit 1: a refill is on its way
+#else
   uint32_t pre;            // word w0 + 64 + lane, requested one refill ahead
+#endif
   uint64_t P;              // read position in bits from st.srcw
   __device__ __forceinline__ uint32_t load(const WarpState &st, uint32_t k) const {
     uint32_t w = 0;
     if (k < st.nwords) asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(w) : "l"(st.srcw + k));
     return w;
   }
+#if ZB_INFLATE_BULK
+  // words [k, k + 32) into their ring slots: by the copy engine when all of them exist (the source is 16-byte aligned by
+  // construction of srcw), else by guarded loads (the last words of a stream)
+  __device__ __forceinline__ void request(WarpWork &wk, uint32_t k, int lane) {
+    if (k + 32u <= wk.st.nwords) {
+      if (lane == 0) {
+        const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&wk.ldbar);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%1], %0;" ::"r"(128u), "r"(bar) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"((uint32_t)__cvta_generic_to_shared(&wk.ring[k & kRingMask])), "l"(wk.st.srcw + k), "r"(128u), "r"(bar) : "memory");
+      }
+      ph |= 2u;
+    } else {
+      wk.ring[(k & kRingMask) + lane] = load(wk.st, k + lane);
+    }
+  }
+  __device__ __forceinline__ void settle(WarpWork &wk) {  // the refill on its way, if any, has arrived (every lane sees it)
+    if (ph & 2u) {
+      const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&wk.ldbar);
+      uint32_t ok = 0;
+      for (uint32_t spins = 0; !ok && spins < (1u << 26); spins++)
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(bar), "r"(ph & 1u) : "memory");
+      ph = (ph & 1u) ^ 1u;
+    }
+    __syncwarp();  // nobody opens the next phase before everybody has seen this one complete
+  }
+  __device__ __forceinline__ void seek_bits(WarpWork &wk, uint64_t bitpos, int lane) {
+    settle(wk);
+    P = bitpos;
+    w0 = (uint32_t)(bitpos >> 5) & ~31u;
+    const uint32_t x = load(wk.st, w0 + lane), y = load(wk.st, w0 + 32 + lane);
+    wk.ring[(w0 & kRingMask) + lane] = x;
+    wk.ring[((w0 + 32u) & kRingMask) + lane] = y;
+    __syncwarp();
+    request(wk, w0 + 64, lane);
+    __syncwarp();
+  }
+#else
   __device__ __forceinline__ void seek_bits(WarpWork &wk, uint64_t bitpos, int lane) {
     P = bitpos;
     w0 = (uint32_t)(bitpos >> 5) & ~31u;
@@ -151,10 +204,11 @@ struct Input {
     pre = load(wk.st, w0 + 64 + lane);
     __syncwarp();
   }
+#endif
   // st.src / st.src_len are set: derive the rest (lane 0 writes) and fill the ring
   __device__ __forceinline__ void open(WarpWork &wk, int lane) {
     if (lane == 0) {
-      const uint32_t a = (uint32_t)((uintptr_t)wk.st.src & 3);
+      const uint32_t a = (uint32_t)((uintptr_t)wk.st.src & (ZB_INFLATE_BULK ? 15 : 3));
       wk.st.srcw = reinterpret_cast<const uint32_t *>(wk.st.src - a);
       wk.st.nwords = (uint32_t)((a + wk.st.src_len + 3) >> 2);
       wk.st.skew = 8 * a;
@@ -166,20 +220,27 @@ struct Input {
   // afterwards words [P >> 5, (P >> 5) + 32] are in the ring
   __device__ __forceinline__ void ensure(WarpWork &wk, int lane) {
     while ((uint32_t)(P >> 5) >= w0 + 32) {
+#if ZB_INFLATE_BULK
+      settle(wk);            // words [w0 + 64, w0 + 96) are there
+      w0 += 32;
+      request(wk, w0 + 64, lane);
+      __syncwarp();
+#else
       __syncwarp();
       wk.ring[(w0 & 32u) + lane] = pre;
       w0 += 32;
       pre = load(wk.st, w0 + 64 + lane);
       __syncwarp();
+#endif
     }
   }
   __device__ __forceinline__ uint32_t peek32(const WarpWork &wk) const {  // the next 32 bits (uniform: broadcast reads)
     uint32_t k = (uint32_t)(P >> 5);
-    return __funnelshift_r(wk.ring[k & 63], wk.ring[(k + 1) & 63], (uint32_t)P & 31u);
+    return __funnelshift_r(wk.ring[k & kRingMask], wk.ring[(k + 1) & kRingMask], (uint32_t)P & 31u);
   }
   __device__ __forceinline__ static uint32_t peek32_at(const WarpWork &wk, uint64_t pos) {
     uint32_t k = (uint32_t)(pos >> 5);
-    return __funnelshift_r(wk.ring[k & 63], wk.ring[(k + 1) & 63], (uint32_t)pos & 31u);
+    return __funnelshift_r(wk.ring[k & kRingMask], wk.ring[(k + 1) & kRingMask], (uint32_t)pos & 31u);
   }
   __device__ __forceinline__ uint32_t get(WarpWork &wk, uint32_t n, int lane) {  // n <= 16
     ensure(wk, lane);
@@ -190,6 +251,18 @@ struct Input {
   __device__ __forceinline__ uint64_t consumed(const WarpWork &wk) const { return P - wk.st.skew; }   // stream bits read
   __device__ __forceinline__ bool overrun(const WarpWork &wk) const { return P > wk.st.limit; }
 };
+
+#if ZB_INFLATE_BULK
+__device__ __forceinline__ void input_bar_init(WarpWork &wk, int lane) {
+  if (lane == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(&wk.ldbar)) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+}
+#else
+__device__ __forceinline__ void input_bar_init(WarpWork &, int) {}
+#endif
 
 // ---- canonical walk for codes longer than the table (the reference's read_symbol, :584-591) --------
 // Returns the symbol and its length, or -1 (the reference would run off counts.(16)).
@@ -483,6 +556,7 @@ inflate_kernel(const InflateTask *__restrict__ tasks, uint32_t ntasks, InflateRe
   // decoder state: identical in all lanes of the warp (no broadcasts needed, branches are uniform)
   uint32_t state = S_IDLE, task = 0, status = ZIPC_OK;
   Input in{};
+  input_bar_init(wk, lane);
   WarpState &st = wk.st;
   uint8_t *dst = nullptr;
   uint64_t out_pos = 0;
@@ -504,7 +578,12 @@ inflate_kernel(const InflateTask *__restrict__ tasks, uint32_t ntasks, InflateRe
         if (lane == 0) task = atomicAdd(queue, 1u);
         task = __shfl_sync(0xffffffffu, task, 0);
       }
-      if (task >= ntasks) break;
+      if (task >= ntasks) {
+#if ZB_INFLATE_BULK
+        in.settle(wk);  // no copy may land in this CTA's shared memory after it is gone
+#endif
+        break;
+      }
       const InflateTask t = tasks[task];
       if (!COUNT_ONLY && !SPEC && ((t.flags >> kInflatePartShift) & kInflatePartMask) && upload_flag) {
         const uint32_t need = upload_serial + ((t.flags >> kInflatePartShift) & kInflatePartMask);
@@ -586,7 +665,7 @@ inflate_kernel(const InflateTask *__restrict__ tasks, uint32_t ntasks, InflateRe
         const uint32_t dist_sa = (uint32_t)__cvta_generic_to_shared(dist_lut);
         uint32_t a[NB + 2];
 #pragma unroll
-        for (int t = 0; t < NB + 2; t++) a[t] = wk.ring[(wi + t) & 63];
+        for (int t = 0; t < NB + 2; t++) a[t] = wk.ring[(wi + t) & kRingMask];
 #pragma unroll
         for (int j = 0; j < NB; j++) {
           const uint32_t lo = __funnelshift_r(a[j], a[j + 1], s), hi = __funnelshift_r(a[j + 1], a[j + 2], s);
@@ -690,7 +769,7 @@ inflate_kernel(const InflateTask *__restrict__ tasks, uint32_t ntasks, InflateRe
           const uint32_t o = oq;
           const uint64_t pb = P0 + o;
           const uint32_t k = (uint32_t)(pb >> 5), sb = (uint32_t)pb & 31u;
-          const uint32_t w0 = wk.ring[k & 63], w1 = wk.ring[(k + 1) & 63], w2 = wk.ring[(k + 2) & 63];
+          const uint32_t w0 = wk.ring[k & kRingMask], w1 = wk.ring[(k + 1) & kRingMask], w2 = wk.ring[(k + 2) & kRingMask];
           const uint32_t lo = __funnelshift_r(w0, w1, sb), hi = __funnelshift_r(w1, w2, sb);
           const uint32_t e = lit_lut[lo & ((1u << LB) - 1u)];
           const uint32_t p = e & 31u;
@@ -919,10 +998,11 @@ find_starts_kernel(const uint8_t *__restrict__ src, uint64_t src_len, uint64_t c
   WarpTabs &mine = tabs[warp];
   WarpWork &wk = works[warp];
   uint16_t *my_syms = g_syms + (size_t)(blockIdx.x * WARPS + warp) * SYMS_PER_SLOT;
+  Input in{};
+  input_bar_init(wk, lane);
   for (uint32_t k = 1 + blockIdx.x * WARPS + warp; k < nchunks; k += gridDim.x * WARPS) {
     __syncwarp();
     if (lane == 0) { wk.st.src = src; wk.st.src_len = src_len; wk.st.out_cap = 0; wk.st.ad_from = 0; }
-    Input in{};
     in.open(wk, lane);
     const uint64_t skew = wk.st.skew, limit = wk.st.limit;
     const uint64_t beg = skew + 8 * (uint64_t)k * chunk_bytes;
@@ -961,6 +1041,9 @@ find_starts_kernel(const uint8_t *__restrict__ src, uint64_t src_len, uint64_t c
     }
     if (lane == 0) found[k] = hit == ~0ull ? ~0ull : hit - skew;
   }
+#if ZB_INFLATE_BULK
+  in.settle(wk);
+#endif
 }
 
 // ---- resolve the speculative symbols ------------------------------------------------------------------------------------------
