@@ -65,7 +65,7 @@ constexpr int ROUND_TOKENS = 32;  // one token per lane
 // Refills of the compressed-input ring: ZB_INFLATE_BULK = 1 asks the copy engine (cp.async.bulk, 128 bytes per refill, completion
 // on a per-warp mbarrier) instead of one coalesced load per lane kept in a register until it is needed.
 #ifndef ZB_INFLATE_BULK
-#define ZB_INFLATE_BULK 0
+#define ZB_INFLATE_BULK 1
 #endif
 constexpr int kRingWords = ZB_INFLATE_BULK ? 128 : 64;
 constexpr uint32_t kRingMask = kRingWords - 1;
