@@ -85,6 +85,24 @@ def measured_peak_gbs():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def bind_near_gpu(index: int):
+    """One process per GPU: run this rank (and the library's threads it spawns) on the CPUs NVML lists as local to its GPU, so
+    that the pinned buffers of the end-to-end path are first touched -- and therefore placed -- on the GPU's own NUMA node."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        hnd = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(hnd, (os.cpu_count() + 63) // 64)
+        cpus = {64 * w + b for w, v in enumerate(words) for b in range(64) if (int(v) >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region."""
 
@@ -782,6 +800,7 @@ def main():
         dist.init_process_group(backend="nccl", device_id=torch.device(f"cuda:{local}"))
         cpu_group = dist.new_group(backend="gloo")
     from zipc_b200 import synth
+    numa = bind_near_gpu(local) if world > 1 else None   # before any pinned allocation: first touch decides where the pages live
     h = Harness(local)
     peak, peak_src = measured_peak_gbs()
 
@@ -860,6 +879,8 @@ def main():
             "e2e": {"value": round(r["e2e"], 3), "unit": "GB/s", "h2d_bytes_per_step": int(r["h2d"]), "d2h_bytes_per_step": int(r["d2h"]),
                     "note": "C-ABI call with pinned host buffers (codec members lie in one pinned buffer, like an in-memory archive); H2D + kernels + D2H per step"},
             "gpu_launches": int(r["launches"]), "roofline": roofline(r)}
+    if numa:
+        line["detail"]["host_cpus_per_rank"] = numa   # (ranks are bound to the CPUs local to their GPU)
     head_sizes = r.get("sizes")
     crc_host = r.get("host")
     oracle_streams = None
