@@ -202,6 +202,15 @@ int zipc_b200_zlib_compress_batch(zipc_b200_ctx *ctx, int level, int adler_mode,
 int zipc_b200_deflate_segmented(zipc_b200_ctx *ctx, int level, const void *src, size_t len, size_t segment_size,
                                 int last_piece, void *dst, size_t dst_cap, size_t *dst_len, uint64_t *index,
                                 size_t index_cap_pairs, size_t *nseg, uint32_t *crc32);
+/* The same with every segment PRIMED with the 32 KiB of input before it (pigz style): matches reach back across segment
+ * boundaries, so the stream is as small as one compressed in one piece (plus 5 bytes per segment for the byte-aligning
+ * empty stored block) while still being compressed by one CTA per segment.  The result is an ordinary RFC 1951 stream;
+ * its segments are NOT independent, so it is decoded like any foreign stream (zipc_b200_inflate_batch: many warps through
+ * block-start search and speculation), not by zipc_b200_inflate_segmented.  index as above (informational).  This is what
+ * one large payload of Zipc.File.deflate_of_binary_string (src/zipc.ml:179-185) should go through. */
+int zipc_b200_deflate_primed(zipc_b200_ctx *ctx, int level, const void *src, size_t len, size_t segment_size,
+                             int last_piece, void *dst, size_t dst_cap, size_t *dst_len, uint64_t *index,
+                             size_t index_cap_pairs, size_t *nseg, uint32_t *crc32);
 /* Zipc_deflate.inflate_and_crc_32 of such a stream WITH its index: segments are decoded in parallel (one
  * warp each).  status = ZIPC_OK or the status of the first bad segment.  Without the index the stream
  * is an ordinary deflate stream (zipc_b200_inflate_batch decodes it serially). */

@@ -242,3 +242,29 @@ def test_segmented_single_stream(ctx):
     bad = stream.copy(); bad[int(index[3, 0]) + 100] ^= 0xFF
     st, out, _ = ctx.inflate_segmented(bad, index)
     assert st != 0 or out.tobytes() != b
+
+
+@pytest.mark.parametrize("level", ["fast", "default", "best"])
+def test_primed_segments_lose_no_ratio(ctx, level):
+    """zipc_b200_deflate_primed: one stream compressed by one CTA per segment, every segment primed with the 32 KiB of input
+    before it.  The result is ONE ordinary RFC 1951 stream (the oracle's and zlib's inflate read it), as small as the same
+    input compressed in one piece (5 bytes per segment for the byte-aligning stored blocks), and smaller than with window
+    resets; the GPU's own foreign-stream decoder reads it back."""
+    n = (3 << 20) + 12345 if level != "best" else (1 << 20) + 777
+    s = synth.text_v1(77, n).tobytes()
+    whole = bytes(zd.deflate(s, level=level).get_ok())
+    for seg in (64 << 10, (96 << 10) + 1000):   # (the second: segment starts that are no multiples of the tile)
+        primed, index, crc = ctx.deflate_segmented(s, level, seg, primed=True)
+        reset, _, _ = ctx.deflate_segmented(s, level, seg, primed=False)
+        nseg = index.shape[0] - 1
+        assert crc == zlib.crc32(s)
+        assert zlib.decompress(bytes(primed), -15) == s
+        assert zo.inflate(bytes(primed)) == s
+        assert len(primed) <= len(whole) * 1.002 + 8 * nseg, (len(primed), len(whole))
+        assert len(primed) < len(reset)
+        out = zd.inflate(bytes(primed), decompressed_size=len(s)).get_ok()
+        assert bytes(out) == s
+    # a non-final piece (a slice of a stream spread over several GPUs) keeps BFINAL off
+    piece, _, _ = ctx.deflate_segmented(s[:300_000], level, 64 << 10, last_piece=False, primed=True)
+    d = zlib.decompressobj(-15)
+    assert d.decompress(bytes(piece)) == s[:300_000] and not d.eof

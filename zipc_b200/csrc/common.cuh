@@ -112,6 +112,9 @@ struct DeflateTask {  // one input to deflate (a ZIP member or an independent se
   uint32_t blk_off;   // index of this member's first entry in the launch's block-length list (see deflate_launch)
 };
 constexpr uint32_t kDeflateNotFinal = 1u;
+// flags bits 8..15: the member is primed with that many 2048-byte tiles of input that lie right BEFORE src (a segment of a
+// larger stream whose matches may reach back into the previous segment's bytes: no window reset, no ratio loss)
+constexpr uint32_t kDeflatePrimeShift = 8, kDeflatePrimeMask = 0xFFu, kDeflatePrimeTile = 2048u;
 struct DeflateResult {
   uint64_t out_len;
   uint32_t status;

@@ -659,9 +659,10 @@ __device__ __forceinline__ void guess_visits(const uint16_t *mlen, const uint32_
 // ---- front end: stage, hash, partition, insert, shallow walks of one tile (FRONT_THREADS threads) -----------------
 // ft: thread index inside the front group; fw: warp index inside the group.  Uses bar_front() only.
 // `state`: bits 0..31 = input bytes resident in the ring or on their way, bit 32 = a bulk copy is in flight.  Returns the new state.
+// Positions below emit_from (a multiple of the tile) only prime the window: hashed and inserted, not searched.
 template <int BW>
 __device__ __noinline__ uint64_t front_end(int gen, const uint8_t *src, uint32_t n, uint32_t ts, uint64_t state,
-                                           int level, int ft, int fw, int lane) {
+                                           int level, int ft, int fw, int lane, uint32_t emit_from) {
   constexpr int FRONT_WARPS = NWARPS - BW, FRONT_THREADS = FRONT_WARPS * 32, BACK_THREADS = BW * 32;
   constexpr int kClasses = FRONT_WARPS, kRankRounds = (kChunk32 + FRONT_WARPS - 1) / FRONT_WARPS;
   static_assert(kClasses >= 16 && kClasses <= kMaxClasses, "a class must span at most 1024 hash values; the counters hold 31 classes");
@@ -817,7 +818,7 @@ __device__ __noinline__ uint64_t front_end(int gen, const uint8_t *src, uint32_t
     if (b >= kTile / 32) break;
     const uint32_t i = b * 32 + lane, p = ts + i;
     uint32_t l = 0, d = 0, rt = p & 0xFFFFu;
-    if (p < te && p + 4 <= n) {
+    if (p < te && p + 4 <= n && p >= emit_from) {
       // every lane walks on its own: at these depths nearly every candidate passes the first test (same hash), so keeping
       // the warp together for the comparisons (as the deep walks do) only adds votes -- measured: 17.0 vs 11.4 clk/byte
       MatchState m;
@@ -835,7 +836,7 @@ __device__ __noinline__ uint64_t front_end(int gen, const uint8_t *src, uint32_t
   bar_front<BW>();
   PH_AT(PH_F_SHALLOW, BACK_THREADS);
   // 4. the positions a parse of this tile is guessed to visit: the deep walks' first queue
-  if (fw == 0 && lp.rounds > 0) guess_visits(G.mlen, nullptr, ts, te, n, sh.vq + gen * kTile, &sh.sc[SC_VQN + gen], lane);
+  if (fw == 0 && lp.rounds > 0 && ts >= emit_from) guess_visits(G.mlen, nullptr, ts, te, n, sh.vq + gen * kTile, &sh.sc[SC_VQN + gen], lane);
   return (uint64_t)loaded | ((uint64_t)in_flight << 32);
 }
 
@@ -1009,8 +1010,11 @@ __device__ void encode_member(const DeflateTask t, int level, uint32_t *toks, De
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const bool back = warp < BACK_WARPS;
   const int ft = tid - BACK_THREADS, fw = warp - BACK_WARPS;
-  const uint8_t *src = t.src;
-  const uint32_t n = (uint32_t)t.src_len;
+  // a primed member: `prime` bytes right before t.src are run through the front end only (ring, hash chains), so that the
+  // member's matches can reach back into them; positions count from the first primed byte
+  const uint32_t prime = ((t.flags >> kDeflatePrimeShift) & kDeflatePrimeMask) * kDeflatePrimeTile;
+  const uint8_t *src = t.src - prime;
+  const uint32_t n = (uint32_t)t.src_len + prime;
   uint32_t *out_words = reinterpret_cast<uint32_t *>(t.dst);
   const uint64_t out_cap_words = t.dst_cap / 4;
   const LevelParams lp = level_params(level);
@@ -1027,13 +1031,13 @@ __device__ void encode_member(const DeflateTask t, int level, uint32_t *toks, De
 
   uint32_t pos = 0, kind = 0, ntok = 0, nblocks = 0;
   uint64_t loaded = 0;  // staging state of the front end (front threads only)
-  uint64_t blk_src_start = 0;
+  uint64_t blk_src_start = prime;
   int tiles_in_block = 0, g = 0;
   PH_DECL
 
   // prologue: tile 0 through the front end, then its jump codes
   if (n) {
-    if (!back) loaded = front_end<BW>(0, src, n, 0, loaded, level, ft, fw, lane);
+    if (!back) loaded = front_end<BW>(0, src, n, 0, loaded, level, ft, fw, lane, prime);
     __syncthreads();
     jump_codes(sh, gen_of(smem_raw, 0), 0, min((uint32_t)kTile, n), tid, THREADS);
     __syncthreads();
@@ -1044,7 +1048,14 @@ __device__ void encode_member(const DeflateTask t, int level, uint32_t *toks, De
     const uint32_t te = min(ts + (uint32_t)kTile, n), tl = te - ts;
     const Gen G = gen_of(smem_raw, g), G1 = gen_of(smem_raw, g ^ 1);
     const bool more = te < n;
-    if (back) {
+    const bool priming = te <= prime;  // (prime is a multiple of the tile: a tile is primed as a whole or not at all)
+    if (back && priming) {
+      // nothing is emitted for this tile: no marks, and the parse of the next tile starts afresh at its first position
+      if (warp == 0) {
+        sh.mk0[2 * lane] = 0; sh.mk0[2 * lane + 1] = 0; sh.mk1[2 * lane] = 0; sh.mk1[2 * lane + 1] = 0;
+        if (lane == 0) sh.sc[SC_EXIT] = kExit;
+      }
+    } else if (back) {
       // ---- back end: parse, deep walks, final parse of tile t ----------------------------------------------------
       const uint32_t te1 = min(te + (uint32_t)kTile, n);
       const uint32_t trim = (more && te1 > (uint32_t)kWindow) ? te1 - (uint32_t)kWindow : 0u;
@@ -1075,7 +1086,7 @@ __device__ void encode_member(const DeflateTask t, int level, uint32_t *toks, De
       PH(PH_PARSE1);
     } else if (more) {
       // ---- front end: tile t + 1 -------------------------------------------------------------------------------------
-      loaded = front_end<BW>(g ^ 1, src, n, te, loaded, level, ft, fw, lane);
+      loaded = front_end<BW>(g ^ 1, src, n, te, loaded, level, ft, fw, lane, prime);
     }
     __syncthreads();
     PH(PH_BACK_WAIT);
@@ -1119,7 +1130,7 @@ __device__ void encode_member(const DeflateTask t, int level, uint32_t *toks, De
     }
     __syncthreads();
     PH(PH_TOKENS);
-    tiles_in_block++;
+    if (!priming) tiles_in_block++;
     const bool last = te == n;
     if (tiles_in_block == kTilesPerBlock || last) {
       const uint32_t blen = sh.sc[SC_BLK_SRCLEN];
@@ -1134,7 +1145,7 @@ __device__ void encode_member(const DeflateTask t, int level, uint32_t *toks, De
     __syncthreads();
     PH(PH_OTHER);
   }
-  if (n == 0) {
+  if (n == 0) {  // (an empty member is never primed)
     finalize_block(src, 0, 0, toks, !not_final, out_words, out_cap_words);
     if (tid == 0 && blk_lens) blk_lens[t.blk_off] = 0;
     nblocks++;

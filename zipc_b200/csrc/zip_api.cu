@@ -332,9 +332,9 @@ int zipc_b200_zlib_compress_batch(zipc_b200_ctx *ctx, int level, int adler_mode,
 }
 
 // ---- segmented single stream -----------------------------------------------------------------------------
-int zipc_b200_deflate_segmented(zipc_b200_ctx *ctx, int level, const void *src, size_t len, size_t segment_size,
-                                int last_piece, void *dst, size_t dst_cap, size_t *dst_len, uint64_t *index,
-                                size_t index_cap_pairs, size_t *nseg_out, uint32_t *crc32) {
+static int deflate_segments(zipc_b200_ctx *ctx, int level, const void *src, size_t len, size_t segment_size,
+                            int last_piece, void *dst, size_t dst_cap, size_t *dst_len, uint64_t *index,
+                            size_t index_cap_pairs, size_t *nseg_out, uint32_t *crc32, bool primed) {
   if (!ctx || level < 0 || level > 3 || (!src && len) || !dst_len || !nseg_out || segment_size < 4096 ||
       segment_size > 0x7FFFFFFFull)
     return ZIPC_ERR_INVALID_ARG;
@@ -352,6 +352,11 @@ int zipc_b200_deflate_segmented(zipc_b200_ctx *ctx, int level, const void *src, 
   std::vector<uint32_t> flags(nseg, kDeflateNotFinal);
   for (size_t i = 0; i < nseg; i++) { d_src[i] = d_base + i * segment_size; slen[i] = std::min(segment_size, len - i * segment_size); }
   if (last_piece) flags[nseg - 1] = 0;
+  if (primed)  // every segment but the first sees the 32 KiB of input before it (whole tiles of it)
+    for (size_t i = 1; i < nseg; i++) {
+      const size_t before = std::min<size_t>(i * segment_size, 32768) / kDeflatePrimeTile;
+      flags[i] |= (uint32_t)before << kDeflatePrimeShift;
+    }
   std::vector<uint8_t *> d_slot;
   std::vector<size_t> cap, clen(nseg);
   std::vector<int> st_m(nseg);
@@ -377,6 +382,18 @@ int zipc_b200_deflate_segmented(zipc_b200_ctx *ctx, int level, const void *src, 
   *dst_len = total;
   if (!dst || dst_cap < total) { ZB_CUDA(ctx, stream_sync(ctx, ctx->stream)); return ZIPC_ERR_DST_TOO_SMALL; }
   return d2h(ctx, dst, ctx->d_out.p, total);
+}
+
+int zipc_b200_deflate_segmented(zipc_b200_ctx *ctx, int level, const void *src, size_t len, size_t segment_size,
+                                int last_piece, void *dst, size_t dst_cap, size_t *dst_len, uint64_t *index,
+                                size_t index_cap_pairs, size_t *nseg_out, uint32_t *crc32) {
+  return deflate_segments(ctx, level, src, len, segment_size, last_piece, dst, dst_cap, dst_len, index, index_cap_pairs, nseg_out, crc32, false);
+}
+
+int zipc_b200_deflate_primed(zipc_b200_ctx *ctx, int level, const void *src, size_t len, size_t segment_size,
+                             int last_piece, void *dst, size_t dst_cap, size_t *dst_len, uint64_t *index,
+                             size_t index_cap_pairs, size_t *nseg_out, uint32_t *crc32) {
+  return deflate_segments(ctx, level, src, len, segment_size, last_piece, dst, dst_cap, dst_len, index, index_cap_pairs, nseg_out, crc32, true);
 }
 
 int zipc_b200_inflate_segmented(zipc_b200_ctx *ctx, const void *src, size_t len, const uint64_t *index, size_t nseg,

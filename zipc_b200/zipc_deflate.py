@@ -245,15 +245,17 @@ class Context:
 
 
     # -- one large stream as independent segments (configs 1 and 5)
-    def deflate_segmented(self, s, level: str = "default", segment_size: int = 256 << 10, last_piece: bool = True):
-        """-> (stream bytes-like, index ndarray[(nseg+1), 2] of (compressed, uncompressed) offsets, crc32 of s)"""
+    def deflate_segmented(self, s, level: str = "default", segment_size: int = 256 << 10, last_piece: bool = True, primed: bool = False):
+        """-> (stream bytes-like, index ndarray[(nseg+1), 2] of (compressed, uncompressed) offsets, crc32 of s).
+        primed: every segment sees the 32 KiB of input before it (zipc_b200_deflate_primed): no ratio loss, but the stream
+        is then decoded like a foreign one (inflate_batch), not by inflate_segmented."""
         v = _as_view(s)
         nseg_max = max(1, -(-v.size // segment_size))
         index = np.zeros((nseg_max + 1, 2), dtype=np.uint64)
         n, nseg, crc = C.c_size_t(), C.c_size_t(), C.c_uint32()
         args = (self.h, LEVELS[level], v.ctypes.data if v.size else None, v.size, segment_size, int(last_piece))
-        st = self.L.zipc_b200_deflate_segmented(*args, None, 0, C.byref(n), index.ctypes.data_as(C.POINTER(C.c_uint64)),
-                                                nseg_max + 1, C.byref(nseg), C.byref(crc))
+        fn = self.L.zipc_b200_deflate_primed if primed else self.L.zipc_b200_deflate_segmented
+        st = fn(*args, None, 0, C.byref(n), index.ctypes.data_as(C.POINTER(C.c_uint64)), nseg_max + 1, C.byref(nseg), C.byref(crc))
         if st != _lib.ERR_DST_TOO_SMALL:
             self._check(st, "deflate_segmented")
         out = np.empty(max(n.value, 1), dtype=np.uint8)
