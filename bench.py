@@ -466,6 +466,27 @@ def run_stream_c1(h: Harness):
         assert crc2.value == crc.value and olen.value == data.size and bytes(obuf[:4096]) == bytes(data[:4096])
         res["seg_%dk" % (seg >> 10)] = {"deflate_e2e_GBps": round(data.size / td / 1e9, 3), "inflate_e2e_GBps": round(data.size / ti / 1e9, 3),
                                        "ratio": round(n.value / data.size, 4), "segments": int(nseg.value)}
+    # the reference's own call shape: ONE payload through the batch entry (n = 1).  A member this large is split into primed
+    # 256 KiB segments, one CTA each (no window reset: the ratio of a single-CTA stream), and decoded as a foreign stream
+    ptr1 = (C.c_void_p * 1)(data.ctypes.data); ln1 = (C.c_size_t * 1)(data.size)
+    need1 = C.c_size_t(); off1 = (C.c_size_t * 1)(); ol1 = (C.c_size_t * 1)(); ck1 = (C.c_uint32 * 1)(); st1 = (C.c_int * 1)()
+    pfn = lambda: L.zipc_b200_deflate_batch(h.ctx.h, 2, 2, 0, 1, ptr1, ln1, cbuf.ctypes.data, cbuf.size, C.byref(need1), off1, ol1, ck1, st1)
+    assert pfn() == 0 and st1[0] == 0 and ck1[0] == zlib.crc32(data)
+    t0 = time.perf_counter()
+    for _ in range(3): pfn()
+    tp = (time.perf_counter() - t0) / 3
+    plen = int(ol1[0])
+    cptr = (C.c_void_p * 1)(cbuf.ctypes.data + int(off1[0])); cln = (C.c_size_t * 1)(plen); mo1 = (C.c_size_t * 1)(data.size)
+    need2 = C.c_size_t(); off2 = (C.c_size_t * 1)(); ol2 = (C.c_size_t * 1)(); ck2 = (C.c_uint32 * 1)(); st2 = (C.c_int * 1)()
+    qfn = lambda: L.zipc_b200_inflate_batch(h.ctx.h, 2, 0, 1, cptr, cln, mo1, obuf.ctypes.data, obuf.size, C.byref(need2), off2, ol2, ck2, st2)
+    assert qfn() == 0 and st2[0] == 0 and ck2[0] == ck1[0]
+    t0 = time.perf_counter()
+    for _ in range(3): qfn()
+    tq = (time.perf_counter() - t0) / 3
+    res["one_member_batch_call"] = {"deflate_e2e_GBps": round(data.size / tp / 1e9, 3), "inflate_e2e_GBps": round(data.size / tq / 1e9, 3),
+                                    "ratio": round(plen / data.size, 4),
+                                    "note": "zipc_b200_deflate_batch / zipc_b200_inflate_batch with n = 1: the member is split into primed 256 KiB segments "
+                                            "(one CTA each, no ratio loss); the stream is decoded by many warps without an index"}
     # the same data as ONE foreign stream (zlib -6, no index): intra-stream parallel inflate
     zs = zlib.compress(data.tobytes(), 6)[2:-4]
     hz = h.pinned(np.frombuffer(zs, dtype=np.uint8))

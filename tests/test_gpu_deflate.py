@@ -268,3 +268,34 @@ def test_primed_segments_lose_no_ratio(ctx, level):
     piece, _, _ = ctx.deflate_segmented(s[:300_000], level, 64 << 10, last_piece=False, primed=True)
     d = zlib.decompressobj(-15)
     assert d.decompress(bytes(piece)) == s[:300_000] and not d.eof
+
+
+def test_large_members_are_split_over_ctas(ctx):
+    """A member of 2 MiB or more is compressed as primed 256 KiB segments, one CTA each (Zipc.File.deflate_of_binary_string of
+    one big payload must not be left to a single SM): still ONE ordinary stream per member, CRC-32 of the whole member,
+    5 bytes per segment larger than the one-CTA result at most, and much faster."""
+    import time
+    big = [synth.text_v1(31, (5 << 20) + 4321).tobytes(), synth.rand_v1(32, (2 << 20) + 17).tobytes(), synth.text_v1(33, 2 << 20).tobytes()]
+    small = [synth.text_v1(40 + i, 50_000 + 1000 * i).tobytes() for i in range(6)]
+    items = [small[0], big[0], small[1], small[2], big[1], big[2], small[3], small[4], small[5]]
+    for level in ("fast", "default"):
+        res = ctx.deflate_batch(items, level, _lib.CK_CRC32)
+        for d, (st, cs, ck) in zip(items, res):
+            assert st == 0 and ck == zlib.crc32(d)
+            assert zlib.decompress(bytes(cs), -15) == d
+            if len(d) >= (2 << 20):
+                assert zo.inflate(bytes(cs)) == d
+        # against the same member compressed by one CTA (below the threshold: the first 2 MiB - 1 of it, scaled)
+        d = big[0]
+        one = ctx.deflate_batch([d[:(2 << 20) - 1]], level, 0)[0][1]
+        split = res[1][1]
+        assert len(split) / len(d) <= len(one) / ((2 << 20) - 1) * 1.01
+    # one 64 MiB payload: seconds on one SM, milliseconds on all of them
+    huge = synth.text_v1(5, 64 << 20)
+    ctx.deflate_batch([huge], "default", _lib.CK_CRC32)
+    t0 = time.perf_counter()
+    st, cs, ck = ctx.deflate_batch([huge], "default", _lib.CK_CRC32)[0]
+    dt = time.perf_counter() - t0
+    assert st == 0 and ck == zlib.crc32(huge) and zlib.decompress(bytes(cs), -15) == huge.tobytes()
+    assert dt < 0.25, dt   # (one CTA: ~0.75 s)
+    assert zd.inflate(bytes(cs), decompressed_size=huge.size).get_ok() == huge.tobytes()

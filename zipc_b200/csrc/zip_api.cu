@@ -198,6 +198,67 @@ int compact(zipc_b200_ctx *ctx, size_t n, const std::vector<uint8_t *> &d_slot, 
   return ZIPC_OK;
 }
 
+// ---- large members over several CTAs -------------------------------------------------------------------------------------
+// A member of ZIPC_B200_SPLIT_MIN bytes or more (default 2 MiB; 0 = never) is compressed as primed segments of 256 KiB, one
+// CTA each: every segment but the last ends with a byte-aligning empty stored block, every segment but the first sees the
+// 32 KiB of input before it, so the concatenation is ONE ordinary RFC 1951 stream, 5 bytes per segment larger than the
+// member compressed by a single CTA -- which would have one SM to itself (~90 MB/s).  Not with Adler-32: the reference
+// folds it per deflate block over a re-packed state, and the blocks of a split member are not those of a whole one.
+constexpr size_t kSplitSegment = 256u << 10;
+struct Pieces {
+  std::vector<uint32_t> member;          // piece -> member
+  std::vector<uint8_t *> d_slot;         // piece -> where the kernel wrote it
+  std::vector<size_t> len, rel;          // piece -> compressed length, offset inside its member's output
+};
+int deflate_members(zipc_b200_ctx *ctx, int level, int ck, int adler_mode, size_t n, const std::vector<const uint8_t *> &d_src,
+                    const size_t *src_len, size_t *out_len, uint32_t *checksum, int *status, Pieces &pc) {
+  static const uint64_t split_min = [] { const char *e = std::getenv("ZIPC_B200_SPLIT_MIN"); return e && *e ? std::strtoull(e, nullptr, 10) : (2ull << 20); }();
+  const bool may_split = split_min && level != ZIPC_LEVEL_NONE && ck != ZIPC_CK_ADLER32;
+  std::vector<const uint8_t *> e_src;
+  std::vector<size_t> e_len;
+  std::vector<uint32_t> e_flags;
+  pc.member.clear();
+  bool any_split = false;
+  for (size_t i = 0; i < n; i++) {
+    if (!may_split || src_len[i] < split_min) { e_src.push_back(d_src[i]); e_len.push_back(src_len[i]); e_flags.push_back(0u); pc.member.push_back((uint32_t)i); continue; }
+    any_split = true;
+    const size_t nseg = (src_len[i] + kSplitSegment - 1) / kSplitSegment;
+    for (size_t k = 0; k < nseg; k++) {
+      e_src.push_back(d_src[i] + k * kSplitSegment);
+      e_len.push_back(std::min(kSplitSegment, src_len[i] - k * kSplitSegment));
+      e_flags.push_back((k + 1 < nseg ? kDeflateNotFinal : 0u) | (k ? (uint32_t)(32768 / kDeflatePrimeTile) << kDeflatePrimeShift : 0u));
+      pc.member.push_back((uint32_t)i);
+    }
+  }
+  const size_t m = e_src.size();
+  std::vector<size_t> cap, e_out(m);
+  std::vector<uint32_t> e_ck(m);
+  std::vector<int> e_st(m);
+  if (int st = make_slots(ctx, m, e_len.data(), pc.d_slot, cap)) return st;
+  if (int st = deflate_run(ctx, level, ck, adler_mode, m, e_src, e_len.data(), pc.d_slot, cap, e_out.data(), checksum ? e_ck.data() : nullptr,
+                           e_st.data(), any_split ? &e_flags : nullptr)) return st;
+  pc.len = e_out;
+  pc.rel.assign(m, 0);
+  for (size_t i = 0; i < n; i++) { out_len[i] = 0; status[i] = ZIPC_OK; if (checksum) checksum[i] = 0; }
+  for (size_t k = 0; k < m; k++) {
+    const uint32_t i = pc.member[k];
+    const bool first = k == 0 || pc.member[k - 1] != i;
+    if (e_st[k] != ZIPC_OK && status[i] == ZIPC_OK) status[i] = e_st[k];
+    pc.rel[k] = out_len[i];
+    out_len[i] += e_out[k];
+    if (checksum) checksum[i] = first ? e_ck[k] : (ck == ZIPC_CK_CRC32 ? zipc_b200_crc32_combine(checksum[i], e_ck[k], e_len[k]) : 0u);
+  }
+  for (size_t k = 0; k < m; k++)
+    if (status[pc.member[k]] != ZIPC_OK) { pc.len[k] = 0; out_len[pc.member[k]] = 0; }
+  return ZIPC_OK;
+}
+// the pieces to their places: member i's output starts at off[i] of ctx->d_out
+int compact_pieces(zipc_b200_ctx *ctx, const Pieces &pc, const std::vector<size_t> &off, size_t total) {
+  std::vector<size_t> poff(pc.member.size());
+  for (size_t k = 0; k < poff.size(); k++) poff[k] = off[pc.member[k]] + pc.rel[k];
+  return compact(ctx, poff.size(), pc.d_slot, pc.len.data(), poff, total);
+}
+
 }  // namespace
 
 int gather_launch(zipc_b200_ctx *ctx, const CopyDesc *d_descs, uint32_t n, cudaStream_t stream) {
@@ -220,15 +281,13 @@ int deflate_batch_layout(zipc_b200_ctx *ctx, int level, int ck, int adler_mode, 
   std::vector<const uint8_t *> d_src;
   if (int st = upload_ranges(ctx, n, src, src_len, d_src)) return st;
   pipe_mark(ctx, "uploaded");
-  std::vector<uint8_t *> d_slot;
-  std::vector<size_t> cap;
-  if (int st = make_slots(ctx, n, src_len, d_slot, cap)) return st;
-  if (int st = deflate_run(ctx, level, ck, adler_mode, n, d_src, src_len, d_slot, cap, dst_len, checksum, status)) return st;
+  Pieces pc;
+  if (int st = deflate_members(ctx, level, ck, adler_mode, n, d_src, src_len, dst_len, checksum, status, pc)) return st;
   pipe_mark(ctx, "deflated");
   std::vector<size_t> off(n);
   size_t total = 0;
   for (size_t i = 0; i < n; i++) { off[i] = total + (gap ? gap[i] : 0); total = off[i] + align_up(dst_len[i], align); }
-  if (int st = compact(ctx, n, d_slot, dst_len, off, total)) return st;
+  if (int st = compact_pieces(ctx, pc, off, total)) return st;
   ctx->last_off = off; ctx->last_len.assign(dst_len, dst_len + n); ctx->last_total = total;
   for (size_t i = 0; i < n; i++) dst_off[i] = off[i];
   if (dst_need) *dst_need = total;
@@ -608,10 +667,8 @@ int zipc_b200_zip_deflate_archive(zipc_b200_ctx *ctx, int level, size_t n, const
   }
   std::vector<const uint8_t *> d_src;
   if (int st = upload_ranges(ctx, n, src, src_len, d_src)) return st;
-  std::vector<uint8_t *> d_slot;
-  std::vector<size_t> cap;
-  if (int st = make_slots(ctx, n, src_len, d_slot, cap)) return st;
-  if (int st = deflate_run(ctx, level, ZIPC_CK_CRC32, 0, n, d_src, src_len, d_slot, cap, clen.data(), crc.data(), st_m.data())) return st;
+  Pieces pc;
+  if (int st = deflate_members(ctx, level, ZIPC_CK_CRC32, 0, n, d_src, src_len, clen.data(), crc.data(), st_m.data(), pc)) return st;
   for (size_t i = 0; i < n; i++) if (st_m[i]) return st_m[i];
   std::vector<zipc_b200_member> ms(n);
   fill_members(ms);
@@ -621,9 +678,10 @@ int zipc_b200_zip_deflate_archive(zipc_b200_ctx *ctx, int level, size_t n, const
   if (int st = zip_assemble_impl(ms.data(), n, first, nullptr, 0, &total, false, poff.data())) return st;
   *out_len = total;
   if (!out || out_cap < total) return ZIPC_ERR_DST_TOO_SMALL;
-  std::vector<size_t> off(n), glen(n);
-  for (size_t i = 0; i < n; i++) { bool in = poff[i] != ~0ull; off[i] = in ? (size_t)poff[i] : 0; glen[i] = in ? clen[i] : 0; }
-  if (int st = compact(ctx, n, d_slot, glen.data(), off, total)) return st;
+  std::vector<size_t> off(n);
+  for (size_t i = 0; i < n; i++) off[i] = poff[i] != ~0ull ? (size_t)poff[i] : 0;
+  for (size_t k = 0; k < pc.member.size(); k++) if (poff[pc.member[k]] == ~0ull) pc.len[k] = 0;  // shadowed by a later duplicate path
+  if (int st = compact_pieces(ctx, pc, off, total)) return st;
   if (int st = d2h(ctx, out, ctx->d_out.p, total)) return st;
   return zip_assemble_impl(ms.data(), n, first, out, out_cap, out_len, false, nullptr);
 }
