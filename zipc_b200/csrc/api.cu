@@ -221,6 +221,10 @@ int upload_ranges(zipc_b200_ctx *ctx, size_t n, const void *const *src, const si
       }
       if (K >= 2) {
         if (!ctx->upload_stream) ZB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->upload_stream, cudaStreamNonBlocking));
+        if (ctx->upload_split_live) {  // (a call that failed half way left its late parts behind: their flag words must not be rewritten under them)
+          ZB_CUDA(ctx, cudaStreamSynchronize(ctx->upload_stream));
+          ctx->upload_split_live = false;
+        }
         if (!ctx->h_gflag) ZB_CUDA(ctx, cudaHostAlloc(reinterpret_cast<void **>(&ctx->h_gflag), 256 * sizeof(uint32_t), cudaHostAllocMapped));
         if (!ctx->d_upflag) {
           ZB_CUDA(ctx, cudaMalloc(reinterpret_cast<void **>(&ctx->d_upflag), 64));
@@ -872,7 +876,10 @@ int zipc_b200_inflate_batch(zipc_b200_ctx *ctx, int ck, int adler_mode, size_t n
   }
   if (int st = ctx->d_out.reserve(total + 64)) return st;
   for (size_t i = 0; i < n; i++) d_dst[i] = ctx->d_out.as<uint8_t>() + off[i];
-  if (int st = inflate_core(ctx, ck, adler_mode, n, d_src, src_len, d_dst, cap, false, dst_len, checksum, status, 0, &plan)) return st;
+  if (int st = inflate_core(ctx, ck, adler_mode, n, d_src, src_len, d_dst, cap, false, dst_len, checksum, status, 0, &plan)) {
+    if (plan.ngroups && ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);  // no copy into the caller's arena outlives the call
+    return st;
+  }
   // a stream of unknown size that failed while being sized keeps that (uncapped) verdict
   for (size_t i = 0; i < n; i++)
     if (was_unknown[i] && cs[i] != ZIPC_OK) { status[i] = cs[i]; dst_len[i] = 0; if (checksum) checksum[i] = 0; }

@@ -533,6 +533,12 @@ int zipc_b200_zip_extract_batch(zipc_b200_ctx *ctx, const zipc_b200_member *ms, 
     if (split.parts) { late.resize(n); for (size_t i = 0; i < n; i++) late[i] = slen[i] ? (char)split.part_of(src[i]) : 0; }
     if (int st = plan_arena(ctx, n, cap.data(), slen.data(), grouped.data(), split.parts ? late.data() : nullptr, dst, dst_cap, off, total, plan)) return st;
   }
+  // whatever way this call ends, no progressive copy into the caller's arena outlives it
+  struct CopyFence {
+    zipc_b200_ctx *c;
+    bool on;
+    ~CopyFence() { if (on && c->copy_stream) cudaStreamSynchronize(c->copy_stream); }
+  } fence{ctx, plan.ngroups != 0};
   if (int st = ctx->d_out.reserve(total + 64)) return st;
   // deflate members through the inflate kernel (with CRC-32 of the output)
   std::vector<uint32_t> idx;
