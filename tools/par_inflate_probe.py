@@ -11,8 +11,11 @@ level = int(sys.argv[2]) if len(sys.argv) > 2 else 6
 ctx = zd.Context(0)
 L = ctx.L
 data = synth.text_v1(1, mib << 20)
-c = zlib.compressobj(level, zlib.DEFLATED, -15)
-zs = np.frombuffer(c.compress(data.tobytes()) + c.flush(), dtype=np.uint8)
+if level < 0:   # our own encoder: a large member, split into primed segments
+    zs = np.array(ctx.deflate_batch([data], "default", 0)[0][1], dtype=np.uint8)
+else:
+    c = zlib.compressobj(level, zlib.DEFLATED, -15)
+    zs = np.frombuffer(c.compress(data.tobytes()) + c.flush(), dtype=np.uint8)
 P = lambda a, t: a.ctypes.data_as(C.POINTER(t))
 dsrc = torch.from_numpy(zs.copy()).cuda()
 ddst = torch.empty(data.size + 64, dtype=torch.uint8, device="cuda")

@@ -424,74 +424,101 @@ static double now_ms() { timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return 
 
 static int par_speculate(zipc_b200_ctx *ctx, const uint8_t *d_src, size_t src_len, bool *ok) {
   *ok = false;
-  const double t_begin = par_debug() ? (cudaStreamSynchronize(ctx->stream), now_ms()) : 0;
   zipc_b200_ctx::ParPlan &plan = ctx->par_plan;
   if (plan.src == d_src && plan.src_len == src_len && plan.epoch == ctx->epoch && !plan.len.empty()) { *ok = true; return ZIPC_OK; }
   plan.len.clear(); plan.spec_off.clear(); plan.total = 0;
   const uint64_t cb = par_chunk_bytes();
-  const uint32_t nch = (uint32_t)((src_len + cb - 1) / cb);
-  if (nch < 4 || src_len > (1ull << 40)) return ZIPC_OK;
-  // 1. block starts
-  const size_t tab = (size_t)nch * (sizeof(uint64_t) * 4 + sizeof(InflateTask) + sizeof(InflateResult)) + 256;
+  const uint32_t nch0 = (uint32_t)((src_len + cb - 1) / cb);
+  if (nch0 < 4 || src_len > (1ull << 40)) return ZIPC_OK;
+  const size_t tab = (size_t)nch0 * (sizeof(uint64_t) * 4 + sizeof(InflateTask) + sizeof(InflateResult)) + 256;
   if (int st = ctx->d_par.reserve(tab)) return st;
   if (int st = ctx->h_res.reserve(tab)) return st;
   uint64_t *d_found = ctx->d_par.as<uint64_t>();
-  if (int st = inflate_find_starts(ctx, d_src, src_len, cb, nch, d_found)) return st;
   uint64_t *h_found = ctx->h_res.as<uint64_t>();
-  ZB_CUDA(ctx, cudaMemcpyAsync(h_found, d_found, (size_t)nch * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
-  ZB_CUDA(ctx, stream_sync(ctx, ctx->stream));
-  const double t_found = par_debug() ? now_ms() : 0;
-  std::vector<uint64_t> start;
-  start.push_back(0);
-  for (uint32_t k = 1; k < nch; k++) if (h_found[k] != ~0ull && h_found[k] > start.back()) start.push_back(h_found[k]);
-  const uint32_t m = (uint32_t)start.size();
-  if (m < 2) return ZIPC_OK;
-  // 2. speculative decode: symbol buffers sized for a 24-fold expansion of every chunk
-  std::vector<uint64_t> spec_off(m), capv(m);
-  uint64_t spec_total = 0;
-  for (uint32_t k = 0; k < m; k++) {
-    const uint64_t stop = k + 1 < m ? start[k + 1] : 8ull * src_len;
-    const uint64_t bytes = (stop - start[k] + 7) / 8;
-    capv[k] = (24 * bytes + 65536 + 7) & ~7ull;
-    spec_off[k] = spec_total;
-    spec_total += capv[k];
+  InflateTask *d_tasks = reinterpret_cast<InflateTask *>(ctx->d_par.as<uint64_t>() + 4 * (size_t)nch0);
+  InflateResult *d_results = reinterpret_cast<InflateResult *>(d_tasks + nch0);
+  InflateResult *h_results = reinterpret_cast<InflateResult *>(ctx->h_res.as<uint64_t>() + 4 * (size_t)nch0);
+  // Passes over what is left of the stream.  A pass: (1) block starts, (2) speculative decode of the chunks between them,
+  // (3) the chunks must chain up exactly -- each one ends, at a block boundary, on the very bit where the next one was found
+  // to start.  A found start that is an accident of the bits inside a block (rare) breaks the chain, and may have hidden the
+  // true start behind it; the chunks before the break stand, and the next pass starts where they end, which IS a block boundary.
+  uint64_t from_bit = 0;      // everything before this bit is covered by accepted chunks
+  uint64_t spec_used = 0;     // symbols of d_spec taken by accepted chunks
+  uint64_t spec_cap = 0;      // symbols d_spec holds (fixed by the first pass: later passes must not move the buffer)
+  for (int pass = 0; pass < 16; pass++) {
+    const double t_begin = par_debug() ? (cudaStreamSynchronize(ctx->stream), now_ms()) : 0;
+    const uint64_t left_bits = 8ull * src_len - from_bit;
+    const uint32_t nch = (uint32_t)std::min<uint64_t>(nch0, (left_bits + 8 * cb - 1) / (8 * cb));
+    std::vector<uint64_t> start;
+    start.push_back(from_bit);
+    if (nch >= 2) {
+      if (int st = inflate_find_starts(ctx, d_src, src_len, from_bit, cb, nch, d_found)) return st;
+      ZB_CUDA(ctx, cudaMemcpyAsync(h_found, d_found, (size_t)nch * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+      ZB_CUDA(ctx, stream_sync(ctx, ctx->stream));
+      for (uint32_t k = 1; k < nch; k++) if (h_found[k] != ~0ull && h_found[k] > start.back()) start.push_back(h_found[k]);
+    }
+    const double t_found = par_debug() ? now_ms() : 0;
+    const uint32_t m = (uint32_t)start.size();
+    if (pass == 0 && m < 2) return ZIPC_OK;   // no starts at all (stored / fixed blocks only): one warp it is
+    // speculative decode: symbol buffers sized for a 24-fold expansion of every chunk
+    std::vector<uint64_t> spec_off(m), capv(m);
+    uint64_t need = spec_used;
+    for (uint32_t k = 0; k < m; k++) {
+      const uint64_t stop = k + 1 < m ? start[k + 1] : 8ull * src_len;
+      const uint64_t bytes = (stop - start[k] + 7) / 8;
+      capv[k] = (24 * bytes + 65536 + 7) & ~7ull;
+      spec_off[k] = need;
+      need += capv[k];
+    }
+    if (pass == 0) {
+      spec_cap = need + need / 8 + (8u << 20);   // (room for the re-cut chunks of later passes)
+      if (spec_cap > (6ull << 30)) return ZIPC_OK;  // 12 GiB of symbols: leave such streams to the serial path
+      if (int st = ctx->d_spec.reserve(spec_cap * 2 + 64)) return st;
+    } else if (need > spec_cap) {
+      return ZIPC_OK;
+    }
+    std::vector<InflateTask> tasks(m);
+    for (uint32_t k = 0; k < m; k++) {
+      InflateTask &t = tasks[k];
+      t.src = d_src; t.src_len = src_len;
+      t.dst = reinterpret_cast<uint8_t *>(ctx->d_spec.as<uint16_t>() + spec_off[k]);
+      t.dst_cap = capv[k]; t.flags = 0; t.group = 0;
+      t.start_bit = start[k]; t.stop_bit = k + 1 < m ? start[k + 1] : ~0ull;
+    }
+    ZB_CUDA(ctx, cudaMemcpyAsync(d_tasks, tasks.data(), m * sizeof(InflateTask), cudaMemcpyHostToDevice, ctx->stream));
+    if (int st = inflate_launch_spec(ctx, d_tasks, m, d_results)) return st;
+    ZB_CUDA(ctx, cudaMemcpyAsync(h_results, d_results, m * sizeof(InflateResult), cudaMemcpyDeviceToHost, ctx->stream));
+    ZB_CUDA(ctx, stream_sync(ctx, ctx->stream));
+    if (par_debug())
+      std::fprintf(stderr, "[par] pass %d from bit %llu of %zu bytes: %u nominal chunks, %u block starts: find %.2f ms, speculative decode %.2f ms\n",
+                   pass, (unsigned long long)from_bit, src_len, nch, m, t_found - t_begin, now_ms() - t_found);
+    // the chain
+    uint32_t used = 0;
+    bool final_seen = false;
+    for (uint32_t k = 0; k < m; k++) {
+      const InflateResult &r = h_results[k];
+      if (r.status != ZIPC_OK) break;   // (chunk 0 starts at a block boundary for sure: its failure is the stream's)
+      used = k + 1;
+      if (r.final_seen) { final_seen = true; break; }  // the stream ends here (bytes after the final block are ignored, as in the reference)
+      if (k + 1 == m || r.end_bit != start[k + 1]) {
+        if (par_debug())
+          std::fprintf(stderr, "[par] chunk %u of %u ends at bit %llu, the next start was found at %llu: re-cutting from there\n", k, m,
+                       (unsigned long long)r.end_bit, (unsigned long long)(k + 1 < m ? start[k + 1] : 0));
+        break;
+      }
+    }
+    if (used == 0) return ZIPC_OK;     // corrupt, or larger than 24 times its compressed size: the serial decoder reports it
+    for (uint32_t k = 0; k < used; k++) { plan.spec_off.push_back(spec_off[k]); plan.len.push_back(h_results[k].out_len); plan.total += h_results[k].out_len; }
+    if (final_seen) {
+      plan.src = d_src; plan.src_len = src_len; plan.epoch = ctx->epoch;
+      *ok = true;
+      return ZIPC_OK;
+    }
+    from_bit = h_results[used - 1].end_bit;
+    spec_used = spec_off[used - 1] + capv[used - 1];
+    if (from_bit >= 8ull * src_len) break;   // ran off the end without a final block
   }
-  if (spec_total > (6ull << 30)) return ZIPC_OK;  // 12 GiB of symbols: leave such streams to the serial path
-  if (int st = ctx->d_spec.reserve(spec_total * 2 + 64)) return st;
-  std::vector<InflateTask> tasks(m);
-  for (uint32_t k = 0; k < m; k++) {
-    InflateTask &t = tasks[k];
-    t.src = d_src; t.src_len = src_len;
-    t.dst = reinterpret_cast<uint8_t *>(ctx->d_spec.as<uint16_t>() + spec_off[k]);
-    t.dst_cap = capv[k]; t.flags = 0; t.group = 0;
-    t.start_bit = start[k]; t.stop_bit = k + 1 < m ? start[k + 1] : ~0ull;
-  }
-  InflateTask *d_tasks = reinterpret_cast<InflateTask *>(ctx->d_par.as<uint64_t>() + 4 * (size_t)nch);
-  InflateResult *d_results = reinterpret_cast<InflateResult *>(d_tasks + nch);
-  ZB_CUDA(ctx, cudaMemcpyAsync(d_tasks, tasks.data(), m * sizeof(InflateTask), cudaMemcpyHostToDevice, ctx->stream));
-  if (int st = inflate_launch_spec(ctx, d_tasks, m, d_results)) return st;
-  InflateResult *h_results = reinterpret_cast<InflateResult *>(ctx->h_res.as<uint64_t>() + 4 * (size_t)nch);
-  ZB_CUDA(ctx, cudaMemcpyAsync(h_results, d_results, m * sizeof(InflateResult), cudaMemcpyDeviceToHost, ctx->stream));
-  ZB_CUDA(ctx, stream_sync(ctx, ctx->stream));
-  if (par_debug())
-    std::fprintf(stderr, "[par] %zu bytes, %u nominal chunks, %u block starts: find %.2f ms, speculative decode %.2f ms\n", src_len, nch, m,
-                 t_found - t_begin, now_ms() - t_found);
-  // 3. the chunks must chain up exactly: each one ends, at a block boundary, where the next one was found to start
-  uint32_t used = 0;
-  for (uint32_t k = 0; k < m; k++) {
-    const InflateResult &r = h_results[k];
-    if (r.status != ZIPC_OK) return ZIPC_OK;
-    used = k + 1;
-    if (r.final_seen) break;  // the stream ends here (bytes after the final block are ignored, as in the reference)
-    if (k + 1 == m || r.end_bit != start[k + 1]) return ZIPC_OK;
-  }
-  if (!h_results[used - 1].final_seen) return ZIPC_OK;
-  plan.src = d_src; plan.src_len = src_len; plan.epoch = ctx->epoch;
-  plan.spec_off.assign(spec_off.begin(), spec_off.begin() + used);
-  plan.len.resize(used);
-  plan.total = 0;
-  for (uint32_t k = 0; k < used; k++) { plan.len[k] = h_results[k].out_len; plan.total += plan.len[k]; }
-  *ok = true;
+  plan.len.clear(); plan.spec_off.clear(); plan.total = 0;
   return ZIPC_OK;
 }
 

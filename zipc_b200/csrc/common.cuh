@@ -293,10 +293,11 @@ int inflate_launch(zipc_b200_ctx *ctx, const InflateTask *d_tasks, uint32_t n, I
                    bool count_only, int adler_mode /* -1: none */, unsigned int *d_group_count = nullptr,
                    uint32_t *group_flag = nullptr, const uint32_t *d_upflag = nullptr, uint32_t upload_serial = 0);
 // intra-stream parallel inflate (a large stream without an index): the three device steps; api.cu orchestrates
-// 1. for every chunk k >= 1 of `chunk_bytes` compressed bytes, the first bit position >= 8 * k * chunk_bytes at which a valid
-//    dynamic-Huffman block header starts (d_found[k], ~0 if none before the next chunk's own search range ends)
-int inflate_find_starts(zipc_b200_ctx *ctx, const uint8_t *d_src, uint64_t src_len, uint64_t chunk_bytes, uint32_t nchunks,
-                        uint64_t *d_found);
+// 1. for every chunk k >= 1 of `chunk_bytes` compressed bytes laid from bit first_bit on, the first bit position
+//    >= first_bit + 8 * k * chunk_bytes at which a valid dynamic-Huffman block header (of some substance) starts
+//    (d_found[k], ~0 if none before the next chunk's own search range ends)
+int inflate_find_starts(zipc_b200_ctx *ctx, const uint8_t *d_src, uint64_t src_len, uint64_t first_bit, uint64_t chunk_bytes,
+                        uint32_t nchunks, uint64_t *d_found);
 // 2. speculative decode of the chunks (tasks carry start_bit / stop_bit, dst = 16-bit symbols)
 int inflate_launch_spec(zipc_b200_ctx *ctx, const InflateTask *d_tasks, uint32_t n, InflateResult *d_results);
 // 3. resolve: windows chunk by chunk, then every symbol to its byte.  d_spec_off / d_out_off / d_len: per chunk (device).

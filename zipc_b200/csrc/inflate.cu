@@ -977,7 +977,7 @@ inflate_kernel(const InflateTask *__restrict__ tasks, uint32_t ntasks, InflateRe
 // guess is caught later: the chunk before it must END exactly there, or the caller falls back to serial decoding.
 // Stored and fixed blocks are not looked for (their headers say too little); the previous chunk just runs through them.
 __global__ void __launch_bounds__(THREADS, 1)
-find_starts_kernel(const uint8_t *__restrict__ src, uint64_t src_len, uint64_t chunk_bytes, uint32_t nchunks,
+find_starts_kernel(const uint8_t *__restrict__ src, uint64_t src_len, uint64_t first_bit, uint64_t chunk_bytes, uint32_t nchunks,
                    uint64_t *__restrict__ found, uint16_t *__restrict__ g_syms) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   WarpTabs *tabs = reinterpret_cast<WarpTabs *>(smem_raw);
@@ -1005,7 +1005,7 @@ find_starts_kernel(const uint8_t *__restrict__ src, uint64_t src_len, uint64_t c
     if (lane == 0) { wk.st.src = src; wk.st.src_len = src_len; wk.st.out_cap = 0; wk.st.ad_from = 0; }
     in.open(wk, lane);
     const uint64_t skew = wk.st.skew, limit = wk.st.limit;
-    const uint64_t beg = skew + 8 * (uint64_t)k * chunk_bytes;
+    const uint64_t beg = skew + first_bit + 8 * (uint64_t)k * chunk_bytes;   // (the nominal chunks are laid from first_bit on)
     uint64_t end = beg + 8 * chunk_bytes;
     if (end > limit) end = limit;
     uint64_t hit = ~0ull;
@@ -1035,8 +1035,17 @@ find_starts_kernel(const uint8_t *__restrict__ src, uint64_t src_len, uint64_t c
         surv &= surv - 1;
         const uint64_t cand = base + l;
         if ((uint32_t)(cand >> 5) < in.w0) in.seek_bits(wk, cand, lane);
+        const uint32_t hlit = 257u + ((Input::peek32_at(wk, cand) >> 3) & 31u);
         in.P = cand + 3;
-        if (!read_dynamic_header(in, wk, mine, my_syms, s_len_tab, s_dist_tab, lane)) { hit = cand; break; }
+        if (read_dynamic_header(in, wk, mine, my_syms, s_len_tab, s_dist_tab, lane)) continue;
+        // A header that checks out can still be an accident of the bits inside a block: nearly all such accidents are
+        // degenerate codes (two symbols of one bit, ...).  A start is only worth something if it is certain, a missed one
+        // costs nothing but parallelism (the chunk before it decodes on through it): ask for a code of some substance.
+        uint32_t coded = 0;
+        for (uint32_t i = lane; i < hlit; i += 32) coded += wk.build.len[i] != 0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) coded += __shfl_xor_sync(0xffffffffu, coded, o);
+        if (coded >= 12u) { hit = cand; break; }
       }
     }
     if (lane == 0) found[k] = hit == ~0ull ? ~0ull : hit - skew;
@@ -1132,8 +1141,8 @@ int inflate_launch(zipc_b200_ctx *ctx, const InflateTask *d_tasks, uint32_t n, I
   return ZIPC_OK;
 }
 
-int inflate_find_starts(zipc_b200_ctx *ctx, const uint8_t *d_src, uint64_t src_len, uint64_t chunk_bytes, uint32_t nchunks,
-                        uint64_t *d_found) {
+int inflate_find_starts(zipc_b200_ctx *ctx, const uint8_t *d_src, uint64_t src_len, uint64_t first_bit, uint64_t chunk_bytes,
+                        uint32_t nchunks, uint64_t *d_found) {
   if (!(g_attr_devs >> (ctx->device & 63) & 1ull)) {
     ZB_CUDA(ctx, cudaFuncSetAttribute(inflate_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
     ZB_CUDA(ctx, cudaFuncSetAttribute(inflate_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
@@ -1146,7 +1155,7 @@ int inflate_find_starts(zipc_b200_ctx *ctx, const uint8_t *d_src, uint64_t src_l
   if (grid == 0) grid = 1;
   size_t sym_bytes = (size_t)(grid * WARPS + grid) * SYMS_PER_SLOT * sizeof(uint16_t);
   if (int st = ctx->d_scratch.reserve(sym_bytes + 256 + 4096)) return st;
-  find_starts_kernel<<<grid, THREADS, kSmemBytes, ctx->stream>>>(d_src, src_len, chunk_bytes, nchunks, d_found, ctx->d_scratch.as<uint16_t>());
+  find_starts_kernel<<<grid, THREADS, kSmemBytes, ctx->stream>>>(d_src, src_len, first_bit, chunk_bytes, nchunks, d_found, ctx->d_scratch.as<uint16_t>());
   ctx->launches++;
   ZB_CUDA(ctx, cudaGetLastError());
   return ZIPC_OK;
