@@ -298,4 +298,9 @@ def test_large_members_are_split_over_ctas(ctx):
     dt = time.perf_counter() - t0
     assert st == 0 and ck == zlib.crc32(huge) and zlib.decompress(bytes(cs), -15) == huge.tobytes()
     assert dt < 0.25, dt   # (one CTA: ~0.75 s)
+    # back through the many-warp decoder -- not the one-warp fallback: this very stream holds an accidental block header
+    # inside a block, which breaks the chain of chunks once; the decoder must re-cut from there and go on in parallel
+    par0, fb0 = ctx.parallel_streams
     assert zd.inflate(bytes(cs), decompressed_size=huge.size).get_ok() == huge.tobytes()
+    par1, fb1 = ctx.parallel_streams
+    assert par1 > par0 and fb1 == fb0
