@@ -15,20 +15,24 @@
 //         bit offsets, the complete token that WOULD start there (literal, or length + distance with
 //         their extra bits: two table lookups, branch free, NB independent chains per lane) and posts
 //         (token, bit length) in shared memory.
-//       - D2 (walk): every lane follows the chain start -> start + bits -> ... through that table (one
-//         LDS + add per token); lane i keeps token i in registers.  Up to 32 tokens per round.
+//       - D2 (walk): every lane follows the chain start -> start + bits -> ... through that table: 32
+//         straight-line steps of four instructions, no exit tests (a candidate that stops the walk counts
+//         as zero bits; a ballot finds the first repeated address).  Up to 32 tokens per round.
 //       - checks (distance, size, input overrun) run in parallel, one token per lane; the first failing
 //         token cuts the round and decides the error, as the serial reference would.
 //   * E (copy): the round's literal bytes and match bytes whose source precedes the round are flattened
 //     over the 32 lanes (byte b of the round's independent bytes -> lane b % 32); matches that read
 //     bytes of the same round follow in order.  Back-references read the stream's own earlier output
 //     from global memory through L2 (ld.global.cg), at most 32 KiB back.
-//   * Compressed input is staged in a 256-byte ring per warp, refilled with coalesced 128-byte loads
-//     that are issued one refill ahead.
+//   * Compressed input is staged in a 512-byte ring per warp, refilled by the copy engine one refill ahead
+//     (cp.async.bulk of 128 bytes against a per-warp mbarrier; guarded loads for the last words of a stream).
 //   * Lookup tables: 2^LB literal/length entries (16 bit) and 2^DB distance entries (32 bit) per warp in
 //     shared memory; longer codes (rare) take the canonical walk.  The fixed-Huffman tables are built
 //     once per CTA; dynamic tables are built cooperatively by the warp.
-//   * 16 warps per CTA, one CTA per SM, streams handed out through a global queue (longest first).
+//   * 32 warps per CTA, one CTA per SM, streams handed out through a global queue (longest first; in download
+//     order when the batch's arena is copied out progressively, api.cu plan_arena).
+//   * One LARGE stream (no index): find_starts_kernel + this kernel in SPEC mode (16-bit symbols with window
+//     markers) + win_*_kernel / resolve_kernel; orchestrated by api.cu par_speculate / par_resolve.
 //
 // Algorithmic bytes: C + U per stream (compressed read + uncompressed written).  The kernel is
 // issue/latency bound (bit parsing), not HBM bound: see DESIGN.md.
