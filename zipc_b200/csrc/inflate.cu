@@ -980,6 +980,7 @@ inflate_kernel(const InflateTask *__restrict__ tasks, uint32_t ntasks, InflateRe
 // that pass are validated by the decoder's own header reader, in order, and the first valid one is reported.  A wrong
 // guess is caught later: the chunk before it must END exactly there, or the caller falls back to serial decoding.
 // Stored and fixed blocks are not looked for (their headers say too little); the previous chunk just runs through them.
+constexpr uint32_t kFindSplit = 4;
 __global__ void __launch_bounds__(THREADS, 1)
 find_starts_kernel(const uint8_t *__restrict__ src, uint64_t src_len, uint64_t first_bit, uint64_t chunk_bytes, uint32_t nchunks,
                    uint64_t *__restrict__ found, uint16_t *__restrict__ g_syms) {
@@ -1004,13 +1005,17 @@ find_starts_kernel(const uint8_t *__restrict__ src, uint64_t src_len, uint64_t f
   uint16_t *my_syms = g_syms + (size_t)(blockIdx.x * WARPS + warp) * SYMS_PER_SLOT;
   Input in{};
   input_bar_init(wk, lane);
-  for (uint32_t k = 1 + blockIdx.x * WARPS + warp; k < nchunks; k += gridDim.x * WARPS) {
+  // kFindSplit warps share a nominal chunk (a quarter of its bit offsets each); the earliest hit wins (atomicMin: `found` starts as ~0)
+  for (uint32_t u = kFindSplit + blockIdx.x * WARPS + warp; u < nchunks * kFindSplit; u += gridDim.x * WARPS) {
+    const uint32_t k = u / kFindSplit, part = u % kFindSplit;
     __syncwarp();
     if (lane == 0) { wk.st.src = src; wk.st.src_len = src_len; wk.st.out_cap = 0; wk.st.ad_from = 0; }
     in.open(wk, lane);
     const uint64_t skew = wk.st.skew, limit = wk.st.limit;
-    const uint64_t beg = skew + first_bit + 8 * (uint64_t)k * chunk_bytes;   // (the nominal chunks are laid from first_bit on)
-    uint64_t end = beg + 8 * chunk_bytes;
+    const uint64_t span = (8 * chunk_bytes / kFindSplit + 31) & ~31ull;
+    const uint64_t cbeg = skew + first_bit + 8 * (uint64_t)k * chunk_bytes;   // (the nominal chunks are laid from first_bit on)
+    const uint64_t beg = cbeg + part * span;
+    uint64_t end = part + 1 == kFindSplit ? cbeg + 8 * chunk_bytes : beg + span;
     if (end > limit) end = limit;
     uint64_t hit = ~0ull;
     in.seek_bits(wk, beg, lane);
@@ -1052,7 +1057,7 @@ find_starts_kernel(const uint8_t *__restrict__ src, uint64_t src_len, uint64_t f
         if (coded >= 12u) { hit = cand; break; }
       }
     }
-    if (lane == 0) found[k] = hit == ~0ull ? ~0ull : hit - skew;
+    if (lane == 0 && hit != ~0ull) atomicMin(reinterpret_cast<unsigned long long *>(&found[k]), (unsigned long long)(hit - skew));
   }
 #if ZB_INFLATE_BULK
   in.settle(wk);
@@ -1154,11 +1159,12 @@ int inflate_find_starts(zipc_b200_ctx *ctx, const uint8_t *d_src, uint64_t src_l
     ZB_CUDA(ctx, cudaFuncSetAttribute(find_starts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
     g_attr_devs |= 1ull << (ctx->device & 63);
   }
-  uint32_t grid = (nchunks + WARPS - 1) / WARPS;
+  uint32_t grid = (nchunks * kFindSplit + WARPS - 1) / WARPS;
   if (grid > (uint32_t)ctx->sm_count) grid = (uint32_t)ctx->sm_count;
   if (grid == 0) grid = 1;
   size_t sym_bytes = (size_t)(grid * WARPS + grid) * SYMS_PER_SLOT * sizeof(uint16_t);
   if (int st = ctx->d_scratch.reserve(sym_bytes + 256 + 4096)) return st;
+  ZB_CUDA(ctx, cudaMemsetAsync(d_found, 0xFF, (size_t)nchunks * sizeof(uint64_t), ctx->stream));
   find_starts_kernel<<<grid, THREADS, kSmemBytes, ctx->stream>>>(d_src, src_len, first_bit, chunk_bytes, nchunks, d_found, ctx->d_scratch.as<uint16_t>());
   ctx->launches++;
   ZB_CUDA(ctx, cudaGetLastError());
