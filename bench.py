@@ -813,6 +813,9 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # the library pipelines a large batch in groups, one host thread each; it sizes that by the cores per VISIBLE GPU, but under
+    # torchrun every rank sees all GPUs of the box while `world` ranks share its cores: tell it this process's share
+    os.environ.setdefault("ZIPC_B200_PIPE", str(max(4, min(24, 2 * (os.cpu_count() or 8) // max(1, world)))))
     import torch
     dist, cpu_group = None, None
     if world > 1:

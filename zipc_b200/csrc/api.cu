@@ -10,6 +10,8 @@
 #include <ctime>
 #include <numeric>
 
+#include <thread>
+
 #include "common.cuh"
 
 namespace zb {
@@ -703,10 +705,19 @@ void pipe_mark(const zipc_b200_ctx *ctx, const char *stage) {
 }
 
 // The pipelined sub-contexts of ctx, or null if this batch should run as one piece: it is small, there is no caller arena
-// to copy into while kernels run, or ctx is a sub-context itself.  ZIPC_B200_PIPE = most groups (default 24: 11.8 / 12.6 / 13.0 GB/s end to end on C4 with 8 / 16 / 24; 0 or 1 = off).
+// to copy into while kernels run, or ctx is a sub-context itself.  ZIPC_B200_PIPE = most groups (default: by the cores per visible GPU, 4 .. 24; 0 or 1 = off).
 zipc_b200_mctx *pipeline_for(zipc_b200_ctx *ctx, size_t n, const size_t *len, const void *dst) {
   if (ctx->is_sub || !dst || n < 1024) return nullptr;
-  static const uint64_t depth = std::min<uint64_t>(env_u64("ZIPC_B200_PIPE", 24), 64);
+  // Every group is a host thread.  A box runs one process per GPU, so the thread budget of this process is its share of the
+  // cores: 24 groups where there are cores to spare (measured on C4, one GPU: 11.8 / 12.6 / 13.0 GB/s end to end with 8 / 16 /
+  // 24), fewer when eight processes share 32 cores (N = 8: 51.9 GB/s in all with 8 groups each, 37.1 with 24).
+  static const uint64_t depth = [] {
+    int ndev = 1;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) ndev = 1;
+    const uint64_t cores = std::max(1u, std::thread::hardware_concurrency());
+    const uint64_t automatic = std::min<uint64_t>(24, std::max<uint64_t>(4, 2 * cores / (uint64_t)ndev));
+    return std::min<uint64_t>(env_u64("ZIPC_B200_PIPE", automatic), 64);
+  }();
   if (depth < 2) return nullptr;
   uint64_t total = 0;
   for (size_t i = 0; i < n; i++) total += len[i];
