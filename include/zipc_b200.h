@@ -254,6 +254,20 @@ uint64_t zipc_b200_zip_encoding_size(const zipc_b200_member *members, size_t n);
  * Host only; out must hold zipc_b200_zip_encoding_size bytes. */
 int zipc_b200_zip_assemble(const zipc_b200_member *members, size_t n, const char *first,
                            void *out, size_t out_cap, size_t *out_len);
+/* ZIP64 (APPNOTE 4.3.14, 4.3.15, 4.5.3).  The reference rejects ZIP64 archives when reading
+ * (zipc.ml:404) and refuses to write what would need it (more than 65,535 members, a size or an offset of 4 GiB or
+ * more: zipc.ml:229-235, 130-133, 550-551); ZIPC_ZIP_REFERENCE keeps exactly that behaviour and is what the calls
+ * without _ex use.  ZIPC_ZIP_ALLOW_ZIP64 goes beyond the reference: the parser follows a ZIP64 end of central
+ * directory locator and takes 64-bit sizes / offsets from the ZIP64 extra fields; the writer emits ZIP64 extra fields,
+ * the ZIP64 end of central directory record and its locator where (and only where) a 16/32-bit field overflows, so
+ * an archive that fits the classic format comes out byte-identical to the reference's.  ZIPC_ZIP_FORCE_ZIP64 (writer)
+ * emits them for every member, as CPython's zipfile does with force_zip64.  The checker for these paths is CPython's
+ * zipfile (the reference has no ZIP64). */
+enum { ZIPC_ZIP_REFERENCE = 0, ZIPC_ZIP_ALLOW_ZIP64 = 1, ZIPC_ZIP_FORCE_ZIP64 = 2 };
+int zipc_b200_zip_parse_ex(const void *bytes, size_t len, unsigned flags, zipc_b200_member **members, size_t *n);
+uint64_t zipc_b200_zip_encoding_size_ex(const zipc_b200_member *members, size_t n, const char *first, unsigned flags);
+int zipc_b200_zip_assemble_ex(const zipc_b200_member *members, size_t n, const char *first, unsigned flags,
+                              void *out, size_t out_cap, size_t *out_len);
 /* Batch form of Zipc.File.to_binary_string (zipc.ml:205-225) over parsed members: stored and
  * deflate members are extracted on the GPU and their CRC-32 compared with the directory's.
  * status[i]: ZIPC_OK, ZIPC_ERR_CORRUPTED, ZIPC_ERR_SIZE_EXCEEDED (both "deflate: "-prefixed in

@@ -306,3 +306,36 @@ def test_large_archive_pipelined_equals_plain(ctx):
     assert zf.testzip() is None and len(zf.namelist()) == n
     for i in (0, 1, n // 2, n - 1):
         assert zf.read(paths[i]) == datas[i].tobytes()
+
+
+def test_zip64_archives_extract_and_create(ctx):
+    """SURVEY.md 8f-4 (beyond the reference, checked against CPython's zipfile): members of a ZIP64 archive made by CPython
+    are extracted on the GPU; an archive of GPU-deflated members written with ZIP64 records is read back by CPython."""
+    n_small = 66_000  # more than 65,535 members: ZIP64 end of central directory record
+    datas = {("big/%03d.txt" % i): synth.text_v1(500 + i, 30_000 + 1111 * i).tobytes() for i in range(24)}
+    bio = io.BytesIO()
+    with zipfile.ZipFile(bio, "w", zipfile.ZIP_DEFLATED) as zf:
+        for i in range(n_small):
+            zf.writestr("s/%05d" % i, b"%d" % i, compress_type=zipfile.ZIP_STORED)
+        for p, d in datas.items():
+            with zf.open(p, "w", force_zip64=True) as fh:
+                fh.write(d)
+    blob = bio.getvalue()
+    z = zipc.of_binary_string(blob, zip64=True).get_ok()
+    assert zipc.member_count(z) == n_small + len(datas)
+    paths = sorted(z)
+    got = zipc.File.to_binary_strings([z[p].kind for p in paths])
+    for p, r in zip(paths, got):
+        want = datas[p.decode()] if p.startswith(b"big/") else b"%d" % int(p[2:])
+        assert r.get_ok() == want
+    # the other direction
+    files = zipc.File.deflate_of_binary_strings(list(datas.values()), "default")
+    ours = {p.encode(): zipc.Member.make(p, f.get_ok()).get_ok() for p, f in zip(datas, files)}
+    forced = zipc.to_binary_string(ours, zip64="force").get_ok()
+    with zipfile.ZipFile(io.BytesIO(forced)) as zf:
+        assert zf.testzip() is None
+        for p, d in datas.items():
+            assert zf.read(p) == d
+    back = zipc.of_binary_string(forced, zip64=True).get_ok()
+    for p, r in zip(sorted(back), zipc.File.to_binary_strings([back[p].kind for p in sorted(back)])):
+        assert r.get_ok() == datas[p.decode()]

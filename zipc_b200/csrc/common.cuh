@@ -287,7 +287,7 @@ int deflate_batch_layout(zipc_b200_ctx *ctx, int level, int ck, int adler_mode, 
                          const uint32_t *gap, size_t align);
 // host_util.cc
 int zip_assemble_impl(const zipc_b200_member *ms, size_t n, const char *first, void *out_v, size_t out_cap,
-                      size_t *out_len, bool copy_payload, uint64_t *payload_off);
+                      size_t *out_len, bool copy_payload, uint64_t *payload_off, unsigned flags = 0 /* ZIPC_ZIP_* */);
 // inflate.cu
 int inflate_launch(zipc_b200_ctx *ctx, const InflateTask *d_tasks, uint32_t n, InflateResult *d_results,
                    bool count_only, int adler_mode /* -1: none */, unsigned int *d_group_count = nullptr,

@@ -66,6 +66,9 @@ namespace {
 #define PH_RESET
 #endif
 #define PH(k) PH_AT(k, 0)
+#ifndef ZB_BACK_HELPS
+#define ZB_BACK_HELPS 1
+#endif
 #define ZB_SMEM extern __shared__ __align__(16) uint8_t smem_raw[]
 enum { PH_FRONT_WAIT = 0, PH_BACK_WAIT, PH_PARSE0, PH_DEEP, PH_PARSE1, PH_TOKENS, PH_FIN_SORT, PH_FIN_HUFF, PH_FIN_HDR, PH_FIN_PACK, PH_OTHER,
        PH_F_STAGE, PH_F_PART, PH_F_INSERT, PH_F_SHALLOW, PH_JUMP };
@@ -172,7 +175,8 @@ struct Shared {
 
 // scalar slots in sh.sc
 enum { SC_TASK = 0, SC_OUTW, SC_CARRY, SC_CBITS, SC_OVERFLOW, SC_M_L, SC_M_D, SC_NHDR, SC_BTYPE, SC_HLIT, SC_HDIST,
-       SC_SUMDYN, SC_SUMFIX, SC_BLK_SRCLEN, SC_NRSYM, SC_HCLEN, SC_HDRBITS, SC_BATCH, SC_QHEAD, SC_OQN, SC_EXIT, SC_VQN /* [2] */, SC_VQN1, SC_LD_PHASES /* bulk copies issued so far */ };
+       SC_SUMDYN, SC_SUMFIX, SC_BLK_SRCLEN, SC_NRSYM, SC_HCLEN, SC_HDRBITS, SC_BATCH, SC_QHEAD, SC_OQN, SC_EXIT, SC_VQN /* [2] */, SC_VQN1, SC_LD_PHASES /* bulk copies issued so far */,
+       SC_WALK_OPEN /* first position of the tile whose shallow walks are being handed out, + 1 */ };
 
 __device__ __forceinline__ Gen gen_of(uint8_t *base, int g) {  // plain arithmetic on the shared base: the address space stays known
   uint8_t *b = base + OFF_GEN + g * GEN_BYTES;
@@ -656,6 +660,38 @@ __device__ __forceinline__ void guess_visits(const uint16_t *mlen, const uint32_
   if (lane == 31) *vqn = incl;
 }
 
+// ---- shallow walks of one tile: batches of 32 consecutive positions, handed out through a counter ---------------------
+// Called by every warp that has nothing better to do (the front group; the parse warp when its tile is done).
+__device__ __forceinline__ void shallow_batches(const Shared &sh, const Gen &G, uint32_t ts, uint32_t te, uint32_t n, const LevelParams &lp,
+                                                uint32_t emit_from, int lane) {
+  const RingView ring{sh.ring};
+  const PrevView prevv{sh.prev};
+  GUARD_DECL(g_s)
+  for (;;) {
+    GUARD(g_s, 1000u, 500);
+    uint32_t b = 0;
+    if (lane == 0) b = atomicAdd(&sh.sc[SC_BATCH], 1u);
+    b = __shfl_sync(0xffffffffu, b, 0);
+    if (b >= kTile / 32) break;
+    const uint32_t i = b * 32 + lane, p = ts + i;
+    uint32_t l = 0, d = 0, rt = p & 0xFFFFu;
+    if (p < te && p + 4 <= n && p >= emit_from) {
+      // every lane walks on its own: at these depths nearly every candidate passes the first test (same hash), so keeping
+      // the warp together for the comparisons (as the deep walks do) only adds votes -- measured: 17.0 vs 11.4 clk/byte
+      MatchState m;
+      match_begin(m, ring, p, n, G.tok[i], lp.shallow);
+      GUARD_DECL(g_m)
+      while (!m.done) { GUARD(g_m, 100000u, 501); match_step(m, ring, prevv, lp.shallow_nice); }
+      l = m.best >= (uint32_t)kMinMatch ? m.best : 0u;
+      d = m.best_dist;
+      rt = match_resume_token(m);
+    }
+    G.mlen[1 + i] = (uint16_t)l;
+    G.mdist[1 + i] = (uint16_t)d;
+    G.tok[i] = (uint16_t)rt;
+  }
+}
+
 // ---- front end: stage, hash, partition, insert, shallow walks of one tile (FRONT_THREADS threads) -----------------
 // ft: thread index inside the front group; fw: warp index inside the group.  Uses bar_front() only.
 // `state`: bits 0..31 = input bytes resident in the ring or on their way, bit 32 = a bulk copy is in flight.  Returns the new state.
@@ -663,7 +699,8 @@ __device__ __forceinline__ void guess_visits(const uint16_t *mlen, const uint32_
 template <int BW>
 __device__ __noinline__ uint64_t front_end(int gen, const uint8_t *src, uint32_t n, uint32_t ts, uint64_t state,
                                            int level, int ft, int fw, int lane, uint32_t emit_from) {
-  constexpr int FRONT_WARPS = NWARPS - BW, FRONT_THREADS = FRONT_WARPS * 32, BACK_THREADS = BW * 32;
+  constexpr int FRONT_WARPS = NWARPS - BW, FRONT_THREADS = FRONT_WARPS * 32;
+  [[maybe_unused]] constexpr int BACK_THREADS = BW * 32;  // (the timing build names the first front thread by it)
   constexpr int kClasses = FRONT_WARPS, kRankRounds = (kChunk32 + FRONT_WARPS - 1) / FRONT_WARPS;
   static_assert(kClasses >= 16 && kClasses <= kMaxClasses, "a class must span at most 1024 hash values; the counters hold 31 classes");
   ZB_SMEM;
@@ -808,31 +845,13 @@ __device__ __noinline__ uint64_t front_end(int gen, const uint8_t *src, uint32_t
   }
   bar_front<BW>();
   PH_AT(PH_F_INSERT, BACK_THREADS);
-  // 3. shallow walk at every position; batches of 32 consecutive positions are handed out through a counter
-  GUARD_DECL(g_s)
-  for (;;) {
-    GUARD(g_s, 1000u, 500);
-    uint32_t b = 0;
-    if (lane == 0) b = atomicAdd(&sh.sc[SC_BATCH], 1u);
-    b = __shfl_sync(0xffffffffu, b, 0);
-    if (b >= kTile / 32) break;
-    const uint32_t i = b * 32 + lane, p = ts + i;
-    uint32_t l = 0, d = 0, rt = p & 0xFFFFu;
-    if (p < te && p + 4 <= n && p >= emit_from) {
-      // every lane walks on its own: at these depths nearly every candidate passes the first test (same hash), so keeping
-      // the warp together for the comparisons (as the deep walks do) only adds votes -- measured: 17.0 vs 11.4 clk/byte
-      MatchState m;
-      match_begin(m, ring, p, n, G.tok[i], lp.shallow);
-      GUARD_DECL(g_m)
-      while (!m.done) { GUARD(g_m, 100000u, 501); match_step(m, ring, prevv, lp.shallow_nice); }
-      l = m.best >= (uint32_t)kMinMatch ? m.best : 0u;
-      d = m.best_dist;
-      rt = match_resume_token(m);
-    }
-    G.mlen[1 + i] = (uint16_t)l;
-    G.mdist[1 + i] = (uint16_t)d;
-    G.tok[i] = (uint16_t)rt;
-  }
+  // 3. shallow walk at every position; batches of 32 consecutive positions are handed out through a counter.  The back
+  //    end's parse warp takes batches too once its own tile is done (ZB_BACK_HELPS): 64 batches over 31 warps are three
+  //    rounds for two warps and two for the rest.
+#if ZB_BACK_HELPS
+  if (BW == 1 && ft == 0) { __threadfence_block(); *(volatile uint32_t *)&sh.sc[SC_WALK_OPEN] = ts + 1u; }
+#endif
+  shallow_batches(sh, G, ts, te, n, lp, emit_from, lane);
   bar_front<BW>();
   PH_AT(PH_F_SHALLOW, BACK_THREADS);
   // 4. the positions a parse of this tile is guessed to visit: the deep walks' first queue
@@ -1024,7 +1043,7 @@ __device__ void encode_member(const DeflateTask t, int level, uint32_t *toks, De
   for (int i = tid; i < kWindow / 2; i += THREADS) reinterpret_cast<uint32_t *>(sh.prev)[i] = 0;
   for (int i = tid; i < 320; i += THREADS) sh.hist_l[i] = 0;
   if (tid == 0) {
-    sh.sc[SC_OUTW] = 0; sh.sc[SC_CARRY] = 0; sh.sc[SC_CBITS] = 0; sh.sc[SC_OVERFLOW] = 0; sh.sc[SC_BLK_SRCLEN] = 0;
+    sh.sc[SC_OUTW] = 0; sh.sc[SC_CARRY] = 0; sh.sc[SC_CBITS] = 0; sh.sc[SC_OVERFLOW] = 0; sh.sc[SC_BLK_SRCLEN] = 0; sh.sc[SC_WALK_OPEN] = 0;
     gen_of(smem_raw, 0).mlen[0] = 0; gen_of(smem_raw, 0).mdist[0] = 0;
   }
   __syncthreads();
@@ -1088,6 +1107,16 @@ __device__ void encode_member(const DeflateTask t, int level, uint32_t *toks, De
       // ---- front end: tile t + 1 -------------------------------------------------------------------------------------
       loaded = front_end<BW>(g ^ 1, src, n, te, loaded, level, ft, fw, lane, prime);
     }
+#if ZB_BACK_HELPS
+    if (BW == 1 && back && more) {
+      // the parse warp is done with tile t: it takes batches of tile t + 1's shallow walks as soon as the front end hands
+      // them out (the chains are complete then); what a walk finds depends on its position alone
+      GUARD_DECL(g_o)
+      while (*(volatile uint32_t *)&sh.sc[SC_WALK_OPEN] != te + 1u) { GUARD(g_o, 4000000u, 502); __nanosleep(64); }
+      __threadfence_block();
+      shallow_batches(sh, G1, te, min(te + (uint32_t)kTile, n), n, lp, prime, lane);
+    }
+#endif
     __syncthreads();
     PH(PH_BACK_WAIT);
     // ---- all warps: tokens of tile t -------------------------------------------------------------------------------------

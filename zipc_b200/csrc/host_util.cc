@@ -130,9 +130,42 @@ static std::vector<size_t> map_order(const zipc_b200_member *ms, size_t n) {
   return out;
 }
 
+static inline uint64_t rd64(const uint8_t *b, size_t o) { return rd32(b, o) | (uint64_t)rd32(b, o + 4) << 32; }
+static inline void wr64(uint8_t *b, size_t o, uint64_t v) { wr32(b, o, (uint32_t)v); wr32(b, o + 4, (uint32_t)(v >> 32)); }
+
+// ZIP64 extended information extra field (header id 0x0001, APPNOTE 4.5.3) of a central directory entry: the 64-bit
+// values stand in the fixed order uncompressed size, compressed size, local header offset, and only those whose 32-bit
+// field holds 0xFFFFFFFF are present.  false: field missing or too short.
+static bool zip64_cd_extra(const uint8_t *x, size_t xlen, uint64_t &usize, uint64_t &csize, uint64_t &lfh) {
+  const bool wu = usize == 0xFFFFFFFFull, wc = csize == 0xFFFFFFFFull, wl = lfh == 0xFFFFFFFFull;
+  if (!wu && !wc && !wl) return true;
+  for (size_t o = 0; o + 4 <= xlen;) {
+    const unsigned id = rd16(x, o), sz = rd16(x, o + 2);
+    if (o + 4 + sz > xlen) return false;
+    if (id == 1) {
+      size_t q = o + 4;
+      const size_t end = q + sz;
+      if (wu) { if (q + 8 > end) return false; usize = rd64(x, q); q += 8; }
+      if (wc) { if (q + 8 > end) return false; csize = rd64(x, q); q += 8; }
+      if (wl) { if (q + 8 > end) return false; lfh = rd64(x, q); q += 8; }
+      return true;
+    }
+    o += 4 + sz;
+  }
+  return false;
+}
+
 // ---- Zipc.of_binary_string (zipc.ml:400-438) ------------------------------------------------------
 int zipc_b200_zip_parse(const void *bytes, size_t len, zipc_b200_member **members, size_t *n_out) {
+  return zipc_b200_zip_parse_ex(bytes, len, ZIPC_ZIP_REFERENCE, members, n_out);
+}
+
+// flags = ZIPC_ZIP_REFERENCE: the reference's behaviour (ZIP64 rejected, zipc.ml:404).  ZIPC_ZIP_ALLOW_ZIP64 (SURVEY.md
+// 8f-4, beyond the reference): a ZIP64 end of central directory locator in front of the EOCD is followed, and central
+// directory entries take their 64-bit sizes / offsets from the ZIP64 extra field.
+int zipc_b200_zip_parse_ex(const void *bytes, size_t len, unsigned flags, zipc_b200_member **members, size_t *n_out) {
   if (!members || !n_out || (!bytes && len)) return ZIPC_ERR_INVALID_ARG;
+  const bool z64 = (flags & ZIPC_ZIP_ALLOW_ZIP64) != 0;
   *members = nullptr;
   *n_out = 0;
   const uint8_t *s = static_cast<const uint8_t *>(bytes);
@@ -144,11 +177,23 @@ int zipc_b200_zip_parse(const void *bytes, size_t len, zipc_b200_member **member
     if (rd32(s, (size_t)at) == 0x06054b50u) break;
   }
   const size_t e = (size_t)at;
-  if (rd16(s, e + 4) == 0xFFFF) return ZIPC_ERR_ZIP_ZIP64;           // zipc.ml:404
-  if (rd16(s, e + 4) != 0 || rd16(s, e + 6) != 0) return ZIPC_ERR_ZIP_MULTIPART;
-  const size_t count = rd16(s, e + 10);
-  const uint64_t cd_size = rd32(s, e + 12), cd_start = rd32(s, e + 16);
-  if (cd_start + cd_size > len) return ZIPC_ERR_ZIP_EOCD;
+  size_t count = rd16(s, e + 10);
+  uint64_t cd_size = rd32(s, e + 12), cd_start = rd32(s, e + 16);
+  if (z64 && e >= 20 && rd32(s, e - 20) == 0x07064b50u) {            // ZIP64 EOCD locator (APPNOTE 4.3.15)
+    if (rd32(s, e - 16) != 0 || rd32(s, e - 4) > 1) return ZIPC_ERR_ZIP_MULTIPART;
+    const uint64_t r = rd64(s, e - 12);
+    if (r > len || len - r < 56 || rd32(s, (size_t)r) != 0x06064b50u) return ZIPC_ERR_ZIP_EOCD;
+    if (rd32(s, (size_t)r + 16) != 0 || rd32(s, (size_t)r + 20) != 0) return ZIPC_ERR_ZIP_MULTIPART;
+    if (rd64(s, (size_t)r + 24) != rd64(s, (size_t)r + 32)) return ZIPC_ERR_ZIP_MULTIPART;
+    count = (size_t)rd64(s, (size_t)r + 32);
+    cd_size = rd64(s, (size_t)r + 40);
+    cd_start = rd64(s, (size_t)r + 48);
+    if (cd_size > len || count > cd_size / 46) return ZIPC_ERR_ZIP_EOCD;  // (a count no directory of that size can hold)
+  } else {
+    if (rd16(s, e + 4) == 0xFFFF) return ZIPC_ERR_ZIP_ZIP64;         // zipc.ml:404
+    if (rd16(s, e + 4) != 0 || rd16(s, e + 6) != 0) return ZIPC_ERR_ZIP_MULTIPART;
+  }
+  if (cd_start > len || cd_size > len - cd_start) return ZIPC_ERR_ZIP_EOCD;
   const int64_t cd_max = (int64_t)(cd_start + cd_size) - 1;
 
   std::vector<zipc_b200_member> ms(count);
@@ -177,11 +222,12 @@ int zipc_b200_zip_parse(const void *bytes, size_t len, zipc_b200_member **member
       m.compressed_size = rd32(s, o + 20);
       m.decompressed_size = rd32(s, o + 24);
       m.crc32 = rd32(s, o + 16);
-      const uint64_t lfh = rd32(s, o + 42);
+      uint64_t lfh = rd32(s, o + 42);
+      if (z64 && !zip64_cd_extra(s + o + 46 + plen, rd16(s, o + 30), m.decompressed_size, m.compressed_size, lfh)) return ZIPC_ERR_ZIP_CDFH;
       if (lfh >= len) return ZIPC_ERR_ZIP_CDFH;                       // zipc.ml:380
       if (lfh + 30 > len || rd32(s, (size_t)lfh) != 0x04034b50u) return ZIPC_ERR_ZIP_LFH;
       const uint64_t data = lfh + 30 + rd16(s, (size_t)lfh + 26) + rd16(s, (size_t)lfh + 28);
-      if (data + m.compressed_size > len) return ZIPC_ERR_ZIP_LFH;    // zipc.ml:335
+      if (data > len || m.compressed_size > len - data) return ZIPC_ERR_ZIP_LFH;  // zipc.ml:335
       if (m.crc32 == 0) m.crc32 = rd32(s, (size_t)lfh + 14);          // zipc.ml:382-385
       m.compressed_bytes = s;
       m.start = data;
@@ -209,7 +255,8 @@ uint64_t zipc_b200_zip_encoding_size(const zipc_b200_member *ms, size_t n) {
 namespace {
 struct Hdr {  // the fields LFH and CDFH share, resolved for directories (zipc.ml:458-465, 499-507)
   unsigned made_by, needed, flags, method, date, time;
-  uint32_t crc, csize, usize;
+  uint32_t crc;
+  uint64_t csize, usize;
 };
 Hdr header_fields(const zipc_b200_member &m) {
   Hdr h;
@@ -217,17 +264,76 @@ Hdr header_fields(const zipc_b200_member &m) {
   zipc_b200_ptime_to_dos(m.mtime, &date, &time);
   h.date = (unsigned)date;
   h.time = (unsigned)time;
-  if (m.is_dir) { h.made_by = 0x314; h.needed = 20; h.flags = 0x800; h.method = 0; h.crc = h.csize = h.usize = 0; }
+  if (m.is_dir) { h.made_by = 0x314; h.needed = 20; h.flags = 0x800; h.method = 0; h.crc = 0; h.csize = h.usize = 0; }
   else {
     h.made_by = (unsigned)m.version_made_by;
     h.needed = (unsigned)m.version_needed;
     h.flags = (unsigned)m.gp_flags & ~8u;  // data-descriptor bit is never written (zipc.ml:442-445)
     h.method = (unsigned)m.compression;
     h.crc = m.crc32;
-    h.csize = (uint32_t)m.compressed_size;
-    h.usize = (uint32_t)m.decompressed_size;
+    h.csize = m.compressed_size;
+    h.usize = m.decompressed_size;
   }
   return h;
+}
+
+// Where everything goes.  Classic format: zipc.ml:447-455.  With ZIP64 allowed, a member whose sizes do not fit 32 bits
+// gets a 20-byte ZIP64 extra field in its local header (both sizes: APPNOTE 4.5.3) and its directory entry one that holds
+// exactly the overflowing values (sizes, local header offset).
+constexpr uint64_t k32 = 0xFFFFFFFFull;
+struct Layout {
+  std::vector<size_t> ord;       // members in archive order
+  std::vector<uint64_t> lfh_at;  // per ord index
+  std::vector<uint8_t> big;      // per ord index: bit 0 sizes need 64 bits, bit 1 local header offset does
+  uint64_t cd_start = 0, cd_size = 0, total = 0;
+  bool eocd64 = false;
+};
+int make_layout(const zipc_b200_member *ms, size_t n, const char *first, unsigned flags, Layout &L) {
+  if (!first) first = "mimetype";
+  const size_t flen = std::strlen(first);
+  const bool allow = (flags & (ZIPC_ZIP_ALLOW_ZIP64 | ZIPC_ZIP_FORCE_ZIP64)) != 0, force = (flags & ZIPC_ZIP_FORCE_ZIP64) != 0;
+  L.ord = map_order(ms, n);
+  if (L.ord.size() > 0xFFFF && !allow) return ZIPC_ERR_ZIP_COUNT;     // zipc.ml:574
+  for (size_t k = 0; k < L.ord.size(); k++) {                          // `first` leads (zipc.ml:575-580)
+    const zipc_b200_member &m = ms[L.ord[k]];
+    if (m.path_len == flen && std::memcmp(m.path, first, flen) == 0) {
+      size_t f = L.ord[k];
+      L.ord.erase(L.ord.begin() + (long)k);
+      L.ord.insert(L.ord.begin(), f);
+      break;
+    }
+  }
+  L.lfh_at.resize(L.ord.size());
+  L.big.assign(L.ord.size(), 0);
+  uint64_t pos = 0;
+  for (size_t j = 0; j < L.ord.size(); j++) {
+    const zipc_b200_member &m = ms[L.ord[j]];
+    const uint64_t cs = m.is_dir ? 0 : m.compressed_size, us = m.is_dir ? 0 : m.decompressed_size;
+    if (m.path_len > 0xFFFF) return ZIPC_ERR_ZIP_PATH_LEN;
+    if (cs >= k32 || us >= k32) {
+      if (!allow) return ZIPC_ERR_ZIP_SIZE;                            // zipc.ml:130-133 (File.make refuses these)
+      L.big[j] |= 1;
+    }
+    if (force) L.big[j] |= 3;
+    if (pos >= k32) L.big[j] |= 2;  // (only reachable with ZIP64 allowed: without it the directory offset check fails below)
+    L.lfh_at[j] = pos;
+    pos += 30 + m.path_len + ((L.big[j] & 1) ? 20 : 0) + cs;
+  }
+  L.cd_start = pos;
+  for (size_t j = 0; j < L.ord.size(); j++) {
+    const unsigned b = L.big[j];
+    pos += 46 + ms[L.ord[j]].path_len + (b ? 4 + ((b & 1) ? 16 : 0) + ((b & 2) ? 8 : 0) : 0);
+  }
+  L.cd_size = pos - L.cd_start;
+  if (L.ord.empty()) L.cd_start = L.cd_size = 0;                       // zipc.ml:571-572
+  L.eocd64 = force || L.ord.size() > 0xFFFF || L.cd_start >= k32 || L.cd_size >= k32;
+  if (!allow) {
+    if (L.cd_start > k32) return ZIPC_ERR_ZIP_CD_OFFSET;               // zipc.ml:550
+    if (L.cd_size > k32) return ZIPC_ERR_ZIP_CD_SIZE;                  // zipc.ml:551
+    L.eocd64 = false;
+  }
+  L.total = pos + (L.eocd64 ? 56 + 20 : 0) + 22;
+  return ZIPC_OK;
 }
 }  // namespace
 
@@ -238,76 +344,75 @@ namespace zb {
 // payload offsets only.  copy_payload == false: payloads are already in place (the GPU gathered them).
 // payload_off[i] (optional) receives the archive offset of member i's payload (members in caller order).
 int zip_assemble_impl(const zipc_b200_member *ms, size_t n, const char *first, void *out_v, size_t out_cap,
-                      size_t *out_len, bool copy_payload, uint64_t *payload_off) {
+                      size_t *out_len, bool copy_payload, uint64_t *payload_off, unsigned flags) {
   if (!out_len || (!ms && n)) return ZIPC_ERR_INVALID_ARG;
-  if (!first) first = "mimetype";
-  const size_t flen = std::strlen(first);
-  std::vector<size_t> ord = map_order(ms, n);
-  if (ord.size() > 0xFFFF) return ZIPC_ERR_ZIP_COUNT;                 // zipc.ml:574
-  for (size_t k = 0; k < ord.size(); k++) {                            // `first` leads (zipc.ml:575-580)
-    const zipc_b200_member &m = ms[ord[k]];
-    if (m.path_len == flen && std::memcmp(m.path, first, flen) == 0) {
-      size_t f = ord[k];
-      ord.erase(ord.begin() + (long)k);
-      ord.insert(ord.begin(), f);
-      break;
-    }
-  }
-  uint64_t total = 22;
-  for (size_t k : ord) total += 30 + ms[k].path_len + (ms[k].is_dir ? 0 : ms[k].compressed_size) + 46 + ms[k].path_len;
-  if (payload_off) {
-    uint64_t at = 0;
-    for (size_t k : ord) {
-      at += 30 + ms[k].path_len;
-      payload_off[k] = at;
-      at += ms[k].is_dir ? 0 : ms[k].compressed_size;
-    }
-  }
-  if (!out_v) { *out_len = (size_t)total; return ZIPC_OK; }
-  if (total > out_cap) { *out_len = (size_t)total; return ZIPC_ERR_DST_TOO_SMALL; }
+  Layout L;
+  if (int st = make_layout(ms, n, first, flags, L)) return st;
+  const std::vector<size_t> &ord = L.ord;
+  if (payload_off)
+    for (size_t j = 0; j < ord.size(); j++)
+      payload_off[ord[j]] = L.lfh_at[j] + 30 + ms[ord[j]].path_len + ((L.big[j] & 1) ? 20 : 0);
+  if (!out_v) { *out_len = (size_t)L.total; return ZIPC_OK; }
+  if (L.total > out_cap) { *out_len = (size_t)L.total; return ZIPC_ERR_DST_TOO_SMALL; }
   uint8_t *b = static_cast<uint8_t *>(out_v);
-  std::vector<uint64_t> lfh_at(ord.size());
   uint64_t pos = 0;
   for (size_t j = 0; j < ord.size(); j++) {  // local headers + payloads (zipc.ml:457-496)
     const zipc_b200_member &m = ms[ord[j]];
     const Hdr h = header_fields(m);
-    lfh_at[j] = pos;
+    const bool big = (L.big[j] & 1) != 0;
     wr32(b, pos, 0x04034b50u);
-    wr16(b, pos + 4, h.needed); wr16(b, pos + 6, h.flags); wr16(b, pos + 8, h.method);
+    wr16(b, pos + 4, big ? std::max(h.needed, 45u) : h.needed); wr16(b, pos + 6, h.flags); wr16(b, pos + 8, h.method);
     wr16(b, pos + 10, h.time); wr16(b, pos + 12, h.date);
-    wr32(b, pos + 14, h.crc); wr32(b, pos + 18, h.csize); wr32(b, pos + 22, h.usize);
-    wr16(b, pos + 26, m.path_len); wr16(b, pos + 28, 0);
+    wr32(b, pos + 14, h.crc); wr32(b, pos + 18, big ? (uint32_t)k32 : (uint32_t)h.csize); wr32(b, pos + 22, big ? (uint32_t)k32 : (uint32_t)h.usize);
+    wr16(b, pos + 26, m.path_len); wr16(b, pos + 28, big ? 20 : 0);
     std::memcpy(b + pos + 30, m.path, m.path_len);
     pos += 30 + m.path_len;
+    if (big) { wr16(b, pos, 1); wr16(b, pos + 2, 16); wr64(b, pos + 4, h.usize); wr64(b, pos + 12, h.csize); pos += 20; }
     if (!m.is_dir && m.compressed_size) {
       if (copy_payload) std::memcpy(b + pos, m.compressed_bytes + m.start, m.compressed_size);
       pos += m.compressed_size;
     }
   }
-  uint64_t cd_start = pos;
   for (size_t j = 0; j < ord.size(); j++) {  // central directory (zipc.ml:498-545)
     const zipc_b200_member &m = ms[ord[j]];
     const Hdr h = header_fields(m);
+    const unsigned bg = L.big[j];
+    const unsigned xlen = bg ? 4 + ((bg & 1) ? 16 : 0) + ((bg & 2) ? 8 : 0) : 0;
     wr32(b, pos, 0x02014b50u);
-    wr16(b, pos + 4, h.made_by); wr16(b, pos + 6, h.needed); wr16(b, pos + 8, h.flags); wr16(b, pos + 10, h.method);
+    wr16(b, pos + 4, h.made_by); wr16(b, pos + 6, bg ? std::max(h.needed, 45u) : h.needed); wr16(b, pos + 8, h.flags); wr16(b, pos + 10, h.method);
     wr16(b, pos + 12, h.time); wr16(b, pos + 14, h.date);
-    wr32(b, pos + 16, h.crc); wr32(b, pos + 20, h.csize); wr32(b, pos + 24, h.usize);
+    wr32(b, pos + 16, h.crc); wr32(b, pos + 20, (bg & 1) ? (uint32_t)k32 : (uint32_t)h.csize); wr32(b, pos + 24, (bg & 1) ? (uint32_t)k32 : (uint32_t)h.usize);
     wr16(b, pos + 28, m.path_len);
-    wr16(b, pos + 30, 0); wr16(b, pos + 32, 0); wr16(b, pos + 34, 0); wr16(b, pos + 36, 0);
+    wr16(b, pos + 30, xlen); wr16(b, pos + 32, 0); wr16(b, pos + 34, 0); wr16(b, pos + 36, 0);
     wr16(b, pos + 38, m.is_dir ? 0x10 : 0);
     wr16(b, pos + 40, (m.is_dir ? 040000u : 0100000u) | ((unsigned)m.mode & 07777u));
-    wr32(b, pos + 42, (uint32_t)lfh_at[j]);
+    wr32(b, pos + 42, (bg & 2) ? (uint32_t)k32 : (uint32_t)L.lfh_at[j]);
     std::memcpy(b + pos + 46, m.path, m.path_len);
     pos += 46 + m.path_len;
+    if (bg) {
+      wr16(b, pos, 1); wr16(b, pos + 2, xlen - 4);
+      size_t q = pos + 4;
+      if (bg & 1) { wr64(b, q, h.usize); wr64(b, q + 8, h.csize); q += 16; }
+      if (bg & 2) wr64(b, q, L.lfh_at[j]);
+      pos += xlen;
+    }
   }
-  uint64_t cd_size = pos - cd_start;
-  if (ord.empty()) cd_start = cd_size = 0;                             // zipc.ml:571-572
-  if (cd_start > 0xFFFFFFFFull) return ZIPC_ERR_ZIP_CD_OFFSET;
-  if (cd_size > 0xFFFFFFFFull) return ZIPC_ERR_ZIP_CD_SIZE;
+  if (L.eocd64) {  // ZIP64 end of central directory record + locator (APPNOTE 4.3.14, 4.3.15)
+    const uint64_t at = pos;
+    wr32(b, pos, 0x06064b50u); wr64(b, pos + 4, 44);
+    wr16(b, pos + 12, 0x314 | 45); wr16(b, pos + 14, 45);
+    wr32(b, pos + 16, 0); wr32(b, pos + 20, 0);
+    wr64(b, pos + 24, ord.size()); wr64(b, pos + 32, ord.size());
+    wr64(b, pos + 40, L.cd_size); wr64(b, pos + 48, L.cd_start);
+    pos += 56;
+    wr32(b, pos, 0x07064b50u); wr32(b, pos + 4, 0); wr64(b, pos + 8, at); wr32(b, pos + 16, 1);
+    pos += 20;
+  }
   wr32(b, pos, 0x06054b50u);                                           // zipc.ml:553-566
   wr16(b, pos + 4, 0); wr16(b, pos + 6, 0);
-  wr16(b, pos + 8, (unsigned)ord.size()); wr16(b, pos + 10, (unsigned)ord.size());
-  wr32(b, pos + 12, (uint32_t)cd_size); wr32(b, pos + 16, (uint32_t)cd_start);
+  const unsigned c16 = (unsigned)std::min<uint64_t>(ord.size(), 0xFFFF);
+  wr16(b, pos + 8, c16); wr16(b, pos + 10, c16);
+  wr32(b, pos + 12, (uint32_t)std::min(L.cd_size, k32)); wr32(b, pos + 16, (uint32_t)std::min(L.cd_start, k32));
   wr16(b, pos + 20, 0);
   *out_len = (size_t)(pos + 22);
   return ZIPC_OK;
@@ -319,7 +424,21 @@ extern "C" {
 int zipc_b200_zip_assemble(const zipc_b200_member *ms, size_t n, const char *first, void *out_v, size_t out_cap,
                            size_t *out_len) {
   if (!out_v) return ZIPC_ERR_INVALID_ARG;
-  return zb::zip_assemble_impl(ms, n, first, out_v, out_cap, out_len, true, nullptr);
+  return zb::zip_assemble_impl(ms, n, first, out_v, out_cap, out_len, true, nullptr, ZIPC_ZIP_REFERENCE);
+}
+
+int zipc_b200_zip_assemble_ex(const zipc_b200_member *ms, size_t n, const char *first, unsigned flags, void *out_v,
+                              size_t out_cap, size_t *out_len) {
+  if (!out_v) return ZIPC_ERR_INVALID_ARG;
+  return zb::zip_assemble_impl(ms, n, first, out_v, out_cap, out_len, true, nullptr, flags);
+}
+
+// Zipc.encoding_size for an archive that may need ZIP64 structures (their presence depends on the offsets, hence `first`).
+// 0 if the members cannot be encoded under `flags`.
+uint64_t zipc_b200_zip_encoding_size_ex(const zipc_b200_member *ms, size_t n, const char *first, unsigned flags) {
+  size_t total = 0;
+  if (zb::zip_assemble_impl(ms, n, first, nullptr, 0, &total, false, nullptr, flags)) return 0;
+  return total;
 }
 
 }  // extern "C"

@@ -23,6 +23,7 @@ from .zipc_deflate import Error, Ok
 DOS_EPOCH = 315532800  # Ptime.dos_epoch, zipc.ml:94
 MAX_SIZE = 0xFFFFFFFF   # File.max_size, zipc.ml:138
 STORED, DEFLATE = 0, 8  # compression_to_int, zipc.ml:29-31
+ZIP_REFERENCE, ZIP_ALLOW_ZIP64, ZIP_FORCE_ZIP64 = 0, 1, 2  # ZIPC_ZIP_* (include/zipc_b200.h)
 
 
 class Ptime:
@@ -224,12 +225,18 @@ def string_has_magic(s) -> bool:
     return len(b) == 4 and b in (b"PK\x03\x04", b"PK\x05\x06")
 
 
-def of_binary_string(s):
-    """Zipc.of_binary_string (zipc.ml:432-438): members alias `s`."""
+def _zip_flags(zip64) -> int:
+    """False: the reference's behaviour; True: ZIP64 structures are read / written where needed; "force": written always."""
+    return ZIP_FORCE_ZIP64 | ZIP_ALLOW_ZIP64 if zip64 == "force" else ZIP_ALLOW_ZIP64 if zip64 else ZIP_REFERENCE
+
+
+def of_binary_string(s, zip64: bool = False):
+    """Zipc.of_binary_string (zipc.ml:432-438): members alias `s`.  zip64=True (beyond the reference, which answers
+    "ZIP64 archives are not supported", zipc.ml:404) also reads archives with ZIP64 records."""
     v = zd._as_view(s)
     L = _lib.lib()
     p, n = C.POINTER(_lib.Member)(), C.c_size_t()
-    st = L.zipc_b200_zip_parse(v.ctypes.data if v.size else None, v.size, C.byref(p), C.byref(n))
+    st = L.zipc_b200_zip_parse_ex(v.ctypes.data if v.size else None, v.size, _zip_flags(zip64), C.byref(p), C.byref(n))
     if st:
         return Error(zd.strerror(st), st)
     z = {}
@@ -245,21 +252,28 @@ def of_binary_string(s):
     return Ok(z)
 
 
-def encoding_size(z: dict) -> int:
+def encoding_size(z: dict, zip64=False, first: str | bytes | None = None) -> int:
+    """Zipc.encoding_size (zipc.ml:447-455); with zip64 the size of the ZIP64 records depends on the offsets, hence `first`."""
     arr, _keep = _to_c(list(z.values()))
-    return _lib.lib().zipc_b200_zip_encoding_size(arr, len(z))
+    if not zip64:
+        return _lib.lib().zipc_b200_zip_encoding_size(arr, len(z))
+    f = first.encode() if isinstance(first, str) else first
+    return _lib.lib().zipc_b200_zip_encoding_size_ex(arr, len(z), f, _zip_flags(zip64))
 
 
-def to_binary_string(z: dict, first: str | bytes | None = None):
-    """Zipc.to_binary_string (zipc.ml:585-588)."""
+def to_binary_string(z: dict, first: str | bytes | None = None, zip64=False):
+    """Zipc.to_binary_string (zipc.ml:585-588).  zip64=True (beyond the reference): more than 65,535 members, sizes and
+    offsets of 4 GiB or more are written with ZIP64 records instead of being refused; an archive that needs none is
+    byte-identical to the reference's.  zip64="force": ZIP64 records for every member."""
     ms = list(z.values())
     arr, _keep = _to_c(ms)
     L = _lib.lib()
-    size = L.zipc_b200_zip_encoding_size(arr, len(ms))
+    f = first.encode() if isinstance(first, str) else first
+    flags = _zip_flags(zip64)
+    size = L.zipc_b200_zip_encoding_size_ex(arr, len(ms), f, flags) or L.zipc_b200_zip_encoding_size(arr, len(ms))
     out = np.empty(max(size, 1), dtype=np.uint8)
     n = C.c_size_t()
-    f = first.encode() if isinstance(first, str) else first
-    st = L.zipc_b200_zip_assemble(arr, len(ms), f, out.ctypes.data, size, C.byref(n))
+    st = L.zipc_b200_zip_assemble_ex(arr, len(ms), f, flags, out.ctypes.data, size, C.byref(n))
     if st:
         return Error(zd.strerror(st), st)
     return Ok(out[:n.value].tobytes())
