@@ -95,10 +95,13 @@ def cmd_decompress(a) -> int:
     return EXIT_OK
 
 
+ZIP64 = False  # --zip64: read and write ZIP64 records (beyond the reference's tool, which refuses them like the library)
+
+
 def _open_archive(path: str):
     from zipc_b200 import zipc
     s = _read(path)
-    r = zipc.of_binary_string(s)
+    r = zipc.of_binary_string(s, zip64=ZIP64)
     if r.is_error():
         print("%s: %s" % (path, r.message), file=sys.stderr)
         return None, s
@@ -243,13 +246,13 @@ def cmd_recode(a) -> int:
     if err:
         print(err, file=sys.stderr)
         return EXIT_SOME
-    r = zipc.to_binary_string(z2)
+    r = zipc.to_binary_string(z2, zip64=ZIP64)
     if r.is_error():
         print("%s: %s" % (a.archive, r.message), file=sys.stderr)
         return EXIT_SOME
     out = r.get_ok()
     if a.test:  # recode_check_in_memory (zipc_tool.ml:498-515)
-        r2 = zipc.of_binary_string(out)
+        r2 = zipc.of_binary_string(out, zip64=ZIP64)
         if r2.is_error():
             print("recode check: %s" % r2.message, file=sys.stderr)
             return EXIT_SOME
@@ -284,7 +287,7 @@ def cmd_zip(a) -> int:
         for nm, d, md, mt in zip(names, payloads, modes, mtimes):
             f = zipc.File.stored_of_binary_string(d).get_ok()
             z = zipc.add(zipc.Member.make(nm, f, mode=md, mtime=mt).get_ok(), z)
-        r = zipc.to_binary_string(z)
+        r = zipc.to_binary_string(z, zip64=ZIP64)
     else:
         r = zipc.archive_of_binary_strings(names, payloads, a.level, modes, mtimes)
     if r.is_error():
@@ -296,6 +299,7 @@ def cmd_zip(a) -> int:
 
 def main(argv=None) -> int:
     ap = argparse.ArgumentParser(prog="zipc_tool", description=__doc__.split("\n\n")[0])
+    ap.add_argument("--zip64", action="store_true", help="accept and write ZIP64 archives (the reference refuses them)")
     sub = ap.add_subparsers(dest="cmd", required=True)
     levels = ["none", "fast", "default", "best"]
     p = sub.add_parser("crc"); p.add_argument("--adler-32", action="store_true"); p.add_argument("infile"); p.set_defaults(fn=cmd_crc)
@@ -314,6 +318,8 @@ def main(argv=None) -> int:
     p = sub.add_parser("zip"); p.add_argument("-o", "--output", required=True); p.add_argument("--stored", action="store_true")
     p.add_argument("--level", choices=levels, default="default"); p.add_argument("--strip-prefix"); p.add_argument("files", nargs="+"); p.set_defaults(fn=cmd_zip)
     a = ap.parse_args(argv)
+    global ZIP64
+    ZIP64 = a.zip64
     try:
         return a.fn(a)
     except OSError as e:

@@ -92,6 +92,10 @@ constexpr uint32_t kExit = 2 * kTile; // jump codes >= kExit leave the tile
 // named barriers (0 is __syncthreads)
 template <int BW> __device__ __forceinline__ void bar_front() { asm volatile("bar.sync 1, %0;" ::"n"((NWARPS - BW) * 32) : "memory"); }
 template <int BW> __device__ __forceinline__ void bar_back() { asm volatile("bar.sync 2, %0;" ::"n"(BW * 32) : "memory"); }
+// barrier 3 (BW = 1 only): the front threads arrive, without waiting, when the chains of their tile are complete; the parse
+// warp waits there before it takes shallow-walk batches of that tile
+__device__ __forceinline__ void bar_walk_open_arrive() { asm volatile("bar.arrive 3, %0;" ::"n"(NWARPS * 32) : "memory"); }
+__device__ __forceinline__ void bar_walk_open_wait() { asm volatile("bar.sync 3, %0;" ::"n"(NWARPS * 32) : "memory"); }
 
 // ---- input staging by the copy engine: cp.async.bulk (global -> shared, 1-D) completing on an mbarrier ---------------------
 // One elected thread asks for the next tile's bytes a whole tile ahead; nobody spends instructions on staging, the front
@@ -175,8 +179,7 @@ struct Shared {
 
 // scalar slots in sh.sc
 enum { SC_TASK = 0, SC_OUTW, SC_CARRY, SC_CBITS, SC_OVERFLOW, SC_M_L, SC_M_D, SC_NHDR, SC_BTYPE, SC_HLIT, SC_HDIST,
-       SC_SUMDYN, SC_SUMFIX, SC_BLK_SRCLEN, SC_NRSYM, SC_HCLEN, SC_HDRBITS, SC_BATCH, SC_QHEAD, SC_OQN, SC_EXIT, SC_VQN /* [2] */, SC_VQN1, SC_LD_PHASES /* bulk copies issued so far */,
-       SC_WALK_OPEN /* first position of the tile whose shallow walks are being handed out, + 1 */ };
+       SC_SUMDYN, SC_SUMFIX, SC_BLK_SRCLEN, SC_NRSYM, SC_HCLEN, SC_HDRBITS, SC_BATCH, SC_QHEAD, SC_OQN, SC_EXIT, SC_VQN /* [2] */, SC_VQN1, SC_LD_PHASES /* bulk copies issued so far */ };
 
 __device__ __forceinline__ Gen gen_of(uint8_t *base, int g) {  // plain arithmetic on the shared base: the address space stays known
   uint8_t *b = base + OFF_GEN + g * GEN_BYTES;
@@ -693,12 +696,13 @@ __device__ __forceinline__ void shallow_batches(const Shared &sh, const Gen &G, 
 }
 
 // ---- front end: stage, hash, partition, insert, shallow walks of one tile (FRONT_THREADS threads) -----------------
-// ft: thread index inside the front group; fw: warp index inside the group.  Uses bar_front() only.
+// ft: thread index inside the front group; fw: warp index inside the group.  Uses bar_front() only (and, with `helper`, one
+// arrival at barrier 3 that tells the parse warp it may take shallow-walk batches of this tile).
 // `state`: bits 0..31 = input bytes resident in the ring or on their way, bit 32 = a bulk copy is in flight.  Returns the new state.
 // Positions below emit_from (a multiple of the tile) only prime the window: hashed and inserted, not searched.
 template <int BW>
 __device__ __noinline__ uint64_t front_end(int gen, const uint8_t *src, uint32_t n, uint32_t ts, uint64_t state,
-                                           int level, int ft, int fw, int lane, uint32_t emit_from) {
+                                           int level, int ft, int fw, int lane, uint32_t emit_from, bool helper) {
   constexpr int FRONT_WARPS = NWARPS - BW, FRONT_THREADS = FRONT_WARPS * 32;
   [[maybe_unused]] constexpr int BACK_THREADS = BW * 32;  // (the timing build names the first front thread by it)
   constexpr int kClasses = FRONT_WARPS, kRankRounds = (kChunk32 + FRONT_WARPS - 1) / FRONT_WARPS;
@@ -849,7 +853,7 @@ __device__ __noinline__ uint64_t front_end(int gen, const uint8_t *src, uint32_t
   //    end's parse warp takes batches too once its own tile is done (ZB_BACK_HELPS): 64 batches over 31 warps are three
   //    rounds for two warps and two for the rest.
 #if ZB_BACK_HELPS
-  if (BW == 1 && ft == 0) { __threadfence_block(); *(volatile uint32_t *)&sh.sc[SC_WALK_OPEN] = ts + 1u; }
+  if (BW == 1 && helper) bar_walk_open_arrive();  // (behind bar_front: every front warp's links are in place)
 #endif
   shallow_batches(sh, G, ts, te, n, lp, emit_from, lane);
   bar_front<BW>();
@@ -1043,7 +1047,7 @@ __device__ void encode_member(const DeflateTask t, int level, uint32_t *toks, De
   for (int i = tid; i < kWindow / 2; i += THREADS) reinterpret_cast<uint32_t *>(sh.prev)[i] = 0;
   for (int i = tid; i < 320; i += THREADS) sh.hist_l[i] = 0;
   if (tid == 0) {
-    sh.sc[SC_OUTW] = 0; sh.sc[SC_CARRY] = 0; sh.sc[SC_CBITS] = 0; sh.sc[SC_OVERFLOW] = 0; sh.sc[SC_BLK_SRCLEN] = 0; sh.sc[SC_WALK_OPEN] = 0;
+    sh.sc[SC_OUTW] = 0; sh.sc[SC_CARRY] = 0; sh.sc[SC_CBITS] = 0; sh.sc[SC_OVERFLOW] = 0; sh.sc[SC_BLK_SRCLEN] = 0;
     gen_of(smem_raw, 0).mlen[0] = 0; gen_of(smem_raw, 0).mdist[0] = 0;
   }
   __syncthreads();
@@ -1056,7 +1060,7 @@ __device__ void encode_member(const DeflateTask t, int level, uint32_t *toks, De
 
   // prologue: tile 0 through the front end, then its jump codes
   if (n) {
-    if (!back) loaded = front_end<BW>(0, src, n, 0, loaded, level, ft, fw, lane, prime);
+    if (!back) loaded = front_end<BW>(0, src, n, 0, loaded, level, ft, fw, lane, prime, false);
     __syncthreads();
     jump_codes(sh, gen_of(smem_raw, 0), 0, min((uint32_t)kTile, n), tid, THREADS);
     __syncthreads();
@@ -1105,15 +1109,13 @@ __device__ void encode_member(const DeflateTask t, int level, uint32_t *toks, De
       PH(PH_PARSE1);
     } else if (more) {
       // ---- front end: tile t + 1 -------------------------------------------------------------------------------------
-      loaded = front_end<BW>(g ^ 1, src, n, te, loaded, level, ft, fw, lane, prime);
+      loaded = front_end<BW>(g ^ 1, src, n, te, loaded, level, ft, fw, lane, prime, true);
     }
 #if ZB_BACK_HELPS
     if (BW == 1 && back && more) {
       // the parse warp is done with tile t: it takes batches of tile t + 1's shallow walks as soon as the front end hands
       // them out (the chains are complete then); what a walk finds depends on its position alone
-      GUARD_DECL(g_o)
-      while (*(volatile uint32_t *)&sh.sc[SC_WALK_OPEN] != te + 1u) { GUARD(g_o, 4000000u, 502); __nanosleep(64); }
-      __threadfence_block();
+      bar_walk_open_wait();
       shallow_batches(sh, G1, te, min(te + (uint32_t)kTile, n), n, lp, prime, lane);
     }
 #endif
