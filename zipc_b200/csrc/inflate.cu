@@ -71,6 +71,11 @@ constexpr int ROUND_TOKENS = 32;  // one token per lane
 #ifndef ZB_INFLATE_BULK
 #define ZB_INFLATE_BULK 1
 #endif
+// the bulk copies carry an L2 evict_first policy: the compressed bytes are read once, the L2 lines are wanted for the streams'
+// 32 KiB histories (C3, ncu: DRAM reads 4.48 -> 4.34 GB per launch, kernel 13.55 -> 13.51 ms; profiles/r02_inflate_evict_first.txt)
+#ifndef ZB_INFLATE_IN_EVICT_FIRST
+#define ZB_INFLATE_IN_EVICT_FIRST 1
+#endif
 constexpr int kRingWords = ZB_INFLATE_BULK ? 128 : 64;
 constexpr uint32_t kRingMask = kRingWords - 1;
 constexpr int SYMS_PER_SLOT = 320;     // sorted symbols: 288 litlen + 32 dist
@@ -167,8 +172,16 @@ struct Input {
         const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&wk.ldbar);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%1], %0;" ::"r"(128u), "r"(bar) : "memory");
+#if ZB_INFLATE_IN_EVICT_FIRST
+        // the compressed bytes are read once: they are the first to leave L2, which the streams' 32 KiB histories need
+        uint64_t pol;
+        asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                     ::"r"((uint32_t)__cvta_generic_to_shared(&wk.ring[k & kRingMask])), "l"(wk.st.srcw + k), "r"(128u), "r"(bar), "l"(pol) : "memory");
+#else
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                      ::"r"((uint32_t)__cvta_generic_to_shared(&wk.ring[k & kRingMask])), "l"(wk.st.srcw + k), "r"(128u), "r"(bar) : "memory");
+#endif
       }
       ph |= 2u;
     } else {
