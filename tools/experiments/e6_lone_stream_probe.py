@@ -3,7 +3,8 @@ ZIPC_B200_LIB=.../libzipc_b200_noe.so (built with -DZB_PROBE_NO_E=1) skips the c
 import ctypes as C, os, sys, time, zlib
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
-os.environ["ZIPC_B200_PAR_MIN"] = "0"   # no many-warp decoding: the one-warp decoder is what is measured
+if not os.environ.get("E6_PAR"):
+    os.environ["ZIPC_B200_PAR_MIN"] = "0"   # no many-warp decoding: the one-warp decoder is what is measured (E6_PAR=1: the library decides)
 import torch
 from zipc_b200 import synth
 from zipc_b200 import zipc_deflate as zd

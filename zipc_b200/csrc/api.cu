@@ -455,6 +455,18 @@ static int inflate_serial_core(zipc_b200_ctx *ctx, int ck, int adler_mode, size_
 // tuning knobs (read on every call, so that tests can vary them): compressed bytes per chunk; smallest stream that is tried
 static uint64_t par_chunk_bytes() { return std::max<uint64_t>(4096, env_u64("ZIPC_B200_PAR_CHUNK", 8192)); }
 static uint64_t par_min_bytes() { return env_u64("ZIPC_B200_PAR_MIN", 262144); }
+// A call with only one or two mid-sized streams (64 KiB of compressed data and more) has nothing else to fill the GPU with: a
+// stream alone runs at ~35 MB/s on its warp (profiles/r02_lone_stream_probe.txt), its blocks on a warp each in a third of the
+// time.  With more streams the one-warp decoder takes them all at once, and the many-warp path (one stream after the other)
+// stays reserved for the large ones.  ZIPC_B200_PAR_MIN, when set, is taken as it is.
+static uint64_t par_min_for(size_t n, const size_t *src_len) {
+  const uint64_t base = par_min_bytes();
+  if (base == 0 || std::getenv("ZIPC_B200_PAR_MIN")) return base;
+  const uint64_t low = 65536;
+  size_t mid = 0;
+  for (size_t i = 0; i < n && mid <= 2; i++) mid += src_len[i] >= low;
+  return mid <= 2 ? low : base;
+}
 
 static bool par_debug() { static const bool v = env_u64("ZIPC_B200_PAR_DEBUG", 0) != 0; return v; }
 
@@ -591,8 +603,9 @@ int inflate_core(zipc_b200_ctx *ctx, int ck, int adler_mode, size_t n, const std
   std::vector<char> done(n, 0);
   size_t ndone = 0;
   if (flags == 0 && ck != ZIPC_CK_ADLER32 && par_min_bytes() != 0 && !(plan && plan->ngroups)) {  // (Adler-32 is folded block by block: serial path)
+    const uint64_t par_min = par_min_for(n, src_len);
     for (size_t i = 0; i < n; i++) {
-      if (src_len[i] < par_min_bytes()) continue;
+      if (src_len[i] < par_min) continue;
       bool ok = false;
       if (int st = par_speculate(ctx, d_src[i], src_len[i], &ok)) return st;
       const uint64_t total = ctx->par_plan.total;
