@@ -127,3 +127,22 @@ def test_throughput_sanity_and_batch_mix(ctx):
     for d, (st, out, crc) in zip(datas, res):
         assert st == 0 and out.tobytes() == d and crc == zlib.crc32(d)
     assert ctx.parallel_streams[0] == before[0] + 2
+
+
+def test_many_mid_sized_streams_stay_on_the_one_warp_decoder(ctx):
+    """The many-warp decoder takes one stream after the other: it is chosen where that shortens the call (one or two mid-sized
+    streams, a few large ones among small ones), not for a batch of equally large streams, which the one-warp decoder takes
+    side by side (148 streams of 1 MiB: 30 ms there, 816 ms one after the other)."""
+    data = synth.text_v1(321, 1 << 20).tobytes()
+    stream = _raw(data, 6)
+    assert len(stream) > 300_000
+    before = ctx.parallel_streams
+    (st, out, crc), = ctx.inflate_batch([stream], [len(data)], _lib.CK_CRC32)          # alone: in parallel
+    assert st == 0 and crc == zlib.crc32(data) and ctx.parallel_streams[0] == before[0] + 1
+    mid = synth.text_v1(322, 200_000).tobytes()                                          # 70 KB compressed: alone, in parallel too
+    (st, out, crc), = ctx.inflate_batch([_raw(mid, 6)], [len(mid)], _lib.CK_CRC32)
+    assert st == 0 and out.tobytes() == mid and ctx.parallel_streams[0] == before[0] + 2
+    before = ctx.parallel_streams
+    res = ctx.inflate_batch([stream] * 60, [len(data)] * 60, _lib.CK_CRC32)             # sixty of them: side by side
+    assert all(st == 0 and crc == zlib.crc32(data) for st, _, crc in res) and res[59][1].tobytes() == data
+    assert ctx.parallel_streams == before

@@ -455,17 +455,39 @@ static int inflate_serial_core(zipc_b200_ctx *ctx, int ck, int adler_mode, size_
 // tuning knobs (read on every call, so that tests can vary them): compressed bytes per chunk; smallest stream that is tried
 static uint64_t par_chunk_bytes() { return std::max<uint64_t>(4096, env_u64("ZIPC_B200_PAR_CHUNK", 8192)); }
 static uint64_t par_min_bytes() { return env_u64("ZIPC_B200_PAR_MIN", 262144); }
-// A call with only one or two mid-sized streams (64 KiB of compressed data and more) has nothing else to fill the GPU with: a
-// stream alone runs at ~35 MB/s on its warp (profiles/r02_lone_stream_probe.txt), its blocks on a warp each in a third of the
-// time.  With more streams the one-warp decoder takes them all at once, and the many-warp path (one stream after the other)
-// stays reserved for the large ones.  ZIPC_B200_PAR_MIN, when set, is taken as it is.
-static uint64_t par_min_for(size_t n, const size_t *src_len) {
+// Which streams of a batch go through the many-warp decoder?  It takes one stream after the other (a few host round trips and
+// the decode of its longest block on one warp: ~4 ms, then ~3 MB of compressed data per ms), while the one-warp decoder takes
+// all streams at once but needs ~1 ms per 12 KB of a stream's compressed data (profiles/r02_lone_stream_probe.txt: 148 streams
+// of 360 KiB took 816 ms one after the other and 30 ms side by side).  So: sort by size, and send the k largest streams to the
+// many-warp decoder for the k that minimises  sum of their times + the one-warp kernel's time for the rest.
+// ZIPC_B200_PAR_MIN, when set, is a plain threshold instead (tests force either path with it); 0 switches the path off.
+static void par_select(size_t n, const size_t *src_len, std::vector<char> &take) {
+  take.assign(n, 0);
   const uint64_t base = par_min_bytes();
-  if (base == 0 || std::getenv("ZIPC_B200_PAR_MIN")) return base;
-  const uint64_t low = 65536;
-  size_t mid = 0;
-  for (size_t i = 0; i < n && mid <= 2; i++) mid += src_len[i] >= low;
-  return mid <= 2 ? low : base;
+  if (base == 0) return;
+  if (std::getenv("ZIPC_B200_PAR_MIN")) { for (size_t i = 0; i < n; i++) take[i] = src_len[i] >= base; return; }
+  const uint64_t floor_bytes = 65536;   // (the block-start search wants a few 8 KiB chunks to work with)
+  std::vector<uint32_t> big;
+  double rest_bytes = 0;
+  for (size_t i = 0; i < n; i++) { rest_bytes += (double)src_len[i]; if (src_len[i] >= floor_bytes && big.size() < 4096) big.push_back((uint32_t)i); }
+  if (big.empty()) return;
+  std::sort(big.begin(), big.end(), [&](uint32_t a, uint32_t b) { return src_len[a] != src_len[b] ? src_len[a] > src_len[b] : a < b; });
+  const double one_warp_bytes_per_ms = 12e3, all_warps_bytes_per_ms = 33e6, many_warp_bytes_per_ms = 3e6, many_warp_fixed_ms = 4.0;
+  auto one_warp_kernel_ms = [&](size_t k) {  // the k largest are gone: the largest stream left, or the throughput of the whole GPU
+    const double largest = k < big.size() ? (double)src_len[big[k]] : (double)floor_bytes;
+    return std::max(largest / one_warp_bytes_per_ms, rest_bytes / all_warps_bytes_per_ms);
+  };
+  double best = one_warp_kernel_ms(0), spent = 0;
+  size_t best_k = 0;
+  for (size_t k = 1; k <= big.size(); k++) {
+    const double len = (double)src_len[big[k - 1]];
+    spent += many_warp_fixed_ms + len / many_warp_bytes_per_ms;
+    rest_bytes -= len;
+    if (spent >= best) break;  // (the sum only grows)
+    const double t = spent + (k == n ? 0.0 : one_warp_kernel_ms(k));
+    if (t < best) { best = t; best_k = k; }
+  }
+  for (size_t k = 0; k < best_k; k++) take[big[k]] = 1;
 }
 
 static bool par_debug() { static const bool v = env_u64("ZIPC_B200_PAR_DEBUG", 0) != 0; return v; }
@@ -603,9 +625,10 @@ int inflate_core(zipc_b200_ctx *ctx, int ck, int adler_mode, size_t n, const std
   std::vector<char> done(n, 0);
   size_t ndone = 0;
   if (flags == 0 && ck != ZIPC_CK_ADLER32 && par_min_bytes() != 0 && !(plan && plan->ngroups)) {  // (Adler-32 is folded block by block: serial path)
-    const uint64_t par_min = par_min_for(n, src_len);
+    std::vector<char> take;
+    par_select(n, src_len, take);
     for (size_t i = 0; i < n; i++) {
-      if (src_len[i] < par_min) continue;
+      if (!take[i]) continue;
       bool ok = false;
       if (int st = par_speculate(ctx, d_src[i], src_len[i], &ok)) return st;
       const uint64_t total = ctx->par_plan.total;
