@@ -503,6 +503,51 @@ def run_stream_c1(h: Harness):
     return {"workload": "C1: 64 MiB text-v1(seed=1) as one RFC 1951 stream; CRC-32 fused both ways; pinned host buffers in and out", **res}
 
 
+def run_few_large(h: Harness):
+    """The shape of the reference's own benchmark recipe (DEVEL.md:39-52: silesia.zip, 12 members of 5-51 MB, 212 MB): few LARGE
+    members instead of many small ones.  Synthetic text of silesia's member sizes; streams made by zlib -6 on the host (a
+    foreign encoder, no index); through the plain batch calls with pinned host buffers."""
+    from concurrent.futures import ThreadPoolExecutor
+    from zipc_b200 import synth
+    L = h.L
+    sizes = [10192446, 51220480, 9970564, 33553445, 6152192, 10085684, 6627202, 21606400, 7251944, 41458703, 5345280, 8474240]
+    datas = [synth.text_v1(700 + i, n) for i, n in enumerate(sizes)]
+    with ThreadPoolExecutor(len(sizes)) as ex:
+        streams = list(ex.map(lambda d: zlib.compress(d.tobytes(), 6)[2:-4], datas))
+    n = len(sizes)
+    total = sum(sizes)
+    hin = h.pinned(np.concatenate(datas))
+    hz = h.pinned(np.frombuffer(b"".join(streams), dtype=np.uint8))
+    obuf = h.pinned(np.zeros(total + 64 * n, dtype=np.uint8))
+    cbuf = h.pinned(np.zeros(total // 2 + (1 << 20), dtype=np.uint8))
+    ptr, ln, mo = (C.c_void_p * n)(), (C.c_size_t * n)(), (C.c_size_t * n)()
+    dptr, dln = (C.c_void_p * n)(), (C.c_size_t * n)()
+    zo_, do_ = 0, 0
+    for i in range(n):
+        ptr[i] = hz.ctypes.data + zo_; ln[i] = len(streams[i]); mo[i] = sizes[i]; zo_ += len(streams[i])
+        dptr[i] = hin.ctypes.data + do_; dln[i] = sizes[i]; do_ += sizes[i]
+    need = C.c_size_t(); off = (C.c_size_t * n)(); ol = (C.c_size_t * n)(); ck = (C.c_uint32 * n)(); st = (C.c_int * n)()
+    ifn = lambda: L.zipc_b200_inflate_batch(h.ctx.h, 2, 0, n, ptr, ln, mo, obuf.ctypes.data, obuf.size, C.byref(need), off, ol, ck, st)
+    assert ifn() == 0 and all(st[i] == 0 and ck[i] == zlib.crc32(datas[i]) and ol[i] == sizes[i] for i in range(n)), list(st)
+    assert bytes(obuf[off[3]:off[3] + 4096]) == bytes(datas[3][:4096])
+    t0 = time.perf_counter()
+    for _ in range(3): ifn()
+    ti = (time.perf_counter() - t0) / 3
+    dfn = lambda: L.zipc_b200_deflate_batch(h.ctx.h, 2, 2, 0, n, dptr, dln, cbuf.ctypes.data, cbuf.size, C.byref(need), off, ol, ck, st)
+    assert dfn() == 0 and all(st[i] == 0 and ck[i] == zlib.crc32(datas[i]) for i in range(n)), list(st)
+    csum = sum(int(ol[i]) for i in range(n))
+    assert zlib.decompress(bytes(cbuf[off[4]:off[4] + ol[4]]), -15) == datas[4].tobytes()
+    t0 = time.perf_counter()
+    for _ in range(3): dfn()
+    td = (time.perf_counter() - t0) / 3
+    return {"workload": "few large members: 12 members with the sizes of silesia's files (5.3-51.2 MB, %d MB in all), text-v1; pinned host buffers; "
+                        "inflate: streams made by zlib -6 on the host, no index; deflate: level default, CRC-32 both ways" % (total // 1000000),
+            "members": n, "uncompressed_bytes": total, "inflate_e2e_GBps": round(total / ti / 1e9, 3), "deflate_e2e_GBps": round(total / td / 1e9, 3),
+            "zlib6_compressed_bytes": zo_, "deflate_ratio": round(csum / total, 4),
+            "note": "every large stream is decoded by many warps (block-start search + speculation), several streams at a time; "
+                    "every member is compressed by one CTA per primed 256 KiB segment"}
+
+
 def run_stream_c5(h: Harness, synth, rank, world, dist, torch, local, slice_bytes=512 << 20, seg=256 << 10):
     """C5: ONE RFC 1951 stream spread over the GPUs of the box (4 GiB at N = 8): every rank compresses its contiguous
     512 MiB slice as a piece of the stream (segment-independent, only the last rank's piece carries BFINAL), the pieces are
@@ -995,6 +1040,7 @@ def main():
             else:
                 guard("archive", lambda: run_archive(h, datas))
             guard("stream_c1", lambda: run_stream_c1(h))
+            guard("few_large_members", lambda: run_few_large(h))
             guard("de_yardstick", lambda: run_de_yardstick(h, datas, get_streams()))
         else:
             # C5: one stream over all GPUs of the box (every rank takes part)

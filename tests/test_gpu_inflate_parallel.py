@@ -130,9 +130,9 @@ def test_throughput_sanity_and_batch_mix(ctx):
 
 
 def test_many_mid_sized_streams_stay_on_the_one_warp_decoder(ctx):
-    """The many-warp decoder takes one stream after the other: it is chosen where that shortens the call (one or two mid-sized
-    streams, a few large ones among small ones), not for a batch of equally large streams, which the one-warp decoder takes
-    side by side (148 streams of 1 MiB: 30 ms there, 816 ms one after the other)."""
+    """The many-warp decoder takes a handful of streams at a time (one lane each): it is chosen where that shortens the call (a
+    few mid-sized or large streams, alone or among small ones), not for hundreds of equally large streams, which the one-warp
+    decoder takes side by side (148 streams of 1 MiB: 30 ms there, 816 ms one after the other)."""
     data = synth.text_v1(321, 1 << 20).tobytes()
     stream = _raw(data, 6)
     assert len(stream) > 300_000
@@ -143,6 +143,10 @@ def test_many_mid_sized_streams_stay_on_the_one_warp_decoder(ctx):
     (st, out, crc), = ctx.inflate_batch([_raw(mid, 6)], [len(mid)], _lib.CK_CRC32)
     assert st == 0 and out.tobytes() == mid and ctx.parallel_streams[0] == before[0] + 2
     before = ctx.parallel_streams
-    res = ctx.inflate_batch([stream] * 60, [len(data)] * 60, _lib.CK_CRC32)             # sixty of them: side by side
-    assert all(st == 0 and crc == zlib.crc32(data) for st, _, crc in res) and res[59][1].tobytes() == data
+    res = ctx.inflate_batch([stream] * 12, [len(data)] * 12, _lib.CK_CRC32)             # a dozen: several at a time, on the lanes
+    assert all(st == 0 and crc == zlib.crc32(data) for st, _, crc in res) and res[11][1].tobytes() == data
+    assert ctx.parallel_streams[0] == before[0] + 12
+    before = ctx.parallel_streams
+    res = ctx.inflate_batch([stream] * 240, [len(data)] * 240, _lib.CK_CRC32)           # hundreds of them: side by side, a warp each
+    assert all(st == 0 and crc == zlib.crc32(data) for st, _, crc in res) and res[239][1].tobytes() == data
     assert ctx.parallel_streams == before

@@ -455,13 +455,13 @@ static int inflate_serial_core(zipc_b200_ctx *ctx, int ck, int adler_mode, size_
 // tuning knobs (read on every call, so that tests can vary them): compressed bytes per chunk; smallest stream that is tried
 static uint64_t par_chunk_bytes() { return std::max<uint64_t>(4096, env_u64("ZIPC_B200_PAR_CHUNK", 8192)); }
 static uint64_t par_min_bytes() { return env_u64("ZIPC_B200_PAR_MIN", 262144); }
-// Which streams of a batch go through the many-warp decoder?  It takes one stream after the other (a few host round trips and
-// the decode of its longest block on one warp: ~4 ms, then ~3 MB of compressed data per ms), while the one-warp decoder takes
+// Which streams of a batch go through the many-warp decoder?  It takes a stream in a few host round trips and the decode of its
+// longest block on one warp (~4 ms, then ~3 MB of compressed data per ms), a handful of streams at a time, while the one-warp decoder takes
 // all streams at once but needs ~1 ms per 12 KB of a stream's compressed data (profiles/r02_lone_stream_probe.txt: 148 streams
 // of 360 KiB took 816 ms one after the other and 30 ms side by side).  So: sort by size, and send the k largest streams to the
 // many-warp decoder for the k that minimises  sum of their times + the one-warp kernel's time for the rest.
 // ZIPC_B200_PAR_MIN, when set, is a plain threshold instead (tests force either path with it); 0 switches the path off.
-static void par_select(size_t n, const size_t *src_len, std::vector<char> &take) {
+static void par_select(size_t n, const size_t *src_len, std::vector<char> &take, size_t lanes) {
   take.assign(n, 0);
   const uint64_t base = par_min_bytes();
   if (base == 0) return;
@@ -472,22 +472,47 @@ static void par_select(size_t n, const size_t *src_len, std::vector<char> &take)
   for (size_t i = 0; i < n; i++) { rest_bytes += (double)src_len[i]; if (src_len[i] >= floor_bytes && big.size() < 4096) big.push_back((uint32_t)i); }
   if (big.empty()) return;
   std::sort(big.begin(), big.end(), [&](uint32_t a, uint32_t b) { return src_len[a] != src_len[b] ? src_len[a] > src_len[b] : a < b; });
-  const double one_warp_bytes_per_ms = 12e3, all_warps_bytes_per_ms = 33e6, many_warp_bytes_per_ms = 3e6, many_warp_fixed_ms = 4.0;
+  const double one_warp_bytes_per_ms = 12e3, all_warps_bytes_per_ms = 33e6, many_warp_bytes_per_ms = 3e6, many_warp_fixed_ms = 4.5;
   auto one_warp_kernel_ms = [&](size_t k) {  // the k largest are gone: the largest stream left, or the throughput of the whole GPU
     const double largest = k < big.size() ? (double)src_len[big[k]] : (double)floor_bytes;
     return std::max(largest / one_warp_bytes_per_ms, rest_bytes / all_warps_bytes_per_ms);
   };
-  double best = one_warp_kernel_ms(0), spent = 0;
+  // (`lanes` streams are decoded at a time, each lane a host thread with a sub-context of its own; the streams are dealt out
+  // largest first to the least loaded lane, here as in inflate_core)
+  double best = one_warp_kernel_ms(0);
   size_t best_k = 0;
+  std::vector<double> load(std::max<size_t>(1, lanes), 0.0);
+  double spent = 0;
   for (size_t k = 1; k <= big.size(); k++) {
     const double len = (double)src_len[big[k - 1]];
-    spent += many_warp_fixed_ms + len / many_warp_bytes_per_ms;
+    double &l = *std::min_element(load.begin(), load.end());
+    l += many_warp_fixed_ms + len / many_warp_bytes_per_ms;
+    spent = std::max(spent, l);
     rest_bytes -= len;
-    if (spent >= best) break;  // (the sum only grows)
+    if (spent >= best) break;  // (it only grows)
     const double t = spent + (k == n ? 0.0 : one_warp_kernel_ms(k));
     if (t < best) { best = t; best_k = k; }
   }
   for (size_t k = 0; k < best_k; k++) take[big[k]] = 1;
+}
+
+// Lanes of the many-warp decoder: how many large streams are decoded at a time (host threads with a sub-context each).
+// ZIPC_B200_PAR_LANES (default: by the cores this process can count on, 2 .. 12; 1 = one stream after the other).
+static size_t par_lane_count() {
+  static const size_t v = [] {
+    int ndev = 1;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) ndev = 1;
+    const uint64_t cores = std::max(1u, std::thread::hardware_concurrency());
+    const uint64_t automatic = std::min<uint64_t>(12, std::max<uint64_t>(2, cores / (uint64_t)ndev));
+    return (size_t)std::min<uint64_t>(std::max<uint64_t>(1, env_u64("ZIPC_B200_PAR_LANES", automatic)), 32);
+  }();
+  return v;
+}
+static zipc_b200_mctx *par_lanes(zipc_b200_ctx *ctx, size_t lanes) {
+  if (!ctx->par_pool) {
+    if (pipeline_create(ctx->device, (int)lanes, &ctx->par_pool) != ZIPC_OK) { ctx->par_pool = nullptr; return nullptr; }
+  }
+  return ctx->par_pool;
 }
 
 static bool par_debug() { static const bool v = env_u64("ZIPC_B200_PAR_DEBUG", 0) != 0; return v; }
@@ -625,29 +650,73 @@ int inflate_core(zipc_b200_ctx *ctx, int ck, int adler_mode, size_t n, const std
   std::vector<char> done(n, 0);
   size_t ndone = 0;
   if (flags == 0 && ck != ZIPC_CK_ADLER32 && par_min_bytes() != 0 && !(plan && plan->ngroups)) {  // (Adler-32 is folded block by block: serial path)
+    const size_t lanes = ctx->is_sub ? 1 : par_lane_count();
     std::vector<char> take;
-    par_select(n, src_len, take);
-    for (size_t i = 0; i < n; i++) {
-      if (!take[i]) continue;
+    par_select(n, src_len, take, lanes);
+    std::vector<uint32_t> sel;
+    for (size_t i = 0; i < n; i++) if (take[i]) sel.push_back((uint32_t)i);
+    // one stream through the many-warp decoder, on context c (ctx itself, or one of its lanes)
+    auto one = [&](zipc_b200_ctx *c, uint32_t i, uint64_t &streams, uint64_t &fallbacks) -> int {
       bool ok = false;
-      if (int st = par_speculate(ctx, d_src[i], src_len[i], &ok)) return st;
-      const uint64_t total = ctx->par_plan.total;
+      if (int st = par_speculate(c, d_src[i], src_len[i], &ok)) return st;
+      const uint64_t total = c->par_plan.total;
       if (ok && cap[i] != ZIPC_SIZE_UNKNOWN && total > cap[i]) ok = false;  // the serial decoder reports the exact error
       if (ok && !count_only) {
-        if (int st = par_resolve(ctx, d_dst[i], &ok)) return st;
+        if (int st = par_resolve(c, d_dst[i], &ok)) return st;
         if (ok && checksum) {
           checksum[i] = 0;
           if (ck == ZIPC_CK_CRC32) {
-            uint32_t *d_crc = ctx->d_small.as<uint32_t>() + 32;
-            if (int st = crc32_launch_buffer(ctx, d_dst[i], total, d_crc)) return st;
-            ZB_CUDA(ctx, cudaMemcpyAsync(&checksum[i], d_crc, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
-            ZB_CUDA(ctx, stream_sync(ctx, ctx->stream));
+            uint32_t *d_crc = c->d_small.as<uint32_t>() + 32;
+            if (int st = crc32_launch_buffer(c, d_dst[i], total, d_crc)) return st;
+            ZB_CUDA(c, cudaMemcpyAsync(&checksum[i], d_crc, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+            ZB_CUDA(c, stream_sync(c, c->stream));
           }
         }
       }
-      if (ok) { done[i] = 1; ndone++; status[i] = ZIPC_OK; out_len[i] = (size_t)total; ctx->par_streams++; }
-      else ctx->par_fallbacks++;
+      if (ok) { done[i] = 1; status[i] = ZIPC_OK; out_len[i] = (size_t)total; streams++; }
+      else fallbacks++;
+      return ZIPC_OK;
+    };
+    zipc_b200_mctx *pool = sel.size() >= 2 && lanes >= 2 ? par_lanes(ctx, lanes) : nullptr;
+    if (!pool) {
+      for (uint32_t i : sel) if (int st = one(ctx, i, ctx->par_streams, ctx->par_fallbacks)) return st;
+    } else {
+      // Several streams at a time: lane k is a host thread with a sub-context (stream, scratch arenas) of its own.  The streams
+      // are dealt out largest first, each to the lane with the least compressed bytes so far (the same deal in the sizing pass and
+      // in the real pass of a call without sizes).  The lanes' streams start behind everything queued on ctx's stream -- the
+      // upload -- and every lane has waited for its own work when its thread ends.
+      const size_t L = std::min(lanes, sel.size());
+      std::vector<uint32_t> order(sel);
+      std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return src_len[a] > src_len[b]; });
+      std::vector<std::vector<uint32_t>> mine(L);
+      std::vector<uint64_t> load(L, 0);
+      for (uint32_t i : order) {
+        const size_t k = (size_t)(std::min_element(load.begin(), load.end()) - load.begin());
+        mine[k].push_back(i);
+        load[k] += src_len[i] + (1u << 20);
+      }
+      if (ctx->upload_split_live) { ZB_CUDA(ctx, cudaStreamSynchronize(ctx->upload_stream)); ctx->upload_split_live = false; }
+      if (!ctx->ev_lanes) ZB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_lanes, cudaEventDisableTiming));
+      ZB_CUDA(ctx, cudaEventRecord(ctx->ev_lanes, ctx->stream));
+      std::vector<int> rc(L, ZIPC_OK);
+      std::vector<uint64_t> ns(L, 0), nf(L, 0);
+      std::vector<std::thread> th;
+      auto lane = [&](size_t k) {
+        zipc_b200_ctx *c = zipc_b200_mctx_ctx(pool, (int)k);
+        cudaSetDevice(ctx->device);
+        c->epoch = ctx->epoch;  // (the input's epoch: a plan cached in the sizing pass of this call serves its real pass, and no other call's)
+        if (cudaError_t e = cudaStreamWaitEvent(c->stream, ctx->ev_lanes, 0)) { rc[k] = set_cuda_error(c, e, "cudaStreamWaitEvent(lane)"); return; }
+        for (uint32_t i : mine[k]) if ((rc[k] = one(c, i, ns[k], nf[k])) != ZIPC_OK) return;
+      };
+      for (size_t k = 1; k < L; k++) th.emplace_back(lane, k);
+      lane(0);
+      for (auto &t : th) t.join();
+      for (size_t k = 0; k < L; k++) {
+        ctx->par_streams += ns[k]; ctx->par_fallbacks += nf[k];
+        if (rc[k]) { ctx->last_error = zipc_b200_last_error(zipc_b200_mctx_ctx(pool, (int)k)); return rc[k]; }
+      }
     }
+    for (size_t i = 0; i < n; i++) ndone += done[i] != 0;
   }
   if (ndone == 0) return inflate_serial_core(ctx, ck, adler_mode, n, d_src, src_len, d_dst, cap, count_only, out_len, checksum, status, flags, plan);
   if (ndone == n) return ZIPC_OK;
@@ -797,7 +866,9 @@ int zipc_b200_ctx_create(int device, zipc_b200_ctx **out) {
 void zipc_b200_ctx_destroy(zipc_b200_ctx *ctx) {
   if (!ctx) return;
   if (ctx->pipe) { zipc_b200_mctx_destroy(ctx->pipe); ctx->pipe = nullptr; }
+  if (ctx->par_pool) { zipc_b200_mctx_destroy(ctx->par_pool); ctx->par_pool = nullptr; }
   cudaSetDevice(ctx->device);
+  if (ctx->ev_lanes) cudaEventDestroy(ctx->ev_lanes);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   ctx->d_in.release(); ctx->d_out.release(); ctx->d_desc.release(); ctx->d_res.release();
   ctx->d_scratch.release(); ctx->d_scratch2.release(); ctx->d_small.release(); ctx->d_slots.release(); ctx->d_desc2.release(); ctx->d_blk.release();
@@ -818,7 +889,7 @@ void zipc_b200_ctx_destroy(zipc_b200_ctx *ctx) {
 
 const char *zipc_b200_last_error(const zipc_b200_ctx *ctx) { return ctx ? ctx->last_error.c_str() : ""; }
 void *zipc_b200_ctx_stream(zipc_b200_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
-uint64_t zipc_b200_ctx_launches(const zipc_b200_ctx *ctx) { return ctx ? ctx->launches : 0; }
+uint64_t zipc_b200_ctx_launches(const zipc_b200_ctx *ctx) { return ctx ? ctx->launches + (ctx->par_pool ? pipeline_launches(ctx->par_pool) : 0) : 0; }
 uint64_t zipc_b200_ctx_counter(const zipc_b200_ctx *ctx, int which) {
   if (!ctx) return 0;
   return which == 0 ? ctx->launches : which == 1 ? ctx->par_streams : which == 2 ? ctx->par_fallbacks : 0;

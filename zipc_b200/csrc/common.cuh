@@ -178,6 +178,8 @@ struct zipc_b200_ctx {
   bool gate_passed = false;
   bool is_sub = false;
   struct zipc_b200_mctx *pipe = nullptr;
+  struct zipc_b200_mctx *par_pool = nullptr;   // lanes of the many-warp inflate: sub-contexts that decode large streams side by side
+  cudaEvent_t ev_lanes = nullptr;              // "everything queued on `stream` so far" for the lanes' streams to wait on
 
   // results of the last batch call kept for zipc_b200_fetch()
   std::vector<size_t> last_off, last_len;
