@@ -698,6 +698,9 @@ int inflate_core(zipc_b200_ctx *ctx, int ck, int adler_mode, size_t n, const std
       if (ctx->upload_split_live) { ZB_CUDA(ctx, cudaStreamSynchronize(ctx->upload_stream)); ctx->upload_split_live = false; }
       if (!ctx->ev_lanes) ZB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_lanes, cudaEventDisableTiming));
       ZB_CUDA(ctx, cudaEventRecord(ctx->ev_lanes, ctx->stream));
+      double sel_bytes = 0;
+      for (uint32_t i : sel) sel_bytes += (double)src_len[i];
+      const double active_bytes = std::max(1.0, sel_bytes * (double)L / (double)sel.size());  // (L of the sel.size() streams at a time)
       std::vector<int> rc(L, ZIPC_OK);
       std::vector<uint64_t> ns(L, 0), nf(L, 0);
       std::vector<std::thread> th;
@@ -706,7 +709,12 @@ int inflate_core(zipc_b200_ctx *ctx, int ck, int adler_mode, size_t n, const std
         cudaSetDevice(ctx->device);
         c->epoch = ctx->epoch;  // (the input's epoch: a plan cached in the sizing pass of this call serves its real pass, and no other call's)
         if (cudaError_t e = cudaStreamWaitEvent(c->stream, ctx->ev_lanes, 0)) { rc[k] = set_cuda_error(c, e, "cudaStreamWaitEvent(lane)"); return; }
-        for (uint32_t i : mine[k]) if ((rc[k] = one(c, i, ns[k], nf[k])) != ZIPC_OK) return;
+        for (uint32_t i : mine[k]) {
+          // this stream's share of the SMs for its speculative decode (a CTA of that kernel owns its SM): by its size among the
+          // streams that are under way at the same time
+          c->sm_share = (uint32_t)std::min<double>(ctx->sm_count, std::max(2.0, ctx->sm_count * (double)src_len[i] / active_bytes));
+          if ((rc[k] = one(c, i, ns[k], nf[k])) != ZIPC_OK) return;
+        }
       };
       for (size_t k = 1; k < L; k++) th.emplace_back(lane, k);
       lane(0);

@@ -179,6 +179,7 @@ struct zipc_b200_ctx {
   bool is_sub = false;
   struct zipc_b200_mctx *pipe = nullptr;
   struct zipc_b200_mctx *par_pool = nullptr;   // lanes of the many-warp inflate: sub-contexts that decode large streams side by side
+  uint32_t sm_share = 0;                       // a lane: the SMs its speculative decode spreads over (0 = all)
   cudaEvent_t ev_lanes = nullptr;              // "everything queued on `stream` so far" for the lanes' streams to wait on
 
   // results of the last batch call kept for zipc_b200_fetch()
