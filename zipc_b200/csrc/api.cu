@@ -658,11 +658,14 @@ int inflate_core(zipc_b200_ctx *ctx, int ck, int adler_mode, size_t n, const std
     // one stream through the many-warp decoder, on context c (ctx itself, or one of its lanes)
     auto one = [&](zipc_b200_ctx *c, uint32_t i, uint64_t &streams, uint64_t &fallbacks) -> int {
       bool ok = false;
-      if (int st = par_speculate(c, d_src[i], src_len[i], &ok)) return st;
+      if (int st = par_speculate(c, d_src[i], src_len[i], &ok)) {
+        if (st != ZIPC_ERR_NOMEM) return st;
+        ok = false;  // no room for this stream's symbols (24 x its compressed size): the one-warp decoder needs none
+      }
       const uint64_t total = c->par_plan.total;
       if (ok && cap[i] != ZIPC_SIZE_UNKNOWN && total > cap[i]) ok = false;  // the serial decoder reports the exact error
       if (ok && !count_only) {
-        if (int st = par_resolve(c, d_dst[i], &ok)) return st;
+        if (int st = par_resolve(c, d_dst[i], &ok)) { if (st != ZIPC_ERR_NOMEM) return st; ok = false; }
         if (ok && checksum) {
           checksum[i] = 0;
           if (ck == ZIPC_CK_CRC32) {
@@ -685,9 +688,20 @@ int inflate_core(zipc_b200_ctx *ctx, int ck, int adler_mode, size_t n, const std
       // are dealt out largest first, each to the lane with the least compressed bytes so far (the same deal in the sizing pass and
       // in the real pass of a call without sizes).  The lanes' streams start behind everything queued on ctx's stream -- the
       // upload -- and every lane has waited for its own work when its thread ends.
-      const size_t L = std::min(lanes, sel.size());
       std::vector<uint32_t> order(sel);
       std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return src_len[a] > src_len[b]; });
+      // every lane keeps the 16-bit symbols of its stream (room for a 24-fold expansion) and two window maps per chunk: as many
+      // lanes as fit half of the free device memory with the largest streams on them
+      size_t L = std::min(lanes, sel.size());
+      {
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); free_b = 8ull << 30; }
+        auto lane_bytes = [&](uint32_t i) { return 64.0 * (double)src_len[i] + (64u << 20); };
+        double need = 0;
+        size_t fit = 0;
+        while (fit < L && need + lane_bytes(order[fit]) <= 0.5 * (double)free_b) need += lane_bytes(order[fit++]);
+        L = std::max<size_t>(1, fit);
+      }
       std::vector<std::vector<uint32_t>> mine(L);
       std::vector<uint64_t> load(L, 0);
       for (uint32_t i : order) {
