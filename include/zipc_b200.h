@@ -149,6 +149,11 @@ int zipc_b200_inflate_batch(zipc_b200_ctx *ctx, int checksum_kind, int adler_mod
                             const void *const *src, const size_t *src_len, const size_t *max_out,
                             void *dst, size_t dst_cap, size_t *dst_need,
                             size_t *dst_off, size_t *dst_len, uint32_t *checksum, int *status);
+/* Which streams of an inflate batch are decoded by many warps each, a few at a time (many_warp[i] = 1), and which by one warp
+ * each, all side by side (0): the host-side decision of zipc_b200_inflate_batch (a cost model over the compressed sizes; see
+ * DESIGN.md 4.6), exposed for tests and capacity planning.  lanes = streams decoded at a time (0: 12).  Host only, no device
+ * needed.  Either way the results are the reference's (zipc_deflate.ml:593-616, 692-709); only the time differs. */
+void zipc_b200_inflate_plan(size_t n, const size_t *src_len, size_t lanes, char *many_warp);
 /* Copy the outputs of the last batch call out of the ctx (after ZIPC_ERR_DST_TOO_SMALL). */
 int zipc_b200_fetch(zipc_b200_ctx *ctx, void *dst, size_t dst_cap);
 /* Device-resident form: streams live in one device buffer d_src at src_off[i]; outputs are

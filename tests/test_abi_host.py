@@ -185,3 +185,35 @@ def test_synth_generators_are_deterministic():
     assert r[:8].tobytes() == np.array([0x975835DE1C9756CE], dtype=np.uint64).tobytes() or r.size == 1000
     s = synth.member_sizes(1000)
     assert s.min() >= 4096 and s.max() <= 4096 + 258048
+
+
+def _plan(lens, lanes=12):
+    L = _lib.lib()
+    n = len(lens)
+    arr = (C.c_size_t * max(n, 1))(*lens)
+    out = C.create_string_buffer(max(n, 1))
+    L.zipc_b200_inflate_plan(n, arr, lanes, out)
+    return [out.raw[i] for i in range(n)]
+
+
+def test_inflate_plan_many_warp_or_one_warp(monkeypatch):
+    """Host logic of the inflate batch calls (api.cu par_select): the many-warp decoder takes a few streams at a time at ~4.5 ms
+    each, the one-warp decoder all streams side by side at ~12 KB of compressed data per ms and stream."""
+    monkeypatch.delenv("ZIPC_B200_PAR_MIN", raising=False)
+    KiB, MiB = 1 << 10, 1 << 20
+    assert _plan([]) == []
+    assert _plan([20 * KiB] * 100) == [0] * 100                      # small members: never
+    assert _plan([91 * KiB]) == [1]                                   # one mid-sized stream alone: 7.7 ms on one warp, ~4 ms on many
+    assert _plan([91 * KiB] * 16) == [0] * 16                         # sixteen of them: side by side is as fast
+    assert _plan([360 * KiB] * 16) == [1] * 16                        # 1 MiB streams: 30 ms on one warp each, two rounds on twelve lanes
+    assert _plan([360 * KiB] * 148) == [0] * 148                      # hundreds: side by side (30 ms) beats thirteen rounds
+    silesia = [10192446, 51220480, 9970564, 33553445, 6152192, 10085684, 6627202, 21606400, 7251944, 41458703, 5345280, 8474240]
+    assert _plan([s * 35 // 100 for s in silesia]) == [1] * 12        # the reference's benchmark shape: every member
+    mix = [30 * KiB] * 5000 + [8 * MiB] + [40 * KiB] * 5000 + [3 * MiB]
+    got = _plan(mix)
+    assert got[5000] == 1 and got[-1] == 1 and sum(got) == 2          # two large streams in a batch of small ones
+    assert _plan([360 * KiB] * 16, lanes=1) == [0] * 16               # one lane: one after the other does not pay
+    monkeypatch.setenv("ZIPC_B200_PAR_MIN", "100000")                 # a set threshold is taken as it is
+    assert _plan([91 * KiB, 200 * KiB, 99 * KiB]) == [0, 1, 1]
+    monkeypatch.setenv("ZIPC_B200_PAR_MIN", "0")
+    assert _plan([8 * MiB]) == [0]

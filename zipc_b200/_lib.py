@@ -34,7 +34,7 @@ EXPORTS = [
     "zipc_b200_deflate_batch", "zipc_b200_deflate_batch_dev", "zipc_b200_deflate_bound",
     "zipc_b200_zlib_compress_batch", "zipc_b200_deflate_segmented", "zipc_b200_deflate_primed", "zipc_b200_inflate_segmented", "zipc_b200_ptime_to_dos", "zipc_b200_ptime_of_dos", "zipc_b200_zip_parse",
     "zipc_b200_zip_encoding_size", "zipc_b200_zip_assemble", "zipc_b200_zip_extract_batch",
-    "zipc_b200_zip_parse_ex", "zipc_b200_zip_encoding_size_ex", "zipc_b200_zip_assemble_ex",
+    "zipc_b200_zip_parse_ex", "zipc_b200_zip_encoding_size_ex", "zipc_b200_zip_assemble_ex", "zipc_b200_inflate_plan",
     "zipc_b200_zip_deflate_archive", "zipc_b200_free", "zipc_b200_synth_text", "zipc_b200_synth_rand",
     "zipc_b200_mctx_create", "zipc_b200_mctx_destroy", "zipc_b200_mctx_device_count", "zipc_b200_mctx_ctx",
     "zipc_b200_mctx_last_error", "zipc_b200_multi_crc32", "zipc_b200_multi_inflate_batch",
@@ -98,6 +98,7 @@ def _declare(L):
         "zipc_b200_zip_parse": (i32, [vp, sz, P(P(Member)), szp]),
         "zipc_b200_zip_encoding_size": (u64, [P(Member), sz]),
         "zipc_b200_zip_assemble": (i32, [P(Member), sz, C.c_char_p, vp, sz, szp]),
+        "zipc_b200_inflate_plan": (None, [sz, szp, sz, C.c_char_p]),
         "zipc_b200_zip_parse_ex": (i32, [vp, sz, C.c_uint, P(P(Member)), szp]),
         "zipc_b200_zip_encoding_size_ex": (u64, [P(Member), sz, C.c_char_p, C.c_uint]),
         "zipc_b200_zip_assemble_ex": (i32, [P(Member), sz, C.c_char_p, C.c_uint, vp, sz, szp]),

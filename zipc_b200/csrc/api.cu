@@ -859,6 +859,14 @@ using namespace zb;
 
 extern "C" {
 
+// The host-side decision of the inflate entry points, for tests and capacity planning (no device needed).
+void zipc_b200_inflate_plan(size_t n, const size_t *src_len, size_t lanes, char *many_warp) {
+  if (!many_warp || (!src_len && n)) return;
+  std::vector<char> take;
+  par_select(n, src_len, take, lanes ? lanes : 12);
+  for (size_t i = 0; i < n; i++) many_warp[i] = take[i];
+}
+
 int zipc_b200_device_count(void) {
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
