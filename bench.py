@@ -467,7 +467,7 @@ def run_stream_c1(h: Harness):
         res["seg_%dk" % (seg >> 10)] = {"deflate_e2e_GBps": round(data.size / td / 1e9, 3), "inflate_e2e_GBps": round(data.size / ti / 1e9, 3),
                                        "ratio": round(n.value / data.size, 4), "segments": int(nseg.value)}
     # the reference's own call shape: ONE payload through the batch entry (n = 1).  A member this large is split into primed
-    # 256 KiB segments, one CTA each (no window reset: the ratio of a single-CTA stream), and decoded as a foreign stream
+    # segments of 64 - 256 KiB, one CTA each (no window reset: the ratio of a single-CTA stream), and decoded as a foreign stream
     ptr1 = (C.c_void_p * 1)(data.ctypes.data); ln1 = (C.c_size_t * 1)(data.size)
     need1 = C.c_size_t(); off1 = (C.c_size_t * 1)(); ol1 = (C.c_size_t * 1)(); ck1 = (C.c_uint32 * 1)(); st1 = (C.c_int * 1)()
     pfn = lambda: L.zipc_b200_deflate_batch(h.ctx.h, 2, 2, 0, 1, ptr1, ln1, cbuf.ctypes.data, cbuf.size, C.byref(need1), off1, ol1, ck1, st1)
@@ -485,7 +485,7 @@ def run_stream_c1(h: Harness):
     tq = (time.perf_counter() - t0) / 3
     res["one_member_batch_call"] = {"deflate_e2e_GBps": round(data.size / tp / 1e9, 3), "inflate_e2e_GBps": round(data.size / tq / 1e9, 3),
                                     "ratio": round(plen / data.size, 4),
-                                    "note": "zipc_b200_deflate_batch / zipc_b200_inflate_batch with n = 1: the member is split into primed 256 KiB segments "
+                                    "note": "zipc_b200_deflate_batch / zipc_b200_inflate_batch with n = 1: the member is split into primed segments of 64 - 256 KiB "
                                             "(one CTA each, no ratio loss); the stream is decoded by many warps without an index"}
     # the same data as ONE foreign stream (zlib -6, no index): intra-stream parallel inflate
     zs = zlib.compress(data.tobytes(), 6)[2:-4]
@@ -545,7 +545,7 @@ def run_few_large(h: Harness):
             "members": n, "uncompressed_bytes": total, "inflate_e2e_GBps": round(total / ti / 1e9, 3), "deflate_e2e_GBps": round(total / td / 1e9, 3),
             "zlib6_compressed_bytes": zo_, "deflate_ratio": round(csum / total, 4),
             "note": "every large stream is decoded by many warps (block-start search + speculation), several streams at a time; "
-                    "every member is compressed by one CTA per primed 256 KiB segment"}
+                    "every member is compressed by one CTA per primed segment (64 - 256 KiB, whole waves over the SMs)"}
 
 
 def run_stream_c5(h: Harness, synth, rank, world, dist, torch, local, slice_bytes=512 << 20, seg=256 << 10):

@@ -178,7 +178,7 @@ int zipc_b200_zlib_decompress_batch(zipc_b200_ctx *ctx, int adler_mode, size_t n
  * Zipc.File.deflate_of_binary_string (zipc.ml:179-185).  Output streams are valid RFC 1951 and
  * inflate to the input bit-exactly with the reference's inflate; they are not byte-identical to
  * the reference's streams (ratio tolerance per level).
- * One member is compressed by one CTA; a member of 2 MiB or more (ZIPC_B200_SPLIT_MIN) by one CTA per 256 KiB segment,
+ * One member is compressed by one CTA; a member of 2 MiB or more (ZIPC_B200_SPLIT_MIN) by one CTA per segment of 64 - 256 KiB,
  * each primed with the 32 KiB before it: still one ordinary stream, 5 bytes per segment larger (not when Adler-32 is
  * asked for: the reference folds it per deflate block).
  * Arena conventions as for zipc_b200_inflate_batch. */

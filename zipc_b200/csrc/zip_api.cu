@@ -199,12 +199,12 @@ int compact(zipc_b200_ctx *ctx, size_t n, const std::vector<uint8_t *> &d_slot, 
 }
 
 // ---- large members over several CTAs -------------------------------------------------------------------------------------
-// A member of ZIPC_B200_SPLIT_MIN bytes or more (default 2 MiB; 0 = never) is compressed as primed segments of 256 KiB, one
+// A member of ZIPC_B200_SPLIT_MIN bytes or more (default 2 MiB; 0 = never) is compressed as primed segments of 64 - 256 KiB, one
 // CTA each: every segment but the last ends with a byte-aligning empty stored block, every segment but the first sees the
 // 32 KiB of input before it, so the concatenation is ONE ordinary RFC 1951 stream, 5 bytes per segment larger than the
 // member compressed by a single CTA -- which would have one SM to itself (~90 MB/s).  Not with Adler-32: the reference
 // folds it per deflate block over a re-packed state, and the blocks of a split member are not those of a whole one.
-constexpr size_t kSplitSegment = 256u << 10;
+constexpr size_t kSplitSegment = 256u << 10, kSplitSegmentMin = 64u << 10;
 struct Pieces {
   std::vector<uint32_t> member;          // piece -> member
   std::vector<uint8_t *> d_slot;         // piece -> where the kernel wrote it
@@ -219,13 +219,25 @@ int deflate_members(zipc_b200_ctx *ctx, int level, int ck, int adler_mode, size_
   std::vector<uint32_t> e_flags;
   pc.member.clear();
   bool any_split = false;
+  // The segment size follows the work: the large members' bytes over the SMs in whole waves (64 MiB on 148 SMs: 293 segments of
+  // 224 KiB = two full waves instead of 256 of 256 KiB = one and three quarters), and never fewer segments than SMs while a
+  // segment stays at 64 KiB or more (a 5 MiB member: 80 segments side by side, not 20).
+  size_t seg_bytes = kSplitSegment;
+  if (may_split) {
+    uint64_t split_bytes = 0;
+    for (size_t i = 0; i < n; i++) if (src_len[i] >= split_min) split_bytes += src_len[i];
+    const uint64_t sms = (uint64_t)std::max(1, ctx->sm_count);
+    const uint64_t waves = std::max<uint64_t>(1, (split_bytes + kSplitSegment * sms - 1) / (kSplitSegment * sms));
+    const uint64_t even = (split_bytes + waves * sms - 1) / (waves * sms);
+    seg_bytes = (size_t)std::min<uint64_t>(kSplitSegment, std::max<uint64_t>(kSplitSegmentMin, (even + 4095) & ~4095ull));
+  }
   for (size_t i = 0; i < n; i++) {
     if (!may_split || src_len[i] < split_min) { e_src.push_back(d_src[i]); e_len.push_back(src_len[i]); e_flags.push_back(0u); pc.member.push_back((uint32_t)i); continue; }
     any_split = true;
-    const size_t nseg = (src_len[i] + kSplitSegment - 1) / kSplitSegment;
+    const size_t nseg = (src_len[i] + seg_bytes - 1) / seg_bytes;
     for (size_t k = 0; k < nseg; k++) {
-      e_src.push_back(d_src[i] + k * kSplitSegment);
-      e_len.push_back(std::min(kSplitSegment, src_len[i] - k * kSplitSegment));
+      e_src.push_back(d_src[i] + k * seg_bytes);
+      e_len.push_back(std::min(seg_bytes, src_len[i] - k * seg_bytes));
       e_flags.push_back((k + 1 < nseg ? kDeflateNotFinal : 0u) | (k ? (uint32_t)(32768 / kDeflatePrimeTile) << kDeflatePrimeShift : 0u));
       pc.member.push_back((uint32_t)i);
     }
