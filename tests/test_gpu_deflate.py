@@ -67,10 +67,18 @@ def _corpus():
 
 
 @pytest.mark.parametrize("level", ["fast", "default", "best"])
-def test_corpus_roundtrip_ratio_and_model_equality(ctx, level):
+def test_corpus_roundtrip_ratio_and_model_equality(ctx, level, monkeypatch):
     corpus = _corpus()
     names = list(corpus)
+    # (the host model is the one-CTA encoder: no member of this thin batch is to be split into primed segments here)
+    monkeypatch.setenv("ZIPC_B200_SPLIT_MIN", str(1 << 40))
     res = ctx.deflate_batch([corpus[k] for k in names], level, _lib.CK_CRC32)
+    monkeypatch.delenv("ZIPC_B200_SPLIT_MIN")
+    # the same batch as a caller gets it: "text_big" (700 KB in a batch that does not fill the GPU) goes over several CTAs
+    for k, (st, cs, crc), (_, one, _) in zip(names, ctx.deflate_batch([corpus[k] for k in names], level, _lib.CK_CRC32), res):
+        assert st == 0 and crc == zo.crc32(corpus[k]) and zlib.decompress(cs.tobytes(), -15) == corpus[k], k
+        assert len(cs) <= len(one) * 1.002 + 8 * 16, k
+        assert (len(cs) != len(one)) == (len(corpus[k]) >= (320 << 10)), k
     zo.set_keep_codelen_freqs(False)
     try:
         for k, (st, cs, crc) in zip(names, res):
@@ -270,7 +278,7 @@ def test_primed_segments_lose_no_ratio(ctx, level):
     assert d.decompress(bytes(piece)) == s[:300_000] and not d.eof
 
 
-def test_large_members_are_split_over_ctas(ctx):
+def test_large_members_are_split_over_ctas(ctx, monkeypatch):
     """A member of 2 MiB or more is compressed as primed 256 KiB segments, one CTA each (Zipc.File.deflate_of_binary_string of
     one big payload must not be left to a single SM): still ONE ordinary stream per member, CRC-32 of the whole member,
     5 bytes per segment larger than the one-CTA result at most, and much faster."""
@@ -287,9 +295,15 @@ def test_large_members_are_split_over_ctas(ctx):
                 assert zo.inflate(bytes(cs)) == d
         # against the same member compressed by one CTA (below the threshold: the first 2 MiB - 1 of it, scaled)
         d = big[0]
+        monkeypatch.setenv("ZIPC_B200_SPLIT_MIN", str(1 << 40))   # (one CTA for the comparison)
         one = ctx.deflate_batch([d[:(2 << 20) - 1]], level, 0)[0][1]
+        monkeypatch.delenv("ZIPC_B200_SPLIT_MIN")
         split = res[1][1]
         assert len(split) / len(d) <= len(one) / ((2 << 20) - 1) * 1.01
+        # a thin batch splits from 256 KiB on: the same bytes within 5 bytes per segment of the one-CTA stream
+        again = ctx.deflate_batch([d[:(2 << 20) - 1]], level, _lib.CK_CRC32)[0]
+        assert again[0] == 0 and again[2] == zlib.crc32(d[:(2 << 20) - 1]) and zlib.decompress(bytes(again[1]), -15) == d[:(2 << 20) - 1]
+        assert len(one) < len(again[1]) <= len(one) * 1.002 + 8 * 32
     # one 64 MiB payload: seconds on one SM, milliseconds on all of them
     huge = synth.text_v1(5, 64 << 20)
     ctx.deflate_batch([huge], "default", _lib.CK_CRC32)

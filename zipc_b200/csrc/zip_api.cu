@@ -199,7 +199,7 @@ int compact(zipc_b200_ctx *ctx, size_t n, const std::vector<uint8_t *> &d_slot, 
 }
 
 // ---- large members over several CTAs -------------------------------------------------------------------------------------
-// A member of ZIPC_B200_SPLIT_MIN bytes or more (default 2 MiB; 0 = never) is compressed as primed segments of 64 - 256 KiB, one
+// A member of ZIPC_B200_SPLIT_MIN bytes or more (default 2 MiB, 320 KiB in a thin batch; 0 = never) is compressed as primed segments of 64 - 256 KiB, one
 // CTA each: every segment but the last ends with a byte-aligning empty stored block, every segment but the first sees the
 // 32 KiB of input before it, so the concatenation is ONE ordinary RFC 1951 stream, 5 bytes per segment larger than the
 // member compressed by a single CTA -- which would have one SM to itself (~90 MB/s).  Not with Adler-32: the reference
@@ -212,7 +212,14 @@ struct Pieces {
 };
 int deflate_members(zipc_b200_ctx *ctx, int level, int ck, int adler_mode, size_t n, const std::vector<const uint8_t *> &d_src,
                     const size_t *src_len, size_t *out_len, uint32_t *checksum, int *status, Pieces &pc) {
-  static const uint64_t split_min = [] { const char *e = std::getenv("ZIPC_B200_SPLIT_MIN"); return e && *e ? std::strtoull(e, nullptr, 10) : (2ull << 20); }();
+  // smallest member that is split: 2 MiB in a batch that fills the GPU with whole members anyway, 320 KiB in a thin one (fewer
+  // members than two per SM: a 1.9 MiB member alone would sit on one SM for 21 ms).  ZIPC_B200_SPLIT_MIN, when set, is taken as
+  // it is (read on every call, so that tests can vary it).
+  const uint64_t split_min = [&]() -> uint64_t {
+    const char *e = std::getenv("ZIPC_B200_SPLIT_MIN");
+    if (e && *e) return std::strtoull(e, nullptr, 10);
+    return !ctx->is_sub && n < 2 * (size_t)std::max(1, ctx->sm_count) ? (320ull << 10) : (2ull << 20);  // (a sub-context's batch is a part of a large one)
+  }();
   const bool may_split = split_min && level != ZIPC_LEVEL_NONE && ck != ZIPC_CK_ADLER32;
   std::vector<const uint8_t *> e_src;
   std::vector<size_t> e_len;
