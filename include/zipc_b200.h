@@ -179,8 +179,9 @@ int zipc_b200_zlib_decompress_batch(zipc_b200_ctx *ctx, int adler_mode, size_t n
  * inflate to the input bit-exactly with the reference's inflate; they are not byte-identical to
  * the reference's streams (ratio tolerance per level).
  * One member is compressed by one CTA; a member of 2 MiB or more (ZIPC_B200_SPLIT_MIN) by one CTA per segment of 64 - 256 KiB,
- * each primed with the 32 KiB before it: still one ordinary stream, 5 bytes per segment larger (not when Adler-32 is
- * asked for: the reference folds it per deflate block).
+ * each primed with the 32 KiB before it: still one ordinary stream, 5 bytes per segment larger.  Adler-32 (this call with
+ * ZIPC_CK_ADLER32, zipc_b200_zlib_compress_batch) is then folded over the blocks of all segments in stream order, which is what the
+ * reference's zlib_decompress recomputes from the stream.
  * Arena conventions as for zipc_b200_inflate_batch. */
 int zipc_b200_deflate_batch(zipc_b200_ctx *ctx, int level, int checksum_kind, int adler_mode,
                             size_t n, const void *const *src, const size_t *src_len,

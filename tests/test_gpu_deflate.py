@@ -147,6 +147,30 @@ def test_zlib_compress_ref_compat_round_trips_through_the_reference(ctx, level):
         assert st == 0 and ad == zlib.adler32(corpus[k]) and zlib.decompress(zs.tobytes()) == corpus[k], k
 
 
+def test_zlib_compress_of_large_payloads_is_split_and_still_the_references_adler(ctx):
+    """A large payload is compressed as primed segments, one CTA each, under the zlib framing too: the trailer is the Adler-32
+    folded over the blocks of all segments in stream order -- what the reference's zlib_decompress recomputes from the stream
+    (on data where its signed remainder differs from RFC 1950) -- and the call takes milliseconds, not the ~35 ms per 3 MiB of
+    one CTA."""
+    import time
+    t = np.frombuffer(synth.text_v1(23, 3 << 20).tobytes(), dtype=np.uint8)
+    big = (t | 0x80).tobytes()[:-777] + b"\xff" * 100_000 + synth.rand_v1(24, 50_001).tobytes()
+    for level in ("fast", "default"):
+        (st, zs, ad), = ctx.zlib_compress_batch([big], level, _lib.ADLER_REF_COMPAT)
+        zs = zs.tobytes()
+        assert st == 0 and int.from_bytes(zs[-4:], "big") == ad
+        out, found = zo.zlib_decompress(zs)              # raises on "Checksum mismatch"
+        assert out == big and found == ad and ad != zlib.adler32(big)
+        assert zd.zlib_decompress(zs).get_ok() == (big, ad)
+        (st, ds, ad2), = ctx.deflate_batch([big], level, _lib.CK_ADLER32, _lib.ADLER_REF_COMPAT)
+        assert st == 0 and ad2 == ad and ds.tobytes() == zs[2:-4]
+        (st, zs2, ad3), = ctx.zlib_compress_batch([big], level, _lib.ADLER_RFC1950)
+        assert st == 0 and ad3 == zlib.adler32(big) and zlib.decompress(zs2.tobytes()) == big
+    t0 = time.perf_counter()
+    ctx.zlib_compress_batch([big], "default", _lib.ADLER_REF_COMPAT)
+    assert time.perf_counter() - t0 < 0.02
+
+
 def test_fixture_redeflate_recode(ctx, zip_docs):  # test/test.ml:58-118 with the GPU codec in the loop
     ms = [m for m in zo.zip_decode(zip_docs)]
     out = []

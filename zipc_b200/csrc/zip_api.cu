@@ -58,7 +58,11 @@ __global__ void __launch_bounds__(256) gather_kernel(const CopyDesc *__restrict_
 int deflate_run(zipc_b200_ctx *ctx, int level, int ck, int adler_mode, size_t n,
                 const std::vector<const uint8_t *> &d_src, const size_t *src_len,
                 const std::vector<uint8_t *> &d_slot, const std::vector<size_t> &slot_cap,
-                size_t *out_len, uint32_t *checksum, int *status, const std::vector<uint32_t> *flags = nullptr) {
+                size_t *out_len, uint32_t *checksum, int *status, const std::vector<uint32_t> *flags = nullptr,
+                std::vector<uint32_t> *blocks_out = nullptr, std::vector<uint32_t> *nblocks_out = nullptr) {
+  // blocks_out / nblocks_out (Adler-32 at a compressing level only): the source lengths of the blocks every input was emitted
+  // as, input after input, and their number per input, INSTEAD of the checksums -- the caller folds them itself (the pieces of a
+  // split member are folded as the one stream they form)
   if (!n) return ZIPC_OK;
   if (n > 0xFFFFFFF0ull) return ZIPC_ERR_INVALID_ARG;
   for (size_t i = 0; i < n; i++) if (src_len[i] > 0xFFFFFFFFull) return ZIPC_ERR_INVALID_ARG;
@@ -146,6 +150,7 @@ int deflate_run(zipc_b200_ctx *ctx, int level, int ck, int adler_mode, size_t n,
       std::vector<uint32_t> lens;
       if (blocks_from_kernel) {
         for (size_t i = 0; i < n; i++) lens.insert(lens.end(), h_blk.begin() + blk_off[i], h_blk.begin() + blk_off[i] + nblk[i]);
+        if (blocks_out && nblocks_out) { *blocks_out = std::move(lens); *nblocks_out = nblk; return ZIPC_OK; }
       } else {  // level `None: stored blocks of kStoredBlock source bytes (reference :1106-1116)
         for (size_t i = 0; i < n; i++) {
           nblk[i] = 0;
@@ -202,8 +207,8 @@ int compact(zipc_b200_ctx *ctx, size_t n, const std::vector<uint8_t *> &d_slot, 
 // A member of ZIPC_B200_SPLIT_MIN bytes or more (default 2 MiB, 320 KiB in a thin batch; 0 = never) is compressed as primed segments of 64 - 256 KiB, one
 // CTA each: every segment but the last ends with a byte-aligning empty stored block, every segment but the first sees the
 // 32 KiB of input before it, so the concatenation is ONE ordinary RFC 1951 stream, 5 bytes per segment larger than the
-// member compressed by a single CTA -- which would have one SM to itself (~90 MB/s).  Not with Adler-32: the reference
-// folds it per deflate block over a re-packed state, and the blocks of a split member are not those of a whole one.
+// member compressed by a single CTA -- which would have one SM to itself (~90 MB/s).  Adler-32 (zlib_compress,
+// adler_32_and_deflate) is folded over the blocks of all pieces in stream order, as the reference's decoder will see them.
 constexpr size_t kSplitSegment = 256u << 10, kSplitSegmentMin = 64u << 10;
 struct Pieces {
   std::vector<uint32_t> member;          // piece -> member
@@ -220,7 +225,7 @@ int deflate_members(zipc_b200_ctx *ctx, int level, int ck, int adler_mode, size_
     if (e && *e) return std::strtoull(e, nullptr, 10);
     return !ctx->is_sub && n < 2 * (size_t)std::max(1, ctx->sm_count) ? (320ull << 10) : (2ull << 20);  // (a sub-context's batch is a part of a large one)
   }();
-  const bool may_split = split_min && level != ZIPC_LEVEL_NONE && ck != ZIPC_CK_ADLER32;
+  const bool may_split = split_min && level != ZIPC_LEVEL_NONE;
   std::vector<const uint8_t *> e_src;
   std::vector<size_t> e_len;
   std::vector<uint32_t> e_flags;
@@ -254,8 +259,13 @@ int deflate_members(zipc_b200_ctx *ctx, int level, int ck, int adler_mode, size_
   std::vector<uint32_t> e_ck(m);
   std::vector<int> e_st(m);
   if (int st = make_slots(ctx, m, e_len.data(), pc.d_slot, cap)) return st;
+  // Adler-32 of a split member: folded block by block over the blocks of ALL its pieces in stream order -- exactly what the
+  // reference's zlib_decompress recomputes from the concatenated stream (the empty stored blocks between the pieces fold
+  // nothing; zipc_deflate.ml:682-690, 1081-1086)
+  const bool fold_here = any_split && checksum && ck == ZIPC_CK_ADLER32;
+  std::vector<uint32_t> blk, nblk;
   if (int st = deflate_run(ctx, level, ck, adler_mode, m, e_src, e_len.data(), pc.d_slot, cap, e_out.data(), checksum ? e_ck.data() : nullptr,
-                           e_st.data(), any_split ? &e_flags : nullptr)) return st;
+                           e_st.data(), any_split ? &e_flags : nullptr, fold_here ? &blk : nullptr, fold_here ? &nblk : nullptr)) return st;
   pc.len = e_out;
   pc.rel.assign(m, 0);
   for (size_t i = 0; i < n; i++) { out_len[i] = 0; status[i] = ZIPC_OK; if (checksum) checksum[i] = 0; }
@@ -265,7 +275,13 @@ int deflate_members(zipc_b200_ctx *ctx, int level, int ck, int adler_mode, size_
     if (e_st[k] != ZIPC_OK && status[i] == ZIPC_OK) status[i] = e_st[k];
     pc.rel[k] = out_len[i];
     out_len[i] += e_out[k];
-    if (checksum) checksum[i] = first ? e_ck[k] : (ck == ZIPC_CK_CRC32 ? zipc_b200_crc32_combine(checksum[i], e_ck[k], e_len[k]) : 0u);
+    if (checksum && !fold_here) checksum[i] = first ? e_ck[k] : (ck == ZIPC_CK_CRC32 ? zipc_b200_crc32_combine(checksum[i], e_ck[k], e_len[k]) : 0u);
+  }
+  if (fold_here) {  // (the pieces of a member follow each other, so do their block lists: per member, just their number)
+    std::vector<uint32_t> member_blocks(n, 0);
+    for (size_t k = 0; k < m; k++) member_blocks[pc.member[k]] += nblk[k];
+    if (int st = adler32_blocked(ctx, d_src.data(), member_blocks.data(), blk.data(), n, adler_mode, checksum)) return st;
+    for (size_t i = 0; i < n; i++) if (status[i] != ZIPC_OK) checksum[i] = 0;
   }
   for (size_t k = 0; k < m; k++)
     if (status[pc.member[k]] != ZIPC_OK) { pc.len[k] = 0; out_len[pc.member[k]] = 0; }
@@ -369,11 +385,10 @@ int zipc_b200_zlib_compress_batch(zipc_b200_ctx *ctx, int level, int adler_mode,
   DeviceGuard g(ctx->device);
   std::vector<const uint8_t *> d_src;
   if (int st = upload_ranges(ctx, n, src, src_len, d_src)) return st;
-  std::vector<uint8_t *> d_slot;
-  std::vector<size_t> cap;
-  if (int st = make_slots(ctx, n, src_len, d_slot, cap)) return st;
   std::vector<uint32_t> ad(n);
-  if (int st = deflate_run(ctx, level, ZIPC_CK_ADLER32, adler_mode, n, d_src, src_len, d_slot, cap, dst_len, ad.data(), status)) return st;
+  Pieces pc;  // (a large payload is compressed as primed segments, one CTA each: several pieces per stream)
+  if (int st = deflate_members(ctx, level, ZIPC_CK_ADLER32, adler_mode, n, d_src, src_len, dst_len, ad.data(), status, pc)) return st;
+  const size_t np = pc.member.size();
   // framing: 2 header bytes, body, big-endian Adler-32 (reference :1264-1277).  Header and trailer bytes are placed
   // by the same device gather as the bodies (one descriptor table, one launch), so fetch() sees complete streams.
   std::vector<size_t> off(n), flen(n);
@@ -384,8 +399,8 @@ int zipc_b200_zlib_compress_batch(zipc_b200_ctx *ctx, int level, int adler_mode,
     const unsigned cmf = 0x78, hdr = (cmf << 8) | ((unsigned)level << 6), flg = (hdr + 31 - hdr % 31) & 0xFF;
     if (int st = ctx->h_res.reserve(n * 8)) return st;
     if (int st = ctx->d_res.reserve(n * 8)) return st;
-    if (int st = ctx->h_desc.reserve(3 * n * sizeof(CopyDesc))) return st;
-    if (int st = ctx->d_desc2.reserve(3 * n * sizeof(CopyDesc))) return st;
+    if (int st = ctx->h_desc.reserve((2 * n + np) * sizeof(CopyDesc))) return st;
+    if (int st = ctx->d_desc2.reserve((2 * n + np) * sizeof(CopyDesc))) return st;
     uint8_t *hb = ctx->h_res.as<uint8_t>();
     uint8_t *db = ctx->d_res.as<uint8_t>(), *dout = ctx->d_out.as<uint8_t>();
     CopyDesc *h = ctx->h_desc.as<CopyDesc>();
@@ -393,13 +408,13 @@ int zipc_b200_zlib_compress_batch(zipc_b200_ctx *ctx, int level, int adler_mode,
       hb[8 * i] = (uint8_t)cmf; hb[8 * i + 1] = (uint8_t)flg;
       hb[8 * i + 2] = (uint8_t)(ad[i] >> 24); hb[8 * i + 3] = (uint8_t)(ad[i] >> 16);
       hb[8 * i + 4] = (uint8_t)(ad[i] >> 8); hb[8 * i + 5] = (uint8_t)ad[i];
-      h[3 * i] = CopyDesc{db + 8 * i, dout + off[i], 2};
-      h[3 * i + 1] = CopyDesc{d_slot[i], dout + off[i] + 2, dst_len[i]};
-      h[3 * i + 2] = CopyDesc{db + 8 * i + 2, dout + off[i] + 2 + dst_len[i], 4};
+      h[2 * i] = CopyDesc{db + 8 * i, dout + off[i], 2};
+      h[2 * i + 1] = CopyDesc{db + 8 * i + 2, dout + off[i] + 2 + dst_len[i], 4};
     }
+    for (size_t k = 0; k < np; k++) h[2 * n + k] = CopyDesc{pc.d_slot[k], dout + off[pc.member[k]] + 2 + pc.rel[k], pc.len[k]};
     ZB_CUDA(ctx, cudaMemcpyAsync(db, hb, n * 8, cudaMemcpyHostToDevice, ctx->stream));
-    ZB_CUDA(ctx, cudaMemcpyAsync(ctx->d_desc2.p, h, 3 * n * sizeof(CopyDesc), cudaMemcpyHostToDevice, ctx->stream));
-    if (int st = gather_launch(ctx, ctx->d_desc2.as<CopyDesc>(), (uint32_t)(3 * n))) return st;
+    ZB_CUDA(ctx, cudaMemcpyAsync(ctx->d_desc2.p, h, (2 * n + np) * sizeof(CopyDesc), cudaMemcpyHostToDevice, ctx->stream));
+    if (int st = gather_launch(ctx, ctx->d_desc2.as<CopyDesc>(), (uint32_t)(2 * n + np))) return st;
   }
   for (size_t i = 0; i < n; i++) dst_off[i] = off[i];
   ctx->last_off = off; ctx->last_len = flen; ctx->last_total = total;
