@@ -150,3 +150,34 @@ def test_many_mid_sized_streams_stay_on_the_one_warp_decoder(ctx):
     res = ctx.inflate_batch([stream] * 240, [len(data)] * 240, _lib.CK_CRC32)           # hundreds of them: side by side, a warp each
     assert all(st == 0 and crc == zlib.crc32(data) for st, _, crc in res) and res[239][1].tobytes() == data
     assert ctx.parallel_streams == before
+
+
+def test_large_zlib_streams_with_adler32_take_the_many_warp_path(ctx):
+    """zlib_decompress / inflate_and_adler_32 of a large stream: decoded by many warps, the Adler-32 folded block by block over
+    the block lengths the chunks report -- bit-exact with the reference's per-block fold (signed remainder, state re-packed
+    between blocks: zipc_deflate.ml:175-198, 682-690) on data where that differs from RFC 1950."""
+    t = np.frombuffer(synth.text_v1(91, 5 << 20).tobytes(), dtype=np.uint8)
+    quirk = (t | 0x80).tobytes()[:-333] + b"\xff" * 300_000 + synth.rand_v1(92, 200_001).tobytes() + bytes(70_000)
+    text = t.tobytes()
+    for data in (text, quirk):
+        raw = _raw(data, 6)
+        want_out, want_ad = zo.inflate_and_adler_32(raw, len(data))       # the reference's fold over zlib's blocks
+        before = ctx.parallel_streams
+        (st, out, ad), = ctx.inflate_batch([raw], [len(data)], _lib.CK_ADLER32, _lib.ADLER_REF_COMPAT)
+        assert st == 0 and out.tobytes() == data == want_out and ad == want_ad
+        assert ctx.parallel_streams[0] == before[0] + 1
+        (st, out, ad), = ctx.inflate_batch([raw], [None], _lib.CK_ADLER32, _lib.ADLER_RFC1950)   # sizing pass first
+        assert st == 0 and out.tobytes() == data and ad == zlib.adler32(data)
+    assert zo.inflate_and_adler_32(_raw(quirk, 6), len(quirk))[1] != zlib.adler32(quirk)         # (the quirk is exercised)
+    # the zlib framing on top: a standard stream of quirk data is a checksum mismatch in the reference's flavour, with its pair
+    z = zlib.compress(quirk, 6)
+    r = zd.zlib_decompress(z)
+    try:
+        zo.zlib_decompress(z)
+        raise AssertionError("the oracle accepted the stream")
+    except zo.OracleError as e:
+        assert r.is_error() and r.info == (e.extra["expect"], e.extra["found"])
+    assert zd.zlib_decompress(z, adler_mode=_lib.ADLER_RFC1950).get_ok() == (quirk, zlib.adler32(quirk))
+    # and our own zlib_compress of a large payload (split over CTAs) comes back through it
+    ad, zs = zd.zlib_compress(quirk, level="default").get_ok()
+    assert zd.zlib_decompress(bytes(zs)).get_ok() == (quirk, ad)

@@ -521,11 +521,11 @@ static int par_speculate(zipc_b200_ctx *ctx, const uint8_t *d_src, size_t src_le
   *ok = false;
   zipc_b200_ctx::ParPlan &plan = ctx->par_plan;
   if (plan.src == d_src && plan.src_len == src_len && plan.epoch == ctx->epoch && !plan.len.empty()) { *ok = true; return ZIPC_OK; }
-  plan.len.clear(); plan.spec_off.clear(); plan.total = 0;
+  plan.len.clear(); plan.spec_off.clear(); plan.blocks.clear(); plan.total = 0;
   const uint64_t cb = par_chunk_bytes();
   const uint32_t nch0 = (uint32_t)((src_len + cb - 1) / cb);
   if (nch0 < 4 || src_len > (1ull << 40)) return ZIPC_OK;
-  const size_t tab = (size_t)nch0 * (sizeof(uint64_t) * 4 + sizeof(InflateTask) + sizeof(InflateResult)) + 256;
+  const size_t tab = (size_t)nch0 * (sizeof(uint64_t) * 4 + sizeof(InflateTask) + sizeof(InflateResult) + kSpecBlocks * sizeof(uint32_t)) + 256;
   if (int st = ctx->d_par.reserve(tab)) return st;
   if (int st = ctx->h_res.reserve(tab)) return st;
   uint64_t *d_found = ctx->d_par.as<uint64_t>();
@@ -533,6 +533,9 @@ static int par_speculate(zipc_b200_ctx *ctx, const uint8_t *d_src, size_t src_le
   InflateTask *d_tasks = reinterpret_cast<InflateTask *>(ctx->d_par.as<uint64_t>() + 4 * (size_t)nch0);
   InflateResult *d_results = reinterpret_cast<InflateResult *>(d_tasks + nch0);
   InflateResult *h_results = reinterpret_cast<InflateResult *>(ctx->h_res.as<uint64_t>() + 4 * (size_t)nch0);
+  // per chunk: the output lengths of its non-empty blocks (the Adler-32 of a zlib stream is folded block by block)
+  unsigned int *d_blk = reinterpret_cast<unsigned int *>(d_results + nch0);
+  const uint32_t *h_blk = reinterpret_cast<const uint32_t *>(h_results + nch0);
   // Passes over what is left of the stream.  A pass: (1) block starts, (2) speculative decode of the chunks between them,
   // (3) the chunks must chain up exactly -- each one ends, at a block boundary, on the very bit where the next one was found
   // to start.  A found start that is an accident of the bits inside a block (rare) breaks the chain, and may have hidden the
@@ -581,8 +584,9 @@ static int par_speculate(zipc_b200_ctx *ctx, const uint8_t *d_src, size_t src_le
       t.start_bit = start[k]; t.stop_bit = k + 1 < m ? start[k + 1] : ~0ull;
     }
     ZB_CUDA(ctx, cudaMemcpyAsync(d_tasks, tasks.data(), m * sizeof(InflateTask), cudaMemcpyHostToDevice, ctx->stream));
-    if (int st = inflate_launch_spec(ctx, d_tasks, m, d_results)) return st;
+    if (int st = inflate_launch_spec(ctx, d_tasks, m, d_results, d_blk)) return st;
     ZB_CUDA(ctx, cudaMemcpyAsync(h_results, d_results, m * sizeof(InflateResult), cudaMemcpyDeviceToHost, ctx->stream));
+    ZB_CUDA(ctx, cudaMemcpyAsync(const_cast<uint32_t *>(h_blk), d_blk, (size_t)m * kSpecBlocks * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
     ZB_CUDA(ctx, stream_sync(ctx, ctx->stream));
     if (par_debug())
       std::fprintf(stderr, "[par] pass %d from bit %llu of %zu bytes: %u nominal chunks, %u block starts: find %.2f ms, speculative decode %.2f ms\n",
@@ -603,7 +607,10 @@ static int par_speculate(zipc_b200_ctx *ctx, const uint8_t *d_src, size_t src_le
       }
     }
     if (used == 0) return ZIPC_OK;     // corrupt, or larger than 24 times its compressed size: the serial decoder reports it
-    for (uint32_t k = 0; k < used; k++) { plan.spec_off.push_back(spec_off[k]); plan.len.push_back(h_results[k].out_len); plan.total += h_results[k].out_len; }
+    for (uint32_t k = 0; k < used; k++) {
+      plan.spec_off.push_back(spec_off[k]); plan.len.push_back(h_results[k].out_len); plan.total += h_results[k].out_len;
+      plan.blocks.insert(plan.blocks.end(), h_blk + (size_t)k * kSpecBlocks, h_blk + (size_t)k * kSpecBlocks + std::min<uint32_t>(h_results[k]._pad2, kSpecBlocks));
+    }
     if (final_seen) {
       plan.src = d_src; plan.src_len = src_len; plan.epoch = ctx->epoch;
       *ok = true;
@@ -613,7 +620,7 @@ static int par_speculate(zipc_b200_ctx *ctx, const uint8_t *d_src, size_t src_le
     spec_used = spec_off[used - 1] + capv[used - 1];
     if (from_bit >= 8ull * src_len) break;   // ran off the end without a final block
   }
-  plan.len.clear(); plan.spec_off.clear(); plan.total = 0;
+  plan.len.clear(); plan.spec_off.clear(); plan.blocks.clear(); plan.total = 0;
   return ZIPC_OK;
 }
 
@@ -649,7 +656,7 @@ int inflate_core(zipc_b200_ctx *ctx, int ck, int adler_mode, size_t n, const std
                  bool count_only, size_t *out_len, uint32_t *checksum, int *status, uint32_t flags, const DownloadPlan *plan) {
   std::vector<char> done(n, 0);
   size_t ndone = 0;
-  if (flags == 0 && ck != ZIPC_CK_ADLER32 && par_min_bytes() != 0 && !(plan && plan->ngroups)) {  // (Adler-32 is folded block by block: serial path)
+  if (flags == 0 && par_min_bytes() != 0 && !(plan && plan->ngroups)) {
     const size_t lanes = ctx->is_sub ? 1 : par_lane_count();
     std::vector<char> take;
     par_select(n, src_len, take, lanes);
@@ -673,6 +680,15 @@ int inflate_core(zipc_b200_ctx *ctx, int ck, int adler_mode, size_t n, const std
             if (int st = crc32_launch_buffer(c, d_dst[i], total, d_crc)) return st;
             ZB_CUDA(c, cudaMemcpyAsync(&checksum[i], d_crc, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
             ZB_CUDA(c, stream_sync(c, c->stream));
+          } else if (ck == ZIPC_CK_ADLER32) {
+            // folded block by block, each block on its own 5552-byte grid with the state re-packed in between, as the reference
+            // does while it decodes (zipc_deflate.ml:682-690): the chunks reported the lengths of their blocks
+            const uint8_t *base = d_dst[i];
+            const uint32_t nb = (uint32_t)c->par_plan.blocks.size();
+            uint64_t sum = 0;
+            for (uint32_t b : c->par_plan.blocks) sum += b;
+            if (sum != total) ok = false;  // (cannot happen; the one-warp decoder folds it then)
+            else if (int st = adler32_blocked(c, &base, &nb, c->par_plan.blocks.data(), 1, adler_mode, &checksum[i])) return st;
           }
         }
       }

@@ -163,6 +163,7 @@ struct zipc_b200_ctx {
     size_t src_len = 0;
     uint64_t epoch = 0;
     std::vector<uint64_t> spec_off, len;
+    std::vector<uint32_t> blocks;      // output lengths of the stream's non-empty deflate blocks, in order (Adler-32 is folded per block)
     uint64_t total = 0;
   } par_plan;
   uint64_t epoch = 1;
@@ -302,7 +303,9 @@ int inflate_launch(zipc_b200_ctx *ctx, const InflateTask *d_tasks, uint32_t n, I
 int inflate_find_starts(zipc_b200_ctx *ctx, const uint8_t *d_src, uint64_t src_len, uint64_t first_bit, uint64_t chunk_bytes,
                         uint32_t nchunks, uint64_t *d_found);
 // 2. speculative decode of the chunks (tasks carry start_bit / stop_bit, dst = 16-bit symbols)
-int inflate_launch_spec(zipc_b200_ctx *ctx, const InflateTask *d_tasks, uint32_t n, InflateResult *d_results);
+// d_block_lists (may be null): kSpecBlocks entries per task, the output lengths of the non-empty blocks of every chunk (for Adler-32)
+constexpr uint32_t kSpecBlocks = 256;
+int inflate_launch_spec(zipc_b200_ctx *ctx, const InflateTask *d_tasks, uint32_t n, InflateResult *d_results, unsigned int *d_block_lists = nullptr);
 // 3. resolve: windows chunk by chunk, then every symbol to its byte.  d_spec_off / d_out_off / d_len: per chunk (device).
 //    d_windows: 4 * 32768 bytes per chunk of scratch.  *d_bad is set if anything refers to bytes before the stream
 int inflate_resolve(zipc_b200_ctx *ctx, const uint16_t *d_spec, const uint64_t *d_spec_off, const uint64_t *d_out_off,

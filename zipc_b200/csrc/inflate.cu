@@ -119,6 +119,7 @@ struct WarpState {
   uint64_t limit;          // first input bit past the stream, counted from srcw
   uint32_t nwords;         // words that may be read
   uint32_t skew;           // bits between srcw and the stream start (0, 8, 16, 24)
+  uint32_t nblk;           // speculative chunks: non-empty blocks decoded so far
 };
 struct __align__(16) WarpWork {
   WarpState st;
@@ -616,7 +617,7 @@ inflate_kernel(const InflateTask *__restrict__ tasks, uint32_t ntasks, InflateRe
         }
       }
       __syncwarp();
-      if (lane == 0) { st.src = t.src; st.src_len = t.src_len; st.out_cap = t.dst_cap; st.ad_from = 0; }
+      if (lane == 0) { st.src = t.src; st.src_len = t.src_len; st.out_cap = t.dst_cap; st.ad_from = 0; st.nblk = 0; }
       dst = t.dst; segment = (t.flags & kInflateSegment) != 0;
       out_pos = 0; status = ZIPC_OK; final_blk = false;
       ad_state = 1; ad_pending = false;
@@ -951,6 +952,19 @@ inflate_kernel(const InflateTask *__restrict__ tasks, uint32_t ntasks, InflateRe
     // Adler-32 restarts its 5552-byte chunk grid at every block and, as written in the reference, reduces
     // with a signed remainder, so it has to be folded block by block to stay bit-exact.
     if (ad_pending) {
+      if (SPEC && group_count) {
+        // speculative chunk: the output length of every non-empty block goes to the chunk's list (group_count is that array in
+        // this mode, kSpecBlocks entries per task): the host folds the Adler-32 of a large zlib stream over these blocks
+        if (lane == 0) {
+          const uint64_t blen = out_pos - st.ad_from;
+          if (blen) {
+            if (st.nblk < kSpecBlocks) group_count[(size_t)task * kSpecBlocks + st.nblk] = (unsigned int)blen;
+            st.nblk++;
+            st.ad_from = out_pos;
+          }
+        }
+        __syncwarp();
+      }
       if (!COUNT_ONLY && !SPEC && adler_mode >= 0) {
         __syncwarp();
         ad_state = adler_update_warp<true>(ad_state, dst + st.ad_from, out_pos - st.ad_from, adler_mode, lane);
@@ -971,7 +985,8 @@ inflate_kernel(const InflateTask *__restrict__ tasks, uint32_t ntasks, InflateRe
         r._pad = status == ZIPC_OK ? ad_state : 0;  // fused Adler-32 of the output (when requested)
         r.end_bit = in.consumed(wk);
         r.final_seen = final_blk ? 1u : 0u;
-        r._pad2 = 0;
+        r._pad2 = SPEC ? st.nblk : 0u;              // (speculative chunks) non-empty blocks decoded: their lengths are in the chunk's list
+        if (SPEC && group_count && st.nblk > kSpecBlocks && status == ZIPC_OK) { r.status = ZIPC_ERR_DST_TOO_SMALL; r.out_len = 0; }  // list full: not this way
         results[task] = r;
       }
       if (!COUNT_ONLY && !SPEC && group_count) {
@@ -1187,7 +1202,7 @@ int inflate_find_starts(zipc_b200_ctx *ctx, const uint8_t *d_src, uint64_t src_l
   return ZIPC_OK;
 }
 
-int inflate_launch_spec(zipc_b200_ctx *ctx, const InflateTask *d_tasks, uint32_t n, InflateResult *d_results) {
+int inflate_launch_spec(zipc_b200_ctx *ctx, const InflateTask *d_tasks, uint32_t n, InflateResult *d_results, unsigned int *d_block_lists) {
   if (n == 0) return ZIPC_OK;
   // Spread the chunks: a chunk is one block of the stream on one warp, and the call waits for the slowest of them -- a warp with
   // few neighbours on its SM decodes nearly twice as fast as one of 32 (35 against 16-20 MB/s).  About four chunks per CTA, over
@@ -1201,7 +1216,7 @@ int inflate_launch_spec(zipc_b200_ctx *ctx, const InflateTask *d_tasks, uint32_t
   unsigned int start = grid * WARPS;  // tasks [0, start) are assigned statically
   ZB_CUDA(ctx, cudaMemcpyAsync(queue, &start, sizeof start, cudaMemcpyHostToDevice, ctx->stream));
   KernelTimer kt(ctx);
-  inflate_kernel<false, true><<<grid, THREADS, kSmemBytes, ctx->stream>>>(d_tasks, n, d_results, queue, ctx->d_scratch.as<uint16_t>(), -1, nullptr, nullptr, nullptr, 0);
+  inflate_kernel<false, true><<<grid, THREADS, kSmemBytes, ctx->stream>>>(d_tasks, n, d_results, queue, ctx->d_scratch.as<uint16_t>(), -1, d_block_lists, nullptr, nullptr, 0);
   ctx->launches++;
   ZB_CUDA(ctx, cudaGetLastError());
   return ZIPC_OK;
