@@ -40,7 +40,7 @@ sys.path.insert(0, ROOT)
 
 GiB = 1 << 30
 METRIC = {"crc32": "crc32_GBps_uncompressed", "inflate": "inflate_GBps_uncompressed", "deflate": "deflate_GBps_uncompressed"}
-LEVELS = {"fast": 1, "default": 2, "best": 3}
+LEVELS = {"none": 0, "fast": 1, "default": 2, "best": 3}
 
 
 def workload_desc(which, level="default", members=10000):
@@ -902,10 +902,11 @@ def main():
         if not r.get("kernel_ms"):
             return None
         ach = r["algo_bytes"] / (r["kernel_ms"] / 1e3) / 1e9
-        which = {"crc32_tiles_kernel": "crc32", "inflate_kernel<false>": "inflate", "deflate_kernel": "deflate"}[r["kernel"]]
-        return {"bound": "hbm", "achieved": round(ach, 1), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4), "traffic": ncu_traffic(which),
+        which = {"crc32_tiles_kernel": "crc32", "inflate_kernel<false>": "inflate", "deflate_kernel": "deflate"}.get(r["kernel"])
+        return {"bound": "hbm", "achieved": round(ach, 1), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4),
+                "traffic": ncu_traffic(which) if which else None,
                 "kernel": r["kernel"], "kernel_ms": round(r["kernel_ms"], 4), "algorithmic_bytes": int(r["algo_bytes"]), "peak_source": peak_src,
-                "ncu": {k: v for k, v in ncu_capture(which).items() if k not in ("traffic_bytes", "kernel")}}
+                "ncu": {k: v for k, v in ncu_capture(which).items() if k not in ("traffic_bytes", "kernel")} if which else None}
 
     def brief(r, which, level=None):
         d = {"metric": METRIC[which], "value": round(r["value"], 2), "unit": "GB/s", "e2e": round(r["e2e"], 3) if r.get("e2e") else None,
@@ -988,6 +989,15 @@ def main():
         for level in ("fast", "default", "best"):
             if level != args.level:
                 guard("deflate_" + level, lambda level=level: lvl_entry(level))
+
+        def none_entry():  # level `None: stored blocks, byte-identical to the reference's output -- a copy with block headers
+            rr = measured(lambda: run_deflate(h, datas, "none", 3, 3, e2e=False))
+            rr["kernel"] = "stored_kernel"
+            rr["algo_bytes"] = 2 * rr["units"]   # every input byte read once and written once (+ 5 bytes per 65,534)
+            d = brief(rr, "deflate", "none")
+            d["note"] = "stored blocks of 65,534 bytes (zipc_deflate.ml:747-750, 1106-1116); roofline: bytes read + bytes written over the kernel's time"
+            return d
+        guard("deflate_none", none_entry)
         if which != "inflate":
             def inflate_entry():
                 get_streams()

@@ -232,7 +232,7 @@ int adler32_blocked(zipc_b200_ctx *ctx, const uint8_t *const *d_ptrs, const uint
 // d_blk_lens (may be null): receives the source length of every deflate block of member i at
 // d_blk_lens[task.blk_off + b], b < result.blocks -- the ranges the reference checksums one by one (:1081-1086)
 int deflate_launch(zipc_b200_ctx *ctx, const DeflateTask *d_tasks, uint32_t n, DeflateResult *d_results, int level,
-                   uint32_t *d_blk_lens = nullptr);
+                   uint32_t *d_blk_lens = nullptr, uint64_t max_src_len = 0 /* level `None: the longest input, sizes the grid */);
 // upper bound of the number of deflate blocks the encoder emits for an input of src_len bytes
 inline uint32_t deflate_max_blocks(uint64_t src_len) { return (uint32_t)(src_len / 61440) + 2; }
 constexpr uint32_t kStoredBlock = 65534;  // source bytes per block at level `None (reference :747-750, :1106-1116)

@@ -1234,27 +1234,51 @@ deflate_kernel(const DeflateTask *__restrict__ tasks, uint32_t ntasks, DeflateRe
   }
 }
 
-// level `None (reference :1106-1116): stored blocks only, one CTA per member.  Blocks hold 65534 bytes as in the
-// reference (:747-750), so the output is byte-identical to Zipc_deflate.deflate ~level:`None.
+// level `None (reference :1106-1116): stored blocks only.  Blocks hold 65534 bytes as in the reference (:747-750), so the
+// output is byte-identical to Zipc_deflate.deflate ~level:`None.  A copy, so it should run at the speed of the memory: every
+// stored block is a unit of its own (header + 65534 bytes), `per_task` CTAs share the blocks of a member (a 64 MiB member is
+// 1025 blocks for the whole grid, not one CTA's), and the bytes move as aligned 32-bit words -- block b's payload lands at
+// 65539 b + 5, its source starts at 65534 b, so the two are misaligned against each other by a different amount in every
+// block: aligned loads, funnel shift, aligned stores (the gather kernel's method, zip_api.cu).
+__device__ __forceinline__ void cta_copy_words(uint8_t *dst, const uint8_t *src, uint64_t len) {
+  uint64_t head = (4 - ((uintptr_t)dst & 3)) & 3;
+  if (head > len) head = len;
+  for (uint64_t i = threadIdx.x; i < head; i += blockDim.x) dst[i] = src[i];
+  const uint8_t *sb = src + head;
+  const uint32_t sh = (uint32_t)((uintptr_t)sb & 3) * 8;
+  const uint32_t *s = reinterpret_cast<const uint32_t *>(sb - (sh >> 3));
+  uint32_t *t = reinterpret_cast<uint32_t *>(dst + head);
+  const uint64_t nw = (len - head) >> 2;
+  if (sh == 0) {
+    for (uint64_t i = threadIdx.x; i < nw; i += blockDim.x) t[i] = __ldg(s + i);
+  } else {
+    // word i of the destination = bytes [4i + sh/8, 4i + sh/8 + 4) of the aligned source words: s[i + 1] holds at least one
+    // byte of the range, so it lies inside the source's last touched word
+    for (uint64_t i = threadIdx.x; i < nw; i += blockDim.x) t[i] = __funnelshift_r(__ldg(s + i), __ldg(s + i + 1), sh);
+  }
+  for (uint64_t i = head + (nw << 2) + threadIdx.x; i < len; i += blockDim.x) dst[i] = src[i];
+}
 __global__ void __launch_bounds__(256)
-stored_kernel(const DeflateTask *__restrict__ tasks, uint32_t ntasks, DeflateResult *__restrict__ results) {
-  const uint32_t task = blockIdx.x;
+stored_kernel(const DeflateTask *__restrict__ tasks, uint32_t ntasks, DeflateResult *__restrict__ results, uint32_t per_task) {
+  const uint32_t task = blockIdx.x / per_task, sub = blockIdx.x % per_task;
   if (task >= ntasks) return;
   const DeflateTask t = tasks[task];
   constexpr uint64_t B = kStoredBlock;
   const uint64_t n = t.src_len, nblk = n ? (n + B - 1) / B : 1, need = n + 5 * nblk;
   if (need > t.dst_cap) {
-    if (threadIdx.x == 0) { results[task].out_len = 0; results[task].status = ZIPC_ERR_DST_TOO_SMALL; results[task].blocks = 0; }
+    if (sub == 0 && threadIdx.x == 0) { results[task].out_len = 0; results[task].status = ZIPC_ERR_DST_TOO_SMALL; results[task].blocks = 0; }
     return;
   }
-  for (uint64_t b = threadIdx.x; b < nblk; b += blockDim.x) {
-    uint64_t len = b + 1 < nblk ? B : n - b * B;
+  for (uint64_t b = sub; b < nblk; b += per_task) {
+    const uint64_t len = b + 1 < nblk ? B : n - b * B;
     uint8_t *h = t.dst + b * (B + 5);
-    h[0] = (b + 1 == nblk && !(t.flags & kDeflateNotFinal)) ? 1 : 0;
-    h[1] = (uint8_t)len; h[2] = (uint8_t)(len >> 8); h[3] = (uint8_t)~len; h[4] = (uint8_t)(~len >> 8);
+    if (threadIdx.x == 0) {
+      h[0] = (b + 1 == nblk && !(t.flags & kDeflateNotFinal)) ? 1 : 0;
+      h[1] = (uint8_t)len; h[2] = (uint8_t)(len >> 8); h[3] = (uint8_t)~len; h[4] = (uint8_t)(~len >> 8);
+    }
+    cta_copy_words(h + 5, t.src + b * B, len);
   }
-  for (uint64_t i = threadIdx.x; i < n; i += blockDim.x) t.dst[i + 5 * (i / B + 1)] = t.src[i];
-  if (threadIdx.x == 0) { results[task].out_len = need; results[task].status = ZIPC_OK; results[task].blocks = (uint32_t)nblk; }
+  if (sub == 0 && threadIdx.x == 0) { results[task].out_len = need; results[task].status = ZIPC_OK; results[task].blocks = (uint32_t)nblk; }
 }
 
 unsigned long long g_attr_devs = 0;  // bit d: attributes set on device d (function attributes are per device)
@@ -1262,10 +1286,16 @@ unsigned long long g_attr_devs = 0;  // bit d: attributes set on device d (funct
 }  // namespace
 
 int deflate_launch(zipc_b200_ctx *ctx, const DeflateTask *d_tasks, uint32_t n, DeflateResult *d_results, int level,
-                   uint32_t *d_blk_lens) {
+                   uint32_t *d_blk_lens, uint64_t max_src_len) {
   if (n == 0) return ZIPC_OK;
   if (level == ZIPC_LEVEL_NONE) {
-    stored_kernel<<<n, 256, 0, ctx->stream>>>(d_tasks, n, d_results);
+    // CTAs per member: as many as its largest member has stored blocks, while the grid stays within ~64 CTAs per SM
+    const uint64_t blocks = max_src_len ? (max_src_len + kStoredBlock - 1) / kStoredBlock : 1;
+    const uint32_t per_task = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(blocks, (uint64_t)ctx->sm_count * 64 / n));
+    {
+      KernelTimer kt(ctx);
+      stored_kernel<<<n * per_task, 256, 0, ctx->stream>>>(d_tasks, n, d_results, per_task);
+    }
     ctx->launches++;
     ZB_CUDA(ctx, cudaGetLastError());
     return ZIPC_OK;

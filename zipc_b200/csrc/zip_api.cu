@@ -117,7 +117,7 @@ int deflate_run(zipc_b200_ctx *ctx, int level, int ck, int adler_mode, size_t n,
     lk.unlock();
     ZB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, gate->done[ticket - 2], 0));
   }
-  const int launch_rc = deflate_launch(ctx, dt, (uint32_t)n, dr, level, d_blk);
+  const int launch_rc = deflate_launch(ctx, dt, (uint32_t)n, dr, level, d_blk, n ? src_len[order[0]] : 0);  // (order: longest first)
   if (ordered) {
     if (launch_rc == ZIPC_OK) cudaEventRecord(gate->done[ticket], ctx->stream);
     { std::lock_guard<std::mutex> lk(gate->m); gate->launched[ticket] = 1; }
