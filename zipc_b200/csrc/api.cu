@@ -929,6 +929,7 @@ void zipc_b200_ctx_destroy(zipc_b200_ctx *ctx) {
   if (ctx->ev_half) cudaEventDestroy(ctx->ev_half);
   if (ctx->ev_block) cudaEventDestroy(ctx->ev_block);
   if (ctx->h_gflag) cudaFreeHost(ctx->h_gflag);
+  if (ctx->h_word) cudaFreeHost(ctx->h_word);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }

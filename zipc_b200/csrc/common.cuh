@@ -154,6 +154,7 @@ struct zipc_b200_ctx {
   cudaEvent_t ev_block = nullptr;      // stream_sync of a sub-context
   cudaEvent_t ev_half = nullptr;       // first half of a split upload is through
   bool upload_split_live = false;      // the late half of the current upload is still on its way
+  uint32_t *h_word = nullptr;          // mapped host memory: the one-word result of a whole-buffer Adler-32, written by the kernel
   uint32_t *h_gflag = nullptr;         // mapped host memory: group-complete flags written by inflate_kernel
 
   // intra-stream parallel inflate: the plan of the last large stream decoded speculatively (a count-only pass is followed by
