@@ -1006,11 +1006,11 @@ int zipc_b200_crc32_dev_async(zipc_b200_ctx *ctx, const void *d_src, size_t len,
 int zipc_b200_crc32_dev(zipc_b200_ctx *ctx, const void *d_src, size_t len, uint32_t *crc) {
   if (!ctx || !crc || (!d_src && len)) return ZIPC_ERR_INVALID_ARG;
   DeviceGuard g(ctx->device);
-  if (int st = ctx->d_small.reserve(256)) return st;
-  uint32_t *d_crc = ctx->d_small.as<uint32_t>() + 32;
-  if (int st = crc32_launch_buffer(ctx, static_cast<const uint8_t *>(d_src), len, d_crc)) return st;
-  ZB_CUDA(ctx, cudaMemcpyAsync(crc, d_crc, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  // the combine kernel's last thread stores the one-word result straight into mapped host memory (as adler32_launch_buffer does)
+  if (!ctx->h_word) ZB_CUDA(ctx, cudaHostAlloc(reinterpret_cast<void **>(&ctx->h_word), 64, cudaHostAllocMapped));
+  if (int st = crc32_launch_buffer(ctx, static_cast<const uint8_t *>(d_src), len, ctx->h_word + 1)) return st;
   ZB_CUDA(ctx, stream_sync(ctx, ctx->stream));
+  *crc = reinterpret_cast<volatile uint32_t *>(ctx->h_word)[1];
   return ZIPC_OK;
 }
 
