@@ -676,10 +676,11 @@ int inflate_core(zipc_b200_ctx *ctx, int ck, int adler_mode, size_t n, const std
         if (ok && checksum) {
           checksum[i] = 0;
           if (ck == ZIPC_CK_CRC32) {
-            uint32_t *d_crc = c->d_small.as<uint32_t>() + 32;
-            if (int st = crc32_launch_buffer(c, d_dst[i], total, d_crc)) return st;
-            ZB_CUDA(c, cudaMemcpyAsync(&checksum[i], d_crc, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+            // (the result word through mapped host memory: a 4-byte copy into the caller's pageable array would hold up every lane)
+            if (!c->h_word) ZB_CUDA(c, cudaHostAlloc(reinterpret_cast<void **>(&c->h_word), 64, cudaHostAllocMapped));
+            if (int st = crc32_launch_buffer(c, d_dst[i], total, c->h_word + 1)) return st;
             ZB_CUDA(c, stream_sync(c, c->stream));
+            checksum[i] = reinterpret_cast<volatile uint32_t *>(c->h_word)[1];
           } else if (ck == ZIPC_CK_ADLER32) {
             // folded block by block, each block on its own 5552-byte grid with the state re-packed in between, as the reference
             // does while it decodes (zipc_deflate.ml:682-690): the chunks reported the lengths of their blocks
