@@ -139,7 +139,8 @@ uint32_t zipc_b200_adler32_combine(uint32_t adler_a, uint32_t adler_b, uint64_t 
  *                   the ctx until the next call and can be fetched with zipc_b200_fetch().
  *   checksum[i]     checksum of output i (0 for ZIPC_CK_NONE)
  *   status[i]       ZIPC_OK / ZIPC_ERR_CORRUPTED / ZIPC_ERR_SIZE_EXCEEDED
- * A stream is decoded by one warp; a LARGE stream (256 KiB of compressed data or more, no index needed) is decoded by many:
+ * A stream is decoded by one warp; LARGE streams (64 KiB of compressed data or more, no index needed; which of a batch's streams is
+ * decided by a cost model over the batch, see zipc_b200_inflate_plan; several at a time; with either checksum) are decoded by many:
  * block starts are found by scanning for valid dynamic-block headers, the chunks between them are decoded speculatively
  * with the preceding 32 KiB unknown, and resolved once the chunks are seen to chain up exactly; any doubt (and any error
  * inside the stream) sends the stream back to the one-warp decoder, so results and statuses are those of the serial
