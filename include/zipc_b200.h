@@ -293,6 +293,14 @@ int zipc_b200_zip_deflate_archive(zipc_b200_ctx *ctx, int level, size_t n,
                                   const int32_t *mode, const int64_t *mtime, const char *first,
                                   void *out, size_t out_cap, size_t *out_len);
 
+/* The same with ZIPC_ZIP_* flags (see zipc_b200_zip_parse_ex): with ZIP64 allowed, more than 65,535 members or an archive of
+ * 4 GiB or more is written with ZIP64 records instead of being refused (zipc.ml:229-235, 550-551, 574). */
+int zipc_b200_zip_deflate_archive_ex(zipc_b200_ctx *ctx, int level, size_t n,
+                                     const char *const *paths, const uint32_t *path_len,
+                                     const void *const *src, const size_t *src_len,
+                                     const int32_t *mode, const int64_t *mtime, const char *first, unsigned flags,
+                                     void *out, size_t out_cap, size_t *out_len);
+
 /* ---- box-wide entry points (SURVEY.md 8b "device_mask", 8e) -------------------------------------------------------- */
 /* One call drives every selected GPU of the node: a multi-context owns one zipc_b200_ctx (stream, arenas) and one
  * host thread per device.  Batches are partitioned over the devices longest-first by member size (members are

@@ -339,3 +339,20 @@ def test_zip64_archives_extract_and_create(ctx):
     back = zipc.of_binary_string(forced, zip64=True).get_ok()
     for p, r in zip(sorted(back), zipc.File.to_binary_strings([back[p].kind for p in sorted(back)])):
         assert r.get_ok() == datas[p.decode()]
+
+
+def test_archive_creation_with_more_than_65535_members(ctx):
+    """zipc_b200_zip_deflate_archive_ex with ZIP64 allowed: one call compresses 66,000 payloads and writes the archive with a
+    ZIP64 end of central directory record (the reference's call refuses: zipc.ml:574); CPython reads it."""
+    n = 66_000
+    paths = ["d/%05d.txt" % i for i in range(n)]
+    payloads = [b"payload %d " % i * (1 + i % 7) for i in range(n)]
+    r = zipc.archive_of_binary_strings(paths, payloads, "fast")
+    assert r.is_error() and r.status == 28
+    blob = zipc.archive_of_binary_strings(paths, payloads, "fast", zip64=True).get_ok()
+    with zipfile.ZipFile(io.BytesIO(blob)) as zf:
+        assert len(zf.namelist()) == n
+        for i in (0, 1, 4999, 65_535, 65_999):
+            assert zf.read(paths[i]) == payloads[i]
+    z = zipc.of_binary_string(blob, zip64=True).get_ok()
+    assert zipc.member_count(z) == n

@@ -642,10 +642,20 @@ int zipc_b200_zip_deflate_archive(zipc_b200_ctx *ctx, int level, size_t n, const
                                   const uint32_t *path_len, const void *const *src, const size_t *src_len,
                                   const int32_t *mode, const int64_t *mtime, const char *first, void *out,
                                   size_t out_cap, size_t *out_len) {
+  return zipc_b200_zip_deflate_archive_ex(ctx, level, n, paths, path_len, src, src_len, mode, mtime, first, ZIPC_ZIP_REFERENCE, out, out_cap, out_len);
+}
+
+// flags: ZIPC_ZIP_* (include/zipc_b200.h).  With ZIP64 allowed more than 65,535 members and an archive of 4 GiB or more are
+// written with ZIP64 records instead of being refused; the payloads are compressed and placed exactly as without the flag.
+int zipc_b200_zip_deflate_archive_ex(zipc_b200_ctx *ctx, int level, size_t n, const char *const *paths,
+                                     const uint32_t *path_len, const void *const *src, const size_t *src_len,
+                                     const int32_t *mode, const int64_t *mtime, const char *first, unsigned flags, void *out,
+                                     size_t out_cap, size_t *out_len) {
   if (!ctx || level < 0 || level > 3 || !out_len || (n && (!paths || !path_len || !src || !src_len)))
     return ZIPC_ERR_INVALID_ARG;
   DeviceGuard g(ctx->device);
-  if (n > 0xFFFF) return ZIPC_ERR_ZIP_COUNT;  // zipc.ml:574
+  const bool zip64 = (flags & (ZIPC_ZIP_ALLOW_ZIP64 | ZIPC_ZIP_FORCE_ZIP64)) != 0;
+  if (n > 0xFFFF && !zip64) return ZIPC_ERR_ZIP_COUNT;  // zipc.ml:574
   // Member.make path rules (zipc.ml:244-255): backslashes become slashes; sizes are checked by File.make
   std::vector<std::string> norm(n);
   for (size_t i = 0; i < n; i++) {
@@ -695,10 +705,10 @@ int zipc_b200_zip_deflate_archive(zipc_b200_ctx *ctx, int level, size_t n, const
         fill_members(ms);
         std::vector<uint64_t> want(n, ~0ull);
         size_t total = 0;
-        if (int st = zip_assemble_impl(ms.data(), n, first, nullptr, 0, &total, false, want.data())) return st;
+        if (int st = zip_assemble_impl(ms.data(), n, first, nullptr, 0, &total, false, want.data(), flags)) return st;
         bool placed = true;
         for (size_t i = 0; i < n && placed; i++) placed = want[i] == poff[i];
-        if (placed) return zip_assemble_impl(ms.data(), n, first, out, out_cap, out_len, false, nullptr);
+        if (placed) return zip_assemble_impl(ms.data(), n, first, out, out_cap, out_len, false, nullptr, flags);
       } else if (rc != ZIPC_ERR_DST_TOO_SMALL) {
         return rc;
       }
@@ -715,7 +725,7 @@ int zipc_b200_zip_deflate_archive(zipc_b200_ctx *ctx, int level, size_t n, const
   // layout first, then the GPU gathers every payload to its archive offset, then headers on the host
   std::vector<uint64_t> poff(n, ~0ull);  // members shadowed by a later duplicate path keep ~0
   size_t total = 0;
-  if (int st = zip_assemble_impl(ms.data(), n, first, nullptr, 0, &total, false, poff.data())) return st;
+  if (int st = zip_assemble_impl(ms.data(), n, first, nullptr, 0, &total, false, poff.data(), flags)) return st;
   *out_len = total;
   if (!out || out_cap < total) return ZIPC_ERR_DST_TOO_SMALL;
   std::vector<size_t> off(n);
@@ -723,7 +733,7 @@ int zipc_b200_zip_deflate_archive(zipc_b200_ctx *ctx, int level, size_t n, const
   for (size_t k = 0; k < pc.member.size(); k++) if (poff[pc.member[k]] == ~0ull) pc.len[k] = 0;  // shadowed by a later duplicate path
   if (int st = compact_pieces(ctx, pc, off, total)) return st;
   if (int st = d2h(ctx, out, ctx->d_out.p, total)) return st;
-  return zip_assemble_impl(ms.data(), n, first, out, out_cap, out_len, false, nullptr);
+  return zip_assemble_impl(ms.data(), n, first, out, out_cap, out_len, false, nullptr, flags);
 }
 
 }  // extern "C"

@@ -280,7 +280,7 @@ def to_binary_string(z: dict, first: str | bytes | None = None, zip64=False):
 
 
 def archive_of_binary_strings(paths: list, payloads: list, level: str = "default", modes=None, mtimes=None,
-                              first: str | bytes | None = None):
+                              first: str | bytes | None = None, zip64=False):
     """Batch form of File.deflate_of_binary_string + Member.make + add + to_binary_string: the payloads are
     compressed on the GPU, gathered to their archive offsets there, and the headers are laid around them."""
     ctx = zd.default_context()
@@ -302,10 +302,10 @@ def archive_of_binary_strings(paths: list, payloads: list, level: str = "default
     need = C.c_size_t()
     lv = zd.LEVELS[level]
     # generous first guess; the call reports the exact size when it does not fit
-    cap = sum(v.size for v in vs) // 2 + 128 * n + 4096
+    cap = sum(v.size for v in vs) // 2 + (128 + (48 if zip64 else 0)) * n + 4096
     for _ in range(2):
         out = np.empty(max(cap, 1), dtype=np.uint8)
-        st = ctx.L.zipc_b200_zip_deflate_archive(ctx.h, lv, n, pp, pl, sp, sl, md, mt, f, out.ctypes.data, cap, C.byref(need))
+        st = ctx.L.zipc_b200_zip_deflate_archive_ex(ctx.h, lv, n, pp, pl, sp, sl, md, mt, f, _zip_flags(zip64), out.ctypes.data, cap, C.byref(need))
         if st == _lib.ERR_DST_TOO_SMALL:
             cap = need.value
             continue
