@@ -289,7 +289,7 @@ def cmd_zip(a) -> int:
             z = zipc.add(zipc.Member.make(nm, f, mode=md, mtime=mt).get_ok(), z)
         r = zipc.to_binary_string(z, zip64=ZIP64)
     else:
-        r = zipc.archive_of_binary_strings(names, payloads, a.level, modes, mtimes)
+        r = zipc.archive_of_binary_strings(names, payloads, a.level, modes, mtimes, zip64=ZIP64)
     if r.is_error():
         print(r.message, file=sys.stderr)
         return EXIT_SOME
